@@ -1,0 +1,195 @@
+/*
+ * maze_b200.h -- C-ABI of the B200 LOKI re-segmentation stage.
+ *
+ * The reference (MAZE-IPP) is pure Python and has no FFI; its hot path is a chain of Python
+ * callables invoked once per vignette (paths relative to the reference root):
+ *
+ *   threshold            image > threshold_brighter                 maze_ipp/loki/pipeline.py:649
+ *   bool cast            np.asarray(pred, dtype=bool)               maze_ipp/loki/pipeline.py:405
+ *   isotropic_erosion    edt(image) > radius                        maze_ipp/isotropic.py:8-36
+ *   isotropic_dilation   edt(image == 0) < radius                   maze_ipp/isotropic.py:39-67
+ *   isotropic_opening    erosion, dilation                          maze_ipp/isotropic.py:70-98
+ *   isotropic_closing    dilation, erosion                          maze_ipp/isotropic.py:101-129
+ *   label                skimage.measure.label(bool), 8-conn        maze_ipp/loki/pipeline.py:430-433
+ *   clear_border         clear_border(labels, out=labels)           maze_ipp/loki/pipeline.py:435-439
+ *   remove_small_objects remove_small_objects(labels, min_size, out=labels)   :442-448
+ *   merge_labels         merge_labels(labels, max_distance, labels_out=labels)
+ *                                                                   maze_ipp/merge_labels.py:29-113
+ *   regionprops          FindRegions / ImageProperties + RegionProperties reads
+ *                                                                   maze_ipp/loki/pipeline.py:589-625, 653-654
+ *
+ * Every entry point below replaces one of those callables for a whole PACKED BATCH of
+ * vignettes.  All pointers are DEVICE pointers unless the name ends in _host; the caller owns
+ * every buffer (the library never allocates); `stream` is a cudaStream_t passed as void*.
+ * Calls are asynchronous on `stream` and re-entrant across streams.  Return value: MAZE_OK or
+ * a negative MAZE_ERR_* code (maze_error_string() gives the text of the last CUDA error seen
+ * by the calling thread).
+ *
+ * Batch geometry
+ * --------------
+ * A batch is n_img vignettes.  Vignette i is h x w pixels; its pixels live row-major and
+ * contiguous (numpy C order, no row padding) at element offset pix_off in every per-pixel
+ * array of the batch (uint8 image, uint8/bool mask, int32 labels, int32 scratch).  pix_off must
+ * be a multiple of 16.  Binary images are additionally kept as BIT PLANES: row y of vignette i
+ * is wpr = ceil(w/32) uint32 words at word offset word_off + y*wpr, pixel x is bit (x & 31) of
+ * word (x >> 5); bits at x >= w are always stored as 0.  The batch is cut into TILES of
+ * MAZE_TILE_WORDS consecutive words of one vignette (a tile never straddles vignettes); one
+ * CTA processes one tile.  tile0 is the index of the vignette's first tile.
+ */
+#ifndef MAZE_B200_H
+#define MAZE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAZE_OK 0
+#define MAZE_ERR_CUDA (-1)      /* a CUDA call or launch failed */
+#define MAZE_ERR_TYPEERROR (-2) /* merge_labels: the reference raises TypeError here (merge_labels.py:19-20) */
+#define MAZE_ERR_BADARG (-3)
+#define MAZE_ERR_CAPACITY (-4)  /* a caller-provided table is too small */
+
+#define MAZE_TILE_WORDS 256
+#define MAZE_MAX_DISK_RADIUS 32 /* bit-plane morphology handles d2 thresholds < 33*33; beyond: maze_edt_sq */
+
+typedef struct maze_vignette {
+    int64_t pix_off;  /* element offset of pixel (0,0) in the per-pixel arrays */
+    int64_t word_off; /* word offset of row 0 in a bit plane */
+    int32_t h, w;
+    int32_t wpr;      /* ceil(w / 32) */
+    int32_t tile0;    /* index of the first tile of this vignette */
+} maze_vignette_t;    /* 32 bytes */
+
+typedef struct maze_tile {
+    int32_t img;   /* vignette index */
+    int32_t word0; /* first word (relative to the vignette's word_off) covered by the tile */
+} maze_tile_t;
+
+/* Feature table: one row of MAZE_NFEAT doubles per object.  Same column layout as the oracle. */
+#define MAZE_NFEAT 64
+#define MAZE_F_LABEL 0
+#define MAZE_F_AREA 1
+#define MAZE_F_BBOX 2         /* 4: min_row, min_col, max_row (excl), max_col (excl) */
+#define MAZE_F_CENTROID 6     /* 2: row, col */
+#define MAZE_F_MU 8           /* 16: central moments mu[p*4+q], p = row power, q = col power */
+#define MAZE_F_NU 24          /* 16: normalised central moments */
+#define MAZE_F_HU 40          /* 7 */
+#define MAZE_F_EIG 47         /* 2: inertia tensor eigenvalues, descending */
+#define MAZE_F_AXIS_MAJOR 49
+#define MAZE_F_AXIS_MINOR 50
+#define MAZE_F_ECC 51
+#define MAZE_F_ORIENT 52
+#define MAZE_F_IMIN 53
+#define MAZE_F_IMAX 54
+#define MAZE_F_IMEAN 55
+#define MAZE_F_FRAC_INVALID 56 /* mean(intensity == 0) inside the region, loki/pipeline.py:617 */
+#define MAZE_F_IMAGE 57        /* vignette index of the object */
+#define MAZE_F_T00 58          /* inertia tensor */
+#define MAZE_F_T01 59
+#define MAZE_F_T11 60
+
+/* Per-object integer accumulators (regionprops pass 1): MAZE_NACC uint64 per object followed,
+ * in a second array, by MAZE_NEXT int32 extrema per object. */
+#define MAZE_NACC 12
+#define MAZE_NEXT 8
+
+#define MAZE_RP_HIGH_ORDER 1 /* also fill mu/nu[p,q] with p+q > 3 (second pass over the labels) */
+
+const char *maze_error_string(void);
+int maze_version(void);
+
+/* loki/pipeline.py:649 (and :405 with t_int = 0): bit = (pixel > t_int).  The caller folds the
+ * float threshold to the integer t_int = floor(threshold) clipped to [-1, 255].
+ * flags[i] receives bit0 = "mask has a 1", bit1 = "mask has a 0" (zeroed by this call). */
+int maze_threshold_pack(const uint8_t *image, const maze_vignette_t *vig, int n_img,
+                        const maze_tile_t *tiles, int n_tiles, int t_int,
+                        uint32_t *bits, uint32_t *flags, void *stream);
+
+/* One thresholded-EDT pass on bit planes.  invert = 0: isotropic_erosion (isotropic.py:35-36),
+ * out = [d2(in) > t]; invert = 1: isotropic_dilation (isotropic.py:66-67), out = [d2(in == 0) <= t].
+ * t is the integer squared-distance threshold folded from the float radius by the caller
+ * (erosion: max{k : sqrt(k) <= radius}; dilation: max{k : sqrt(k) < radius}; -1 = none) and must
+ * be < (MAZE_MAX_DISK_RADIUS+1)^2.  flags_in are the flags of `in`; flags_out (zeroed by this
+ * call) receive the flags of `out`.  in != out. */
+int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vignette_t *vig, int n_img,
+                    const maze_tile_t *tiles, int n_tiles, int t, int invert,
+                    const uint32_t *flags_in, uint32_t *flags_out, void *stream);
+
+/* bit plane -> one byte per pixel (numpy bool). */
+int maze_unpack_mask(const uint32_t *bits, const maze_vignette_t *vig, int n_img,
+                     const maze_tile_t *tiles, int n_tiles, uint8_t *mask, void *stream);
+
+/* Exact squared Euclidean distance transform (scipy.ndimage.distance_transform_edt as used at
+ * isotropic.py:35,66 and merge_labels.py:17,22): d2[p] = squared distance from pixel p to the
+ * nearest 0 bit of `bits`, 0 where the bit is 0; a plane without any 0 bit behaves as if a
+ * single 0 sat at (-1, 0).  invert = 1 transforms the complement plane (distance to the nearest 1
+ * bit).  d2 is per-pixel int32 and doubles as the column-pass scratch; max_h / max_w are the
+ * largest vignette height / width of the batch; flag_scratch holds n_img uint32. */
+int maze_edt_sq(const uint32_t *bits, const maze_vignette_t *vig, int n_img, int max_h, int max_w,
+                int invert, int32_t *d2, uint32_t *flag_scratch, void *stream);
+
+/* out bit = (d2 > t) (greater = 1) or (d2 <= t) (greater = 0): the compare of isotropic.py:36,67
+ * for radii beyond MAZE_MAX_DISK_RADIUS. */
+int maze_compare_pack(const int32_t *d2, const maze_vignette_t *vig, int n_img,
+                      const maze_tile_t *tiles, int n_tiles, int t, int greater,
+                      uint32_t *bits, uint32_t *flags, void *stream);
+
+/* loki/pipeline.py:430-433: 8-connected components, labels 1..N in raster order of each
+ * component's first pixel, background 0, int32.  parent: per-pixel int32 scratch (touched only
+ * at run starts).  tile_scan: n_tiles + 1 int32 scratch.  lab_off: n_img + 1 int32, receives the
+ * exclusive prefix sum of the per-vignette label counts (object index of (i, l) = lab_off[i] + l - 1). */
+int maze_label(const uint32_t *bits, const maze_vignette_t *vig, int n_img,
+               const maze_tile_t *tiles, int n_tiles, int32_t *parent, int32_t *labels,
+               int32_t *tile_scan, int32_t *lab_off, void *stream);
+
+/* loki/pipeline.py:435-439 and :442-448, in place, no renumbering.  Labels must lie in
+ * [0, lab_off[i+1]-lab_off[i]]; obj_scratch holds lab_off[n_img] int32 (n_obj_cap entries are
+ * cleared by the call). */
+int maze_clear_border(int32_t *labels, const maze_vignette_t *vig, int n_img,
+                      const maze_tile_t *tiles, int n_tiles, const int32_t *lab_off,
+                      int32_t *obj_scratch, int n_obj_cap, void *stream);
+int maze_remove_small_objects(int32_t *labels, const maze_vignette_t *vig, int n_img,
+                              const maze_tile_t *tiles, int n_tiles, const int32_t *lab_off,
+                              int32_t *obj_scratch, int n_obj_cap, int64_t min_size, void *stream);
+
+/* largest label of every vignette (for label images that did not come from maze_label). */
+int maze_max_label(const int32_t *labels, const maze_vignette_t *vig, int n_img,
+                   const maze_tile_t *tiles, int n_tiles, int32_t *max_label, void *stream);
+
+/* Per-label regionprops (loki/pipeline.py:589-625, 653-654).  labels may be NULL, in which case
+ * `bits` is read as a label image with the single label 1 (ImageProperties semantics).  image may
+ * be NULL (no intensity columns).  acc: n_obj_cap * MAZE_NACC uint64; ext: n_obj_cap * MAZE_NEXT
+ * int32; table: n_obj_cap * MAZE_NFEAT doubles.  Rows of absent labels get area 0 and NaN. */
+int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t *image,
+                     const maze_vignette_t *vig, int n_img, const maze_tile_t *tiles, int n_tiles,
+                     const int32_t *lab_off, int n_obj_cap, unsigned long long *acc, int32_t *ext,
+                     double *table, int flags, void *stream);
+
+/* maze_ipp/merge_labels.py:29-113 for every vignette of the batch, one CTA per vignette.
+ * labels: read by the loop; labels_out: written (pass the same pointer for the pipeline's aliased
+ * call, loki/pipeline.py:452-457).  index/index_off: optional explicit label lists (index_off has
+ * n_img + 1 entries) or NULL for "sorted positive labels".  lab_off bounds the label values as in
+ * maze_clear_border.  have_max = 0 restates max_distance=None.  d2a, d2b, d2c: per-pixel int32 scratch;
+ * obj_scratch: 2 * n_obj_cap int32.  merge_dist (n_obj_cap doubles, optional) / n_merge (n_img):
+ * the distances at which labels were merged.  index_state (2 * n_img int32): the length of the
+ * label list the loop started from and how many entries it popped (the list itself, popped entries
+ * first, is left in obj_scratch + 2 * lab_off[i]).  status (n_img int32): MAZE_OK or
+ * MAZE_ERR_TYPEERROR per vignette. */
+int maze_merge_labels(const int32_t *labels, int32_t *labels_out, const maze_vignette_t *vig, int n_img,
+                      const int32_t *lab_off, int n_obj_cap, const int32_t *index, const int32_t *index_off,
+                      int have_max, double max_distance, double path_tolerance,
+                      int32_t *d2a, int32_t *d2b, int32_t *d2c, int32_t *obj_scratch,
+                      double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status, void *stream);
+
+/* Synthetic LOKI-shaped vignettes for the benchmark: dark noisy background plus
+ * 1-6 anisotropic Gaussian blobs per vignette, counter-based RNG keyed by (seed, vignette, pixel). */
+int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,
+                         const maze_tile_t *tiles, int n_tiles, uint64_t seed, int64_t img_index0,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAZE_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of ``libmaze_b200.so`` (the C-ABI declared in ``include/maze_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a symbol cannot be resolved the
+import of the product package's device modules fails with :class:`MazeLibraryError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libmaze_b200.so")
+
+MAZE_OK = 0
+MAZE_ERR_CUDA = -1
+MAZE_ERR_TYPEERROR = -2
+MAZE_ERR_BADARG = -3
+MAZE_ERR_CAPACITY = -4
+
+TILE_WORDS = 256
+MAX_DISK_RADIUS = 32
+NFEAT = 64
+NACC = 12
+NEXT = 8
+RP_HIGH_ORDER = 1
+
+
+class MazeLibraryError(RuntimeError):
+    pass
+
+
+class MazeCudaError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "maze_b200.h"))
+    if not force and os.path.exists(SO_PATH):
+        so_m = os.path.getmtime(SO_PATH)
+        if all(os.path.getmtime(s) <= so_m for s in srcs):
+            return SO_PATH
+    cmd = ["sh", os.path.join(CSRC, "build.sh")]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_u64 = ctypes.c_uint64
+_d = ctypes.c_double
+
+# name -> argtypes (restype is int unless noted); order as in include/maze_b200.h
+SIGNATURES = {
+    "maze_threshold_pack": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp],
+    "maze_morph_pass": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "maze_unpack_mask": [_vp, _vp, _i, _vp, _i, _vp, _vp],
+    "maze_edt_sq": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "maze_compare_pack": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "maze_label": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "maze_clear_border": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "maze_remove_small_objects": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i64, _vp],
+    "maze_max_label": [_vp, _vp, _i, _vp, _i, _vp, _vp],
+    "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
+    "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "maze_synth_vignettes": [_vp, _vp, _i, _vp, _i, _u64, _i64, _vp],
+}
+OTHER_SYMBOLS = ["maze_error_string", "maze_version"]
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises MazeLibraryError when it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise MazeLibraryError(
+            f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the maze_b200 kernels)")
+    try:
+        handle = ctypes.CDLL(SO_PATH)
+    except OSError as e:  # pragma: no cover
+        raise MazeLibraryError(f"cannot load {SO_PATH}: {e}") from e
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError as e:
+            raise MazeLibraryError(f"{SO_PATH} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    handle.maze_error_string.restype = ctypes.c_char_p
+    handle.maze_version.restype = ctypes.c_int
+    _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc == MAZE_OK:
+        return
+    if rc == MAZE_ERR_CUDA:
+        raise MazeCudaError(f"{what}: {lib().maze_error_string().decode()}")
+    if rc == MAZE_ERR_BADARG:
+        raise ValueError(f"{what}: bad argument")
+    if rc == MAZE_ERR_CAPACITY:
+        raise MemoryError(f"{what}: table capacity exceeded")
+    raise RuntimeError(f"{what}: error {rc}")

@@ -1,0 +1,125 @@
+// Shared device helpers for the maze_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "maze_b200.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define MAZE_CTA 256 /* threads per CTA == MAZE_TILE_WORDS: one thread per word or 8 warps x 32 words */
+#define FULL 0xffffffffu
+
+extern thread_local char maze_err_buf[256];
+void maze_set_err(cudaError_t e, const char *where);
+
+#define MAZE_LAUNCH_CHECK(where)                      \
+    do {                                              \
+        cudaError_t e__ = cudaGetLastError();         \
+        if (e__ != cudaSuccess) {                     \
+            maze_set_err(e__, where);                 \
+            return MAZE_ERR_CUDA;                     \
+        }                                             \
+    } while (0)
+
+#define MAZE_CUDA(call, where)                        \
+    do {                                              \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess) {                     \
+            maze_set_err(e__, where);                 \
+            return MAZE_ERR_CUDA;                     \
+        }                                             \
+    } while (0)
+
+// bits of word k of a row of width w that are real pixels
+__device__ __forceinline__ uint32_t valid_mask(int w, int k)
+{
+    int rem = w - 32 * k;
+    return rem >= 32 ? FULL : ((1u << rem) - 1u);
+}
+
+// first bit of the horizontal run (inside this word) that contains bit b of m
+__device__ __forceinline__ int run_start_in_word(uint32_t m, int b)
+{
+    uint32_t z = ~m & ((1u << b) - 1u);
+    return z ? 32 - __clz(z) : 0;
+}
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *(const volatile int *)p; }
+
+// Union-find on per-vignette pixel indices; the root of a set is its smallest index, i.e. the
+// component's first pixel in raster order.
+__device__ __forceinline__ int uf_find(const int *P, int n)
+{
+    int p = ld_volatile(P + n);
+    while (p != n) {
+        n = p;
+        p = ld_volatile(P + n);
+    }
+    return n;
+}
+
+__device__ __forceinline__ void uf_union(int *P, int a, int b)
+{
+    while (true) {
+        a = uf_find(P, a);
+        b = uf_find(P, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(P + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// exclusive scan of one int per thread over a 256-thread CTA; returns the exclusive prefix,
+// *total receives the CTA sum.  smem: >= 9 ints.
+__device__ __forceinline__ int cta_exclusive_scan(int v, int *smem, int *total)
+{
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int nw = blockDim.x >> 5;
+        int s = lane < nw ? smem[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(FULL, si, d);
+            if (lane >= d) si += t;
+        }
+        if (lane < nw) smem[lane] = si - s;
+        if (lane == nw - 1) smem[nw] = si;
+    }
+    __syncthreads();
+    int res = smem[warp] + inc - v;
+    *total = smem[blockDim.x >> 5];
+    __syncthreads();
+    return res;
+}
+
+struct TileCtx {
+    maze_vignette_t v;
+    int img;
+    int word0;
+    int nwords; // words in the vignette
+};
+
+__device__ __forceinline__ TileCtx load_tile(const maze_vignette_t *vig, const maze_tile_t *tiles)
+{
+    TileCtx c;
+    maze_tile_t t = tiles[blockIdx.x];
+    c.img = t.img;
+    c.word0 = t.word0;
+    c.v = vig[t.img];
+    c.nwords = c.v.h * c.v.wpr;
+    return c;
+}

@@ -1,0 +1,316 @@
+"""Packed-batch geometry and the device-side operators (thin wrappers over the C-ABI).
+
+PyTorch is used for device memory, streams and pinned host buffers only; every computation is a
+kernel of ``libmaze_b200.so``.  Layout (see ``include/maze_b200.h``): all vignettes of a batch are
+concatenated in flat per-pixel arrays (numpy C order per vignette, vignette starts aligned to 16
+elements); binary images are bit planes with rows padded to 32-bit words; the batch is cut into
+256-word tiles, one CTA each.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, TILE_WORDS, check, lib
+
+VIG_DTYPE = np.dtype([("pix_off", "<i8"), ("word_off", "<i8"), ("h", "<i4"), ("w", "<i4"),
+                      ("wpr", "<i4"), ("tile0", "<i4")])
+TILE_DTYPE = np.dtype([("img", "<i4"), ("word0", "<i4")])
+assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8
+
+_DISK_T_LIMIT = (MAX_DISK_RADIUS + 1) ** 2
+_INT_MAX = 2 ** 31 - 1
+
+
+class BatchGeometry:
+    """Host-side description of a packed batch (numpy only, no device access)."""
+
+    def __init__(self, heights, widths):
+        hs = np.asarray(heights, dtype=np.int64).ravel()
+        ws = np.asarray(widths, dtype=np.int64).ravel()
+        if hs.shape != ws.shape:
+            raise ValueError("heights and widths differ in length")
+        if hs.size and (hs.min() < 1 or ws.min() < 1):
+            raise ValueError("empty vignettes cannot be packed")
+        if hs.size and (hs * ws).max() >= 2 ** 31:
+            raise ValueError("a vignette must have fewer than 2**31 pixels")
+        self.n_img = int(hs.size)
+        self.h = hs
+        self.w = ws
+        self.npx = hs * ws
+        wpr = (ws + 31) // 32
+        nwords = hs * wpr
+        padded = (self.npx + 15) // 16 * 16
+        self.pix_off = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
+        self.word_off = np.concatenate([[0], np.cumsum(nwords)]).astype(np.int64)
+        ntiles = (nwords + TILE_WORDS - 1) // TILE_WORDS
+        self.tile0 = np.concatenate([[0], np.cumsum(ntiles)]).astype(np.int64)
+        self.total_px = int(self.pix_off[-1]) + 16  # tail slack for vector loads
+        self.pixels = int(self.npx.sum())
+        self.total_words = int(self.word_off[-1])
+        self.n_tiles = int(self.tile0[-1])
+        if self.n_tiles >= 2 ** 31 or self.total_words >= 2 ** 40:
+            raise ValueError("batch too large")
+        self.max_h = int(hs.max()) if hs.size else 0
+        self.max_w = int(ws.max()) if ws.size else 0
+        vig = np.zeros(self.n_img, VIG_DTYPE)
+        vig["pix_off"] = self.pix_off[:-1]
+        vig["word_off"] = self.word_off[:-1]
+        vig["h"] = hs
+        vig["w"] = ws
+        vig["wpr"] = wpr
+        vig["tile0"] = self.tile0[:-1]
+        self.vig = vig
+        tiles = np.zeros(self.n_tiles, TILE_DTYPE)
+        img_of_tile = np.repeat(np.arange(self.n_img, dtype=np.int64), ntiles)
+        tiles["img"] = img_of_tile
+        tiles["word0"] = (np.arange(self.n_tiles, dtype=np.int64) - self.tile0[img_of_tile]) * TILE_WORDS
+        self.tiles = tiles
+
+    @classmethod
+    def from_images(cls, images):
+        return cls([im.shape[0] for im in images], [im.shape[1] for im in images])
+
+    def view(self, flat, i):
+        """(h, w) view of vignette i inside a flat per-pixel host array."""
+        o = int(self.pix_off[i])
+        return flat[o:o + int(self.npx[i])].reshape(int(self.h[i]), int(self.w[i]))
+
+    def pack_host(self, images, out=None, dtype=np.uint8):
+        """Copy a list of (h, w) arrays into one flat host array laid out like the device batch."""
+        if out is None:
+            out = np.zeros(self.total_px, dtype)
+        for i, im in enumerate(images):
+            o = int(self.pix_off[i])
+            out[o:o + int(self.npx[i])] = np.asarray(im).reshape(-1)
+        return out
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def fold_erosion_radius(radius) -> int:
+    """max{k : sqrt_f64(k) <= radius} (or -1): ``dist > radius`` <=> ``d2 > k`` (isotropic.py:36)."""
+    r = float(radius)
+    if math.isnan(r):
+        return _INT_MAX  # dist > nan is False everywhere
+    if r < 0:
+        return -1
+    if r >= 46340.0:
+        return _INT_MAX
+    k = int(math.floor(r * r))
+    while math.sqrt(k + 1) <= r:
+        k += 1
+    while k >= 0 and math.sqrt(k) > r:
+        k -= 1
+    return k
+
+
+def fold_dilation_radius(radius) -> int:
+    """max{k : sqrt_f64(k) < radius} (or -1): ``dist < radius`` <=> ``d2 <= k`` (isotropic.py:67)."""
+    r = float(radius)
+    if math.isnan(r) or r <= 0:
+        return -1
+    if r >= 46340.0:
+        return _INT_MAX
+    k = int(math.floor(r * r))
+    while math.sqrt(k + 1) < r:
+        k += 1
+    while k >= 0 and not (math.sqrt(k) < r):
+        k -= 1
+    return k
+
+
+def fold_threshold(thr) -> int:
+    """uint8 pixel > thr  <=>  pixel > floor(thr) (loki/pipeline.py:649, float threshold)."""
+    t = float(thr)
+    if math.isnan(t):
+        return 255  # px > nan is False
+    return int(min(255, max(-1, math.floor(t))))
+
+
+class DeviceBatch:
+    """A packed batch resident on one GPU plus the operators that act on it."""
+
+    def __init__(self, geometry: BatchGeometry, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.MazeLibraryError("maze_b200 needs a CUDA device (there is no CPU fallback)")
+        lib()
+        self.g = geometry
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):
+            self.d_vig = torch.from_numpy(geometry.vig.view(np.uint8).copy()).to(self.device, non_blocking=False)
+            self.d_tiles = torch.from_numpy(geometry.tiles.view(np.uint8).copy()).to(self.device, non_blocking=False)
+
+    # ---- buffers -------------------------------------------------------------------------------
+    def empty_px(self, dtype):
+        return torch.empty(self.g.total_px, dtype=dtype, device=self.device)
+
+    def empty_plane(self):
+        return torch.empty(max(self.g.total_words, 1), dtype=torch.int32, device=self.device)
+
+    def empty_flags(self):
+        return torch.empty(max(self.g.n_img, 1), dtype=torch.int32, device=self.device)
+
+    def upload(self, host_flat):
+        t = torch.from_numpy(host_flat) if isinstance(host_flat, np.ndarray) else host_flat
+        return t.to(self.device, non_blocking=True)
+
+    def _geo(self):
+        g = self.g
+        return self.d_vig.data_ptr(), g.n_img, self.d_tiles.data_ptr(), g.n_tiles
+
+    # ---- operators -----------------------------------------------------------------------------
+    def threshold_pack(self, d_image, t_int: int):
+        """loki/pipeline.py:649 -> (bit plane, flags)."""
+        vig, n, tiles, nt = self._geo()
+        bits, flags = self.empty_plane(), self.empty_flags()
+        check(lib().maze_threshold_pack(d_image.data_ptr(), vig, n, tiles, nt, int(t_int), bits.data_ptr(),
+                                        flags.data_ptr(), _stream()), "maze_threshold_pack")
+        return bits, flags
+
+    def morph_pass(self, bits, flags, t: int, invert: int):
+        vig, n, tiles, nt = self._geo()
+        out, fout = self.empty_plane(), self.empty_flags()
+        check(lib().maze_morph_pass(bits.data_ptr(), out.data_ptr(), vig, n, tiles, nt, int(t), int(invert),
+                                    flags.data_ptr(), fout.data_ptr(), _stream()), "maze_morph_pass")
+        return out, fout
+
+    def edt_sq(self, bits, invert: int = 0):
+        """Exact squared EDT of the plane (or of its complement) as per-pixel int32."""
+        g = self.g
+        d2 = self.empty_px(torch.int32)
+        scratch = self.empty_flags()
+        check(lib().maze_edt_sq(bits.data_ptr(), self.d_vig.data_ptr(), g.n_img, g.max_h, g.max_w, int(invert),
+                                d2.data_ptr(), scratch.data_ptr(), _stream()), "maze_edt_sq")
+        return d2
+
+    def compare_pack(self, d2, t: int, greater: int):
+        vig, n, tiles, nt = self._geo()
+        bits, flags = self.empty_plane(), self.empty_flags()
+        check(lib().maze_compare_pack(d2.data_ptr(), vig, n, tiles, nt, int(t), int(greater), bits.data_ptr(),
+                                      flags.data_ptr(), _stream()), "maze_compare_pack")
+        return bits, flags
+
+    def erosion(self, bits, flags, radius):
+        """isotropic.py:35-36."""
+        t = fold_erosion_radius(radius)
+        if t < _DISK_T_LIMIT:
+            return self.morph_pass(bits, flags, t, 0)
+        return self.compare_pack(self.edt_sq(bits, 0), t, 1)
+
+    def dilation(self, bits, flags, radius):
+        """isotropic.py:66-67 (strict <)."""
+        t = fold_dilation_radius(radius)
+        if t < _DISK_T_LIMIT:
+            return self.morph_pass(bits, flags, t, 1)
+        return self.compare_pack(self.edt_sq(bits, 1), t, 0)
+
+    def opening(self, bits, flags, radius):
+        """isotropic.py:97-98."""
+        return self.dilation(*self.erosion(bits, flags, radius), radius)
+
+    def closing(self, bits, flags, radius):
+        """isotropic.py:128-129."""
+        return self.erosion(*self.dilation(bits, flags, radius), radius)
+
+    def unpack_mask(self, bits, out=None):
+        vig, n, tiles, nt = self._geo()
+        mask = self.empty_px(torch.uint8) if out is None else out
+        check(lib().maze_unpack_mask(bits.data_ptr(), vig, n, tiles, nt, mask.data_ptr(), _stream()),
+              "maze_unpack_mask")
+        return mask
+
+    def label(self, bits, labels=None):
+        """loki/pipeline.py:430-433 -> (labels int32 per pixel, lab_off int32[n_img+1])."""
+        vig, n, tiles, nt = self._geo()
+        if labels is None:
+            labels = self.empty_px(torch.int32)
+        parent = self.empty_px(torch.int32)
+        tile_scan = torch.empty(self.g.n_tiles + 1, dtype=torch.int32, device=self.device)
+        lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device)
+        check(lib().maze_label(bits.data_ptr(), vig, n, tiles, nt, parent.data_ptr(), labels.data_ptr(),
+                               tile_scan.data_ptr(), lab_off.data_ptr(), _stream()), "maze_label")
+        return labels, lab_off
+
+    def max_label(self, labels):
+        vig, n, tiles, nt = self._geo()
+        out = self.empty_flags()
+        check(lib().maze_max_label(labels.data_ptr(), vig, n, tiles, nt, out.data_ptr(), _stream()),
+              "maze_max_label")
+        return out
+
+    def lab_off_from_bounds(self, bounds):
+        """Exclusive prefix sum of per-vignette label bounds (host array) as a device lab_off."""
+        off = np.concatenate([[0], np.cumsum(np.asarray(bounds, dtype=np.int64))])
+        if off[-1] >= 2 ** 31:
+            raise ValueError("too many labels")
+        return torch.from_numpy(off.astype(np.int32)).to(self.device), int(off[-1])
+
+    def clear_border(self, labels, lab_off, n_obj: int):
+        vig, n, tiles, nt = self._geo()
+        if n_obj <= 0:
+            return labels
+        scratch = torch.empty(n_obj, dtype=torch.int32, device=self.device)
+        check(lib().maze_clear_border(labels.data_ptr(), vig, n, tiles, nt, lab_off.data_ptr(), scratch.data_ptr(),
+                                      int(n_obj), _stream()), "maze_clear_border")
+        return labels
+
+    def remove_small_objects(self, labels, lab_off, n_obj: int, min_size: int):
+        vig, n, tiles, nt = self._geo()
+        if n_obj <= 0:
+            return labels
+        scratch = torch.empty(n_obj, dtype=torch.int32, device=self.device)
+        check(lib().maze_remove_small_objects(labels.data_ptr(), vig, n, tiles, nt, lab_off.data_ptr(),
+                                              scratch.data_ptr(), int(n_obj), int(min_size), _stream()),
+              "maze_remove_small_objects")
+        return labels
+
+    def regionprops(self, lab_off, n_obj: int, labels=None, bits=None, image=None, high_order=True):
+        """Feature table (n_obj, NFEAT) float64 on the device."""
+        vig, n, tiles, nt = self._geo()
+        table = torch.empty((max(n_obj, 0), NFEAT), dtype=torch.float64, device=self.device)
+        if n_obj <= 0:
+            return table
+        acc = torch.empty(n_obj * NACC, dtype=torch.int64, device=self.device)
+        ext = torch.empty(n_obj * NEXT, dtype=torch.int32, device=self.device)
+        check(lib().maze_regionprops(_ptr(labels), _ptr(bits), _ptr(image), vig, n, tiles, nt, lab_off.data_ptr(),
+                                     int(n_obj), acc.data_ptr(), ext.data_ptr(), table.data_ptr(),
+                                     RP_HIGH_ORDER if high_order else 0, _stream()), "maze_regionprops")
+        return table
+
+    def merge_labels(self, labels, labels_out, lab_off, n_obj: int, max_distance, path_tolerance=5.0,
+                     index=None, index_off=None):
+        """merge_labels.py:29-113 for every vignette.  Returns (merge_dist, n_merge, index_state, status,
+        obj_scratch) device tensors."""
+        g = self.g
+        n_obj = max(int(n_obj), 1)
+        d2a, d2b, d2c = (self.empty_px(torch.int32) for _ in range(3))
+        obj_scratch = torch.zeros(2 * n_obj, dtype=torch.int32, device=self.device)
+        merge_dist = torch.zeros(n_obj, dtype=torch.float64, device=self.device)
+        n_merge = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
+        index_state = torch.zeros(2 * g.n_img, dtype=torch.int32, device=self.device)
+        status = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
+        have_max = max_distance is not None
+        check(lib().maze_merge_labels(labels.data_ptr(), labels_out.data_ptr(), self.d_vig.data_ptr(), g.n_img,
+                                      lab_off.data_ptr(), n_obj, _ptr(index), _ptr(index_off), int(have_max),
+                                      float(max_distance) if have_max else 0.0, float(path_tolerance),
+                                      d2a.data_ptr(), d2b.data_ptr(), d2c.data_ptr(), obj_scratch.data_ptr(),
+                                      merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
+                                      status.data_ptr(), _stream()), "maze_merge_labels")
+        return merge_dist, n_merge, index_state, status, obj_scratch
+
+    def synth(self, seed: int, img_index0: int = 0, out=None):
+        vig, n, tiles, nt = self._geo()
+        img = self.empty_px(torch.uint8) if out is None else out
+        check(lib().maze_synth_vignettes(img.data_ptr(), vig, n, tiles, nt, int(seed), int(img_index0), _stream()),
+              "maze_synth_vignettes")
+        return img

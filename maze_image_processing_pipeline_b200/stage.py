@@ -1,0 +1,209 @@
+"""The batched LOKI re-segmentation stage.
+
+Takes the two EXISTING config objects of the reference as its parameters
+(``ThresholdSegmentationConfig``, ``SegmentationPostprocessingConfig``,
+maze_ipp/loki/config_schema.py:8-37 -- any object with the same attributes works) and runs, for a
+whole batch of vignettes at once and entirely on the GPU, the chain the reference runs per vignette:
+
+* ``threshold`` only (loki/pipeline.py:648-656): ``mask = image > threshold_brighter``; vignettes
+  with an empty mask are dropped; the whole mask is ONE region (``ImageProperties``).
+* ``postprocess`` only (loki/pipeline.py:396-459, 589-625): bool cast of the model's foreground
+  prediction, opening, closing, label, clear_border, remove_small_objects, merge_labels, then one
+  region per surviving label (``FindRegions``).
+* both (benchmark configuration): threshold feeding the post-processing chain.
+
+Opening runs BEFORE closing, as in the reference.  Morphology is the EDT-based
+``maze_ipp/isotropic.py`` (the north-star contract), not the live ``disk(r, "crosses")`` footprints.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import MAZE_ERR_TYPEERROR, NFEAT
+from .device import BatchGeometry, DeviceBatch, fold_threshold
+
+
+@dataclass
+class ThresholdSegmentationConfig:
+    """Mirror of maze_ipp/loki/config_schema.py:32-37."""
+    threshold_brighter: float
+
+
+@dataclass
+class SegmentationPostprocessingConfig:
+    """Mirror of maze_ipp/loki/config_schema.py:8-29 (same names, same defaults)."""
+    closing_radius: int = 0
+    opening_radius: int = 0
+    merge_segments_distance: int = 0
+    min_area: int = 0
+    n_threads: int = 0
+    clear_border: bool = False
+
+
+class DeviceResult:
+    """Outputs of one batch, still on the device."""
+
+    def __init__(self, batch, bits, labels, lab_off, table, n_obj, keep=None, merge_status=None):
+        self.batch = batch
+        self.bits = bits
+        self.labels = labels
+        self.lab_off = lab_off
+        self.table = table
+        self.n_obj = n_obj
+        self.keep = keep
+        self.merge_status = merge_status
+
+
+class StageResult:
+    """Host-side outputs: flat mask / label buffers with per-vignette views and the object table."""
+
+    def __init__(self, geometry: BatchGeometry, mask_flat, labels_flat, lab_off, table, keep=None):
+        self.geometry = geometry
+        self._mask = mask_flat
+        self._labels = labels_flat
+        self.lab_off = lab_off
+        self.table = table
+        self.keep = keep  # threshold branch: vignettes that survive the empty-mask filter
+
+    def __len__(self):
+        return self.geometry.n_img
+
+    def mask(self, i) -> np.ndarray:
+        return self.geometry.view(self._mask, i).view(bool)
+
+    def labels(self, i) -> Optional[np.ndarray]:
+        return None if self._labels is None else self.geometry.view(self._labels, i)
+
+    def features(self, i) -> np.ndarray:
+        """Rows of the object table that belong to vignette i (row k = label k + 1)."""
+        return self.table[int(self.lab_off[i]):int(self.lab_off[i + 1])]
+
+
+class _PinnedPool:
+    """Reusable pinned host staging buffers (one per purpose), grown on demand."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, n, dtype):
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+            self._bufs[key] = t
+        return t[:n]
+
+
+class LokiSegmentationStage:
+    def __init__(self, threshold=None, postprocess=None, device=None, high_order=True):
+        if threshold is None and postprocess is None:
+            raise ValueError("exactly one of threshold / postprocess (or both, for the composite stage) is required")
+        self.threshold = threshold
+        self.postprocess = postprocess
+        self.device = device
+        self.high_order = high_order
+        self._pool = _PinnedPool()
+
+    # ---- device-resident core ----------------------------------------------------------------------
+    def run_device(self, batch: DeviceBatch, d_image, d_pred=None) -> DeviceResult:
+        """All kernels for one resident batch.  d_image: flat uint8 intensities; d_pred: flat uint8
+        foreground prediction (postprocess-only mode)."""
+        pp = self.postprocess
+        if self.threshold is not None:
+            bits, flags = batch.threshold_pack(d_image, fold_threshold(self.threshold.threshold_brighter))
+        else:
+            bits, flags = batch.threshold_pack(d_pred, 0)  # np.asarray(pred, dtype=bool), :405
+        if pp is None:
+            # ImageProperties(mask, image): one region per vignette; empty masks are dropped (:651)
+            lab_off, n_obj = batch.lab_off_from_bounds(np.ones(batch.g.n_img, np.int64))
+            table = batch.regionprops(lab_off, n_obj, bits=bits, image=d_image, high_order=self.high_order)
+            keep = (flags & 1).bool()
+            return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep)
+        if pp.opening_radius > 0:
+            bits, flags = batch.opening(bits, flags, pp.opening_radius)
+        if pp.closing_radius > 0:
+            bits, flags = batch.closing(bits, flags, pp.closing_radius)
+        labels, lab_off = batch.label(bits)
+        need_count = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
+        n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
+        merge_status = None
+        if need_count and n_obj > 0:
+            if pp.clear_border:
+                batch.clear_border(labels, lab_off, n_obj)
+            if pp.min_area > 0:
+                batch.remove_small_objects(labels, lab_off, n_obj, pp.min_area)
+            if pp.merge_segments_distance > 0:
+                merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance)[3]
+        table = batch.regionprops(lab_off, n_obj, labels=labels, image=d_image, high_order=self.high_order)
+        return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status)
+
+    # ---- host entry: numpy in, numpy out --------------------------------------------------------------
+    def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,
+                 want_mask=True, want_labels=True) -> StageResult:
+        if self.threshold is None and foreground_pred is None:
+            raise ValueError("postprocess-only stage needs foreground_pred")
+        geom = BatchGeometry.from_images(images)
+        if geom.n_img == 0:
+            return StageResult(geom, np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(1, np.int32),
+                               np.zeros((0, NFEAT)))
+        dev = self.device
+        with torch.cuda.device(dev if dev is not None else torch.cuda.current_device()):
+            batch = DeviceBatch(geom, dev)
+            h_img = self._pool.get("img", geom.total_px, torch.uint8)
+            geom.pack_host(images, out=h_img.numpy())
+            d_image = h_img.to(batch.device, non_blocking=True)
+            d_pred = None
+            if self.threshold is None:
+                h_pred = self._pool.get("pred", geom.total_px, torch.uint8)
+                geom.pack_host([np.asarray(p, dtype=bool) for p in foreground_pred], out=h_pred.numpy())
+                d_pred = h_pred.to(batch.device, non_blocking=True)
+            res = self.run_device(batch, d_image, d_pred)
+            mask_flat = labels_flat = None
+            if want_mask:
+                h_mask = self._pool.get("mask", geom.total_px, torch.uint8)
+                h_mask.copy_(batch.unpack_mask(res.bits), non_blocking=True)
+                mask_flat = h_mask.numpy()
+            if want_labels and res.labels is not None:
+                h_lab = self._pool.get("labels", geom.total_px, torch.int32)
+                h_lab.copy_(res.labels, non_blocking=True)
+                labels_flat = h_lab.numpy()
+            h_tab = self._pool.get("table", res.table.numel(), torch.float64)
+            h_tab.copy_(res.table.reshape(-1), non_blocking=True)
+            h_off = self._pool.get("lab_off", geom.n_img + 1, torch.int32)
+            h_off.copy_(res.lab_off, non_blocking=True)
+            keep = None if res.keep is None else res.keep.cpu().numpy()
+            status = None if res.merge_status is None else res.merge_status.cpu().numpy()
+            torch.cuda.current_stream().synchronize()
+        if status is not None and (status == MAZE_ERR_TYPEERROR).any():
+            # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
+            raise TypeError("'NoneType' object is not iterable")
+        table = h_tab.numpy().reshape(-1, NFEAT)
+        return StageResult(geom, mask_flat, labels_flat, h_off.numpy(), table, keep=keep)
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of n_items for `rank` of `world` (images are independent)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_object_tables(table: np.ndarray, image_index0: int, group=None):
+    """Concatenate the per-rank object tables on rank 0 in image order (no collective on the hot path:
+    this is the host-side gather of the results).  Column MAZE_F_IMAGE is rebased to global indices."""
+    import torch.distributed as dist
+
+    local = table.copy()
+    if local.size:
+        local[:, 57] += image_index0
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    parts = [None] * world if dist.get_rank(group) == 0 else None
+    dist.gather_object(local, parts, dst=0, group=group)
+    if parts is None:
+        return None
+    return np.concatenate([p.reshape(-1, NFEAT) for p in parts], axis=0)

@@ -1,0 +1,130 @@
+"""The reference chain written against scipy.ndimage (TEST INFRASTRUCTURE ONLY).
+
+The reference's arithmetic lives in scipy's C code (``distance_transform_edt``, ``label``,
+``find_objects``), called from ``maze_ipp/isotropic.py`` and ``maze_ipp/merge_labels.py``.
+``/root/reference`` does not exist on the GPU box, so this module restates those call
+sequences against the same scipy entry points.  It therefore has the reference's CPU cost
+profile and is what ``bench.py`` times as ``cpu_baseline`` (kind "port") and under
+``--impl reference``.  It is checked against the real reference files in
+``tests/golden/make_golden.py`` and against the independent C restatement in
+``tests/test_oracle.py``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy import ndimage as ndi
+
+from . import regionprops_table as _c_regionprops
+
+_EIGHT = np.ones((3, 3), dtype=bool)
+
+
+def _edt_cmp(fg, radius, keep_far, out=None):
+    # isotropic.py:35-36 (keep_far: dist > radius) and :66-67 (dist < radius, strict)
+    dist = ndi.distance_transform_edt(fg)
+    return np.greater(dist, radius, out=out) if keep_far else np.less(dist, radius, out=out)
+
+
+def erosion(mask, radius, out=None):
+    return _edt_cmp(mask, radius, True, out)
+
+
+def dilation(mask, radius, out=None):
+    return _edt_cmp(mask == 0, radius, False, out)
+
+
+def opening(mask, radius, out=None):  # isotropic.py:97-98
+    return dilation(erosion(mask, radius, out=out), radius, out=out)
+
+
+def closing(mask, radius, out=None):  # isotropic.py:128-129
+    return erosion(dilation(mask, radius, out=out), radius, out=out)
+
+
+def label(mask):
+    """loki/pipeline.py:430-433: skimage.measure.label(bool) == ndi.label with the full 3x3."""
+    lab, n = ndi.label(mask, structure=_EIGHT)
+    return lab.astype(np.int32, copy=False), int(n)
+
+
+def clear_border(labels):  # loki/pipeline.py:435-439, in place
+    edge = np.concatenate([labels[0, :], labels[-1, :], labels[:, 0], labels[:, -1]])
+    hit = np.unique(edge[edge > 0])
+    if hit.size:
+        labels[np.isin(labels, hit)] = 0
+    return labels
+
+
+def remove_small_objects(labels, min_size):  # loki/pipeline.py:442-448, in place
+    sizes = np.bincount(labels.ravel())
+    small = sizes < min_size
+    small[0] = False
+    labels[small[labels]] = 0
+    return labels
+
+
+def _window_dist(mask, pad):
+    # merge_labels.py:12-26
+    if pad is None:
+        return ndi.distance_transform_edt(~mask)
+    (box,) = ndi.find_objects(mask, 1)
+    box = tuple(slice(max(0, s.start - (pad + 1)), s.stop + pad + 1) for s in box)  # raises TypeError on None
+    inner = ndi.distance_transform_edt(~mask[box])
+    full = np.full(mask.shape, inner.max())
+    full[box] = inner
+    return full
+
+
+def merge_labels(labels, index=None, max_distance=None, path_tolerance=5, return_merge_distances=False, labels_out=None):
+    """merge_labels.py:29-113 restated: one seed cluster, nearest-first, stop at the first far label."""
+    if index is None:
+        u = np.unique(labels)
+        index = u[u > 0].tolist()
+    if len(index) < 2:
+        return (labels, []) if return_merge_distances else labels
+    if labels_out is None:
+        labels_out = labels.copy()
+    seed = index.pop(0)
+    seed_mask = labels == seed
+    labels_out[seed_mask] = seed
+    pad = math.ceil(max_distance) if max_distance is not None else None
+    near = _window_dist(seed_mask, pad)
+    far = near.max()
+    dists = []
+    while index:
+        k = int(np.argmin([near[labels == l].min(initial=far) for l in index]))
+        cur = index.pop(k)
+        cur_mask = labels == cur
+        cur_near = _window_dist(cur_mask, pad)
+        both = near + cur_near
+        d = both.min()
+        if max_distance is not None and d > max_distance:
+            break
+        bridge = cur_mask | (both <= d + path_tolerance)
+        dists.append(d)
+        labels_out[bridge] = seed
+        closer = cur_near < near
+        near[closer] = cur_near[closer]
+    return (labels_out, dists) if return_merge_distances else labels_out
+
+
+def loki_chain(image, threshold_brighter=40, opening_radius=1, closing_radius=2, clear_border_flag=False,
+               min_area=0, merge_segments_distance=0, with_props=True):
+    """One vignette through threshold -> opening -> closing -> label -> filters -> merge -> regionprops
+    in the order of loki/pipeline.py:405-457 (opening BEFORE closing)."""
+    mask = image > threshold_brighter
+    if opening_radius > 0:
+        mask = opening(mask, opening_radius)
+    if closing_radius > 0:
+        mask = closing(mask, closing_radius)
+    labels, _ = label(mask)
+    if clear_border_flag:
+        clear_border(labels)
+    if min_area > 0:
+        remove_small_objects(labels, min_area)
+    if merge_segments_distance > 0:
+        labels = merge_labels(labels, max_distance=merge_segments_distance, labels_out=labels)
+    table = _c_regionprops(np.ascontiguousarray(labels), image) if with_props else None
+    return mask, labels, table

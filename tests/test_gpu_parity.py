@@ -1,0 +1,359 @@
+"""Parity of the CUDA path (through the C-ABI) with the reference-pinned oracle.  Bit-exact for
+masks, labels, distances (float64 merge distances included) and all integer features; float
+features within rel 1e-5 (north_star) with an absolute floor scaled by area^((p+q)/2+1)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import scipy_chain
+from conftest import ISO_OPS, ISO_RADII, iso_cases, merge_case_args, unpack, unpack_as
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mz():
+    import torch
+    import maze_image_processing_pipeline_b200 as pkg
+    from maze_image_processing_pipeline_b200 import device, isotropic, measure, merge_labels, stage, synth, _lib
+    _lib.lib()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.device, ns.isotropic, ns.measure, ns.stage, ns.synth = torch, device, isotropic, measure, stage, synth
+    ns.merge_labels = merge_labels.merge_labels
+    return ns
+
+
+# ------------------------------------------------------------------------------------------------
+def test_threshold_float_thresholds(mz):
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in [(7, 33), (64, 64), (5, 100), (1, 1), (40, 31)]]
+    geom = mz.device.BatchGeometry.from_images(imgs)
+    batch = mz.device.DeviceBatch(geom)
+    d_img = batch.upload(geom.pack_host(imgs))
+    for thr in (-3, -0.5, 0, 0.5, 30, 30.5, 127.999, 254, 254.5, 255, 300.0):
+        bits, flags = batch.threshold_pack(d_img, mz.device.fold_threshold(thr))
+        mask = batch.unpack_mask(bits).cpu().numpy()
+        fl = flags.cpu().numpy()
+        for i, im in enumerate(imgs):
+            want = im > thr
+            assert np.array_equal(geom.view(mask, i).astype(bool), want), (thr, i)
+            assert bool(fl[i] & 1) == bool(want.any()) and bool(fl[i] & 2) == bool((~want).any())
+
+
+def test_isotropic_golden_per_image_api(mz, golden_isotropic):
+    z = golden_isotropic
+    for name in iso_cases(z):
+        m = unpack(z, name)
+        for r in (0, 0.5, 1, 1.5, 2, 3, 32):
+            for op in ISO_OPS:
+                want = unpack_as(z, f"{name}/{op}/{r}", m.shape)
+                got = getattr(mz.isotropic, f"isotropic_{op}")(m, r)
+                assert got.dtype == bool and np.array_equal(got, want), (name, op, r)
+    # uint8 0/255 input and out= conventions (isotropic.py:36: np.greater(..., out=out) returns out)
+    m = unpack(z, "blob0")
+    buf = np.zeros(m.shape, bool)
+    ret = mz.isotropic.isotropic_opening(m.astype(np.uint8) * 255, 2, out=buf)
+    assert ret is buf and np.array_equal(buf, unpack_as(z, "blob0/opening/2", m.shape))
+
+
+def test_isotropic_golden_batched_all_radii(mz, golden_isotropic):
+    z = golden_isotropic
+    names = iso_cases(z)
+    masks = [unpack(z, n) for n in names]
+    geom = mz.device.BatchGeometry.from_images(masks)
+    batch = mz.device.DeviceBatch(geom)
+    d = batch.upload(geom.pack_host([m.view(np.uint8) for m in masks]))
+    bits, flags = batch.threshold_pack(d, 0)
+    n = 0
+    for r in ISO_RADII:
+        for op in ISO_OPS:
+            out_bits, _ = getattr(batch, op)(bits, flags, r)
+            got = batch.unpack_mask(out_bits).cpu().numpy()
+            for i, name in enumerate(names):
+                want = unpack_as(z, f"{name}/{op}/{r}", masks[i].shape)
+                assert np.array_equal(geom.view(got, i).astype(bool), want), (name, op, r)
+                n += 1
+    assert n == 880
+
+
+def test_isotropic_large_radius_edt_path(mz):
+    rng = np.random.default_rng(5)
+    img = mz.synth.synth_batch(3, 1, size=(150, 190))[0]
+    masks = [img > 40, rng.random((90, 140)) < 0.97, np.ones((60, 45), bool), np.zeros((50, 70), bool)]
+    for m in masks:
+        for r in (33, 40.5, 64, 200):
+            for op in ISO_OPS:
+                want = getattr(oracle, f"isotropic_{op}")(m, r)
+                got = getattr(mz.isotropic, f"isotropic_{op}")(m, r)
+                assert np.array_equal(got, want), (m.shape, op, r)
+
+
+def test_edt_sq_exact(mz):
+    rng = np.random.default_rng(6)
+    cases = [rng.random((37, 53)) < 0.8, rng.random((128, 200)) < 0.995, np.ones((20, 31), bool),
+             np.ones((1, 17), bool), np.ones((17, 1), bool), np.zeros((4, 4), bool), rng.random((1, 64)) < 0.7,
+             rng.random((300, 3)) < 0.9]
+    for m in cases:
+        want = oracle.edt_sq(m)
+        got = mz.isotropic.distance_transform_edt_sq(m)
+        assert got.dtype == np.int32 and np.array_equal(got, want), m.shape
+
+
+# ------------------------------------------------------------------------------------------------
+def test_label_golden(mz, golden_labels):
+    z = golden_labels
+    for name in iso_cases(z):
+        m = unpack(z, name)
+        lab, n = mz.measure.label(m, return_num=True)
+        assert lab.dtype == np.int32 and n == int(z[f"{name}/n"])
+        assert np.array_equal(lab, z[f"{name}/labels"]), name
+
+
+@pytest.mark.parametrize("shape,p", [((64, 64), 0.5), ((257, 1023), 0.55), ((1024, 1024), 0.6), ((333, 77), 0.3),
+                                     ((2048, 2048), 0.45), ((31, 2000), 0.7), ((2000, 31), 0.7), ((5, 32), 1.0),
+                                     ((9, 64), 0.0), ((100, 33), 0.59)])
+def test_label_random_vs_oracle(mz, shape, p):
+    rng = np.random.default_rng(hash(shape) % 1000)
+    m = rng.random(shape) < p
+    want, n = oracle.label(m)
+    got, gn = mz.measure.label(m, return_num=True)
+    assert gn == n
+    assert np.array_equal(got, want)
+
+
+def test_label_batched_blobs_and_dense_frame(mz):
+    imgs = mz.synth.synth_batch(9, 24, lo=64, hi=300)
+    imgs.append(mz.synth.synth_dense_frame(4, size=1536, n_blobs=900))
+    geom = mz.device.BatchGeometry.from_images(imgs)
+    batch = mz.device.DeviceBatch(geom)
+    d = batch.upload(geom.pack_host(imgs))
+    bits, flags = batch.threshold_pack(d, 40)
+    labels, lab_off = batch.label(bits)
+    lab = labels.cpu().numpy()
+    off = lab_off.cpu().numpy()
+    for i, im in enumerate(imgs):
+        want, n = oracle.label(im > 40)
+        assert off[i + 1] - off[i] == n
+        assert np.array_equal(geom.view(lab, i), want), i
+    assert off[-1] - off[-2] > 500  # the dense frame has hundreds of labels
+
+
+def test_label_filters(mz):
+    imgs = mz.synth.synth_batch(19, 6, lo=60, hi=200)
+    for im in imgs:
+        lab, _ = oracle.label(im > 30)
+        for min_size in (1, 5, 50):
+            want = oracle.remove_small_objects(lab.copy(), min_size)
+            work = lab.copy()
+            ret = mz.measure.remove_small_objects(work, min_size=min_size, out=work)
+            assert ret is work and np.array_equal(work, want)
+        want = oracle.clear_border(lab.copy())
+        work = lab.copy()
+        ret = mz.measure.clear_border(work, out=work)
+        assert ret is work and np.array_equal(work, want)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_merge_labels_golden(mz, golden_merge):
+    z, meta = golden_merge
+    checked = raised = 0
+    for key, info in meta.items():
+        name, kw = merge_case_args(key)
+        lab = z[f"{name}/input"]
+        work = lab.copy()
+        if "index" in kw:
+            idx = [int(v) for v in kw["index"].split("-")]
+            call = lambda: mz.merge_labels(work, index=list(idx), max_distance=20, return_merge_distances=True,
+                                           labels_out=work)
+        else:
+            md = None if kw["md"] == "None" else float(kw["md"])
+            alias = kw["alias"] == "1"
+            call = lambda: mz.merge_labels(work, max_distance=md, path_tolerance=float(kw["tol"]),
+                                           return_merge_distances=True, labels_out=work if alias else None)
+        if info["raises"]:
+            with pytest.raises(TypeError):
+                call()
+            raised += 1
+            continue
+        res, dists = call()
+        assert np.array_equal(np.asarray(res), z[key + "/labels"]), key
+        assert np.array_equal(np.asarray(dists, np.float64), z[key + "/dists"]), key
+        if "identity" in info:
+            assert (res is work) == info["identity"], key
+        checked += 1
+    assert checked > 300 and raised == 5
+
+
+def test_merge_labels_index_list_is_popped_like_the_reference(mz, golden_merge):
+    z, _ = golden_merge
+    lab = z["sparse/input"]
+    for idx in ([5, 1, 3, 8], [8, 7, 6, 5, 4, 3, 2, 1]):
+        a, b = list(idx), list(idx)
+        scipy_chain.merge_labels(lab.copy(), index=a, max_distance=20)
+        mz.merge_labels(lab.copy(), index=b, max_distance=20)
+        assert a == b
+
+
+def test_merge_labels_batched_vs_oracle(mz):
+    imgs = mz.synth.synth_batch(23, 12, lo=48, hi=160)
+    labs = []
+    for im in imgs:
+        m = oracle.isotropic_closing(oracle.isotropic_opening(im > 40, 1), 2)
+        labs.append(oracle.label(m)[0])
+    geom = mz.device.BatchGeometry.from_images(labs)
+    batch = mz.device.DeviceBatch(geom)
+    d_lab = batch.upload(geom.pack_host(labs, dtype=np.int32))
+    bounds = [int(l.max()) for l in labs]
+    lab_off, n_obj = batch.lab_off_from_bounds(bounds)
+    md, nm, _, status, _ = batch.merge_labels(d_lab, d_lab, lab_off, n_obj, 10.0)
+    got = d_lab.cpu().numpy()
+    md, nm, off = md.cpu().numpy(), nm.cpu().numpy(), lab_off.cpu().numpy()
+    for i, l in enumerate(labs):
+        work = l.copy()
+        want, dists = oracle.merge_labels(work, max_distance=10.0, return_merge_distances=True, labels_out=work)
+        assert np.array_equal(geom.view(got, i), want), i
+        assert list(md[off[i]:off[i] + nm[i]]) == list(dists)
+    assert (status.cpu().numpy() == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+def assert_tables_close(got, want, with_image=True):
+    F = oracle
+    assert got.shape == want.shape
+    for g, w in zip(got, want):
+        assert g[F.F_LABEL] == w[F.F_LABEL] and g[F.F_AREA] == w[F.F_AREA]
+        if w[F.F_AREA] == 0:
+            continue
+        area = w[F.F_AREA]
+        assert np.array_equal(g[F.F_BBOX:F.F_BBOX + 4], w[F.F_BBOX:F.F_BBOX + 4])
+        np.testing.assert_allclose(g[F.F_CENTROID:F.F_CENTROID + 2], w[F.F_CENTROID:F.F_CENTROID + 2], rtol=1e-14)
+        gm, wm = g[F.F_MU:F.F_MU + 16].reshape(4, 4), w[F.F_MU:F.F_MU + 16].reshape(4, 4)
+        gn, wn = g[F.F_NU:F.F_NU + 16].reshape(4, 4), w[F.F_NU:F.F_NU + 16].reshape(4, 4)
+        for p in range(4):
+            for q in range(4):
+                scale = area ** ((p + q) / 2 + 1)
+                assert abs(gm[p, q] - wm[p, q]) <= 1e-5 * abs(wm[p, q]) + 1e-9 * scale, (p, q, gm[p, q], wm[p, q])
+                if p + q >= 2:
+                    assert abs(gn[p, q] - wn[p, q]) <= 1e-5 * abs(wn[p, q]) + 1e-9, (p, q)
+                else:
+                    assert np.isnan(gn[p, q]) and np.isnan(wn[p, q])
+        np.testing.assert_allclose(g[F.F_HU:F.F_HU + 7], w[F.F_HU:F.F_HU + 7], rtol=1e-5, atol=1e-12)
+        for c in (F.F_EIG, F.F_EIG + 1, F.F_AXIS_MAJOR, F.F_AXIS_MINOR, F.F_T00, F.F_T01, F.F_T11):
+            np.testing.assert_allclose(g[c], w[c], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(g[F.F_ECC], w[F.F_ECC], rtol=1e-5, atol=2e-7)
+        if abs(w[F.F_T00] - w[F.F_T11]) > 1e-6 * max(1.0, abs(w[F.F_T00])) or w[F.F_T00] == w[F.F_T11]:
+            d = abs(g[F.F_ORIENT] - w[F.F_ORIENT])
+            assert min(d, abs(d - np.pi)) <= 1e-5, (g[F.F_ORIENT], w[F.F_ORIENT])
+        if with_image:
+            assert g[F.F_IMIN] == w[F.F_IMIN] and g[F.F_IMAX] == w[F.F_IMAX]
+            np.testing.assert_allclose(g[F.F_IMEAN], w[F.F_IMEAN], rtol=1e-14)
+            np.testing.assert_allclose(g[F.F_FRAC_INVALID], w[F.F_FRAC_INVALID], rtol=1e-14)
+
+
+def test_regionprops_golden_cases(mz, golden_props):
+    z, _ = golden_props
+    for name in ("ellipse", "square", "pixel", "hline", "blobs"):
+        lab, inten = z[f"{name}/labels"], z[f"{name}/intensity"]
+        want = oracle.regionprops_table(lab, inten)
+        got = mz.measure.regionprops_table(lab, inten)
+        assert_tables_close(got, want)
+    lab = np.zeros((12, 12), np.int32)
+    lab[2:8, 3:9] = 1
+    t = mz.measure.regionprops_table(lab)[0]
+    assert t[oracle.F_ORIENT] == -np.pi / 4          # T00 == T11 branch, exact
+    lab = np.zeros((5, 5), np.int32)
+    lab[2, 3] = 1
+    t = mz.measure.regionprops_table(lab)[0]
+    assert t[oracle.F_ECC] == 0 and t[oracle.F_AXIS_MAJOR] == 0
+
+
+def test_regionprops_random_label_images_and_gaps(mz):
+    rng = np.random.default_rng(11)
+    # arbitrary label image: noise labels with gaps (labels 3 and 6 absent), intensity with zeros
+    lab = rng.integers(0, 9, size=(70, 101)).astype(np.int32)
+    lab[lab == 3] = 0
+    lab[lab == 6] = 0
+    inten = rng.integers(0, 256, size=lab.shape, dtype=np.uint8)
+    inten[rng.random(lab.shape) < 0.2] = 0
+    assert_tables_close(mz.measure.regionprops_table(lab, inten), oracle.regionprops_table(lab, inten))
+    assert_tables_close(mz.measure.regionprops_table(lab), oracle.regionprops_table(lab), with_image=False)
+    # big coordinates: a frame-sized label image
+    img = mz.synth.synth_dense_frame(2, size=2048, n_blobs=600)
+    lab, n = oracle.label(img > 40)
+    assert_tables_close(mz.measure.regionprops_table(lab, img), oracle.regionprops_table(lab, img))
+
+
+def test_mask_properties_image_properties_semantics(mz):
+    img = mz.synth.synth_batch(5, 1, size=(120, 90))[0]
+    mask = img > 40
+    want = oracle.regionprops_table(mask.astype(np.int32), img)
+    assert_tables_close(mz.measure.mask_properties(mask, img), want)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("merge", [0, 10])
+@pytest.mark.parametrize("filters", [False, True])
+def test_stage_composite_vs_reference_chain(mz, merge, filters):
+    S = mz.stage
+    imgs = mz.synth.synth_batch(101 + merge, 20, lo=64, hi=320)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1, merge_segments_distance=merge,
+                                            min_area=12 if filters else 0, clear_border=filters)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+    res = st(imgs)
+    assert len(res) == len(imgs)
+    for i, im in enumerate(imgs):
+        mask, labels, table = scipy_chain.loki_chain(im, 40, 1, 2, clear_border_flag=filters,
+                                                     min_area=12 if filters else 0, merge_segments_distance=merge)
+        assert np.array_equal(res.mask(i), mask), i
+        assert np.array_equal(res.labels(i), labels), i
+        feats = res.features(i)
+        nrow = min(len(feats), len(table))
+        assert len(feats) >= len(table)
+        assert_tables_close(feats[:nrow], table[:nrow])
+        assert (feats[nrow:, oracle.F_AREA] == 0).all()  # labels removed by the filters leave empty rows
+
+
+def test_stage_threshold_branch(mz):
+    S = mz.stage
+    imgs = mz.synth.synth_batch(7, 8, lo=64, hi=200)
+    imgs.append(np.zeros((50, 60), np.uint8))  # empty mask -> dropped by the Filter (loki/pipeline.py:651)
+    st = S.LokiSegmentationStage(threshold=S.ThresholdSegmentationConfig(35.5))
+    res = st(imgs)
+    assert list(res.keep) == [True] * 8 + [False]
+    for i, im in enumerate(imgs[:8]):
+        mask = im > 35.5
+        assert np.array_equal(res.mask(i), mask)
+        assert_tables_close(res.features(i), oracle.regionprops_table(mask.astype(np.int32), im))
+
+
+def test_stage_postprocess_branch_on_model_prediction(mz):
+    S = mz.stage
+    imgs = mz.synth.synth_batch(8, 6, lo=64, hi=200)
+    preds = [(im > 50).astype(np.float32) * 0.9 for im in imgs]  # "foreground_pred" of a model
+    pp = S.SegmentationPostprocessingConfig(closing_radius=3, opening_radius=2)
+    res = S.LokiSegmentationStage(postprocess=pp)(imgs, foreground_pred=preds)
+    for i, (im, pr) in enumerate(zip(imgs, preds)):
+        m = scipy_chain.closing(scipy_chain.opening(np.asarray(pr, dtype=bool), 2), 3)
+        lab, _ = scipy_chain.label(m)
+        assert np.array_equal(res.mask(i), m) and np.array_equal(res.labels(i), lab)
+
+
+def test_full_size_properties_without_oracle(mz):
+    """Size-independent properties on a BASELINE-sized vignette mix (1024-px sides)."""
+    S = mz.stage
+    imgs = mz.synth.synth_batch(55, 6, lo=700, hi=1024)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    res = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)(imgs)
+    for i in range(len(imgs)):
+        lab, mask = res.labels(i), res.mask(i)
+        assert np.array_equal(lab > 0, mask)
+        flat = lab.ravel()
+        first = flat[np.sort(np.unique(flat, return_index=True)[1])]
+        first = first[first > 0]
+        assert np.array_equal(first, np.arange(1, len(first) + 1))  # raster order of first pixels
+        feats = res.features(i)
+        assert feats[:, oracle.F_AREA].sum() == mask.sum()            # areas partition the mask
+        assert np.array_equal(feats[:, oracle.F_AREA], np.bincount(flat)[1:])

@@ -1,0 +1,158 @@
+"""Host-side logic and the C-ABI surface (CPU only; no kernel is launched)."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_geometry_layout():
+    from maze_image_processing_pipeline_b200.device import BatchGeometry, TILE_DTYPE, VIG_DTYPE
+    g = BatchGeometry([3, 64, 1], [5, 70, 1])
+    assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8
+    assert list(g.vig["wpr"]) == [1, 3, 1]
+    assert list(g.pix_off[:3]) == [0, 16, 16 + 4480]
+    assert (g.pix_off % 16 == 0).all()
+    assert list(g.word_off) == [0, 3, 3 + 192, 3 + 192 + 1]
+    assert g.n_tiles == 3 and list(g.tiles["img"]) == [0, 1, 2] and list(g.tiles["word0"]) == [0, 0, 0]
+    g2 = BatchGeometry([100], [1000])  # 100 rows x 32 words = 3200 words = 13 tiles
+    assert g2.n_tiles == 13 and list(g2.tiles["word0"][:3]) == [0, 256, 512]
+    imgs = [np.arange(15, dtype=np.uint8).reshape(3, 5), np.ones((64, 70), np.uint8), np.full((1, 1), 7, np.uint8)]
+    flat = g.pack_host(imgs)
+    for i, im in enumerate(imgs):
+        assert np.array_equal(g.view(flat, i), im)
+    with pytest.raises(ValueError):
+        BatchGeometry([0], [4])
+
+
+def test_radius_folding_matches_float64_compare():
+    from maze_image_processing_pipeline_b200.device import fold_dilation_radius, fold_erosion_radius, fold_threshold
+    ks = np.arange(0, 5000)
+    d = np.sqrt(ks.astype(np.float64))
+    for r in [0, 0.5, 1, 1.5, 2, 2.5, 3, 5, 8, 13, 32, math.sqrt(2), math.sqrt(5), 2.2360679, 2.23606798, 7.07, 70.7]:
+        te, td = fold_erosion_radius(r), fold_dilation_radius(r)
+        assert np.array_equal(d > r, ks > te), r
+        assert np.array_equal(d < r, ks <= td), r
+    assert fold_erosion_radius(-1) == -1 and fold_dilation_radius(0) == -1 and fold_dilation_radius(-2) == -1
+    px = np.arange(256)
+    for t in (-5, -0.1, 0, 0.5, 30, 30.5, 254.99, 255, 1e9):
+        assert np.array_equal(px > t, px > fold_threshold(t)), t
+
+
+def test_shard_bounds_cover_everything():
+    from maze_image_processing_pipeline_b200.stage import shard_bounds
+    for n in (0, 1, 7, 100, 1001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "maze_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(maze_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from maze_image_processing_pipeline_b200 import _lib
+    _lib.build()
+    handle = ctypes.CDLL(_lib.SO_PATH)
+    declared = _header_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/maze_b200.h but not exported"
+    assert set(declared) == set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS)
+    lib = _lib.lib()
+    assert lib.maze_version() >= 100
+
+
+def test_sass_is_sm100a_only():
+    from maze_image_processing_pipeline_b200 import _lib
+    _lib.build()
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from maze_image_processing_pipeline_b200 import _lib, isotropic
+    with pytest.raises(_lib.MazeLibraryError):
+        isotropic.isotropic_erosion(np.ones((4, 4), bool), 1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "maze_image_processing_pipeline_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "libmaze_oracle" not in text, f
+
+
+def test_config_mirrors_match_reference_schema_golden():
+    import dataclasses
+    import json
+    from maze_image_processing_pipeline_b200.stage import SegmentationPostprocessingConfig, ThresholdSegmentationConfig
+    doc = json.load(open(os.path.join(ROOT, "tests", "golden", "config_schema.json")))
+    ref = doc["SegmentationPostprocessingConfig"]
+    mine = {f.name: f.default for f in dataclasses.fields(SegmentationPostprocessingConfig)}
+    assert set(mine) == set(ref)
+    for k, v in ref.items():
+        assert mine[k] == v["default"], k
+    assert [f.name for f in dataclasses.fields(ThresholdSegmentationConfig)] == list(doc["ThresholdSegmentationConfig"])
+    assert doc["short_forms"]["postprocess: true"] == dataclasses.asdict(SegmentationPostprocessingConfig())
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from maze_image_processing_pipeline_b200.stage import gather_object_tables, shard_bounds
+dist.init_process_group("gloo", init_method="env://")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_img = 11
+lo, hi = shard_bounds(n_img, rank, world)
+# each image i contributes (i % 3) objects; local image index in column 57
+rows = []
+for i in range(lo, hi):
+    for l in range(i % 3):
+        r = np.zeros(64); r[0] = l + 1; r[1] = 10 * i + l; r[57] = i - lo
+        rows.append(r)
+local = np.array(rows).reshape(-1, 64)
+full = gather_object_tables(local, lo)
+if rank == 0:
+    want = [(i, l + 1, 10 * i + l) for i in range(n_img) for l in range(i % 3)]
+    got = [(int(r[57]), int(r[0]), int(r[1])) for r in full]
+    assert got == want, (got, want)
+    print("GATHER_OK", len(got))
+else:
+    assert full is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_tables_are_concatenated_in_image_order_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29591", WORLD_SIZE="2")
+    procs = []
+    for rank in range(2):
+        e = dict(env, RANK=str(rank), LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK 10" in outs[0]

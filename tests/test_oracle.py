@@ -1,0 +1,166 @@
+"""Pins the CPU oracle (oracle/) against the golden vectors generated from the REAL reference
+(tests/golden/make_golden.py imported maze_ipp/isotropic.py and maze_ipp/merge_labels.py from
+/root/reference; labels come from scipy.ndimage.label, what skimage.measure.label calls for bool
+input; the regionprops pins are OpenCV moments).  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import scipy_chain
+from conftest import ISO_OPS, ISO_RADII, iso_cases, merge_case_args, unpack, unpack_as
+
+
+def test_isotropic_c_oracle_matches_reference_golden(golden_isotropic):
+    z = golden_isotropic
+    n = 0
+    for name in iso_cases(z):
+        m = unpack(z, name)
+        for r in ISO_RADII:
+            for op in ISO_OPS:
+                want = unpack_as(z, f"{name}/{op}/{r}", m.shape)
+                got = getattr(oracle, f"isotropic_{op}")(m, r)
+                assert np.array_equal(got, want), (name, op, r)
+                n += 1
+    assert n == 880
+
+
+def test_isotropic_scipy_chain_matches_reference_golden(golden_isotropic):
+    z = golden_isotropic
+    for name in iso_cases(z):
+        m = unpack(z, name)
+        for r in (0.5, 1, 2, 5):
+            for op in ISO_OPS:
+                want = unpack_as(z, f"{name}/{op}/{r}", m.shape)
+                assert np.array_equal(getattr(scipy_chain, op)(m, r), want), (name, op, r)
+
+
+def test_edt_fast_equals_bruteforce():
+    rng = np.random.default_rng(3)
+    for shape, p in [((17, 23), 0.7), ((9, 40), 0.95), ((30, 5), 0.5), ((6, 6), 1.0), ((1, 9), 1.0)]:
+        m = rng.random(shape) < p
+        assert np.array_equal(oracle.edt_sq(m), oracle.edt_sq(m, bruteforce=True))
+
+
+def test_label_oracle_matches_scipy_golden(golden_labels):
+    z = golden_labels
+    for name in iso_cases(z):
+        m = unpack(z, name)
+        lab, n = oracle.label(m)
+        assert n == int(z[f"{name}/n"])
+        assert lab.dtype == np.int32
+        assert np.array_equal(lab, z[f"{name}/labels"]), name
+
+
+def _run_merge(fn, lab, kw, alias):
+    work = lab.copy()
+    md = None if kw["md"] == "None" else float(kw["md"])
+    return work, fn(work, max_distance=md, path_tolerance=float(kw["tol"]), return_merge_distances=True,
+                    labels_out=work if alias else None)
+
+
+@pytest.mark.parametrize("impl", ["c", "scipy"])
+def test_merge_labels_oracle_matches_reference_golden(golden_merge, impl):
+    z, meta = golden_merge
+    fn = oracle.merge_labels if impl == "c" else scipy_chain.merge_labels
+    checked = raised = 0
+    for key, info in meta.items():
+        name, kw = merge_case_args(key)
+        lab = z[f"{name}/input"]
+        if "index" in kw:
+            idx = [int(v) for v in kw["index"].split("-")]
+            work = lab.copy()
+            call = lambda: fn(work, index=list(idx), max_distance=20, return_merge_distances=True, labels_out=work)
+        else:
+            alias = kw["alias"] == "1"
+            call = lambda: _run_merge(fn, lab, kw, alias)[1]
+        if info["raises"]:
+            with pytest.raises(TypeError):
+                call()
+            raised += 1
+            continue
+        res, dists = call()
+        assert np.array_equal(np.asarray(res), z[key + "/labels"]), key
+        assert np.array_equal(np.asarray(dists, np.float64), z[key + "/dists"]), key  # bit-exact float64
+        checked += 1
+    assert checked > 300 and raised == 5
+
+
+def test_merge_identity_when_fewer_than_two_labels():
+    lab = np.zeros((8, 8), np.int32)
+    lab[2:4, 2:4] = 3
+    assert oracle.merge_labels(lab, max_distance=5) is lab
+    assert scipy_chain.merge_labels(lab, max_distance=5) is lab
+
+
+def test_regionprops_oracle_vs_opencv(golden_props):
+    z, cols = golden_props
+    ci = {c: i for i, c in enumerate(cols)}
+    for name in ("ellipse", "square", "pixel", "hline", "blobs"):
+        lab, inten, cv = z[f"{name}/labels"], z[f"{name}/intensity"], z[f"{name}/cv2"]
+        t = oracle.regionprops_table(lab, inten)
+        assert t.shape[0] == cv.shape[0]
+        for row, ref in zip(t, cv):
+            area = ref[ci["area"]]
+            assert row[oracle.F_AREA] == area
+            assert list(row[oracle.F_BBOX:oracle.F_BBOX + 4]) == [ref[ci[f"bbox{k}"]] for k in range(4)]
+            np.testing.assert_allclose(row[oracle.F_CENTROID:oracle.F_CENTROID + 2],
+                                       [ref[ci["centroid_r"]], ref[ci["centroid_c"]]], rtol=1e-12)
+            mu = row[oracle.F_MU:oracle.F_MU + 16].reshape(4, 4)
+            nu = row[oracle.F_NU:oracle.F_NU + 16].reshape(4, 4)
+            for key, (p, q) in {"20": (2, 0), "11": (1, 1), "02": (0, 2), "30": (3, 0), "21": (2, 1),
+                                "12": (1, 2), "03": (0, 3)}.items():
+                scale = area ** ((p + q) / 2 + 1)
+                assert abs(mu[p, q] - ref[ci["mu" + key]]) <= 1e-9 * scale, (name, key)
+                assert abs(nu[p, q] - ref[ci["nu" + key]]) <= 1e-9, (name, key)
+            hu = row[oracle.F_HU:oracle.F_HU + 7]
+            ref_hu = np.array([ref[ci[f"hu{k}"]] for k in range(7)])
+            # cv2 ran on the transposed crop, so its (x, y) powers are skimage's (row, col) powers and
+            # hu[6] already carries skimage's sign (it is the opposite of cv2 on the untransposed crop)
+            np.testing.assert_allclose(hu, ref_hu, rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(row[oracle.F_IMIN:oracle.F_IMIN + 4],
+                                       [ref[ci["imin"]], ref[ci["imax"]], ref[ci["imean"]], ref[ci["frac0"]]],
+                                       rtol=1e-12)
+
+
+def test_regionprops_known_answers():
+    # single pixel: zero inertia -> eccentricity 0, axes 0
+    lab = np.zeros((5, 5), np.int32)
+    lab[2, 3] = 1
+    t = oracle.regionprops_table(lab)[0]
+    assert t[oracle.F_ECC] == 0 and t[oracle.F_AXIS_MAJOR] == 0 and t[oracle.F_AREA] == 1
+    # square: T00 == T11 -> the +-pi/4 branch (T01 == 0 -> -pi/4)
+    lab = np.zeros((12, 12), np.int32)
+    lab[2:8, 3:9] = 1
+    t = oracle.regionprops_table(lab)[0]
+    assert t[oracle.F_ORIENT] == -np.pi / 4 and abs(t[oracle.F_ECC]) < 1e-7
+    # horizontal line of length n: major axis 4*sqrt((n^2-1)/12), orientation +-pi/2
+    lab = np.zeros((5, 40), np.int32)
+    lab[2, 5:30] = 1
+    t = oracle.regionprops_table(lab)[0]
+    np.testing.assert_allclose(t[oracle.F_AXIS_MAJOR], 4 * np.sqrt((25 ** 2 - 1) / 12), rtol=1e-12)
+    assert abs(abs(t[oracle.F_ORIENT]) - np.pi / 2) < 1e-12 and t[oracle.F_ECC] == 1.0
+
+
+def test_label_filters_oracle():
+    lab = np.zeros((10, 12), np.int32)
+    lab[0:2, 0:2] = 1      # touches border
+    lab[4:6, 4:7] = 2      # 6 px
+    lab[8, 8] = 3          # 1 px
+    a = oracle.clear_border(lab.copy())
+    assert set(np.unique(a)) == {0, 2, 3}
+    b = oracle.remove_small_objects(lab.copy(), 4)
+    assert set(np.unique(b)) == {0, 1, 2}
+    assert np.array_equal(scipy_chain.clear_border(lab.copy()), a)
+    assert np.array_equal(scipy_chain.remove_small_objects(lab.copy(), 4), b)
+
+
+def test_chain_c_oracle_equals_scipy_chain():
+    from maze_image_processing_pipeline_b200.synth import synth_batch
+    for k, img in enumerate(synth_batch(77, 6, lo=40, hi=120)):
+        mask, labels, table = scipy_chain.loki_chain(img, 40, 1, 2, merge_segments_distance=10 if k % 2 else 0)
+        m = oracle.isotropic_closing(oracle.isotropic_opening(oracle.threshold(img, 40), 1), 2)
+        assert np.array_equal(m, mask)
+        lab, n = oracle.label(m)
+        if k % 2:
+            lab = oracle.merge_labels(lab, max_distance=10, labels_out=lab)
+        assert np.array_equal(lab, labels)
