@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the LOKI re-segmentation stage (BASELINE.json metric: vignettes/s and MPix/s for
+seg + CCL + regionprops, HBM % of peak).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): 100 000 synthetic variable-size LOKI vignettes (H, W
+independently log-uniform in [64, 1024]), processed in batches of --batch vignettes; one STEP is one
+pass of the whole chain (threshold 40 -> isotropic opening r=1 -> isotropic closing r=2 -> 8-connected
+labelling -> regionprops, mask bytes written) over one batch.  Batch b holds vignettes
+[b*B, (b+1)*B) of the job; rank r of N works on batches r, r+N, ... (weak scaling, no collective on
+the data path).  Every batch is > L2 (about 250 MB of pixels), so no L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+JOB_VIGNETTES = 100_000
+SIZE_SEED = 1        # C2 uses seed 1
+PIXEL_SEED = 20261018
+THRESHOLD, R_OPEN, R_CLOSE = 40, 1, 2
+
+# algorithmic bytes per pixel of each kernel (inputs it must read + outputs it must write)
+KERNEL_BYTES_PER_PX = {
+    "k_threshold_pack": 1.125, "k_morph_pass": 0.25, "k_unpack_mask": 1.125, "k_ccl_init": 0.125,
+    "k_ccl_union": 0.125, "k_ccl_flatten": 0.125, "k_ccl_assign": 0.125, "k_ccl_write": 4.125,
+    "k_props_accumulate": 5.0, "k_props_high_order": 4.0, "k_label_zero": 8.0, "k_label_count": 4.0,
+    "k_vignette_fused": 6.125, "k_props_runs": 5.0, "k_props_runs_high": 4.0,
+}
+STAGE_BYTES_PER_PX = 6.0  # 1 R image + 1 W mask + 4 W labels
+
+
+def job_sizes():
+    from maze_image_processing_pipeline_b200.synth import synth_sizes
+    return synth_sizes(SIZE_SEED, JOB_VIGNETTES, 64, 1024)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's scipy restatement of the reference chain on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(img):
+    from oracle import scipy_chain
+    mask, labels, table = scipy_chain.loki_chain(img, THRESHOLD, R_OPEN, R_CLOSE)
+    return int(labels.max()), int(mask.sum())
+
+
+def _cpu_pool(cores):
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import oracle
+    oracle.build()
+    ctx = mp.get_context("fork")
+    return ctx.Pool(cores)
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample_images(n, first=0):
+    """The first n vignettes of the job from index `first`, regenerated on the host with the SAME
+    sizes; pixel content comes from the numpy generator (same image model as the device generator)."""
+    from maze_image_processing_pipeline_b200.synth import synth_vignette
+    hs, ws = job_sizes()
+    rng = np.random.default_rng(PIXEL_SEED + first)
+    return [synth_vignette(rng, int(hs[(first + i) % JOB_VIGNETTES]), int(ws[(first + i) % JOB_VIGNETTES]))
+            for i in range(n)]
+
+
+def time_cpu(pool, imgs):
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_one, imgs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return dt, sum(o[0] for o in out)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    per_step = max(cores, min(4 * cores, 256))
+    pool = _cpu_pool(cores)
+    imgs = cpu_sample_images(per_step)
+    px = sum(int(i.size) for i in imgs)
+    for _ in range(args.warmup):
+        time_cpu(pool, imgs[: max(cores, per_step // 4)])
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = time_cpu(pool, imgs)
+        total += dt
+    pool.close()
+    v = per_step * args.steps / total
+    sample = f"{per_step} vignettes ({px / 1e6:.1f} MPix) of configs[1] per step, multiprocessing.Pool({cores})"
+    line = {
+        "impl": "reference", "metric": "loki_vignettes_per_s", "value": v, "unit": "vignettes/s",
+        "mpix_per_s": px * args.steps / total / 1e6, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, per_step),
+        "cpu_baseline": {"value": v, "unit": "vignettes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "vignettes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, batch):
+    return {"workload": "configs[1]: 100k synthetic variable-size vignettes (64-1024 px, log-uniform), "
+                        f"batches of {batch}", "batch_vignettes": batch, "threshold_brighter": THRESHOLD,
+            "opening_radius": R_OPEN, "closing_radius": R_CLOSE, "merge_segments_distance": args.merge,
+            "min_area": 0, "clear_border": False, "regionprops": "full table incl. high-order moments",
+            "l2": "each batch is larger than L2 (no flush needed)", "parallelism": f"images sharded over {args.gpus} GPU(s)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from maze_image_processing_pipeline_b200 import _lib
+    from maze_image_processing_pipeline_b200 import stage as S
+    from maze_image_processing_pipeline_b200.device import BatchGeometry, DeviceBatch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hs, ws = job_sizes()
+    B = args.batch
+    n_batches_job = (JOB_VIGNETTES + B - 1) // B
+    need = args.steps + args.warmup
+    pp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN,
+                                            merge_segments_distance=args.merge)
+    stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp)
+
+    # resident inputs: the batches this rank will touch, generated on the device
+    batches = []
+    for s in range(need):
+        b = (rank + s * world) % n_batches_job
+        lo = b * B
+        hi = min(lo + B, JOB_VIGNETTES)
+        geom = BatchGeometry(hs[lo:hi], ws[lo:hi])
+        db = DeviceBatch(geom)
+        img = db.synth(PIXEL_SEED, lo)
+        batches.append((db, img))
+    torch.cuda.synchronize()
+
+    def step(i):
+        db, img = batches[i]
+        res = stage.run_device(db, img)
+        return res, res.mask
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    n_vig = n_px = n_obj = 0
+    for i in range(args.warmup, need):
+        res, _ = step(i)
+        n_vig += batches[i][0].g.n_img
+        n_px += batches[i][0].g.pixels
+        n_obj += res.n_obj
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # instrumented repeat of the same steps: per-kernel CUDA-event durations for the roofline
+    _lib.prof_enable(True)
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record()
+    for i in range(args.warmup, need):
+        step(i)
+    evp1.record()
+    torch.cuda.synchronize()
+    _lib.prof_enable(False)
+    prof = _lib.prof_collect()
+    ms_instr = evp0.elapsed_time(evp1)
+
+    # end to end through the public stage call: host numpy in, host numpy out, copies timed
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host_batches = []
+    for i in range(args.warmup, args.warmup + e2e_steps):
+        db, img = batches[i]
+        flat = img.cpu().numpy()
+        host_batches.append([db.g.view(flat, k) for k in range(db.g.n_img)])
+    stage(host_batches[0])  # warm the pinned pool
+    barrier()
+    t0 = time.perf_counter()
+    e2e_vig = e2e_px = 0
+    h2d = d2h = 0
+    for hb in host_batches:
+        r = stage(hb)
+        e2e_vig += len(hb)
+        e2e_px += r.geometry.pixels
+        h2d += r.geometry.total_px
+        d2h += r.geometry.total_px * 5 + r.table.nbytes + r.lab_off.nbytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_s, float(n_vig), float(n_px), float(e2e_vig), float(e2e_px), float(launches)],
+                         dtype=torch.float64, device="cuda")
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[1])
+        n_vig, n_px, e2e_vig, e2e_px, launches = (float(sm[k]) for k in (2, 3, 4, 5, 6))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    px_per_launch = (n_px / world) / args.steps  # one rank's batch
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    top_name, (top_ms, top_cnt) = top
+    bpp = KERNEL_BYTES_PER_PX.get(top_name, STAGE_BYTES_PER_PX)
+    launches_per_step = top_cnt / args.steps
+    alg_bytes = bpp * px_per_launch / max(launches_per_step, 1)
+    avg_s = top_ms / top_cnt / 1e3
+    achieved = alg_bytes / avg_s / 1e9
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_px": bpp, "avg_launch_ms": top_ms / top_cnt,
+                "share_of_step": top_ms / ms_instr}
+    stage_gbs = STAGE_BYTES_PER_PX * n_px / (ms / 1e3) / 1e9
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        n_s = max(cores, min(4 * cores, 256))
+        pool = _cpu_pool(cores)
+        imgs = host_batches[0][:n_s]
+        time_cpu(pool, imgs[: max(1, len(imgs) // 4)])
+        dt, _ = time_cpu(pool, imgs)
+        pool.close()
+        cpu_baseline = {"value": len(imgs) / dt, "unit": "vignettes/s", "cores": cores, "kind": "port",
+                        "mpix_per_s": sum(int(i.size) for i in imgs) / dt / 1e6,
+                        "sample": f"first {len(imgs)} vignettes of the first timed batch (same pixels as the GPU run), "
+                                  f"oracle/scipy_chain.py (the reference chain on scipy.ndimage), Pool({cores})"}
+
+    line = {
+        "metric": "loki_vignettes_per_s", "value": n_vig / (ms / 1e3), "unit": "vignettes/s",
+        "mpix_per_s": n_px / (ms / 1e3) / 1e6, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args, B),
+        "objects_per_step": n_obj / args.steps,
+        "roofline": roofline,
+        "stage_hbm": {"achieved": stage_gbs / world, "unit": "GB/s per GPU", "bytes_per_px": STAGE_BYTES_PER_PX,
+                      "frac_of_measured": stage_gbs / world / peak, "frac_of_nominal_8TBps": stage_gbs / world / 8000.0},
+        "kernels": kernels, "ms_per_step_instrumented": ms_instr / args.steps,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_vig / e2e_s, "unit": "vignettes/s", "mpix_per_s": e2e_px / e2e_s / 1e6,
+                "steps": e2e_steps, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--merge", type=int, default=0, help="merge_segments_distance (0 = off, the schema default)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

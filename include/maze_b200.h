@@ -96,6 +96,8 @@ typedef struct maze_tile {
 #define MAZE_NEXT 8
 
 #define MAZE_RP_HIGH_ORDER 1 /* also fill mu/nu[p,q] with p+q > 3 (second pass over the labels) */
+#define MAZE_RP_RUNS 2       /* labels AND bits given, labels are constant along the runs of bits (output of
+                                maze_label, also after the label filters): run-based reduction */
 
 const char *maze_error_string(void);
 int maze_version(void);
@@ -188,6 +190,36 @@ int maze_merge_labels(const int32_t *labels, int32_t *labels_out, const maze_vig
 int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,
                          const maze_tile_t *tiles, int n_tiles, uint64_t seed, int64_t img_index0,
                          void *stream);
+
+/* Vignette-resident fused stage: threshold -> n_pass (<= 4) thresholded-EDT passes -> label(), one CTA
+ * per vignette with the bit planes and the union-find in shared memory; writes the final bit plane,
+ * the mask bytes, the int32 label image and n_labels[i] for every listed vignette.
+ * img_list (device) holds the vignette indices grouped into three size classes (h*wpr words <=
+ * MAZE_FUSED_CAP0 / CAP1 / CAP2); class c is img_list[class_off_host[c] .. class_off_host[c+1]).
+ * Larger vignettes must go through the per-operator entry points above.  pass_t_host /
+ * pass_invert_host: the d2 threshold and erosion(0)/dilation(1) flag of every pass, as for
+ * maze_morph_pass.  fallback[i] = 1 marks a listed vignette with more word runs than union-find
+ * slots (nothing was written for it; use the per-operator path). */
+#define MAZE_FUSED_CAP0 1024
+#define MAZE_FUSED_CAP1 4096
+#define MAZE_FUSED_CAP2 18432
+int maze_vignette_stage(const uint8_t *image, const maze_vignette_t *vig, const int32_t *img_list,
+                        const int32_t *class_off_host, int t_int, int n_pass, const int32_t *pass_t_host,
+                        const int32_t *pass_invert_host, uint32_t *bits, uint8_t *mask, int32_t *labels,
+                        int32_t *n_labels, int32_t *fallback, void *stream);
+
+/* lab_off[0..n_img] = exclusive prefix sum of n_labels[0..n_img). */
+int maze_count_scan(const int32_t *n_labels, int n_img, int32_t *lab_off, void *stream);
+
+/* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
+ * maze_launch_count: kernels launched by this library since load.  With maze_prof_enable(1) every
+ * launch is bracketed by an event pair; maze_prof_collect waits for them and ADDS elapsed
+ * milliseconds / launch counts per kernel id into the caller's zeroed HOST arrays of length n. */
+long long maze_launch_count(void);
+int maze_prof_kernel_count(void);
+const char *maze_prof_kernel_name(int kid);
+int maze_prof_enable(int on);
+int maze_prof_collect(double *ms_host, long long *counts_host, int n);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,8 @@ NFEAT = 64
 NACC = 12
 NEXT = 8
 RP_HIGH_ORDER = 1
+RP_RUNS = 2
+FUSED_CAPS = (1024, 4096, 18432)
 
 
 class MazeLibraryError(RuntimeError):
@@ -70,8 +72,11 @@ SIGNATURES = {
     "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
     "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "maze_synth_vignettes": [_vp, _vp, _i, _vp, _i, _u64, _i64, _vp],
+    "maze_vignette_stage": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "maze_count_scan": [_vp, _i, _vp, _vp],
 }
-OTHER_SYMBOLS = ["maze_error_string", "maze_version"]
+OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",
+                 "maze_prof_kernel_name", "maze_prof_enable", "maze_prof_collect"]
 
 _lib = None
 
@@ -98,6 +103,11 @@ def lib():
         fn.restype = ctypes.c_int
     handle.maze_error_string.restype = ctypes.c_char_p
     handle.maze_version.restype = ctypes.c_int
+    handle.maze_launch_count.restype = ctypes.c_longlong
+    handle.maze_prof_kernel_name.restype = ctypes.c_char_p
+    handle.maze_prof_kernel_name.argtypes = [ctypes.c_int]
+    handle.maze_prof_enable.argtypes = [ctypes.c_int]
+    handle.maze_prof_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     _lib = handle
     return _lib
 
@@ -112,3 +122,21 @@ def check(rc: int, what: str):
     if rc == MAZE_ERR_CAPACITY:
         raise MemoryError(f"{what}: table capacity exceeded")
     raise RuntimeError(f"{what}: error {rc}")
+
+
+def launch_count() -> int:
+    return int(lib().maze_launch_count())
+
+
+def prof_enable(on: bool):
+    lib().maze_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """{kernel name: (total ms, launches)} for everything recorded since the last collect."""
+    import numpy as np
+    n = lib().maze_prof_kernel_count()
+    ms = np.zeros(n, np.float64)
+    cnt = np.zeros(n, np.int64)
+    check(lib().maze_prof_collect(ms.ctypes.data, cnt.ctypes.data, n), "maze_prof_collect")
+    return {lib().maze_prof_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}

@@ -227,18 +227,12 @@ extern "C" int maze_label(const uint32_t *bits, const maze_vignette_t *vig, int 
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
-    k_ccl_init<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent);
-    MAZE_LAUNCH_CHECK("k_ccl_init");
-    k_ccl_union<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent);
-    MAZE_LAUNCH_CHECK("k_ccl_union");
-    k_ccl_flatten<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, tile_scan);
-    MAZE_LAUNCH_CHECK("k_ccl_flatten");
-    k_tile_scan<<<1, 1024, 0, s>>>(tile_scan, n_tiles, vig, n_img, lab_off);
-    MAZE_LAUNCH_CHECK("k_tile_scan");
-    k_ccl_assign<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, tile_scan, labels);
-    MAZE_LAUNCH_CHECK("k_ccl_assign");
-    k_ccl_write<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, labels);
-    MAZE_LAUNCH_CHECK("k_ccl_write");
+    MAZE_KERNEL(KID_CCL_INIT, s, k_ccl_init<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent));
+    MAZE_KERNEL(KID_CCL_UNION, s, k_ccl_union<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent));
+    MAZE_KERNEL(KID_CCL_FLATTEN, s, k_ccl_flatten<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, tile_scan));
+    MAZE_KERNEL(KID_TILE_SCAN, s, k_tile_scan<<<1, 1024, 0, s>>>(tile_scan, n_tiles, vig, n_img, lab_off));
+    MAZE_KERNEL(KID_CCL_ASSIGN, s, k_ccl_assign<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, tile_scan, labels));
+    MAZE_KERNEL(KID_CCL_WRITE, s, k_ccl_write<<<n_tiles, MAZE_CTA, 0, s>>>(bits, vig, tiles, parent, labels));
     return MAZE_OK;
 }
 
@@ -338,10 +332,8 @@ extern "C" int maze_clear_border(int32_t *labels, const maze_vignette_t *vig, in
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0 || n_obj_cap <= 0) return MAZE_OK;
     MAZE_CUDA(cudaMemsetAsync(obj_scratch, 0, sizeof(int32_t) * (size_t)n_obj_cap, s), "clear_border scratch");
-    k_border_mark<<<n_img, 256, 0, s>>>(labels, vig, lab_off, obj_scratch, n_obj_cap);
-    MAZE_LAUNCH_CHECK("k_border_mark");
-    k_label_zero<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap, 0, 0);
-    MAZE_LAUNCH_CHECK("k_label_zero");
+    MAZE_KERNEL(KID_BORDER_MARK, s, k_border_mark<<<n_img, 256, 0, s>>>(labels, vig, lab_off, obj_scratch, n_obj_cap));
+    MAZE_KERNEL(KID_LABEL_ZERO, s, k_label_zero<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap, 0, 0));
     return MAZE_OK;
 }
 
@@ -352,10 +344,8 @@ extern "C" int maze_remove_small_objects(int32_t *labels, const maze_vignette_t 
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0 || n_obj_cap <= 0) return MAZE_OK;
     MAZE_CUDA(cudaMemsetAsync(obj_scratch, 0, sizeof(int32_t) * (size_t)n_obj_cap, s), "remove_small scratch");
-    k_label_count<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap);
-    MAZE_LAUNCH_CHECK("k_label_count");
-    k_label_zero<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap, 1, (i64)min_size);
-    MAZE_LAUNCH_CHECK("k_label_zero");
+    MAZE_KERNEL(KID_LABEL_COUNT, s, k_label_count<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap));
+    MAZE_KERNEL(KID_LABEL_ZERO, s, k_label_zero<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, lab_off, obj_scratch, n_obj_cap, 1, (i64)min_size));
     return MAZE_OK;
 }
 
@@ -387,7 +377,6 @@ extern "C" int maze_max_label(const int32_t *labels, const maze_vignette_t *vig,
     if (n_img <= 0) return MAZE_OK;
     MAZE_CUDA(cudaMemsetAsync(max_label, 0, sizeof(int32_t) * (size_t)n_img, s), "max_label");
     if (n_tiles <= 0) return MAZE_OK;
-    k_max_label<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, max_label);
-    MAZE_LAUNCH_CHECK("k_max_label");
+    MAZE_KERNEL(KID_MAX_LABEL, s, k_max_label<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, max_label));
     return MAZE_OK;
 }

@@ -329,10 +329,9 @@ extern "C" int maze_merge_labels(const int32_t *labels, int32_t *labels_out, con
 {
     if (n_img <= 0) return MAZE_OK;
     if (index && !index_off) return MAZE_ERR_BADARG;
-    k_merge_labels<<<n_img, MG_CTA, 0, (cudaStream_t)stream>>>(labels, labels_out, vig, lab_off, n_obj_cap, index,
+    MAZE_KERNEL(KID_MERGE_LABELS, (cudaStream_t)stream, k_merge_labels<<<n_img, MG_CTA, 0, (cudaStream_t)stream>>>(labels, labels_out, vig, lab_off, n_obj_cap, index,
                                                                 index_off, have_max, max_distance, path_tolerance,
                                                                 d2a, d2b, gbuf, obj_scratch, merge_dist, n_merge,
-                                                                index_state, status);
-    MAZE_LAUNCH_CHECK("k_merge_labels");
+                                                                index_state, status));
     return MAZE_OK;
 }

@@ -54,8 +54,7 @@ extern "C" int maze_threshold_pack(const uint8_t *image, const maze_vignette_t *
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
     MAZE_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)n_img, s), "threshold flags");
-    k_threshold_pack<<<n_tiles, MAZE_CTA, 0, s>>>(image, vig, tiles, t_int, bits, flags);
-    MAZE_LAUNCH_CHECK("k_threshold_pack");
+    MAZE_KERNEL(KID_THRESHOLD_PACK, s, k_threshold_pack<<<n_tiles, MAZE_CTA, 0, s>>>(image, vig, tiles, t_int, bits, flags));
     return MAZE_OK;
 }
 
@@ -98,8 +97,7 @@ extern "C" int maze_compare_pack(const int32_t *d2, const maze_vignette_t *vig, 
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
     MAZE_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)n_img, s), "compare flags");
-    k_compare_pack<<<n_tiles, MAZE_CTA, 0, s>>>(d2, vig, tiles, t, greater, bits, flags);
-    MAZE_LAUNCH_CHECK("k_compare_pack");
+    MAZE_KERNEL(KID_COMPARE_PACK, s, k_compare_pack<<<n_tiles, MAZE_CTA, 0, s>>>(d2, vig, tiles, t, greater, bits, flags));
     return MAZE_OK;
 }
 
@@ -130,8 +128,7 @@ extern "C" int maze_unpack_mask(const uint32_t *bits, const maze_vignette_t *vig
                                 const maze_tile_t *tiles, int n_tiles, uint8_t *mask, void *stream)
 {
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
-    k_unpack_mask<<<n_tiles, MAZE_CTA, 0, (cudaStream_t)stream>>>(bits, vig, tiles, mask);
-    MAZE_LAUNCH_CHECK("k_unpack_mask");
+    MAZE_KERNEL(KID_UNPACK_MASK, (cudaStream_t)stream, k_unpack_mask<<<n_tiles, MAZE_CTA, 0, (cudaStream_t)stream>>>(bits, vig, tiles, mask));
     return MAZE_OK;
 }
 
@@ -231,8 +228,7 @@ extern "C" int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vig
         for (int dy = 0; dy <= disk.R; dy++) disk.w[dy] = isqrt_host(t - dy * dy);
     }
     MAZE_CUDA(cudaMemsetAsync(flags_out, 0, sizeof(uint32_t) * (size_t)n_img, s), "morph flags");
-    k_morph_pass<<<n_tiles, MAZE_CTA, 0, s>>>(in, out, vig, tiles, disk, invert, flags_in, flags_out);
-    MAZE_LAUNCH_CHECK("k_morph_pass");
+    MAZE_KERNEL(KID_MORPH_PASS, s, k_morph_pass<<<n_tiles, MAZE_CTA, 0, s>>>(in, out, vig, tiles, disk, invert, flags_in, flags_out));
     return MAZE_OK;
 }
 
@@ -330,11 +326,9 @@ extern "C" int maze_edt_sq(const uint32_t *bits, const maze_vignette_t *vig, int
     if ((size_t)max_w * 4 > 200 * 1024) return MAZE_ERR_BADARG;
     uint32_t *pool = has_zero;
     MAZE_CUDA(cudaMemsetAsync(pool, 0, sizeof(uint32_t) * (size_t)n_img, s), "edt flags");
-    k_plane_has_zero<<<n_img, 256, 0, s>>>(bits, vig, invert, pool);
-    MAZE_LAUNCH_CHECK("k_plane_has_zero");
+    MAZE_KERNEL(KID_PLANE_HAS_ZERO, s, k_plane_has_zero<<<n_img, 256, 0, s>>>(bits, vig, invert, pool));
     dim3 gc(n_img, (max_w + 127) / 128);
-    k_edt_cols<<<gc, 128, 0, s>>>(bits, vig, invert, pool, d2);
-    MAZE_LAUNCH_CHECK("k_edt_cols");
+    MAZE_KERNEL(KID_EDT_COLS, s, k_edt_cols<<<gc, 128, 0, s>>>(bits, vig, invert, pool, d2));
     int gy = max_h;
     if ((i64)gy * n_img > 65535 * 8) gy = (int)((65535 * 8) / n_img);
     if (gy < 1) gy = 1;
@@ -342,7 +336,6 @@ extern "C" int maze_edt_sq(const uint32_t *bits, const maze_vignette_t *vig, int
     size_t smem = (size_t)max_w * 4;
     if (smem > 48 * 1024)
         MAZE_CUDA(cudaFuncSetAttribute(k_edt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "edt smem");
-    k_edt_rows<<<dim3(n_img, gy), 256, smem, s>>>(vig, d2);
-    MAZE_LAUNCH_CHECK("k_edt_rows");
+    MAZE_KERNEL(KID_EDT_ROWS, s, k_edt_rows<<<dim3(n_img, gy), 256, smem, s>>>(vig, d2));
     return MAZE_OK;
 }

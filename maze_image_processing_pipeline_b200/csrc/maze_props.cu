@@ -118,6 +118,117 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_accumulate(const int32_t *__
     }
 }
 
+// Run-based variant for label images whose labels are constant along the word runs of `bits`
+// (the output of maze_label, also after clear_border / remove_small_objects): one thread per word,
+// only words with foreground do any work, the label is read once per run.
+__global__ void __launch_bounds__(MAZE_CTA) k_props_runs(const int32_t *__restrict__ labels,
+                                                         const uint32_t *__restrict__ bits,
+                                                         const uint8_t *__restrict__ image,
+                                                         const maze_vignette_t *__restrict__ vig,
+                                                         const maze_tile_t *__restrict__ tiles,
+                                                         const int32_t *__restrict__ lab_off, int n_obj_cap,
+                                                         u64 *acc, int32_t *ext)
+{
+    TileCtx c = load_tile(vig, tiles);
+    int widx = c.word0 + threadIdx.x;
+    if (widx >= c.nwords) return;
+    uint32_t m = __ldg(bits + c.v.word_off + widx);
+    if (!m) return;
+    const int W = c.v.w;
+    int y = widx / c.v.wpr, k = widx - y * c.v.wpr;
+    int obj0 = lab_off[c.img];
+    int nlab = lab_off[c.img + 1] - obj0;
+    const int32_t *L = labels + c.v.pix_off + (i64)y * W + 32 * k;
+    const uint8_t *I = image ? image + c.v.pix_off + (i64)y * W + 32 * k : nullptr;
+    uint32_t starts = m & ~(m << 1);
+    while (starts) {
+        int b0 = __ffs(starts) - 1;
+        starts &= starts - 1;
+        uint32_t run = ~(m >> b0);
+        int len = run ? __ffs(run) - 1 : 32 - b0;
+        int l = L[b0];
+        if (l <= 0 || l > nlab) continue;
+        int row = obj0 + l - 1;
+        if (row >= n_obj_cap) continue;
+        u64 a = (u64)(32 * k + b0), b = a + len - 1, n = (u64)len, r = (u64)y;
+        u64 s1 = n * (a + b) / 2;
+        u64 s2 = pow2sum(b) - (a ? pow2sum(a - 1) : 0);
+        u64 s3 = pow3sum(b) - (a ? pow3sum(a - 1) : 0);
+        u64 *A = acc + (i64)row * MAZE_NACC;
+        atomicAdd(A + A_N, n);
+        atomicAdd(A + A_R, n * r);
+        atomicAdd(A + A_C, s1);
+        atomicAdd(A + A_RR, n * r * r);
+        atomicAdd(A + A_RC, r * s1);
+        atomicAdd(A + A_CC, s2);
+        atomicAdd(A + A_RRR, n * r * r * r);
+        atomicAdd(A + A_RRC, r * r * s1);
+        atomicAdd(A + A_RCC, r * s2);
+        atomicAdd(A + A_CCC, s3);
+        int32_t *E = ext + (i64)row * MAZE_NEXT;
+        atomicMin(E + E_RMIN, y);
+        atomicMax(E + E_RMAX, y);
+        atomicMin(E + E_CMIN, (int)a);
+        atomicMax(E + E_CMAX, (int)b);
+        if (I) {
+            int sv = 0, sz = 0, mn = 255, mx = 0;
+            for (int j = 0; j < len; j++) {
+                int v = (int)__ldg(I + b0 + j);
+                sv += v; sz += (v == 0); mn = min(mn, v); mx = max(mx, v);
+            }
+            atomicAdd(A + A_V, (u64)sv);
+            atomicAdd(A + A_Z, (u64)sz);
+            atomicMin(E + E_VMIN, mn);
+            atomicMax(E + E_VMAX, mx);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MAZE_CTA) k_props_runs_high(const int32_t *__restrict__ labels,
+                                                              const uint32_t *__restrict__ bits,
+                                                              const maze_vignette_t *__restrict__ vig,
+                                                              const maze_tile_t *__restrict__ tiles,
+                                                              const int32_t *__restrict__ lab_off, int n_obj_cap,
+                                                              double *table)
+{
+    TileCtx c = load_tile(vig, tiles);
+    int widx = c.word0 + threadIdx.x;
+    if (widx >= c.nwords) return;
+    uint32_t m = __ldg(bits + c.v.word_off + widx);
+    if (!m) return;
+    const int W = c.v.w;
+    int y = widx / c.v.wpr, k = widx - y * c.v.wpr;
+    int obj0 = lab_off[c.img];
+    int nlab = lab_off[c.img + 1] - obj0;
+    const int32_t *L = labels + c.v.pix_off + (i64)y * W + 32 * k;
+    uint32_t starts = m & ~(m << 1);
+    while (starts) {
+        int b0 = __ffs(starts) - 1;
+        starts &= starts - 1;
+        uint32_t run = ~(m >> b0);
+        int len = run ? __ffs(run) - 1 : 32 - b0;
+        int l = L[b0];
+        if (l <= 0 || l > nlab) continue;
+        int row = obj0 + l - 1;
+        if (row >= n_obj_cap) continue;
+        double *f = table + (i64)row * MAZE_NFEAT;
+        double dr = (double)y - f[MAZE_F_CENTROID];
+        double cc = f[MAZE_F_CENTROID + 1];
+        double s1 = 0, s2 = 0, s3 = 0;
+        for (int j = 0; j < len; j++) {
+            double dc = (double)(32 * k + b0 + j) - cc;
+            s1 += dc; s2 += dc * dc; s3 += dc * dc * dc;
+        }
+        double dr2 = dr * dr, dr3 = dr2 * dr;
+        atomicAdd(f + MAZE_F_MU + 1 * 4 + 3, dr * s3);
+        atomicAdd(f + MAZE_F_MU + 2 * 4 + 2, dr2 * s2);
+        atomicAdd(f + MAZE_F_MU + 3 * 4 + 1, dr3 * s1);
+        atomicAdd(f + MAZE_F_MU + 2 * 4 + 3, dr2 * s3);
+        atomicAdd(f + MAZE_F_MU + 3 * 4 + 2, dr3 * s2);
+        atomicAdd(f + MAZE_F_MU + 3 * 4 + 3, dr3 * s3);
+    }
+}
+
 __device__ __forceinline__ double i128_to_double(__int128 v)
 {
     bool neg = v < 0;
@@ -310,17 +421,19 @@ extern "C" int maze_regionprops(const int32_t *labels, const uint32_t *bits, con
     if (!labels && !bits) return MAZE_ERR_BADARG;
     int nb = (n_obj_cap + 255) / 256;
     int high = (flags & MAZE_RP_HIGH_ORDER) ? 1 : 0;
-    k_props_init<<<nb, 256, 0, s>>>(acc, ext, n_obj_cap);
-    MAZE_LAUNCH_CHECK("k_props_init");
-    k_props_accumulate<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext);
-    MAZE_LAUNCH_CHECK("k_props_accumulate");
-    k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 0, table);
-    MAZE_LAUNCH_CHECK("k_props_finish");
+    MAZE_KERNEL(KID_PROPS_INIT, s, k_props_init<<<nb, 256, 0, s>>>(acc, ext, n_obj_cap));
+    const bool runs = (flags & MAZE_RP_RUNS) && labels && bits;
+    if (runs)
+        MAZE_KERNEL(KID_PROPS_RUNS, s, k_props_runs<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
+    else
+        MAZE_KERNEL(KID_PROPS_ACCUMULATE, s, k_props_accumulate<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
+    MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 0, table));
     if (high) {
-        k_props_high_order<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table);
-        MAZE_LAUNCH_CHECK("k_props_high_order");
-        k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 1, table);
-        MAZE_LAUNCH_CHECK("k_props_finish2");
+        if (runs)
+            MAZE_KERNEL(KID_PROPS_RUNS_HIGH, s, k_props_runs_high<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
+        else
+            MAZE_KERNEL(KID_PROPS_HIGH_ORDER, s, k_props_high_order<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
+        MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 1, table));
     }
     return MAZE_OK;
 }

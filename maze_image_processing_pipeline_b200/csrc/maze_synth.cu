@@ -70,7 +70,6 @@ extern "C" int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, 
                                     int n_tiles, uint64_t seed, int64_t img_index0, void *stream)
 {
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
-    k_synth<<<n_tiles, MAZE_CTA, 0, (cudaStream_t)stream>>>(image, vig, tiles, (u64)seed, (i64)img_index0);
-    MAZE_LAUNCH_CHECK("k_synth");
+    MAZE_KERNEL(KID_SYNTH, (cudaStream_t)stream, k_synth<<<n_tiles, MAZE_CTA, 0, (cudaStream_t)stream>>>(image, vig, tiles, (u64)seed, (i64)img_index0));
     return MAZE_OK;
 }

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, TILE_WORDS, check, lib
+from ._lib import FUSED_CAPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS, TILE_WORDS, check, lib
 
 VIG_DTYPE = np.dtype([("pix_off", "<i8"), ("word_off", "<i8"), ("h", "<i4"), ("w", "<i4"),
                       ("wpr", "<i4"), ("tile0", "<i4")])
@@ -28,7 +28,7 @@ _INT_MAX = 2 ** 31 - 1
 class BatchGeometry:
     """Host-side description of a packed batch (numpy only, no device access)."""
 
-    def __init__(self, heights, widths):
+    def __init__(self, heights, widths, _pix_off=None, _word_off=None, _total_px=None, _total_words=None):
         hs = np.asarray(heights, dtype=np.int64).ravel()
         ws = np.asarray(widths, dtype=np.int64).ravel()
         if hs.shape != ws.shape:
@@ -44,8 +44,12 @@ class BatchGeometry:
         wpr = (ws + 31) // 32
         nwords = hs * wpr
         padded = (self.npx + 15) // 16 * 16
+        self.nwords = nwords
         self.pix_off = np.concatenate([[0], np.cumsum(padded)]).astype(np.int64)
         self.word_off = np.concatenate([[0], np.cumsum(nwords)]).astype(np.int64)
+        if _pix_off is not None:  # a subset that addresses its parent's buffers
+            self.pix_off = np.concatenate([np.asarray(_pix_off, np.int64), [_total_px - 16]])
+            self.word_off = np.concatenate([np.asarray(_word_off, np.int64), [_total_words]])
         ntiles = (nwords + TILE_WORDS - 1) // TILE_WORDS
         self.tile0 = np.concatenate([[0], np.cumsum(ntiles)]).astype(np.int64)
         self.total_px = int(self.pix_off[-1]) + 16  # tail slack for vector loads
@@ -69,6 +73,27 @@ class BatchGeometry:
         tiles["img"] = img_of_tile
         tiles["word0"] = (np.arange(self.n_tiles, dtype=np.int64) - self.tile0[img_of_tile]) * TILE_WORDS
         self.tiles = tiles
+
+    def subset(self, indices):
+        """Geometry of some vignettes of this batch that keeps THEIR offsets, so kernels launched on the
+        subset read and write the parent's buffers in place."""
+        idx = np.asarray(indices, dtype=np.int64)
+        return BatchGeometry(self.h[idx], self.w[idx], _pix_off=self.pix_off[idx], _word_off=self.word_off[idx],
+                             _total_px=self.total_px, _total_words=self.total_words)
+
+    def fused_classes(self):
+        """(img_list, class_off[4], leftovers): vignette indices grouped by the size classes of
+        maze_vignette_stage (largest first inside a class), and the ones too large for it."""
+        order, off = [], [0]
+        lo = 0
+        for cap in FUSED_CAPS:
+            sel = np.nonzero((self.nwords > lo) & (self.nwords <= cap))[0]
+            sel = sel[np.argsort(-self.nwords[sel], kind="stable")]
+            order.append(sel)
+            off.append(off[-1] + len(sel))
+            lo = cap
+        left = np.nonzero(self.nwords > FUSED_CAPS[-1])[0]
+        return np.concatenate(order).astype(np.int32), np.asarray(off, np.int32), left
 
     @classmethod
     def from_images(cls, images):
@@ -274,8 +299,9 @@ class DeviceBatch:
               "maze_remove_small_objects")
         return labels
 
-    def regionprops(self, lab_off, n_obj: int, labels=None, bits=None, image=None, high_order=True):
-        """Feature table (n_obj, NFEAT) float64 on the device."""
+    def regionprops(self, lab_off, n_obj: int, labels=None, bits=None, image=None, high_order=True, runs=False):
+        """Feature table (n_obj, NFEAT) float64 on the device.  runs=True: `labels` are constant along the
+        word runs of `bits` (straight from label() or the label filters) -> run-based reduction."""
         vig, n, tiles, nt = self._geo()
         table = torch.empty((max(n_obj, 0), NFEAT), dtype=torch.float64, device=self.device)
         if n_obj <= 0:
@@ -284,7 +310,8 @@ class DeviceBatch:
         ext = torch.empty(n_obj * NEXT, dtype=torch.int32, device=self.device)
         check(lib().maze_regionprops(_ptr(labels), _ptr(bits), _ptr(image), vig, n, tiles, nt, lab_off.data_ptr(),
                                      int(n_obj), acc.data_ptr(), ext.data_ptr(), table.data_ptr(),
-                                     RP_HIGH_ORDER if high_order else 0, _stream()), "maze_regionprops")
+                                     (RP_HIGH_ORDER if high_order else 0) | (RP_RUNS if runs else 0), _stream()),
+              "maze_regionprops")
         return table
 
     def merge_labels(self, labels, labels_out, lab_off, n_obj: int, max_distance, path_tolerance=5.0,
@@ -307,6 +334,29 @@ class DeviceBatch:
                                       merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
                                       status.data_ptr(), _stream()), "maze_merge_labels")
         return merge_dist, n_merge, index_state, status, obj_scratch
+
+    def vignette_stage(self, d_image, t_int: int, passes, bits, mask, labels, n_labels, fallback):
+        """maze_vignette_stage on every vignette that fits its size classes; returns the leftovers."""
+        g = self.g
+        if not hasattr(self, "_fused"):
+            img_list, class_off, left = g.fused_classes()
+            self._fused = (torch.from_numpy(img_list).to(self.device), class_off, left)
+        d_list, class_off, left = self._fused
+        if class_off[-1] > 0:
+            pt = np.asarray([p[0] for p in passes] + [0] * (4 - len(passes)), np.int32)
+            pi = np.asarray([p[1] for p in passes] + [0] * (4 - len(passes)), np.int32)
+            check(lib().maze_vignette_stage(d_image.data_ptr(), self.d_vig.data_ptr(), d_list.data_ptr(),
+                                            class_off.ctypes.data, int(t_int), len(passes), pt.ctypes.data,
+                                            pi.ctypes.data, bits.data_ptr(), mask.data_ptr(), labels.data_ptr(),
+                                            n_labels.data_ptr(), fallback.data_ptr(), _stream()),
+                  "maze_vignette_stage")
+        return left
+
+    def count_scan(self, n_labels):
+        lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device)
+        check(lib().maze_count_scan(n_labels.data_ptr(), self.g.n_img, lab_off.data_ptr(), _stream()),
+              "maze_count_scan")
+        return lab_off
 
     def synth(self, seed: int, img_index0: int = 0, out=None):
         vig, n, tiles, nt = self._geo()

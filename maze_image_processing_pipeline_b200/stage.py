@@ -24,7 +24,8 @@ import numpy as np
 import torch
 
 from ._lib import MAZE_ERR_TYPEERROR, NFEAT
-from .device import BatchGeometry, DeviceBatch, fold_threshold
+from ._lib import MAX_DISK_RADIUS
+from .device import (BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
 
 @dataclass
@@ -47,7 +48,8 @@ class SegmentationPostprocessingConfig:
 class DeviceResult:
     """Outputs of one batch, still on the device."""
 
-    def __init__(self, batch, bits, labels, lab_off, table, n_obj, keep=None, merge_status=None):
+    def __init__(self, batch, bits, labels, lab_off, table, n_obj, keep=None, merge_status=None, mask=None):
+        self.mask = mask
         self.batch = batch
         self.bits = bits
         self.labels = labels
@@ -98,7 +100,8 @@ class _PinnedPool:
 
 
 class LokiSegmentationStage:
-    def __init__(self, threshold=None, postprocess=None, device=None, high_order=True):
+    def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True):
+        self.fused = fused
         if threshold is None and postprocess is None:
             raise ValueError("exactly one of threshold / postprocess (or both, for the composite stage) is required")
         self.threshold = threshold
@@ -108,37 +111,89 @@ class LokiSegmentationStage:
         self._pool = _PinnedPool()
 
     # ---- device-resident core ----------------------------------------------------------------------
-    def run_device(self, batch: DeviceBatch, d_image, d_pred=None) -> DeviceResult:
-        """All kernels for one resident batch.  d_image: flat uint8 intensities; d_pred: flat uint8
-        foreground prediction (postprocess-only mode)."""
+    def _passes(self):
+        """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path."""
         pp = self.postprocess
-        if self.threshold is not None:
-            bits, flags = batch.threshold_pack(d_image, fold_threshold(self.threshold.threshold_brighter))
-        else:
-            bits, flags = batch.threshold_pack(d_pred, 0)  # np.asarray(pred, dtype=bool), :405
-        if pp is None:
-            # ImageProperties(mask, image): one region per vignette; empty masks are dropped (:651)
-            lab_off, n_obj = batch.lab_off_from_bounds(np.ones(batch.g.n_img, np.int64))
-            table = batch.regionprops(lab_off, n_obj, bits=bits, image=d_image, high_order=self.high_order)
-            keep = (flags & 1).bool()
-            return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep)
+        out = []
+        if pp.opening_radius > 0:   # isotropic.py:97-98
+            out += [(fold_erosion_radius(pp.opening_radius), 0), (fold_dilation_radius(pp.opening_radius), 1)]
+        if pp.closing_radius > 0:   # isotropic.py:128-129
+            out += [(fold_dilation_radius(pp.closing_radius), 1), (fold_erosion_radius(pp.closing_radius), 0)]
+        if any(t >= (MAX_DISK_RADIUS + 1) ** 2 for t, _ in out):
+            return None
+        return out
+
+    def _front_generic(self, batch, d_src, t_int, labels=None, mask=None):
+        """Per-operator kernels: threshold -> opening -> closing -> label (any size, any radius)."""
+        pp = self.postprocess
+        bits, flags = batch.threshold_pack(d_src, t_int)
         if pp.opening_radius > 0:
             bits, flags = batch.opening(bits, flags, pp.opening_radius)
         if pp.closing_radius > 0:
             bits, flags = batch.closing(bits, flags, pp.closing_radius)
-        labels, lab_off = batch.label(bits)
-        need_count = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
-        n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
+        labels, lab_off = batch.label(bits, labels=labels)
+        mask = batch.unpack_mask(bits, out=mask)
+        return bits, labels, lab_off, mask
+
+    def run_device(self, batch: DeviceBatch, d_image, d_pred=None) -> DeviceResult:
+        """All kernels for one resident batch.  d_image: flat uint8 intensities; d_pred: flat uint8
+        foreground prediction (postprocess-only mode)."""
+        pp = self.postprocess
+        g = batch.g
+        if self.threshold is not None:
+            d_src, t_int = d_image, fold_threshold(self.threshold.threshold_brighter)
+        else:
+            d_src, t_int = d_pred, 0  # np.asarray(pred, dtype=bool), loki/pipeline.py:405
+        if pp is None:
+            # ImageProperties(mask, image): one region per vignette; empty masks are dropped (:651)
+            bits, flags = batch.threshold_pack(d_src, t_int)
+            lab_off, n_obj = batch.lab_off_from_bounds(np.ones(g.n_img, np.int64))
+            table = batch.regionprops(lab_off, n_obj, bits=bits, image=d_image, high_order=self.high_order)
+            keep = (flags & 1).bool()
+            return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
+        passes = self._passes() if self.fused else None
+        if passes is None:
+            bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
+            n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
+        else:
+            # vignette-resident fused kernel; vignettes it cannot hold go through the per-operator path
+            bits = batch.empty_plane()
+            mask = batch.empty_px(torch.uint8)
+            labels = batch.empty_px(torch.int32)
+            counts = torch.zeros(2 * g.n_img, dtype=torch.int32, device=batch.device)
+            n_labels, fallback = counts[:g.n_img], counts[g.n_img:]
+            left = batch.vignette_stage(d_src, t_int, passes, bits, mask, labels, n_labels, fallback)
+            if len(left):
+                self._redo_generic(batch, left, d_src, t_int, bits, mask, labels, n_labels)
+            h_counts = counts.cpu().numpy()  # the one readback of the batch: label counts + fallback flags
+            redo = np.nonzero(h_counts[g.n_img:])[0]
+            if len(redo):
+                self._redo_generic(batch, redo, d_src, t_int, bits, mask, labels, n_labels)
+                h_counts = counts.cpu().numpy()
+            lab_off, n_obj = batch.lab_off_from_bounds(h_counts[:g.n_img])
         merge_status = None
-        if need_count and n_obj > 0:
+        if n_obj > 0:
             if pp.clear_border:
                 batch.clear_border(labels, lab_off, n_obj)
             if pp.min_area > 0:
                 batch.remove_small_objects(labels, lab_off, n_obj, pp.min_area)
             if pp.merge_segments_distance > 0:
                 merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance)[3]
-        table = batch.regionprops(lab_off, n_obj, labels=labels, image=d_image, high_order=self.high_order)
-        return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status)
+        # merge_labels paints bridges over background, so only then do labels leave the runs of `bits`
+        runs = merge_status is None
+        table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
+                                  high_order=self.high_order, runs=runs)
+        return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
+
+    def _redo_generic(self, batch, indices, d_src, t_int, bits, mask, labels, n_labels):
+        """Run the per-operator kernels on a few vignettes of the batch, in place in the batch buffers."""
+        sub = DeviceBatch(batch.g.subset(indices), batch.device)
+        sbits, _, slab_off, _ = self._front_generic(sub, d_src, t_int, labels=labels, mask=mask)
+        for i in indices:
+            w0, w1 = int(batch.g.word_off[i]), int(batch.g.word_off[i]) + int(batch.g.nwords[i])
+            bits[w0:w1] = sbits[w0:w1]
+        idx = torch.as_tensor(np.asarray(indices, np.int64), device=batch.device)
+        n_labels[idx] = slab_off[1:] - slab_off[:-1]
 
     # ---- host entry: numpy in, numpy out --------------------------------------------------------------
     def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,
@@ -164,7 +219,7 @@ class LokiSegmentationStage:
             mask_flat = labels_flat = None
             if want_mask:
                 h_mask = self._pool.get("mask", geom.total_px, torch.uint8)
-                h_mask.copy_(batch.unpack_mask(res.bits), non_blocking=True)
+                h_mask.copy_(res.mask, non_blocking=True)
                 mask_flat = h_mask.numpy()
             if want_labels and res.labels is not None:
                 h_lab = self._pool.get("labels", geom.total_px, torch.int32)

@@ -357,3 +357,50 @@ def test_full_size_properties_without_oracle(mz):
         feats = res.features(i)
         assert feats[:, oracle.F_AREA].sum() == mask.sum()            # areas partition the mask
         assert np.array_equal(feats[:, oracle.F_AREA], np.bincount(flat)[1:])
+
+
+def _edge_images(mz):
+    rng = np.random.default_rng(77)
+    imgs = mz.synth.synth_batch(202, 10, lo=64, hi=400)
+    imgs += [np.zeros((70, 90), np.uint8), np.full((65, 64), 255, np.uint8), np.full((1, 1), 200, np.uint8),
+             np.full((1, 77), 99, np.uint8), np.full((130, 1), 99, np.uint8),
+             (rng.random((200, 300)) < 0.5).astype(np.uint8) * 200,      # noise: more runs than UF slots -> fallback
+             (rng.random((96, 33)) < 0.9).astype(np.uint8) * 200,
+             mz.synth.synth_batch(203, 1, size=(1024, 1000))[0],          # too large for the fused kernel
+             mz.synth.synth_batch(204, 1, size=(580, 1016))[0],           # largest fused class
+             np.full((40, 40), 41, np.uint8)]                             # all ones after threshold (phantom in erosion)
+    faint = np.zeros((64, 64), np.uint8)
+    faint[10, 10] = 255                                                   # eroded away -> empty plane feeds the dilation
+    imgs.append(faint)
+    return imgs
+
+
+@pytest.mark.parametrize("radii", [(1, 2), (2, 3), (0, 2), (3, 0), (0, 0), (1.5, 2.5)])
+def test_fused_vignette_kernel_equals_reference_chain(mz, radii):
+    S = mz.stage
+    r_open, r_close = radii
+    imgs = _edge_images(mz)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=r_close, opening_radius=r_open)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+    res = st(imgs)
+    for i, im in enumerate(imgs):
+        mask, labels, table = scipy_chain.loki_chain(im, 40, r_open, r_close)
+        assert np.array_equal(res.mask(i), mask), (i, im.shape)
+        assert np.array_equal(res.labels(i), labels), (i, im.shape)
+        assert len(res.features(i)) == len(table)
+        assert_tables_close(res.features(i), table)
+
+
+def test_fused_and_generic_paths_agree_bitwise(mz):
+    S = mz.stage
+    imgs = _edge_images(mz)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1, min_area=9, clear_border=True)
+    a = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, fused=True)(imgs)
+    am = [a.mask(i).copy() for i in range(len(imgs))]
+    al = [a.labels(i).copy() for i in range(len(imgs))]
+    at, ao = a.table.copy(), a.lab_off.copy()
+    b = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, fused=False)(imgs)
+    assert np.array_equal(ao, b.lab_off)
+    for i in range(len(imgs)):
+        assert np.array_equal(am[i], b.mask(i)) and np.array_equal(al[i], b.labels(i))
+    assert np.array_equal(np.nan_to_num(at, nan=-1.0)[:, :8], np.nan_to_num(b.table, nan=-1.0)[:, :8])
