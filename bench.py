@@ -228,7 +228,7 @@ def run_b200(args):
         lo = b * B
         hi = min(lo + B, JOB_VIGNETTES)
         geom = BatchGeometry(hs[lo:hi], ws[lo:hi])
-        db = DeviceBatch(geom)
+        db = stage.prepare(DeviceBatch(geom))
         img = db.synth(PIXEL_SEED, lo)
         batches.append((db, img))
     torch.cuda.synchronize()

@@ -163,11 +163,13 @@ int maze_max_label(const int32_t *labels, const maze_vignette_t *vig, int n_img,
 /* Per-label regionprops (loki/pipeline.py:589-625, 653-654).  labels may be NULL, in which case
  * `bits` is read as a label image with the single label 1 (ImageProperties semantics).  image may
  * be NULL (no intensity columns).  acc: n_obj_cap * MAZE_NACC uint64; ext: n_obj_cap * MAZE_NEXT
- * int32; table: n_obj_cap * MAZE_NFEAT doubles.  Rows of absent labels get area 0 and NaN. */
+ * int32; table: n_obj_cap * MAZE_NFEAT doubles.  Rows of absent labels get area 0 and NaN.
+ * acc_base (optional, n_img int32): rows of vignettes with acc_base[i] >= 0 are not touched (they
+ * come from maze_props_finish_staged). */
 int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t *image,
                      const maze_vignette_t *vig, int n_img, const maze_tile_t *tiles, int n_tiles,
                      const int32_t *lab_off, int n_obj_cap, unsigned long long *acc, int32_t *ext,
-                     double *table, int flags, void *stream);
+                     double *table, int flags, const int32_t *acc_base, void *stream);
 
 /* maze_ipp/merge_labels.py:29-113 for every vignette of the batch, one CTA per vignette.
  * labels: read by the loop; labels_out: written (pass the same pointer for the pipeline's aliased
@@ -191,22 +193,40 @@ int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,
                          const maze_tile_t *tiles, int n_tiles, uint64_t seed, int64_t img_index0,
                          void *stream);
 
-/* Vignette-resident fused stage: threshold -> n_pass (<= 4) thresholded-EDT passes -> label(), one CTA
- * per vignette with the bit planes and the union-find in shared memory; writes the final bit plane,
- * the mask bytes, the int32 label image and n_labels[i] for every listed vignette.
- * img_list (device) holds the vignette indices grouped into three size classes (h*wpr words <=
- * MAZE_FUSED_CAP0 / CAP1 / CAP2); class c is img_list[class_off_host[c] .. class_off_host[c+1]).
+/* Vignette-resident fused stage: threshold -> n_pass (<= 4) thresholded-EDT passes -> label() ->
+ * per-label regionprops accumulators, one CTA per vignette with the bit planes, the union-find and
+ * the accumulators in shared memory.  Writes the final bit plane, the mask bytes, the int32 label
+ * image, n_labels[i] and -- into the staging arrays -- one accumulator row per label.
+ * image: bytes that are thresholded (pixel > t_int); intensity: bytes the intensity features are
+ * taken from (may be the same pointer, or NULL).
+ * img_list (device) holds the vignette indices grouped into MAZE_FUSED_CLASSES size classes (h*wpr
+ * words <= MAZE_FUSED_CAP0..3); class c is img_list[class_off_host[c] .. class_off_host[c+1]).
  * Larger vignettes must go through the per-operator entry points above.  pass_t_host /
  * pass_invert_host: the d2 threshold and erosion(0)/dilation(1) flag of every pass, as for
- * maze_morph_pass.  fallback[i] = 1 marks a listed vignette with more word runs than union-find
- * slots (nothing was written for it; use the per-operator path). */
+ * maze_morph_pass.  flags: MAZE_RP_HIGH_ORDER, MAZE_FUSED_NO_PROPS.
+ * fallback[i] = 1 marks a listed vignette with more word runs than union-find slots (nothing was
+ * written for it; use the per-operator path).  acc_base[i] receives the first staging row of
+ * vignette i (label l is row acc_base[i] + l - 1) or -1 when it was not staged (fallback, or the
+ * stage_cap rows of acc_stage [MAZE_NACC u64 each] / hi_stage [8 doubles] / ext_stage [MAZE_NEXT
+ * int32] were used up: use maze_regionprops for those).  stage_counter: one int32 of scratch. */
+#define MAZE_FUSED_NO_PROPS 4 /* flag: labels only, no accumulators are staged (acc_base[i] = -1) */
+#define MAZE_FUSED_CLASSES 4
 #define MAZE_FUSED_CAP0 1024
 #define MAZE_FUSED_CAP1 4096
-#define MAZE_FUSED_CAP2 18432
-int maze_vignette_stage(const uint8_t *image, const maze_vignette_t *vig, const int32_t *img_list,
-                        const int32_t *class_off_host, int t_int, int n_pass, const int32_t *pass_t_host,
-                        const int32_t *pass_invert_host, uint32_t *bits, uint8_t *mask, int32_t *labels,
-                        int32_t *n_labels, int32_t *fallback, void *stream);
+#define MAZE_FUSED_CAP2 12288
+#define MAZE_FUSED_CAP3 28320
+int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig,
+                        const int32_t *img_list, const int32_t *class_off_host, int t_int, int n_pass,
+                        const int32_t *pass_t_host, const int32_t *pass_invert_host, int flags,
+                        uint32_t *bits, uint8_t *mask, int32_t *labels, int32_t *n_labels, int32_t *fallback,
+                        int32_t *acc_base, int32_t *stage_counter, int stage_cap,
+                        unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, void *stream);
+
+/* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
+ * acc_base[i] >= 0 (the others are left to maze_regionprops). */
+int maze_props_finish_staged(const unsigned long long *acc_stage, const double *hi_stage, const int32_t *ext_stage,
+                             const int32_t *acc_base, const int32_t *lab_off, int n_img, int n_obj,
+                             int has_intensity, int flags, double *table, void *stream);
 
 /* lab_off[0..n_img] = exclusive prefix sum of n_labels[0..n_img). */
 int maze_count_scan(const int32_t *n_labels, int n_img, int32_t *lab_off, void *stream);

@@ -26,7 +26,8 @@ NACC = 12
 NEXT = 8
 RP_HIGH_ORDER = 1
 RP_RUNS = 2
-FUSED_CAPS = (1024, 4096, 18432)
+FUSED_CAPS = (1024, 4096, 12288, 28320)
+FUSED_NO_PROPS = 4
 
 
 class MazeLibraryError(RuntimeError):
@@ -69,10 +70,12 @@ SIGNATURES = {
     "maze_clear_border": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "maze_remove_small_objects": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i64, _vp],
     "maze_max_label": [_vp, _vp, _i, _vp, _i, _vp, _vp],
-    "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp],
+    "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "maze_synth_vignettes": [_vp, _vp, _i, _vp, _i, _u64, _i64, _vp],
-    "maze_vignette_stage": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "maze_vignette_stage": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
+                            _vp, _vp, _vp, _vp],
+    "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
 }
 OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",

@@ -1,7 +1,8 @@
 // Vignette-resident fused stage: ONE CTA runs threshold -> up to four thresholded-EDT passes ->
-// 8-connected labelling for one whole vignette with its bit planes and the union-find resident in
-// shared memory, then streams out the mask bytes, the int32 label image and the final bit plane.
-// sm_100a; sized for up to 227 KB of shared memory per CTA.
+// 8-connected labelling -> per-label regionprops accumulation for one whole vignette, with its bit
+// planes, the union-find and the per-label accumulators resident in shared memory, and streams out
+// the mask bytes, the int32 label image, the final bit plane and one accumulator row per label.
+// sm_100a; sized for up to 227 KB of shared memory per CTA (8 bytes per 32-pixel word).
 //
 // Reference behaviour restated (paths relative to the reference root):
 //   maze_ipp/loki/pipeline.py:649 / :405      threshold / bool cast
@@ -9,9 +10,18 @@
 //                                             phantom background pixel for uniform planes -- the CTA
 //                                             sees the whole vignette, so the flags are exact)
 //   maze_ipp/loki/pipeline.py:430-433         label(): raster-order labels, 8-connectivity
+//   maze_ipp/loki/pipeline.py:589-625         per-label RegionProperties reads (accumulators only;
+//                                             k_props_finish_staged derives the features)
 //
-// HBM traffic per pixel: 1 B image read + 1 B mask + 4 B labels + 1/8 B bit plane written.
+// HBM traffic per pixel: 1 B image read + 1 B mask + 4 B labels + 1/8 B bit plane written; the
+// intensity re-read of foreground pixels hits L2 (the CTA read the vignette a moment earlier).
 #include "maze_common.cuh"
+
+#define FUSED_LCAP 24 /* labels per vignette whose accumulators live in shared memory */
+
+enum { A_N = 0, A_R, A_C, A_RR, A_RC, A_CC, A_RRR, A_RRC, A_RCC, A_CCC, A_V, A_Z };
+enum { E_RMIN = 0, E_RMAX, E_CMIN, E_CMAX, E_VMIN, E_VMAX };
+enum { H_13 = 0, H_22, H_31, H_23, H_32, H_33, H_CR, H_CC };
 
 struct FusedPass {
     int R;
@@ -21,7 +31,16 @@ struct FusedPass {
 struct FusedParams {
     int t_int;
     int n_pass;
+    int high_order;
+    int stage_cap; // rows available in the staging arrays
+    int do_props;  // 0: labels only, nothing is staged
     FusedPass pass[4];
+};
+
+struct AccRow { // shared-memory accumulator of one label
+    u64 a[MAZE_NACC];
+    double h[8];
+    int e[MAZE_NEXT];
 };
 
 __device__ __forceinline__ uint32_t smem_plane_load(const uint32_t *plane, int H, int W, int wpr, int yy, int kk,
@@ -33,7 +52,7 @@ __device__ __forceinline__ uint32_t smem_plane_load(const uint32_t *plane, int H
     return v | ~valid_mask(W, kk);
 }
 
-// block-wide exclusive scan for any power-of-two block size <= 1024; s_warp: >= 33 ints
+// block-wide exclusive scan for any block size that is a multiple of 32 and <= 1024; s_warp: >= 33 ints
 template <int T>
 __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int *total)
 {
@@ -65,61 +84,88 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int *tot
     return res;
 }
 
-__device__ __forceinline__ int smem_find(const int *P, int n)
+// ---- union-find on 16-bit run ids in shared memory; values >= 0x8000 later encode "root, label" ----
+typedef unsigned short u16;
+
+__device__ __forceinline__ int find16(const u16 *P, int n)
 {
-    int p = ld_volatile(P + n);
+    int p = *(const volatile u16 *)(P + n);
     while (p != n) {
         n = p;
-        p = ld_volatile(P + n);
+        p = *(const volatile u16 *)(P + n);
     }
     return n;
 }
 
-__device__ __forceinline__ void smem_union(int *P, int a, int b)
+__device__ __forceinline__ void union16(u16 *P, int a, int b)
 {
     while (true) {
-        a = smem_find(P, a);
-        b = smem_find(P, b);
+        a = find16(P, a);
+        b = find16(P, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
-        int old = atomicMin(P + a, b);
+        int old = atomicCAS(P + a, (u16)a, (u16)b); // a stays a root only while P[a] == a
         if (old == a) return;
         a = old;
     }
 }
 
 // id of the word run that contains bit b of word m (runs are numbered in raster order)
-__device__ __forceinline__ int run_id(const int *RB, int w, uint32_t m, int b)
+__device__ __forceinline__ int run_id(const u16 *RB, int w, uint32_t m, int b)
 {
     uint32_t starts = m & ~(m << 1);
     uint32_t low = b == 31 ? FULL : ((2u << b) - 1u);
-    return RB[w] + __popc(starts & low) - 1;
+    return (int)RB[w] + __popc(starts & low) - 1;
 }
 
-template <int T>
-__global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict__ image,
-                                                      const maze_vignette_t *__restrict__ vig,
-                                                      const int32_t *__restrict__ img_list, FusedParams prm, int wcap,
-                                                      uint32_t *__restrict__ bits_out, uint8_t *__restrict__ mask,
-                                                      int32_t *__restrict__ labels, int32_t *__restrict__ n_labels,
-                                                      int32_t *__restrict__ fallback)
+__device__ __forceinline__ int label_of(const u16 *P, int rid)
 {
-    extern __shared__ uint32_t s_mem[];
+    int p = P[rid];
+    if (p < 0x8000) p = P[p];
+    return p & 0x7fff;
+}
+
+__device__ __forceinline__ u64 f_pow2sum(u64 m) { return m * (m + 1) * (2 * m + 1) / 6; }
+__device__ __forceinline__ u64 f_pow3sum(u64 m) { u64 t = m * (m + 1) / 2; return t * t; }
+
+template <int T>
+__global__ void __launch_bounds__(T) k_vignette_fused(
+    const uint8_t *__restrict__ image, const uint8_t *__restrict__ intensity, const maze_vignette_t *__restrict__ vig,
+    const int32_t *__restrict__ img_list, FusedParams prm, int wcap, uint32_t *__restrict__ bits_out,
+    uint8_t *__restrict__ mask, int32_t *__restrict__ labels, int32_t *__restrict__ n_labels,
+    int32_t *__restrict__ fallback, int32_t *__restrict__ acc_base, int32_t *stage_counter, u64 *acc_stage,
+    double *hi_stage, int32_t *ext_stage)
+{
+    extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ int s_warp[34];
+    __shared__ int s_base;
     const int img = img_list[blockIdx.x];
     const maze_vignette_t v = vig[img];
     const int H = v.h, W = v.w, wpr = v.wpr, words = H * wpr;
     uint32_t *A = s_mem, *B = s_mem + wcap;
-    int *P = (int *)(s_mem + 2 * wcap);
+    AccRow *ACC = (AccRow *)(s_mem + 2 * wcap);
     const int tid = threadIdx.x;
+
+    // ---- 0. zero-fill the mask and label image first: the stores drain while the CTA computes ----------
+    {
+        const int npx = H * W;
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *l4 = (uint4 *)(labels + v.pix_off);
+        for (int i = tid; i < (npx + 3) / 4; i += T) l4[i] = z;
+        uint4 *m4 = (uint4 *)(mask + v.pix_off);
+        for (int i = tid; i < (npx + 15) / 16; i += T) m4[i] = z;
+    }
+    // word walk without divisions: thread t visits words t, t + T, ...; (y, k) advance by (T / wpr, T % wpr)
+    const int step_y = T / wpr, step_k = T - step_y * wpr;
+    const int y_first = tid / wpr, k_first = tid - y_first * wpr;
 
     // ---- 1. threshold + pack (loki/pipeline.py:649) -------------------------------------------------
     {
         const uint8_t *base = image + v.pix_off;
         const int t = prm.t_int;
         const uint32_t t4 = (uint32_t)(t & 0xff) * 0x01010101u;
+        int y = y_first, k = k_first;
         for (int w = tid; w < words; w += T) {
-            int y = w / wpr, k = w - y * wpr;
             int nvalid = min(32, W - 32 * k);
             const uint8_t *p = base + (size_t)y * W + 32 * k;
             uint32_t a = (uint32_t)((uintptr_t)p & 3u);
@@ -141,6 +187,8 @@ __global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict_
                 }
             }
             A[w] = word & valid_mask(W, k);
+            y += step_y; k += step_k;
+            if (k >= wpr) { k -= wpr; y++; }
         }
     }
     __syncthreads();
@@ -152,36 +200,61 @@ __global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict_
         const uint32_t inv = prm.pass[ps].invert ? FULL : 0u;
         // scipy's phantom background pixel: the (inverted) plane has no 0 at all
         bool has_zero = false;
-        for (int w = tid; w < words; w += T) {
-            int k = w % wpr;
-            has_zero |= ((src[w] ^ inv) | ~valid_mask(W, k)) != FULL;
+        {
+            int k = k_first;
+            for (int w = tid; w < words; w += T) {
+                has_zero |= ((src[w] ^ inv) | ~valid_mask(W, k)) != FULL;
+                k += step_k;
+                if (k >= wpr) k -= wpr;
+            }
         }
         const bool phantom = !__syncthreads_or(has_zero);
+        int y = y_first, k = k_first;
         for (int w = tid; w < words; w += T) {
-            int y = w / wpr, k = w - y * wpr;
             uint32_t acc = FULL;
-            for (int dy = -R; dy <= R; dy++) {
-                int yy = y + dy;
-                int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
-                uint32_t C = smem_plane_load(src, H, W, wpr, yy, k, inv, phantom);
-                uint32_t h = C;
-                if (hw > 0) {
-                    uint32_t L = smem_plane_load(src, H, W, wpr, yy, k - 1, inv, phantom);
-                    uint32_t Rw = smem_plane_load(src, H, W, wpr, yy, k + 1, inv, phantom);
-                    for (int d = 1; d <= hw; d++) {
-                        h &= __funnelshift_rc(C, Rw, d);
-                        h &= __funnelshift_lc(L, C, d);
+            const bool interior = y >= R && y + R < H && k > 0 && (k + 2 < wpr || ((W & 31) == 0 && k + 1 < wpr));
+            if (interior) { // no border, no padding bits, no phantom row in reach
+                for (int dy = -R; dy <= R; dy++) {
+                    const uint32_t *row = src + w + dy * wpr;
+                    int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
+                    uint32_t C = row[0] ^ inv;
+                    uint32_t h = C;
+                    if (hw > 0) {
+                        uint32_t L = row[-1] ^ inv, Rw = row[1] ^ inv;
+                        for (int d = 1; d <= hw; d++) {
+                            h &= __funnelshift_rc(C, Rw, d);
+                            h &= __funnelshift_lc(L, C, d);
+                        }
                     }
+                    acc &= h;
                 }
-                acc &= h;
+            } else {
+                for (int dy = -R; dy <= R; dy++) {
+                    int yy = y + dy;
+                    int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
+                    uint32_t C = smem_plane_load(src, H, W, wpr, yy, k, inv, phantom);
+                    uint32_t h = C;
+                    if (hw > 0) {
+                        uint32_t L = smem_plane_load(src, H, W, wpr, yy, k - 1, inv, phantom);
+                        uint32_t Rw = smem_plane_load(src, H, W, wpr, yy, k + 1, inv, phantom);
+                        for (int d = 1; d <= hw; d++) {
+                            h &= __funnelshift_rc(C, Rw, d);
+                            h &= __funnelshift_lc(L, C, d);
+                        }
+                    }
+                    acc &= h;
+                }
             }
             dst[w] = (acc ^ inv) & valid_mask(W, k);
+            y += step_y; k += step_k;
+            if (k >= wpr) { k -= wpr; y++; }
         }
         __syncthreads();
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
-    const uint32_t *M = src; // final plane
-    int *RB = (int *)dst;    // free plane: first run id of every word
+    const uint32_t *M = src;   // final plane
+    u16 *RB = (u16 *)dst;      // free plane: first run id of every word ...
+    u16 *P = RB + wcap;        // ... and the union-find over run ids
 
     // ---- 3. labelling on word runs in shared memory (loki/pipeline.py:430-433) -----------------------
     const int chunk = (words + T - 1) / T;
@@ -193,16 +266,16 @@ __global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict_
     }
     int n_runs;
     int run = block_exclusive_scan<T>(cnt, s_warp, &n_runs);
-    if (n_runs > wcap) { // more runs than union-find slots: leave this vignette to the generic kernels
-        if (tid == 0) { fallback[img] = 1; n_labels[img] = 0; }
+    if (n_runs > wcap || n_runs >= 0x8000) { // more runs than union-find slots: per-operator kernels take over
+        if (tid == 0) { fallback[img] = 1; n_labels[img] = 0; acc_base[img] = -1; }
         return;
     }
     for (int w = lo; w < hi; w++) {
         uint32_t m = M[w];
-        RB[w] = run;
+        RB[w] = (u16)run;
         run += __popc(m & ~(m << 1));
     }
-    for (int r = tid; r < n_runs; r += T) P[r] = r;
+    for (int r = tid; r < n_runs; r += T) P[r] = (u16)r;
     __syncthreads();
     for (int w = tid; w < words; w += T) {
         uint32_t m = M[w];
@@ -210,7 +283,7 @@ __global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict_
         int y = w / wpr, k = w - y * wpr;
         uint32_t prev = k > 0 ? M[w - 1] : 0u;
         uint32_t next = k + 1 < wpr ? M[w + 1] : 0u;
-        if ((m & 1u) && (prev >> 31)) smem_union(P, RB[w], run_id(RB, w - 1, prev, 31));
+        if ((m & 1u) && (prev >> 31)) union16(P, RB[w], run_id(RB, w - 1, prev, 31));
         if (y == 0) continue;
         uint32_t uc = M[w - wpr];
         uint32_t ulw = k > 0 ? M[w - wpr - 1] : 0u;
@@ -224,73 +297,298 @@ __global__ void __launch_bounds__(T) k_vignette_fused(const uint8_t *__restrict_
         while (need_up) {
             int b = __ffs(need_up) - 1;
             need_up &= need_up - 1;
-            smem_union(P, run_id(RB, w, m, b), run_id(RB, w - wpr, uc, b));
+            union16(P, run_id(RB, w, m, b), run_id(RB, w - wpr, uc, b));
         }
         while (need_ul) {
             int b = __ffs(need_ul) - 1;
             need_ul &= need_ul - 1;
             int tgt = b > 0 ? run_id(RB, w - wpr, uc, b - 1) : run_id(RB, w - wpr - 1, ulw, 31);
-            smem_union(P, run_id(RB, w, m, b), tgt);
+            union16(P, run_id(RB, w, m, b), tgt);
         }
         while (need_ur) {
             int b = __ffs(need_ur) - 1;
             need_ur &= need_ur - 1;
-            int tgt = b < 31 ? run_id(RB, w - wpr, uc, b + 1) : RB[w - wpr + 1];
-            smem_union(P, run_id(RB, w, m, b), tgt);
+            int tgt = b < 31 ? run_id(RB, w - wpr, uc, b + 1) : (int)RB[w - wpr + 1];
+            union16(P, run_id(RB, w, m, b), tgt);
         }
     }
     __syncthreads();
     for (int r = tid; r < n_runs; r += T) {
-        int root = smem_find(P, r);
-        if (root != r) P[r] = root;
+        int root = find16(P, r);
+        if (root != r) P[r] = (u16)root;
     }
     __syncthreads();
-    // roots in raster order get labels 1..N, stored negated in their own slot
+    // roots in raster order get labels 1..N, stored in their own slot with the top bit set
     const int rchunk = (n_runs + T - 1) / T;
     const int rlo = min(tid * rchunk, n_runs), rhi = min(rlo + rchunk, n_runs);
     int nroot = 0;
     for (int r = rlo; r < rhi; r++) nroot += (P[r] == r);
     int n_lab;
     int rank = block_exclusive_scan<T>(nroot, s_warp, &n_lab);
-    __syncthreads();
     for (int r = rlo; r < rhi; r++)
-        if (P[r] == r) P[r] = -(++rank);
-    if (tid == 0) { n_labels[img] = n_lab; fallback[img] = 0; }
+        if (P[r] == r) P[r] = (u16)(0x8000 | (++rank));
+    if (tid == 0) {
+        n_labels[img] = n_lab;
+        fallback[img] = 0;
+        int base = -1;
+        if (prm.do_props) {
+            base = n_lab ? atomicAdd(stage_counter, n_lab) : 0;
+            if (base + n_lab > prm.stage_cap) base = -1; // staging full: maze_regionprops takes this vignette
+        }
+        s_base = base;
+        acc_base[img] = base;
+    }
 
-    // ---- 4. outputs: final bit plane, zero-filled mask / labels, then the foreground runs -------------
+    // ---- 4. outputs: final bit plane, then the foreground runs over the zero-filled mask / labels -----
     {
         uint32_t *gb = bits_out + v.word_off;
         for (int w = tid; w < words; w += T) gb[w] = M[w];
-        const int npx = H * W;
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 *l4 = (uint4 *)(labels + v.pix_off);
-        for (int i = tid; i < (npx + 3) / 4; i += T) l4[i] = z;
-        uint4 *m4 = (uint4 *)(mask + v.pix_off);
-        for (int i = tid; i < (npx + 15) / 16; i += T) m4[i] = z;
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int i = tid; i < nsm * (int)(sizeof(AccRow) / 4); i += T) ((uint32_t *)ACC)[i] = 0;
     }
-    __syncthreads();
+    __syncthreads(); // labels in P are final; the zero-fill of step 0 is ordered before the stores below
+    const int base = s_base;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = T / 32;
     {
-        const int lane = tid & 31, warp = tid >> 5;
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int l = tid; l < nsm; l += T) {
+            ACC[l].e[E_RMIN] = 0x7fffffff; ACC[l].e[E_RMAX] = -1; ACC[l].e[E_CMIN] = 0x7fffffff; ACC[l].e[E_CMAX] = -1;
+            ACC[l].e[E_VMIN] = 0x7fffffff; ACC[l].e[E_VMAX] = -1;
+        }
+        if (base >= 0)
+            for (int l = FUSED_LCAP + tid; l < n_lab; l += T) { // labels beyond the shared table accumulate in HBM
+                u64 *ga = acc_stage + (i64)(base + l) * MAZE_NACC;
+                for (int j = 0; j < MAZE_NACC; j++) ga[j] = 0;
+                double *gh = hi_stage + (i64)(base + l) * 8;
+                for (int j = 0; j < 8; j++) gh[j] = 0.0;
+                int32_t *ge = ext_stage + (i64)(base + l) * MAZE_NEXT;
+                ge[E_RMIN] = 0x7fffffff; ge[E_RMAX] = -1; ge[E_CMIN] = 0x7fffffff; ge[E_CMAX] = -1;
+                ge[E_VMIN] = 0x7fffffff; ge[E_VMAX] = -1; ge[6] = 0; ge[7] = 0;
+            }
         int32_t *gl = labels + v.pix_off;
         uint8_t *gm = mask + v.pix_off;
-        for (int wb = warp * 32; wb < words; wb += T) {
-            int w = wb + lane;
-            uint32_t m = w < words ? M[w] : 0u;
-            uint32_t nz = __ballot_sync(FULL, m != 0u);
-            while (nz) {
-                int j = __ffs(nz) - 1;
-                nz &= nz - 1;
-                uint32_t mj = __shfl_sync(FULL, m, j);
-                if ((mj >> lane) & 1u) {
-                    int wj = wb + j;
-                    int y = wj / wpr, k = wj - y * wpr;
-                    int p = P[run_id(RB, wj, mj, lane)];
-                    int lab = p < 0 ? -p : -P[p];
-                    int o = y * W + 32 * k + lane;
-                    gl[o] = lab;
-                    gm[o] = 1;
+        // one warp per row, one lane per word: coalesced 4-byte label / 1-byte mask stores of set pixels
+        for (int y = warp; y < H; y += NWARP) {
+            for (int kc = 0; kc < wpr; kc += 32) {
+                int k = kc + lane;
+                uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
+                uint32_t nz = __ballot_sync(FULL, m != 0u);
+                while (nz) {
+                    int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t mj = __shfl_sync(FULL, m, j);
+                    if ((mj >> lane) & 1u) {
+                        int o = y * W + 32 * (kc + j) + lane;
+                        gl[o] = label_of(P, run_id(RB, y * wpr + kc + j, mj, lane));
+                        gm[o] = 1;
+                    }
                 }
             }
+        }
+    }
+    __syncthreads();
+    if (base < 0) return;
+
+    // ---- 5. per-label accumulators (loki/pipeline.py:589-625) -----------------------------------------
+    // One warp per row, one lane per word.  The runs of one label in a row are reduced across the warp
+    // with redux instructions and added to registers of lane (label - 1): no atomics in the loop.
+    const uint8_t *gi = intensity ? intensity + v.pix_off : nullptr;
+    {
+        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0, aV = 0, aZ = 0;
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1, vmin = 0x7fffffff, vmax = -1;
+        for (int y = warp; y < H; y += NWARP) {
+            for (int kc = 0; kc < wpr; kc += 32) {
+                const int k = kc + lane;
+                const uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
+                if (!__ballot_sync(FULL, m != 0u)) continue;
+                const uint32_t starts = m & ~(m << 1);
+                const int rid0 = m ? (int)RB[y * wpr + k] : 0;
+                uint32_t pending = m;
+                while (__ballot_sync(FULL, pending != 0u)) {
+                    int L = 0x7fffffff, b0 = 0;
+                    if (pending) {
+                        b0 = __ffs(pending) - 1;
+                        L = label_of(P, rid0 + __popc(starts & ((2u << b0) - 1u)) - 1);
+                    }
+                    const int Lmin = __reduce_min_sync(FULL, L);
+                    // my lowest pending run if it carries label Lmin (relative columns inside the 1024-px chunk)
+                    uint32_t n = 0, s1 = 0, s2 = 0, sv = 0, sz = 0;
+                    u64 s3 = 0;
+                    int c0 = 0x7fffffff, c1 = -1, v0 = 0x7fffffff, v1 = -1;
+                    if (L == Lmin) {
+                        uint32_t rest = ~(pending >> b0);
+                        int len = rest ? __ffs(rest) - 1 : 32 - b0;
+                        pending &= ~(len == 32 ? FULL : (((1u << len) - 1u) << b0));
+                        uint32_t a = 32 * lane + b0, b = a + len - 1;
+                        n = len;
+                        s1 = n * (a + b) / 2;
+                        s2 = (uint32_t)(f_pow2sum(b) - (a ? f_pow2sum(a - 1) : 0));
+                        s3 = f_pow3sum(b) - (a ? f_pow3sum(a - 1) : 0);
+                        c0 = a; c1 = b;
+                        if (gi) {
+                            const uint8_t *pi = gi + (size_t)y * W + 32 * kc + a;
+                            int mn = 255, mx = 0;
+                            for (int j = 0; j < len; j++) {
+                                int val = (int)__ldg(pi + j);
+                                sv += val; sz += (val == 0); mn = min(mn, val); mx = max(mx, val);
+                            }
+                            v0 = mn; v1 = mx;
+                        }
+                    }
+                    n = __reduce_add_sync(FULL, n);
+                    s1 = __reduce_add_sync(FULL, s1);
+                    s2 = __reduce_add_sync(FULL, s2);
+                    uint32_t s3l = __reduce_add_sync(FULL, (uint32_t)(s3 & 0xfffffu));   // < 2^20 each
+                    uint32_t s3h = __reduce_add_sync(FULL, (uint32_t)(s3 >> 20));        // < 2^21 each
+                    c0 = __reduce_min_sync(FULL, c0);
+                    c1 = __reduce_max_sync(FULL, c1);
+                    if (gi) {
+                        sv = __reduce_add_sync(FULL, sv);
+                        sz = __reduce_add_sync(FULL, sz);
+                        v0 = __reduce_min_sync(FULL, v0);
+                        v1 = __reduce_max_sync(FULL, v1);
+                    }
+                    const u64 cb = 32 * (u64)kc, yy = (u64)y, N1 = n;
+                    const u64 S1 = s1 + cb * N1;
+                    const u64 S2 = s2 + 2 * cb * s1 + cb * cb * N1;
+                    const u64 S3 = (((u64)s3h << 20) + s3l) + 3 * cb * s2 + 3 * cb * cb * s1 + cb * cb * cb * N1;
+                    if (Lmin <= FUSED_LCAP) {
+                        if (lane == Lmin - 1) {
+                            aN += N1; aR += yy * N1; aC += S1; aRR += yy * yy * N1; aRC += yy * S1; aCC += S2;
+                            aRRR += yy * yy * yy * N1; aRRC += yy * yy * S1; aRCC += yy * S2; aCCC += S3;
+                            aV += sv; aZ += sz;
+                            rmin = min(rmin, y); rmax = max(rmax, y);
+                            cmin = min(cmin, (int)cb + c0); cmax = max(cmax, (int)cb + c1);
+                            vmin = min(vmin, v0); vmax = max(vmax, v1);
+                        }
+                    } else if (lane == 0) { // rare: more labels than lanes -> HBM accumulator row
+                        u64 *Aa = acc_stage + (i64)(base + Lmin - 1) * MAZE_NACC;
+                        int *Ee = ext_stage + (i64)(base + Lmin - 1) * MAZE_NEXT;
+                        atomicAdd(Aa + A_N, N1); atomicAdd(Aa + A_R, yy * N1); atomicAdd(Aa + A_C, S1);
+                        atomicAdd(Aa + A_RR, yy * yy * N1); atomicAdd(Aa + A_RC, yy * S1); atomicAdd(Aa + A_CC, S2);
+                        atomicAdd(Aa + A_RRR, yy * yy * yy * N1); atomicAdd(Aa + A_RRC, yy * yy * S1);
+                        atomicAdd(Aa + A_RCC, yy * S2); atomicAdd(Aa + A_CCC, S3);
+                        atomicMin(Ee + E_RMIN, y); atomicMax(Ee + E_RMAX, y);
+                        atomicMin(Ee + E_CMIN, (int)cb + c0); atomicMax(Ee + E_CMAX, (int)cb + c1);
+                        if (gi) {
+                            atomicAdd(Aa + A_V, (u64)sv); atomicAdd(Aa + A_Z, (u64)sz);
+                            atomicMin(Ee + E_VMIN, v0); atomicMax(Ee + E_VMAX, v1);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane < FUSED_LCAP && aN) { // one flush per warp and label
+            AccRow &r = ACC[lane];
+            atomicAdd(&r.a[A_N], aN); atomicAdd(&r.a[A_R], aR); atomicAdd(&r.a[A_C], aC);
+            atomicAdd(&r.a[A_RR], aRR); atomicAdd(&r.a[A_RC], aRC); atomicAdd(&r.a[A_CC], aCC);
+            atomicAdd(&r.a[A_RRR], aRRR); atomicAdd(&r.a[A_RRC], aRRC); atomicAdd(&r.a[A_RCC], aRCC);
+            atomicAdd(&r.a[A_CCC], aCCC);
+            atomicMin(&r.e[E_RMIN], rmin); atomicMax(&r.e[E_RMAX], rmax);
+            atomicMin(&r.e[E_CMIN], cmin); atomicMax(&r.e[E_CMAX], cmax);
+            if (gi) {
+                atomicAdd(&r.a[A_V], aV); atomicAdd(&r.a[A_Z], aZ);
+                atomicMin(&r.e[E_VMIN], vmin); atomicMax(&r.e[E_VMAX], vmax);
+            }
+        }
+    }
+    __syncthreads();
+    if (prm.high_order) {
+        // float64 central moments with p + q > 3 about the exact centroid, from the row sums again:
+        // sum_c (c - cc)^q over a row follows from n, S1, S2, S3 of that row
+        for (int l = FUSED_LCAP + tid; l < n_lab; l += T) {
+            const u64 *Aa = acc_stage + (i64)(base + l) * MAZE_NACC;
+            double *Hh = hi_stage + (i64)(base + l) * 8;
+            double dn = (double)*(const volatile u64 *)(Aa + A_N);
+            Hh[H_CR] = (double)*(const volatile u64 *)(Aa + A_R) / dn;
+            Hh[H_CC] = (double)*(const volatile u64 *)(Aa + A_C) / dn;
+        }
+        double cr = 0.0, cc = 0.0;
+        if (lane < min(n_lab, FUSED_LCAP)) {
+            double dn = (double)ACC[lane].a[A_N];
+            cr = (double)ACC[lane].a[A_R] / dn;
+            cc = (double)ACC[lane].a[A_C] / dn;
+        }
+        __syncthreads();
+        double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0;
+        for (int y = warp; y < H; y += NWARP) {
+            for (int kc = 0; kc < wpr; kc += 32) {
+                const int k = kc + lane;
+                const uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
+                if (!__ballot_sync(FULL, m != 0u)) continue;
+                const uint32_t starts = m & ~(m << 1);
+                const int rid0 = m ? (int)RB[y * wpr + k] : 0;
+                uint32_t pending = m;
+                while (__ballot_sync(FULL, pending != 0u)) {
+                    int L = 0x7fffffff, b0 = 0;
+                    if (pending) {
+                        b0 = __ffs(pending) - 1;
+                        L = label_of(P, rid0 + __popc(starts & ((2u << b0) - 1u)) - 1);
+                    }
+                    const int Lmin = __reduce_min_sync(FULL, L);
+                    uint32_t n = 0, s1 = 0, s2 = 0;
+                    u64 s3 = 0;
+                    if (L == Lmin) {
+                        uint32_t rest = ~(pending >> b0);
+                        int len = rest ? __ffs(rest) - 1 : 32 - b0;
+                        pending &= ~(len == 32 ? FULL : (((1u << len) - 1u) << b0));
+                        uint32_t a = 32 * lane + b0, b = a + len - 1;
+                        n = len;
+                        s1 = n * (a + b) / 2;
+                        s2 = (uint32_t)(f_pow2sum(b) - (a ? f_pow2sum(a - 1) : 0));
+                        s3 = f_pow3sum(b) - (a ? f_pow3sum(a - 1) : 0);
+                    }
+                    n = __reduce_add_sync(FULL, n);
+                    s1 = __reduce_add_sync(FULL, s1);
+                    s2 = __reduce_add_sync(FULL, s2);
+                    uint32_t s3l = __reduce_add_sync(FULL, (uint32_t)(s3 & 0xfffffu));
+                    uint32_t s3h = __reduce_add_sync(FULL, (uint32_t)(s3 >> 20));
+                    const bool mine = Lmin <= FUSED_LCAP ? (lane == Lmin - 1) : (lane == 0);
+                    if (mine) {
+                        double ccl = cc, crl = cr;
+                        double *Hh = nullptr;
+                        if (Lmin > FUSED_LCAP) {
+                            Hh = hi_stage + (i64)(base + Lmin - 1) * 8;
+                            crl = *(volatile double *)(Hh + H_CR);
+                            ccl = *(volatile double *)(Hh + H_CC);
+                        }
+                        // relative to the chunk origin: u = c - (cc - cb)
+                        const double cb = 32.0 * kc, o = ccl - cb, dn = (double)n;
+                        const double S1 = (double)s1, S2 = (double)s2, S3 = (double)(((u64)s3h << 20) + s3l);
+                        const double T1 = S1 - dn * o;
+                        const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
+                        const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+                        const double dr = (double)y - crl, dr2 = dr * dr, dr3 = dr2 * dr;
+                        if (Hh) {
+                            atomicAdd(Hh + H_13, dr * T3); atomicAdd(Hh + H_22, dr2 * T2); atomicAdd(Hh + H_31, dr3 * T1);
+                            atomicAdd(Hh + H_23, dr2 * T3); atomicAdd(Hh + H_32, dr3 * T2); atomicAdd(Hh + H_33, dr3 * T3);
+                        } else {
+                            h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
+                            h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+                        }
+                    }
+                }
+            }
+        }
+        if (lane < min(n_lab, FUSED_LCAP)) {
+            double *Hh = ACC[lane].h;
+            atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
+            atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
+        }
+        __syncthreads();
+    }
+    // shared rows -> staging
+    {
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int i = tid; i < nsm * MAZE_NACC; i += T) {
+            int l = i / MAZE_NACC, j = i - l * MAZE_NACC;
+            acc_stage[(i64)(base + l) * MAZE_NACC + j] = ACC[l].a[j];
+        }
+        for (int i = tid; i < nsm * 8; i += T) {
+            int l = i >> 3, j = i & 7;
+            hi_stage[(i64)(base + l) * 8 + j] = ACC[l].h[j];
+            ext_stage[(i64)(base + l) * MAZE_NEXT + j] = ACC[l].e[j];
         }
     }
 }
@@ -320,29 +618,74 @@ static int isqrt_i(int v)
     return r;
 }
 
+struct FusedArgs {
+    const uint8_t *image, *intensity;
+    const maze_vignette_t *vig;
+    uint32_t *bits;
+    uint8_t *mask;
+    int32_t *labels, *n_labels, *fallback, *acc_base, *stage_counter;
+    u64 *acc_stage;
+    double *hi_stage;
+    int32_t *ext_stage;
+};
+
+// Forked streams for the concurrent class launches (per host thread and device; created on first use).
+struct ForkStreams {
+    int device;
+    cudaStream_t aux[MAZE_FUSED_CLASSES];
+    cudaEvent_t fork, join[MAZE_FUSED_CLASSES];
+};
+
+static ForkStreams *fork_streams()
+{
+    static thread_local ForkStreams pool[16];
+    static thread_local int n_pool = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < n_pool; i++)
+        if (pool[i].device == dev) return &pool[i];
+    if (n_pool >= 16) return nullptr;
+    ForkStreams *f = &pool[n_pool];
+    f->device = dev;
+    if (cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int c = 0; c < MAZE_FUSED_CLASSES; c++) {
+        if (cudaStreamCreateWithFlags(&f->aux[c], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f->join[c], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    n_pool++;
+    return f;
+}
+
 template <int T>
-static int launch_class(int n, size_t smem, cudaStream_t s, const uint8_t *image, const maze_vignette_t *vig,
-                        const int32_t *list, const FusedParams &prm, int wcap, uint32_t *bits, uint8_t *mask,
-                        int32_t *labels, int32_t *n_labels, int32_t *fallback)
+static int launch_class(int n, int wcap, cudaStream_t s, const int32_t *list, const FusedParams &prm,
+                        const FusedArgs &a)
 {
     if (n <= 0) return MAZE_OK;
+    size_t smem = (size_t)wcap * 8 + FUSED_LCAP * sizeof(AccRow);
     MAZE_CUDA(cudaFuncSetAttribute(k_vignette_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
               "fused smem attribute");
-    MAZE_KERNEL(KID_VIGNETTE_FUSED, s, k_vignette_fused<T><<<n, T, smem, s>>>(image, vig, list, prm, wcap, bits, mask,
-                                                                             labels, n_labels, fallback));
+    MAZE_KERNEL(KID_VIGNETTE_FUSED, s,
+                k_vignette_fused<T><<<n, T, smem, s>>>(a.image, a.intensity, a.vig, list, prm, wcap, a.bits, a.mask,
+                                                       a.labels, a.n_labels, a.fallback, a.acc_base, a.stage_counter,
+                                                       a.acc_stage, a.hi_stage, a.ext_stage));
     return MAZE_OK;
 }
 
-extern "C" int maze_vignette_stage(const uint8_t *image, const maze_vignette_t *vig, const int32_t *img_list,
-                                   const int32_t *class_off_host, int t_int, int n_pass, const int32_t *pass_t_host,
-                                   const int32_t *pass_invert_host, uint32_t *bits, uint8_t *mask, int32_t *labels,
-                                   int32_t *n_labels, int32_t *fallback, void *stream)
+extern "C" int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig,
+                                   const int32_t *img_list, const int32_t *class_off_host, int t_int, int n_pass,
+                                   const int32_t *pass_t_host, const int32_t *pass_invert_host, int flags,
+                                   uint32_t *bits, uint8_t *mask, int32_t *labels, int32_t *n_labels,
+                                   int32_t *fallback, int32_t *acc_base, int32_t *stage_counter, int stage_cap,
+                                   unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_pass < 0 || n_pass > 4) return MAZE_ERR_BADARG;
     FusedParams prm;
     prm.t_int = t_int;
     prm.n_pass = n_pass;
+    prm.high_order = (flags & MAZE_RP_HIGH_ORDER) ? 1 : 0;
+    prm.stage_cap = stage_cap;
+    prm.do_props = (flags & MAZE_FUSED_NO_PROPS) ? 0 : 1;
     for (int p = 0; p < 4; p++) {
         prm.pass[p].R = -1;
         prm.pass[p].invert = 0;
@@ -357,19 +700,35 @@ extern "C" int maze_vignette_stage(const uint8_t *image, const maze_vignette_t *
             for (int dy = 0; dy <= prm.pass[p].R; dy++) prm.pass[p].w[dy] = isqrt_i(t - dy * dy);
         }
     }
-    const int caps[3] = {MAZE_FUSED_CAP0, MAZE_FUSED_CAP1, MAZE_FUSED_CAP2};
-    int rc;
-    for (int c = 0; c < 3; c++) {
+    MAZE_CUDA(cudaMemsetAsync(stage_counter, 0, sizeof(int32_t), s), "stage counter");
+    FusedArgs a = {image, intensity, vig, bits, mask, labels, n_labels, fallback, acc_base, stage_counter,
+                   (u64 *)acc_stage, hi_stage, ext_stage};
+    const int caps[MAZE_FUSED_CLASSES] = {MAZE_FUSED_CAP0, MAZE_FUSED_CAP1, MAZE_FUSED_CAP2, MAZE_FUSED_CAP3};
+    // The size classes touch disjoint vignettes, so their kernels run CONCURRENTLY: the class of the
+    // largest vignettes (one long CTA per SM) goes to the caller's stream, the others to forked streams,
+    // and the small CTAs fill the SMs the big ones leave idle.
+    ForkStreams *fk = fork_streams();
+    if (!fk) return MAZE_ERR_CUDA;
+    MAZE_CUDA(cudaEventRecord(fk->fork, s), "fork record");
+    for (int c = MAZE_FUSED_CLASSES - 1; c >= 0; c--) {
         int n = class_off_host[c + 1] - class_off_host[c];
+        if (n <= 0) continue;
         const int32_t *list = img_list + class_off_host[c];
-        size_t smem = (size_t)caps[c] * 12;
-        if (c == 0)
-            rc = launch_class<128>(n, smem, s, image, vig, list, prm, caps[c], bits, mask, labels, n_labels, fallback);
-        else if (c == 1)
-            rc = launch_class<256>(n, smem, s, image, vig, list, prm, caps[c], bits, mask, labels, n_labels, fallback);
-        else
-            rc = launch_class<1024>(n, smem, s, image, vig, list, prm, caps[c], bits, mask, labels, n_labels, fallback);
+        cudaStream_t sc = s;
+        if (c != MAZE_FUSED_CLASSES - 1) {
+            sc = fk->aux[c];
+            MAZE_CUDA(cudaStreamWaitEvent(sc, fk->fork, 0), "fork wait");
+        }
+        int rc;
+        if (c == 0) rc = launch_class<128>(n, caps[c], sc, list, prm, a);
+        else if (c == 1) rc = launch_class<256>(n, caps[c], sc, list, prm, a);
+        else if (c == 2) rc = launch_class<512>(n, caps[c], sc, list, prm, a);
+        else rc = launch_class<1024>(n, caps[c], sc, list, prm, a);
         if (rc != MAZE_OK) return rc;
+        if (sc != s) {
+            MAZE_CUDA(cudaEventRecord(fk->join[c], sc), "join record");
+            MAZE_CUDA(cudaStreamWaitEvent(s, fk->join[c], 0), "join wait");
+        }
     }
     return MAZE_OK;
 }

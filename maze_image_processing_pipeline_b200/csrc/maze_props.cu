@@ -292,16 +292,19 @@ __device__ void finish_shape(double *f, const double mu[4][4], bool high_order)
     else f[MAZE_F_ORIENT] = 0.5 * atan2(-2 * b, c - a);
 }
 
+__device__ void finish_row(double *f, const u64 *A, const int32_t *E, int img, int label, int has_image, int high_order);
+
 // stage 0: everything from the integer accumulators (high-order mu zeroed for pass 2 if requested)
 // stage 1: re-derive nu / Hu once the float64 high-order central moments have been accumulated
 __global__ void k_props_finish(const u64 *__restrict__ acc, const int32_t *__restrict__ ext,
                                const int32_t *__restrict__ lab_off, int n_img, int n_obj_cap, int has_image,
-                               int high_order, int stage, double *table)
+                               int high_order, int stage, const int32_t *__restrict__ acc_base, double *table)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     int total = min(lab_off[n_img], n_obj_cap);
     if (row >= total) return;
     double *f = table + (i64)row * MAZE_NFEAT;
+    if (acc_base && acc_base[find_image(lab_off, n_img, row)] >= 0) return; // staged by the fused kernel
     if (stage == 1) {
         if (!(f[MAZE_F_AREA] > 0)) return;
         double mu[4][4];
@@ -312,8 +315,12 @@ __global__ void k_props_finish(const u64 *__restrict__ acc, const int32_t *__res
     }
     int img = find_image(lab_off, n_img, row);
     int label = row - lab_off[img] + 1;
-    const u64 *A = acc + (i64)row * MAZE_NACC;
-    const int32_t *E = ext + (i64)row * MAZE_NEXT;
+    finish_row(f, acc + (i64)row * MAZE_NACC, ext + (i64)row * MAZE_NEXT, img, label, has_image, high_order);
+}
+
+// everything that derives from the integer accumulators of one object
+__device__ void finish_row(double *f, const u64 *A, const int32_t *E, int img, int label, int has_image, int high_order)
+{
     for (int j = 0; j < MAZE_NFEAT; j++) f[j] = nan("");
     f[MAZE_F_LABEL] = (double)label;
     f[MAZE_F_IMAGE] = (double)img;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_high_order(const int32_t *__
 extern "C" int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t *image,
                                 const maze_vignette_t *vig, int n_img, const maze_tile_t *tiles, int n_tiles,
                                 const int32_t *lab_off, int n_obj_cap, unsigned long long *acc, int32_t *ext,
-                                double *table, int flags, void *stream)
+                                double *table, int flags, const int32_t *acc_base, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_tiles <= 0 || n_obj_cap <= 0) return MAZE_OK;
@@ -427,13 +434,53 @@ extern "C" int maze_regionprops(const int32_t *labels, const uint32_t *bits, con
         MAZE_KERNEL(KID_PROPS_RUNS, s, k_props_runs<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
     else
         MAZE_KERNEL(KID_PROPS_ACCUMULATE, s, k_props_accumulate<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
-    MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 0, table));
+    MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 0, acc_base, table));
     if (high) {
         if (runs)
             MAZE_KERNEL(KID_PROPS_RUNS_HIGH, s, k_props_runs_high<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
         else
             MAZE_KERNEL(KID_PROPS_HIGH_ORDER, s, k_props_high_order<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
-        MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 1, table));
+        MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 1, acc_base, table));
     }
+    return MAZE_OK;
+}
+
+
+// Feature rows from the accumulators staged by k_vignette_fused (maze_fused.cu).
+__global__ void k_props_finish_staged(const u64 *__restrict__ acc_stage, const double *__restrict__ hi_stage,
+                                      const int32_t *__restrict__ ext_stage, const int32_t *__restrict__ acc_base,
+                                      const int32_t *__restrict__ lab_off, int n_img, int n_obj, int has_image,
+                                      int high_order, double *table)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_obj) return;
+    int img = find_image(lab_off, n_img, row);
+    int base = acc_base[img];
+    if (base < 0) return;
+    int l = row - lab_off[img];
+    i64 src = (i64)base + l;
+    double *f = table + (i64)row * MAZE_NFEAT;
+    finish_row(f, acc_stage + src * MAZE_NACC, ext_stage + src * MAZE_NEXT, img, l + 1, has_image, 0);
+    if (high_order && f[MAZE_F_AREA] > 0) {
+        const double *h = hi_stage + src * 8;
+        double mu[4][4];
+        for (int p = 0; p < 4; p++)
+            for (int q = 0; q < 4; q++) mu[p][q] = f[MAZE_F_MU + p * 4 + q];
+        mu[1][3] = h[0]; mu[2][2] = h[1]; mu[3][1] = h[2]; mu[2][3] = h[3]; mu[3][2] = h[4]; mu[3][3] = h[5];
+        finish_shape(f, mu, true);
+    }
+}
+
+extern "C" int maze_props_finish_staged(const unsigned long long *acc_stage, const double *hi_stage,
+                                        const int32_t *ext_stage, const int32_t *acc_base, const int32_t *lab_off,
+                                        int n_img, int n_obj, int has_intensity, int flags, double *table,
+                                        void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_img <= 0 || n_obj <= 0) return MAZE_OK;
+    MAZE_KERNEL(KID_PROPS_FINISH_STAGED, s,
+                k_props_finish_staged<<<(n_obj + 127) / 128, 128, 0, s>>>((const u64 *)acc_stage, hi_stage, ext_stage,
+                                                                          acc_base, lab_off, n_img, n_obj, has_intensity,
+                                                                          (flags & MAZE_RP_HIGH_ORDER) ? 1 : 0, table));
     return MAZE_OK;
 }

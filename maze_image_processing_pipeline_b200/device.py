@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FUSED_CAPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS, TILE_WORDS, check, lib
+from ._lib import FUSED_CAPS, FUSED_NO_PROPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS, TILE_WORDS, check, lib
 
 VIG_DTYPE = np.dtype([("pix_off", "<i8"), ("word_off", "<i8"), ("h", "<i4"), ("w", "<i4"),
                       ("wpr", "<i4"), ("tile0", "<i4")])
@@ -52,6 +52,7 @@ class BatchGeometry:
             self.word_off = np.concatenate([np.asarray(_word_off, np.int64), [_total_words]])
         ntiles = (nwords + TILE_WORDS - 1) // TILE_WORDS
         self.tile0 = np.concatenate([[0], np.cumsum(ntiles)]).astype(np.int64)
+        self.ntiles = ntiles
         self.total_px = int(self.pix_off[-1]) + 16  # tail slack for vector loads
         self.pixels = int(self.npx.sum())
         self.total_words = int(self.word_off[-1])
@@ -299,19 +300,23 @@ class DeviceBatch:
               "maze_remove_small_objects")
         return labels
 
-    def regionprops(self, lab_off, n_obj: int, labels=None, bits=None, image=None, high_order=True, runs=False):
+    def regionprops(self, lab_off, n_obj: int, labels=None, bits=None, image=None, high_order=True, runs=False,
+                    table=None, acc_base=None, tiles=None):
         """Feature table (n_obj, NFEAT) float64 on the device.  runs=True: `labels` are constant along the
         word runs of `bits` (straight from label() or the label filters) -> run-based reduction."""
-        vig, n, tiles, nt = self._geo()
-        table = torch.empty((max(n_obj, 0), NFEAT), dtype=torch.float64, device=self.device)
-        if n_obj <= 0:
+        vig, n, d_tiles, nt = self._geo()
+        if tiles is not None:  # a device tile list restricted to some vignettes of the batch
+            d_tiles, nt = tiles.data_ptr(), tiles.numel() // 8
+        if table is None:
+            table = torch.empty((max(n_obj, 0), NFEAT), dtype=torch.float64, device=self.device)
+        if n_obj <= 0 or nt == 0:
             return table
         acc = torch.empty(n_obj * NACC, dtype=torch.int64, device=self.device)
         ext = torch.empty(n_obj * NEXT, dtype=torch.int32, device=self.device)
-        check(lib().maze_regionprops(_ptr(labels), _ptr(bits), _ptr(image), vig, n, tiles, nt, lab_off.data_ptr(),
+        check(lib().maze_regionprops(_ptr(labels), _ptr(bits), _ptr(image), vig, n, d_tiles, nt, lab_off.data_ptr(),
                                      int(n_obj), acc.data_ptr(), ext.data_ptr(), table.data_ptr(),
-                                     (RP_HIGH_ORDER if high_order else 0) | (RP_RUNS if runs else 0), _stream()),
-              "maze_regionprops")
+                                     (RP_HIGH_ORDER if high_order else 0) | (RP_RUNS if runs else 0),
+                                     _ptr(acc_base), _stream()), "maze_regionprops")
         return table
 
     def merge_labels(self, labels, labels_out, lab_off, n_obj: int, max_distance, path_tolerance=5.0,
@@ -335,22 +340,50 @@ class DeviceBatch:
                                       status.data_ptr(), _stream()), "maze_merge_labels")
         return merge_dist, n_merge, index_state, status, obj_scratch
 
-    def vignette_stage(self, d_image, t_int: int, passes, bits, mask, labels, n_labels, fallback):
-        """maze_vignette_stage on every vignette that fits its size classes; returns the leftovers."""
-        g = self.g
+    def fused_lists(self):
         if not hasattr(self, "_fused"):
-            img_list, class_off, left = g.fused_classes()
+            img_list, class_off, left = self.g.fused_classes()
             self._fused = (torch.from_numpy(img_list).to(self.device), class_off, left)
-        d_list, class_off, left = self._fused
+        return self._fused
+
+    def tiles_of(self, indices):
+        """Device tile list (full-batch vignette indices) restricted to the given vignettes (cached)."""
+        key = tuple(int(i) for i in indices)
+        cache = self.__dict__.setdefault("_tiles_cache", {})
+        if key not in cache:
+            sel = np.isin(self.g.tiles["img"], np.asarray(indices, np.int32))
+            t = np.ascontiguousarray(self.g.tiles[sel])
+            cache[key] = torch.from_numpy(t.view(np.uint8).copy()).to(self.device)
+        return cache[key]
+
+    def vignette_stage(self, d_image, d_intensity, t_int: int, passes, bits, mask, labels, counts, staging,
+                       stage_cap, high_order=True, props=True):
+        """maze_vignette_stage on every vignette that fits its size classes.  counts: int32[3*n_img] =
+        n_labels | fallback | acc_base; staging = (acc, hi, ext, counter) tensors with stage_cap rows.
+        Returns the indices of the vignettes that are too large for it."""
+        g = self.g
+        d_list, class_off, left = self.fused_lists()
+        n = g.n_img
+        acc, hi, ext, counter = staging
         if class_off[-1] > 0:
             pt = np.asarray([p[0] for p in passes] + [0] * (4 - len(passes)), np.int32)
             pi = np.asarray([p[1] for p in passes] + [0] * (4 - len(passes)), np.int32)
-            check(lib().maze_vignette_stage(d_image.data_ptr(), self.d_vig.data_ptr(), d_list.data_ptr(),
-                                            class_off.ctypes.data, int(t_int), len(passes), pt.ctypes.data,
-                                            pi.ctypes.data, bits.data_ptr(), mask.data_ptr(), labels.data_ptr(),
-                                            n_labels.data_ptr(), fallback.data_ptr(), _stream()),
-                  "maze_vignette_stage")
+            flags = (RP_HIGH_ORDER if high_order else 0) | (0 if props else FUSED_NO_PROPS)
+            check(lib().maze_vignette_stage(
+                d_image.data_ptr(), _ptr(d_intensity), self.d_vig.data_ptr(), d_list.data_ptr(), class_off.ctypes.data,
+                int(t_int), len(passes), pt.ctypes.data, pi.ctypes.data, flags, bits.data_ptr(), mask.data_ptr(),
+                labels.data_ptr(), counts.data_ptr(), counts[n:].data_ptr(), counts[2 * n:].data_ptr(),
+                counter.data_ptr(), int(stage_cap), acc.data_ptr(), hi.data_ptr(), ext.data_ptr(), _stream()),
+                "maze_vignette_stage")
         return left
+
+    def props_finish_staged(self, staging, acc_base, lab_off, n_obj, has_intensity, high_order, table):
+        acc, hi, ext = staging[:3]
+        check(lib().maze_props_finish_staged(acc.data_ptr(), hi.data_ptr(), ext.data_ptr(), acc_base.data_ptr(),
+                                             lab_off.data_ptr(), self.g.n_img, int(n_obj), int(has_intensity),
+                                             RP_HIGH_ORDER if high_order else 0, table.data_ptr(), _stream()),
+              "maze_props_finish_staged")
+        return table
 
     def count_scan(self, n_labels):
         lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device)

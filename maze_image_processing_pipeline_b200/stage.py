@@ -23,7 +23,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import MAZE_ERR_TYPEERROR, NFEAT
+from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT
 from ._lib import MAX_DISK_RADIUS
 from .device import (BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
@@ -85,6 +85,22 @@ class StageResult:
         return self.table[int(self.lab_off[i]):int(self.lab_off[i + 1])]
 
 
+class Workspace:
+    """Device buffers of the fused path, allocated once and grown on demand so that the steady state
+    makes no allocator calls.  Results of run_device alias these buffers and stay valid until the
+    next run_device on the same stage."""
+
+    def __init__(self):
+        self._t = {}
+
+    def get(self, key, n, dtype, device):
+        t = self._t.get(key)
+        if t is None or t.numel() < n or t.device != device:
+            t = torch.empty(int(n * 1.25) + 16, dtype=dtype, device=device)
+            self._t[key] = t
+        return t[:n]
+
+
 class _PinnedPool:
     """Reusable pinned host staging buffers (one per purpose), grown on demand."""
 
@@ -109,6 +125,7 @@ class LokiSegmentationStage:
         self.device = device
         self.high_order = high_order
         self._pool = _PinnedPool()
+        self._ws = Workspace()
 
     # ---- device-resident core ----------------------------------------------------------------------
     def _passes(self):
@@ -152,27 +169,39 @@ class LokiSegmentationStage:
             keep = (flags & 1).bool()
             return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
         passes = self._passes() if self.fused else None
+        filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
+        staged = None
         if passes is None:
             bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
             n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
         else:
             # vignette-resident fused kernel; vignettes it cannot hold go through the per-operator path
-            bits = batch.empty_plane()
-            mask = batch.empty_px(torch.uint8)
-            labels = batch.empty_px(torch.int32)
-            counts = torch.zeros(2 * g.n_img, dtype=torch.int32, device=batch.device)
-            n_labels, fallback = counts[:g.n_img], counts[g.n_img:]
-            left = batch.vignette_stage(d_src, t_int, passes, bits, mask, labels, n_labels, fallback)
+            n = g.n_img
+            ws, dev = self._ws, batch.device
+            bits = ws.get("bits", max(g.total_words, 1), torch.int32, dev)
+            mask = ws.get("mask", g.total_px, torch.uint8, dev)
+            labels = ws.get("labels", g.total_px, torch.int32, dev)
+            counts = ws.get("counts", 3 * n, torch.int32, dev)
+            counts[:2 * n].zero_()
+            counts[2 * n:].fill_(-1)
+            n_labels = counts[:n]
+            cap = 16 * n + 1024
+            staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
+                       ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
+            left = batch.vignette_stage(d_src, d_image, t_int, passes, bits, mask, labels, counts, staging, cap,
+                                        high_order=self.high_order, props=not filters)
             if len(left):
                 self._redo_generic(batch, left, d_src, t_int, bits, mask, labels, n_labels)
-            h_counts = counts.cpu().numpy()  # the one readback of the batch: label counts + fallback flags
-            redo = np.nonzero(h_counts[g.n_img:])[0]
+            h_counts = counts.cpu().numpy()  # the one readback of the batch: label counts, fallback flags, staging rows
+            redo = np.nonzero(h_counts[n:2 * n])[0]
             if len(redo):
                 self._redo_generic(batch, redo, d_src, t_int, bits, mask, labels, n_labels)
                 h_counts = counts.cpu().numpy()
-            lab_off, n_obj = batch.lab_off_from_bounds(h_counts[:g.n_img])
+            lab_off, n_obj = batch.lab_off_from_bounds(h_counts[:n])
+            if not filters:
+                staged = (staging, counts[2 * n:], np.nonzero((h_counts[2 * n:] < 0) & (h_counts[:n] > 0))[0])
         merge_status = None
-        if n_obj > 0:
+        if n_obj > 0 and filters:
             if pp.clear_border:
                 batch.clear_border(labels, lab_off, n_obj)
             if pp.min_area > 0:
@@ -181,18 +210,45 @@ class LokiSegmentationStage:
                 merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance)[3]
         # merge_labels paints bridges over background, so only then do labels leave the runs of `bits`
         runs = merge_status is None
-        table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
-                                  high_order=self.high_order, runs=runs)
+        if staged is None:
+            table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
+                                      high_order=self.high_order, runs=runs)
+        else:
+            staging, acc_base, unstaged = staged
+            table = self._ws.get("table", max(n_obj, 1) * NFEAT, torch.float64, batch.device)[:n_obj * NFEAT]
+            table = table.view(n_obj, NFEAT)
+            batch.props_finish_staged(staging, acc_base, lab_off, n_obj, True, self.high_order, table)
+            if len(unstaged):  # too large / too many runs / staging full: accumulate with the per-operator kernels
+                batch.regionprops(lab_off, n_obj, labels=labels, bits=bits, image=d_image, high_order=self.high_order,
+                                  runs=True, table=table, acc_base=acc_base, tiles=batch.tiles_of(unstaged))
         return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
+
+    def prepare(self, batch: DeviceBatch):
+        """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
+        per-operator path) ahead of run_device; part of making a batch resident."""
+        if self.postprocess is not None and self.fused and self._passes() is not None:
+            left = batch.fused_lists()[2]
+            if len(left):
+                self._sub(batch, left)
+                batch.tiles_of(left)
+        return batch
+
+    def _sub(self, batch, indices):
+        key = tuple(int(i) for i in indices)
+        cache = batch.__dict__.setdefault("_sub_cache", {})
+        if key not in cache:
+            g = batch.g
+            sub = DeviceBatch(g.subset(indices), batch.device)
+            word_idx = np.concatenate([np.arange(g.word_off[i], g.word_off[i] + g.nwords[i]) for i in indices])
+            cache[key] = (sub, torch.from_numpy(word_idx).to(batch.device),
+                          torch.as_tensor(np.asarray(indices, np.int64), device=batch.device))
+        return cache[key]
 
     def _redo_generic(self, batch, indices, d_src, t_int, bits, mask, labels, n_labels):
         """Run the per-operator kernels on a few vignettes of the batch, in place in the batch buffers."""
-        sub = DeviceBatch(batch.g.subset(indices), batch.device)
+        sub, word_idx, idx = self._sub(batch, indices)
         sbits, _, slab_off, _ = self._front_generic(sub, d_src, t_int, labels=labels, mask=mask)
-        for i in indices:
-            w0, w1 = int(batch.g.word_off[i]), int(batch.g.word_off[i]) + int(batch.g.nwords[i])
-            bits[w0:w1] = sbits[w0:w1]
-        idx = torch.as_tensor(np.asarray(indices, np.int64), device=batch.device)
+        bits[word_idx] = sbits[word_idx]
         n_labels[idx] = slab_off[1:] - slab_off[:-1]
 
     # ---- host entry: numpy in, numpy out --------------------------------------------------------------
