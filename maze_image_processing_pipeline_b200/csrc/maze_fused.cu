@@ -125,11 +125,12 @@ __device__ __forceinline__ int label_of(const u16 *P, int rid)
     return p & 0x7fff;
 }
 
-__device__ __forceinline__ u64 f_pow2sum(u64 m) { return m * (m + 1) * (2 * m + 1) / 6; }
-__device__ __forceinline__ u64 f_pow3sum(u64 m) { u64 t = m * (m + 1) / 2; return t * t; }
+// power sums of 0..m for m < 1024 (columns relative to a 1024-pixel chunk): 32-bit arithmetic suffices
+__device__ __forceinline__ uint32_t f_pow2sum(uint32_t m) { return m * (m + 1) / 2 * (2 * m + 1) / 3; }
+__device__ __forceinline__ u64 f_pow3sum(uint32_t m) { uint32_t t = m * (m + 1) / 2; return (u64)t * t; }
 
 template <int T>
-__global__ void __launch_bounds__(T) k_vignette_fused(
+__global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     const uint8_t *__restrict__ image, const uint8_t *__restrict__ intensity, const maze_vignette_t *__restrict__ vig,
     const int32_t *__restrict__ img_list, FusedParams prm, int wcap, uint32_t *__restrict__ bits_out,
     uint8_t *__restrict__ mask, int32_t *__restrict__ labels, int32_t *__restrict__ n_labels,
@@ -427,13 +428,27 @@ __global__ void __launch_bounds__(T) k_vignette_fused(
                         s3 = f_pow3sum(b) - (a ? f_pow3sum(a - 1) : 0);
                         c0 = a; c1 = b;
                         if (gi) {
-                            const uint8_t *pi = gi + (size_t)y * W + 32 * kc + a;
-                            int mn = 255, mx = 0;
-                            for (int j = 0; j < len; j++) {
-                                int val = (int)__ldg(pi + j);
-                                sv += val; sz += (val == 0); mn = min(mn, val); mx = max(mx, val);
+                            // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
+                            const uint32_t runmask = (len == 32 ? FULL : ((1u << len) - 1u)) << b0;
+                            const uint8_t *pw = gi + (size_t)y * W + 32 * (size_t)(kc + lane);
+                            const uint32_t al = (uint32_t)((uintptr_t)pw & 3u);
+                            const uint32_t *q = (const uint32_t *)(pw - al);
+                            const int g0 = b0 >> 2, g1 = (b0 + len - 1) >> 2;
+                            uint32_t lo = __ldg(q + g0), vmn = FULL, vmx = 0u;
+                            for (int g = g0; g <= g1; g++) {
+                                uint32_t hi = __ldg(q + g + 1); // <= 4 bytes past the row: inside the padded slot
+                                uint32_t px = __funnelshift_r(lo, hi, 8 * al);
+                                lo = hi;
+                                uint32_t nib = (runmask >> (4 * g)) & 0xfu;
+                                uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                                sv += __vsadu4(px & bm, 0u);
+                                sz += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
+                                vmn = __vminu4(vmn, px | ~bm);
+                                vmx = __vmaxu4(vmx, px & bm);
                             }
-                            v0 = mn; v1 = mx;
+                            vmn = __vminu4(vmn, vmn >> 16); vmn = __vminu4(vmn, vmn >> 8);
+                            vmx = __vmaxu4(vmx, vmx >> 16); vmx = __vmaxu4(vmx, vmx >> 8);
+                            v0 = (int)(vmn & 0xffu); v1 = (int)(vmx & 0xffu);
                         }
                     }
                     n = __reduce_add_sync(FULL, n);
@@ -664,6 +679,8 @@ static int launch_class(int n, int wcap, cudaStream_t s, const int32_t *list, co
     size_t smem = (size_t)wcap * 8 + FUSED_LCAP * sizeof(AccRow);
     MAZE_CUDA(cudaFuncSetAttribute(k_vignette_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
               "fused smem attribute");
+    MAZE_CUDA(cudaFuncSetAttribute(k_vignette_fused<T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared), "fused carveout");
     MAZE_KERNEL(KID_VIGNETTE_FUSED, s,
                 k_vignette_fused<T><<<n, T, smem, s>>>(a.image, a.intensity, a.vig, list, prm, wcap, a.bits, a.mask,
                                                        a.labels, a.n_labels, a.fallback, a.acc_base, a.stage_counter,

@@ -2,6 +2,7 @@
 // Every kernel of the library is launched through MAZE_KERNEL (maze_common.cuh): the launch is always
 // counted; when timing is enabled a start/stop event pair is recorded around it on the launching
 // stream and maze_prof_collect() sums the elapsed times per kernel.
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -63,18 +64,41 @@ extern "C" int maze_prof_enable(int on)
 }
 
 // Waits for all recorded events, adds the elapsed milliseconds / launch counts per kernel id into
-// ms[0..n) / counts[0..n) (host arrays the caller zeroed) and forgets the records.
+// ms[0..n) / counts[0..n) (host arrays the caller zeroed) and forgets the records.  Launches of one
+// kernel id that overlap in time (the concurrent size classes of the fused stage) are counted once:
+// ms is the length of the UNION of the [start, stop] intervals of that id.
 extern "C" int maze_prof_collect(double *ms, long long *counts, int n)
 {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (g_recs.empty()) return MAZE_OK;
+    std::vector<std::vector<std::pair<double, double>>> iv((size_t)n);
+    cudaEvent_t ref = g_recs[0].a;
     for (auto &r : g_recs) {
         MAZE_CUDA(cudaEventSynchronize(r.b), "prof sync");
-        float t = 0.f;
-        MAZE_CUDA(cudaEventElapsedTime(&t, r.a, r.b), "prof elapsed");
+        float t0 = 0.f, t1 = 0.f;
+        MAZE_CUDA(cudaEventElapsedTime(&t0, ref, r.a), "prof elapsed");
+        MAZE_CUDA(cudaEventElapsedTime(&t1, ref, r.b), "prof elapsed");
         if (r.kid >= 0 && r.kid < n) {
-            ms[r.kid] += (double)t;
+            iv[(size_t)r.kid].push_back({(double)t0, (double)t1});
             counts[r.kid] += 1;
         }
+    }
+    for (int k = 0; k < n; k++) {
+        auto &v = iv[(size_t)k];
+        std::sort(v.begin(), v.end());
+        double lo = 0, hi = -1;
+        for (auto &p : v) {
+            if (hi < lo || p.first > hi) {
+                if (hi >= lo) ms[k] += hi - lo;
+                lo = p.first;
+                hi = p.second;
+            } else if (p.second > hi) {
+                hi = p.second;
+            }
+        }
+        if (hi >= lo) ms[k] += hi - lo;
+    }
+    for (auto &r : g_recs) {
         g_free.push_back(r.a);
         g_free.push_back(r.b);
     }

@@ -110,7 +110,7 @@ class _PinnedPool:
     def get(self, key, n, dtype):
         t = self._bufs.get(key)
         if t is None or t.numel() < n or t.dtype != dtype:
-            t = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+            t = torch.empty(int(max(n, 1) * 1.3) + 64, dtype=dtype, pin_memory=True)  # pinning is slow: grow rarely
             self._bufs[key] = t
         return t[:n]
 
@@ -138,7 +138,9 @@ class LokiSegmentationStage:
             out += [(fold_dilation_radius(pp.closing_radius), 1), (fold_erosion_radius(pp.closing_radius), 0)]
         if any(t >= (MAX_DISK_RADIUS + 1) ** 2 for t, _ in out):
             return None
-        return out
+        # a pass with d2 threshold 0 is the identity for both compares (d2 > 0 and d2 <= 0 both mean
+        # "is foreground"; the phantom pixel lies outside the image): e.g. the dilation of opening r=1
+        return [(t, inv) for t, inv in out if t != 0]
 
     def _front_generic(self, batch, d_src, t_int, labels=None, mask=None):
         """Per-operator kernels: threshold -> opening -> closing -> label (any size, any radius)."""
