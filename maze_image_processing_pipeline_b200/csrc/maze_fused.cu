@@ -129,6 +129,67 @@ __device__ __forceinline__ int label_of(const u16 *P, int rid)
 __device__ __forceinline__ uint32_t f_pow2sum(uint32_t m) { return m * (m + 1) / 2 * (2 * m + 1) / 3; }
 __device__ __forceinline__ u64 f_pow3sum(uint32_t m) { uint32_t t = m * (m + 1) / 2; return (u64)t * t; }
 
+// One thresholded-EDT pass as a COLUMN WALK: a thread owns word column k and a strip of rows and slides
+// down, keeping for the last 2R+1 rows the chord tests at the R+1 chord widths in registers, so every
+// word is loaded once and every chord test is computed once (instead of 2R+1 times).
+template <int R, int T>
+__device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int H, int W,
+                                              int wpr, const int *__restrict__ wtab, uint32_t inv, bool phantom,
+                                              int nstrip, int S)
+{
+    int wd[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; j++) wd[j] = wtab[j];
+    const int nitems = wpr * nstrip;
+    for (int q = threadIdx.x; q < nitems; q += T) {
+        const int s = q / wpr, k = q - s * wpr;
+        const int y0 = s * S, y1 = min(H, y0 + S);
+        if (y0 >= y1) continue;
+        const uint32_t padC = ~valid_mask(W, k);
+        const uint32_t padR = (k + 1 < wpr) ? ~valid_mask(W, k + 1) : 0u;
+        uint32_t win[2 * R + 1][R + 1]; // win[i][j]: row (y - R + i) of the current output row y, chord width wd[j]
+#pragma unroll
+        for (int i = 0; i < 2 * R + 1; i++)
+#pragma unroll
+            for (int j = 0; j <= R; j++) win[i][j] = FULL;
+        for (int r = y0 - R; r < y1 + R; r++) {
+            uint32_t L = FULL, C = FULL, Rw = FULL;
+            if (r >= 0 && r < H) {
+                const uint32_t *row = src + r * wpr + k;
+                C = (row[0] ^ inv) | padC;
+                if (k > 0) L = row[-1] ^ inv;
+                if (k + 1 < wpr) Rw = (row[1] ^ inv) | padR;
+            } else if (phantom && r == -1) {
+                if (k == 0) C = 0xfffffffeu;
+                if (k == 1) L = 0xfffffffeu;
+            }
+            // slide the window up by one row
+#pragma unroll
+            for (int i = 0; i < 2 * R; i++)
+#pragma unroll
+                for (int j = 0; j <= R; j++) win[i][j] = win[i + 1][j];
+            // chord tests of the new row, narrow to wide (wd[j] is non-increasing in j)
+            uint32_t cur = C;
+            int d = 0;
+#pragma unroll
+            for (int j = R; j >= 0; j--) {
+                while (d < wd[j]) {
+                    d++;
+                    cur &= __funnelshift_rc(C, Rw, d) & __funnelshift_lc(L, C, d);
+                }
+                win[2 * R][j] = cur;
+            }
+            const int y = r - R;
+            if (y >= y0) {
+                uint32_t acc = FULL;
+#pragma unroll
+                for (int i = 0; i < 2 * R + 1; i++) acc &= win[i][i < R ? R - i : i - R];
+                dst[y * wpr + k] = (acc ^ inv) & ~padC;
+            }
+        }
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     const uint8_t *__restrict__ image, const uint8_t *__restrict__ intensity, const maze_vignette_t *__restrict__ vig,
@@ -210,45 +271,56 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             }
         }
         const bool phantom = !__syncthreads_or(has_zero);
-        int y = y_first, k = k_first;
-        for (int w = tid; w < words; w += T) {
-            uint32_t acc = FULL;
-            const bool interior = y >= R && y + R < H && k > 0 && (k + 2 < wpr || ((W & 31) == 0 && k + 1 < wpr));
-            if (interior) { // no border, no padding bits, no phantom row in reach
-                for (int dy = -R; dy <= R; dy++) {
-                    const uint32_t *row = src + w + dy * wpr;
-                    int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
-                    uint32_t C = row[0] ^ inv;
-                    uint32_t h = C;
-                    if (hw > 0) {
-                        uint32_t L = row[-1] ^ inv, Rw = row[1] ^ inv;
-                        for (int d = 1; d <= hw; d++) {
-                            h &= __funnelshift_rc(C, Rw, d);
-                            h &= __funnelshift_lc(L, C, d);
+        if (R >= 0 && R <= 3) {
+            // strips of S rows x word columns: about one work item per thread
+            const int nstrip = max(1, min(H, (T + wpr - 1) / wpr));
+            const int S = (H + nstrip - 1) / nstrip;
+            const int *wt = prm.pass[ps].w;
+            if (R == 0) morph_columns<0, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
+            else if (R == 1) morph_columns<1, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
+            else if (R == 2) morph_columns<2, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
+            else morph_columns<3, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
+        } else {
+            int y = y_first, k = k_first;
+            for (int w = tid; w < words; w += T) {
+                uint32_t acc = FULL;
+                const bool interior = y >= R && y + R < H && k > 0 && (k + 2 < wpr || ((W & 31) == 0 && k + 1 < wpr));
+                if (interior) { // no border, no padding bits, no phantom row in reach
+                    for (int dy = -R; dy <= R; dy++) {
+                        const uint32_t *row = src + w + dy * wpr;
+                        int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
+                        uint32_t C = row[0] ^ inv;
+                        uint32_t h = C;
+                        if (hw > 0) {
+                            uint32_t L = row[-1] ^ inv, Rw = row[1] ^ inv;
+                            for (int d = 1; d <= hw; d++) {
+                                h &= __funnelshift_rc(C, Rw, d);
+                                h &= __funnelshift_lc(L, C, d);
+                            }
                         }
+                        acc &= h;
                     }
-                    acc &= h;
-                }
-            } else {
-                for (int dy = -R; dy <= R; dy++) {
-                    int yy = y + dy;
-                    int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
-                    uint32_t C = smem_plane_load(src, H, W, wpr, yy, k, inv, phantom);
-                    uint32_t h = C;
-                    if (hw > 0) {
-                        uint32_t L = smem_plane_load(src, H, W, wpr, yy, k - 1, inv, phantom);
-                        uint32_t Rw = smem_plane_load(src, H, W, wpr, yy, k + 1, inv, phantom);
-                        for (int d = 1; d <= hw; d++) {
-                            h &= __funnelshift_rc(C, Rw, d);
-                            h &= __funnelshift_lc(L, C, d);
+                } else {
+                    for (int dy = -R; dy <= R; dy++) {
+                        int yy = y + dy;
+                        int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
+                        uint32_t C = smem_plane_load(src, H, W, wpr, yy, k, inv, phantom);
+                        uint32_t h = C;
+                        if (hw > 0) {
+                            uint32_t L = smem_plane_load(src, H, W, wpr, yy, k - 1, inv, phantom);
+                            uint32_t Rw = smem_plane_load(src, H, W, wpr, yy, k + 1, inv, phantom);
+                            for (int d = 1; d <= hw; d++) {
+                                h &= __funnelshift_rc(C, Rw, d);
+                                h &= __funnelshift_lc(L, C, d);
+                            }
                         }
+                        acc &= h;
                     }
-                    acc &= h;
                 }
+                dst[w] = (acc ^ inv) & valid_mask(W, k);
+                y += step_y; k += step_k;
+                if (k >= wpr) { k -= wpr; y++; }
             }
-            dst[w] = (acc ^ inv) & valid_mask(W, k);
-            y += step_y; k += step_k;
-            if (k >= wpr) { k -= wpr; y++; }
         }
         __syncthreads();
         uint32_t *tmp = src; src = dst; dst = tmp;
@@ -392,204 +464,157 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     if (base < 0) return;
 
     // ---- 5. per-label accumulators (loki/pipeline.py:589-625) -----------------------------------------
-    // One warp per row, one lane per word.  The runs of one label in a row are reduced across the warp
-    // with redux instructions and added to registers of lane (label - 1): no atomics in the loop.
+    // COLUMN WALK: a thread owns word column k and a strip of rows.  Objects are vertically coherent, so
+    // consecutive runs in a column almost always carry the same label: the sums of the current label stay
+    // in registers and are flushed (shared-memory atomics) only when the label changes.
     const uint8_t *gi = intensity ? intensity + v.pix_off : nullptr;
-    {
-        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0, aV = 0, aZ = 0;
-        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1, vmin = 0x7fffffff, vmax = -1;
-        for (int y = warp; y < H; y += NWARP) {
-            for (int kc = 0; kc < wpr; kc += 32) {
-                const int k = kc + lane;
-                const uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
-                if (!__ballot_sync(FULL, m != 0u)) continue;
-                const uint32_t starts = m & ~(m << 1);
-                const int rid0 = m ? (int)RB[y * wpr + k] : 0;
-                uint32_t pending = m;
-                while (__ballot_sync(FULL, pending != 0u)) {
-                    int L = 0x7fffffff, b0 = 0;
-                    if (pending) {
-                        b0 = __ffs(pending) - 1;
-                        L = label_of(P, rid0 + __popc(starts & ((2u << b0) - 1u)) - 1);
-                    }
-                    const int Lmin = __reduce_min_sync(FULL, L);
-                    // my lowest pending run if it carries label Lmin (relative columns inside the 1024-px chunk)
-                    uint32_t n = 0, s1 = 0, s2 = 0, sv = 0, sz = 0;
-                    u64 s3 = 0;
-                    int c0 = 0x7fffffff, c1 = -1, v0 = 0x7fffffff, v1 = -1;
-                    if (L == Lmin) {
-                        uint32_t rest = ~(pending >> b0);
-                        int len = rest ? __ffs(rest) - 1 : 32 - b0;
-                        pending &= ~(len == 32 ? FULL : (((1u << len) - 1u) << b0));
-                        uint32_t a = 32 * lane + b0, b = a + len - 1;
-                        n = len;
-                        s1 = n * (a + b) / 2;
-                        s2 = (uint32_t)(f_pow2sum(b) - (a ? f_pow2sum(a - 1) : 0));
-                        s3 = f_pow3sum(b) - (a ? f_pow3sum(a - 1) : 0);
-                        c0 = a; c1 = b;
+    const int p_nstrip = max(1, min(H, (T + wpr - 1) / wpr));
+    const int p_S = (H + p_nstrip - 1) / p_nstrip;
+    const int p_items = wpr * p_nstrip;
+    for (int q = tid; q < p_items; q += T) {
+        const int st = q / wpr, k = q - st * wpr;
+        const int y0 = st * p_S, y1 = min(H, y0 + p_S);
+        int cur = 0;
+        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
+        uint32_t aV = 0, aZ = 0;
+        int rmin = 0, rmax = 0, cmin = 0x7fffffff, cmax = -1;
+        uint32_t vmn = FULL, vmx = 0u;
+        const u64 cb = 32 * (u64)k;
+        for (int y = y0; y <= y1; y++) {
+            const uint32_t m = y < y1 ? M[y * wpr + k] : 0u;
+            uint32_t pend = m;
+            int rid = m ? (int)RB[y * wpr + k] : 0;
+            bool last = (y == y1);
+            while (pend || last) {
+                int L = 0, b0 = 0, len = 0;
+                if (!last) {
+                    b0 = __ffs(pend) - 1;
+                    uint32_t rest = ~(pend >> b0);
+                    len = rest ? __ffs(rest) - 1 : 32 - b0;
+                    pend &= ~((len == 32 ? FULL : ((1u << len) - 1u)) << b0);
+                    L = label_of(P, rid++);
+                }
+                if (L != cur) {
+                    if (cur) { // flush the finished label
+                        u64 *Aa;
+                        int *Ee;
+                        if (cur <= FUSED_LCAP) { Aa = ACC[cur - 1].a; Ee = ACC[cur - 1].e; }
+                        else { Aa = acc_stage + (i64)(base + cur - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + cur - 1) * MAZE_NEXT; }
+                        atomicAdd(Aa + A_N, aN); atomicAdd(Aa + A_R, aR); atomicAdd(Aa + A_C, aC);
+                        atomicAdd(Aa + A_RR, aRR); atomicAdd(Aa + A_RC, aRC); atomicAdd(Aa + A_CC, aCC);
+                        atomicAdd(Aa + A_RRR, aRRR); atomicAdd(Aa + A_RRC, aRRC); atomicAdd(Aa + A_RCC, aRCC);
+                        atomicAdd(Aa + A_CCC, aCCC);
+                        atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
+                        atomicMin(Ee + E_CMIN, cmin); atomicMax(Ee + E_CMAX, cmax);
                         if (gi) {
-                            // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
-                            const uint32_t runmask = (len == 32 ? FULL : ((1u << len) - 1u)) << b0;
-                            const uint8_t *pw = gi + (size_t)y * W + 32 * (size_t)(kc + lane);
-                            const uint32_t al = (uint32_t)((uintptr_t)pw & 3u);
-                            const uint32_t *q = (const uint32_t *)(pw - al);
-                            const int g0 = b0 >> 2, g1 = (b0 + len - 1) >> 2;
-                            uint32_t lo = __ldg(q + g0), vmn = FULL, vmx = 0u;
-                            for (int g = g0; g <= g1; g++) {
-                                uint32_t hi = __ldg(q + g + 1); // <= 4 bytes past the row: inside the padded slot
-                                uint32_t px = __funnelshift_r(lo, hi, 8 * al);
-                                lo = hi;
-                                uint32_t nib = (runmask >> (4 * g)) & 0xfu;
-                                uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                                sv += __vsadu4(px & bm, 0u);
-                                sz += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
-                                vmn = __vminu4(vmn, px | ~bm);
-                                vmx = __vmaxu4(vmx, px & bm);
-                            }
+                            atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ);
                             vmn = __vminu4(vmn, vmn >> 16); vmn = __vminu4(vmn, vmn >> 8);
                             vmx = __vmaxu4(vmx, vmx >> 16); vmx = __vmaxu4(vmx, vmx >> 8);
-                            v0 = (int)(vmn & 0xffu); v1 = (int)(vmx & 0xffu);
+                            atomicMin(Ee + E_VMIN, (int)(vmn & 0xffu)); atomicMax(Ee + E_VMAX, (int)(vmx & 0xffu));
                         }
                     }
-                    n = __reduce_add_sync(FULL, n);
-                    s1 = __reduce_add_sync(FULL, s1);
-                    s2 = __reduce_add_sync(FULL, s2);
-                    uint32_t s3l = __reduce_add_sync(FULL, (uint32_t)(s3 & 0xfffffu));   // < 2^20 each
-                    uint32_t s3h = __reduce_add_sync(FULL, (uint32_t)(s3 >> 20));        // < 2^21 each
-                    c0 = __reduce_min_sync(FULL, c0);
-                    c1 = __reduce_max_sync(FULL, c1);
-                    if (gi) {
-                        sv = __reduce_add_sync(FULL, sv);
-                        sz = __reduce_add_sync(FULL, sz);
-                        v0 = __reduce_min_sync(FULL, v0);
-                        v1 = __reduce_max_sync(FULL, v1);
-                    }
-                    const u64 cb = 32 * (u64)kc, yy = (u64)y, N1 = n;
-                    const u64 S1 = s1 + cb * N1;
-                    const u64 S2 = s2 + 2 * cb * s1 + cb * cb * N1;
-                    const u64 S3 = (((u64)s3h << 20) + s3l) + 3 * cb * s2 + 3 * cb * cb * s1 + cb * cb * cb * N1;
-                    if (Lmin <= FUSED_LCAP) {
-                        if (lane == Lmin - 1) {
-                            aN += N1; aR += yy * N1; aC += S1; aRR += yy * yy * N1; aRC += yy * S1; aCC += S2;
-                            aRRR += yy * yy * yy * N1; aRRC += yy * yy * S1; aRCC += yy * S2; aCCC += S3;
-                            aV += sv; aZ += sz;
-                            rmin = min(rmin, y); rmax = max(rmax, y);
-                            cmin = min(cmin, (int)cb + c0); cmax = max(cmax, (int)cb + c1);
-                            vmin = min(vmin, v0); vmax = max(vmax, v1);
-                        }
-                    } else if (lane == 0) { // rare: more labels than lanes -> HBM accumulator row
-                        u64 *Aa = acc_stage + (i64)(base + Lmin - 1) * MAZE_NACC;
-                        int *Ee = ext_stage + (i64)(base + Lmin - 1) * MAZE_NEXT;
-                        atomicAdd(Aa + A_N, N1); atomicAdd(Aa + A_R, yy * N1); atomicAdd(Aa + A_C, S1);
-                        atomicAdd(Aa + A_RR, yy * yy * N1); atomicAdd(Aa + A_RC, yy * S1); atomicAdd(Aa + A_CC, S2);
-                        atomicAdd(Aa + A_RRR, yy * yy * yy * N1); atomicAdd(Aa + A_RRC, yy * yy * S1);
-                        atomicAdd(Aa + A_RCC, yy * S2); atomicAdd(Aa + A_CCC, S3);
-                        atomicMin(Ee + E_RMIN, y); atomicMax(Ee + E_RMAX, y);
-                        atomicMin(Ee + E_CMIN, (int)cb + c0); atomicMax(Ee + E_CMAX, (int)cb + c1);
-                        if (gi) {
-                            atomicAdd(Aa + A_V, (u64)sv); atomicAdd(Aa + A_Z, (u64)sz);
-                            atomicMin(Ee + E_VMIN, v0); atomicMax(Ee + E_VMAX, v1);
-                        }
+                    aN = aR = aC = aRR = aRC = aCC = aRRR = aRRC = aRCC = aCCC = 0;
+                    aV = aZ = 0; cmin = 0x7fffffff; cmax = -1; vmn = FULL; vmx = 0u;
+                    rmin = y;
+                    cur = L;
+                }
+                if (last) break;
+                // run [b0, b0 + len) of this word: column sums relative to the word, shifted to absolute columns
+                const uint32_t ja = b0, jb = b0 + len - 1, n = len;
+                const uint32_t s1 = n * (ja + jb) / 2;
+                const uint32_t s2 = f_pow2sum(jb) - (ja ? f_pow2sum(ja - 1) : 0u);
+                const uint32_t t3b = jb * (jb + 1) / 2, t3a = ja ? (ja - 1) * ja / 2 : 0u;
+                const uint32_t s3 = t3b * t3b - t3a * t3a;
+                const u64 S1 = s1 + cb * n;
+                const u64 S2 = s2 + 2 * cb * s1 + cb * cb * n;
+                const u64 S3 = s3 + 3 * cb * s2 + 3 * cb * cb * s1 + cb * cb * cb * n;
+                const u64 yy = (u64)y;
+                aN += n; aR += yy * n; aC += S1; aRR += yy * yy * n; aRC += yy * S1; aCC += S2;
+                aRRR += yy * yy * yy * n; aRRC += yy * yy * S1; aRCC += yy * S2; aCCC += S3;
+                rmax = y;
+                cmin = min(cmin, (int)cb + (int)ja); cmax = max(cmax, (int)cb + (int)jb);
+                if (gi) { // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
+                    const uint32_t runmask = (len == 32 ? FULL : ((1u << len) - 1u)) << b0;
+                    const uint8_t *pw = gi + (size_t)y * W + 32 * (size_t)k;
+                    const uint32_t al = (uint32_t)((uintptr_t)pw & 3u);
+                    const uint32_t *qq = (const uint32_t *)(pw - al);
+                    const int g0 = b0 >> 2, g1 = (b0 + len - 1) >> 2;
+                    uint32_t lo32 = __ldg(qq + g0);
+                    for (int g = g0; g <= g1; g++) {
+                        uint32_t hi32 = __ldg(qq + g + 1); // <= 4 bytes past the row: inside the padded slot
+                        uint32_t px = __funnelshift_r(lo32, hi32, 8 * al);
+                        lo32 = hi32;
+                        uint32_t nib = (runmask >> (4 * g)) & 0xfu;
+                        uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                        aV += __vsadu4(px & bm, 0u);
+                        aZ += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
+                        vmn = __vminu4(vmn, px | ~bm);
+                        vmx = __vmaxu4(vmx, px & bm);
                     }
                 }
-            }
-        }
-        if (lane < FUSED_LCAP && aN) { // one flush per warp and label
-            AccRow &r = ACC[lane];
-            atomicAdd(&r.a[A_N], aN); atomicAdd(&r.a[A_R], aR); atomicAdd(&r.a[A_C], aC);
-            atomicAdd(&r.a[A_RR], aRR); atomicAdd(&r.a[A_RC], aRC); atomicAdd(&r.a[A_CC], aCC);
-            atomicAdd(&r.a[A_RRR], aRRR); atomicAdd(&r.a[A_RRC], aRRC); atomicAdd(&r.a[A_RCC], aRCC);
-            atomicAdd(&r.a[A_CCC], aCCC);
-            atomicMin(&r.e[E_RMIN], rmin); atomicMax(&r.e[E_RMAX], rmax);
-            atomicMin(&r.e[E_CMIN], cmin); atomicMax(&r.e[E_CMAX], cmax);
-            if (gi) {
-                atomicAdd(&r.a[A_V], aV); atomicAdd(&r.a[A_Z], aZ);
-                atomicMin(&r.e[E_VMIN], vmin); atomicMax(&r.e[E_VMAX], vmax);
             }
         }
     }
     __syncthreads();
     if (prm.high_order) {
-        // float64 central moments with p + q > 3 about the exact centroid, from the row sums again:
-        // sum_c (c - cc)^q over a row follows from n, S1, S2, S3 of that row
-        for (int l = FUSED_LCAP + tid; l < n_lab; l += T) {
-            const u64 *Aa = acc_stage + (i64)(base + l) * MAZE_NACC;
-            double *Hh = hi_stage + (i64)(base + l) * 8;
+        // float64 central moments with p + q > 3 about the exact centroid: sum_c (c - cc)^q over a run
+        // follows from its n, S1, S2, S3; same column walk, six doubles per current label in registers
+        for (int l = tid; l < n_lab; l += T) {
+            const u64 *Aa = l < FUSED_LCAP ? ACC[l].a : acc_stage + (i64)(base + l) * MAZE_NACC;
+            double *Hh = l < FUSED_LCAP ? ACC[l].h : hi_stage + (i64)(base + l) * 8;
             double dn = (double)*(const volatile u64 *)(Aa + A_N);
             Hh[H_CR] = (double)*(const volatile u64 *)(Aa + A_R) / dn;
             Hh[H_CC] = (double)*(const volatile u64 *)(Aa + A_C) / dn;
         }
-        double cr = 0.0, cc = 0.0;
-        if (lane < min(n_lab, FUSED_LCAP)) {
-            double dn = (double)ACC[lane].a[A_N];
-            cr = (double)ACC[lane].a[A_R] / dn;
-            cc = (double)ACC[lane].a[A_C] / dn;
-        }
         __syncthreads();
-        double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0;
-        for (int y = warp; y < H; y += NWARP) {
-            for (int kc = 0; kc < wpr; kc += 32) {
-                const int k = kc + lane;
-                const uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
-                if (!__ballot_sync(FULL, m != 0u)) continue;
-                const uint32_t starts = m & ~(m << 1);
-                const int rid0 = m ? (int)RB[y * wpr + k] : 0;
-                uint32_t pending = m;
-                while (__ballot_sync(FULL, pending != 0u)) {
-                    int L = 0x7fffffff, b0 = 0;
-                    if (pending) {
-                        b0 = __ffs(pending) - 1;
-                        L = label_of(P, rid0 + __popc(starts & ((2u << b0) - 1u)) - 1);
+        for (int q = tid; q < p_items; q += T) {
+            const int st = q / wpr, k = q - st * wpr;
+            const int y0 = st * p_S, y1 = min(H, y0 + p_S);
+            int cur = 0;
+            double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0, cr = 0, o = 0;
+            double *Hh = nullptr;
+            for (int y = y0; y <= y1; y++) {
+                const uint32_t m = y < y1 ? M[y * wpr + k] : 0u;
+                uint32_t pend = m;
+                int rid = m ? (int)RB[y * wpr + k] : 0;
+                bool last = (y == y1);
+                while (pend || last) {
+                    int L = 0, b0 = 0, len = 0;
+                    if (!last) {
+                        b0 = __ffs(pend) - 1;
+                        uint32_t rest = ~(pend >> b0);
+                        len = rest ? __ffs(rest) - 1 : 32 - b0;
+                        pend &= ~((len == 32 ? FULL : ((1u << len) - 1u)) << b0);
+                        L = label_of(P, rid++);
                     }
-                    const int Lmin = __reduce_min_sync(FULL, L);
-                    uint32_t n = 0, s1 = 0, s2 = 0;
-                    u64 s3 = 0;
-                    if (L == Lmin) {
-                        uint32_t rest = ~(pending >> b0);
-                        int len = rest ? __ffs(rest) - 1 : 32 - b0;
-                        pending &= ~(len == 32 ? FULL : (((1u << len) - 1u) << b0));
-                        uint32_t a = 32 * lane + b0, b = a + len - 1;
-                        n = len;
-                        s1 = n * (a + b) / 2;
-                        s2 = (uint32_t)(f_pow2sum(b) - (a ? f_pow2sum(a - 1) : 0));
-                        s3 = f_pow3sum(b) - (a ? f_pow3sum(a - 1) : 0);
-                    }
-                    n = __reduce_add_sync(FULL, n);
-                    s1 = __reduce_add_sync(FULL, s1);
-                    s2 = __reduce_add_sync(FULL, s2);
-                    uint32_t s3l = __reduce_add_sync(FULL, (uint32_t)(s3 & 0xfffffu));
-                    uint32_t s3h = __reduce_add_sync(FULL, (uint32_t)(s3 >> 20));
-                    const bool mine = Lmin <= FUSED_LCAP ? (lane == Lmin - 1) : (lane == 0);
-                    if (mine) {
-                        double ccl = cc, crl = cr;
-                        double *Hh = nullptr;
-                        if (Lmin > FUSED_LCAP) {
-                            Hh = hi_stage + (i64)(base + Lmin - 1) * 8;
-                            crl = *(volatile double *)(Hh + H_CR);
-                            ccl = *(volatile double *)(Hh + H_CC);
+                    if (L != cur) {
+                        if (cur) {
+                            atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
+                            atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
                         }
-                        // relative to the chunk origin: u = c - (cc - cb)
-                        const double cb = 32.0 * kc, o = ccl - cb, dn = (double)n;
-                        const double S1 = (double)s1, S2 = (double)s2, S3 = (double)(((u64)s3h << 20) + s3l);
-                        const double T1 = S1 - dn * o;
-                        const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
-                        const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
-                        const double dr = (double)y - crl, dr2 = dr * dr, dr3 = dr2 * dr;
-                        if (Hh) {
-                            atomicAdd(Hh + H_13, dr * T3); atomicAdd(Hh + H_22, dr2 * T2); atomicAdd(Hh + H_31, dr3 * T1);
-                            atomicAdd(Hh + H_23, dr2 * T3); atomicAdd(Hh + H_32, dr3 * T2); atomicAdd(Hh + H_33, dr3 * T3);
-                        } else {
-                            h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
-                            h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+                        h13 = h22 = h31 = h23 = h32 = h33 = 0;
+                        cur = L;
+                        if (L) {
+                            Hh = L <= FUSED_LCAP ? ACC[L - 1].h : hi_stage + (i64)(base + L - 1) * 8;
+                            cr = *(volatile double *)(Hh + H_CR);
+                            o = *(volatile double *)(Hh + H_CC) - 32.0 * k; // centroid column relative to the word
                         }
                     }
+                    if (last) break;
+                    const uint32_t ja = b0, jb = b0 + len - 1, n = len;
+                    const uint32_t s1 = n * (ja + jb) / 2;
+                    const uint32_t s2 = f_pow2sum(jb) - (ja ? f_pow2sum(ja - 1) : 0u);
+                    const uint32_t t3b = jb * (jb + 1) / 2, t3a = ja ? (ja - 1) * ja / 2 : 0u;
+                    const uint32_t s3 = t3b * t3b - t3a * t3a;
+                    const double dn = (double)n, S1 = (double)s1, S2 = (double)s2, S3 = (double)s3;
+                    const double T1 = S1 - dn * o;
+                    const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
+                    const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+                    const double dr = (double)y - cr, dr2 = dr * dr, dr3 = dr2 * dr;
+                    h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
+                    h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
                 }
             }
-        }
-        if (lane < min(n_lab, FUSED_LCAP)) {
-            double *Hh = ACC[lane].h;
-            atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
-            atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
         }
         __syncthreads();
     }

@@ -453,7 +453,7 @@ __global__ void k_props_finish_staged(const u64 *__restrict__ acc_stage, const d
                                       int high_order, double *table)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_obj) return;
+    if (row >= min(n_obj, lab_off[n_img])) return; // n_obj may be a capacity: the true total is on the device
     int img = find_image(lab_off, n_img, row);
     int base = acc_base[img];
     if (base < 0) return;

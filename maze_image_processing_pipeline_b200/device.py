@@ -385,8 +385,8 @@ class DeviceBatch:
               "maze_props_finish_staged")
         return table
 
-    def count_scan(self, n_labels):
-        lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device)
+    def count_scan(self, n_labels, out=None):
+        lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device) if out is None else out
         check(lib().maze_count_scan(n_labels.data_ptr(), self.g.n_img, lab_off.data_ptr(), _stream()),
               "maze_count_scan")
         return lab_off

@@ -46,18 +46,37 @@ class SegmentationPostprocessingConfig:
 
 
 class DeviceResult:
-    """Outputs of one batch, still on the device."""
+    """Outputs of one batch, still on the device.  On the asynchronous fused path the object counts are
+    read back lazily: ``finalize()`` (called by every accessor that needs them) waits for the readback
+    and, in the rare case that a vignette overflowed the fused kernel's tables, redoes the batch with the
+    per-operator kernels."""
 
-    def __init__(self, batch, bits, labels, lab_off, table, n_obj, keep=None, merge_status=None, mask=None):
+    def __init__(self, batch, bits, labels, lab_off, table, n_obj, keep=None, merge_status=None, mask=None,
+                 pending=None):
         self.mask = mask
         self.batch = batch
         self.bits = bits
         self.labels = labels
         self.lab_off = lab_off
-        self.table = table
-        self.n_obj = n_obj
+        self._table = table
+        self._n_obj = n_obj
         self.keep = keep
         self.merge_status = merge_status
+        self._pending = pending
+
+    def finalize(self):
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            pending(self)
+        return self
+
+    @property
+    def n_obj(self):
+        return self.finalize()._n_obj
+
+    @property
+    def table(self):
+        return self.finalize()._table
 
 
 class StageResult:
@@ -126,6 +145,8 @@ class LokiSegmentationStage:
         self.high_order = high_order
         self._pool = _PinnedPool()
         self._ws = Workspace()
+        self._side = None
+        self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
     def _passes(self):
@@ -172,12 +193,14 @@ class LokiSegmentationStage:
             return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
         passes = self._passes() if self.fused else None
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
+        if passes is not None and not filters:
+            return self._run_fused_async(batch, d_src, d_image, t_int, passes)
         staged = None
         if passes is None:
             bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
             n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
         else:
-            # vignette-resident fused kernel; vignettes it cannot hold go through the per-operator path
+            # fused kernel for the labels only (the filters change them before the features are taken)
             n = g.n_img
             ws, dev = self._ws, batch.device
             bits = ws.get("bits", max(g.total_words, 1), torch.int32, dev)
@@ -187,21 +210,18 @@ class LokiSegmentationStage:
             counts[:2 * n].zero_()
             counts[2 * n:].fill_(-1)
             n_labels = counts[:n]
-            cap = 16 * n + 1024
-            staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
-                       ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
-            left = batch.vignette_stage(d_src, d_image, t_int, passes, bits, mask, labels, counts, staging, cap,
-                                        high_order=self.high_order, props=not filters)
+            staging = tuple(ws.get(k, 8, dt, dev) for k, dt in (("acc", torch.int64), ("hi", torch.float64),
+                                                                 ("ext", torch.int32), ("counter", torch.int32)))
+            left = batch.vignette_stage(d_src, d_image, t_int, passes, bits, mask, labels, counts, staging, 0,
+                                        high_order=self.high_order, props=False)
             if len(left):
                 self._redo_generic(batch, left, d_src, t_int, bits, mask, labels, n_labels)
-            h_counts = counts.cpu().numpy()  # the one readback of the batch: label counts, fallback flags, staging rows
+            h_counts = counts.cpu().numpy()
             redo = np.nonzero(h_counts[n:2 * n])[0]
             if len(redo):
                 self._redo_generic(batch, redo, d_src, t_int, bits, mask, labels, n_labels)
                 h_counts = counts.cpu().numpy()
             lab_off, n_obj = batch.lab_off_from_bounds(h_counts[:n])
-            if not filters:
-                staged = (staging, counts[2 * n:], np.nonzero((h_counts[2 * n:] < 0) & (h_counts[:n] > 0))[0])
         merge_status = None
         if n_obj > 0 and filters:
             if pp.clear_border:
@@ -212,18 +232,85 @@ class LokiSegmentationStage:
                 merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance)[3]
         # merge_labels paints bridges over background, so only then do labels leave the runs of `bits`
         runs = merge_status is None
-        if staged is None:
-            table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
-                                      high_order=self.high_order, runs=runs)
-        else:
-            staging, acc_base, unstaged = staged
-            table = self._ws.get("table", max(n_obj, 1) * NFEAT, torch.float64, batch.device)[:n_obj * NFEAT]
-            table = table.view(n_obj, NFEAT)
-            batch.props_finish_staged(staging, acc_base, lab_off, n_obj, True, self.high_order, table)
-            if len(unstaged):  # too large / too many runs / staging full: accumulate with the per-operator kernels
-                batch.regionprops(lab_off, n_obj, labels=labels, bits=bits, image=d_image, high_order=self.high_order,
-                                  runs=True, table=table, acc_base=acc_base, tiles=batch.tiles_of(unstaged))
+        table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
+                                  high_order=self.high_order, runs=runs)
         return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
+
+    def _run_fused_async(self, batch, d_src, d_image, t_int, passes) -> DeviceResult:
+        """threshold -> morphology -> label -> regionprops with no host synchronisation: the
+        vignette-resident kernel on the current stream, the few vignettes it cannot hold through the
+        per-operator kernels on a forked stream, label offsets scanned on the device, counts read back
+        asynchronously (DeviceResult.finalize)."""
+        g, ws, dev = batch.g, self._ws, batch.device
+        n = g.n_img
+        main = torch.cuda.current_stream()
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        bits = ws.get("bits", max(g.total_words, 1), torch.int32, dev)
+        mask = ws.get("mask", g.total_px, torch.uint8, dev)
+        labels = ws.get("labels", g.total_px, torch.int32, dev)
+        counts = ws.get("counts", 3 * n, torch.int32, dev)
+        lab_off = ws.get("lab_off", n + 1, torch.int32, dev)
+        counts[:2 * n].zero_()
+        counts[2 * n:].fill_(-1)
+        n_labels, acc_base = counts[:n], counts[2 * n:]
+        cap = 16 * n + 1024
+        staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
+                   ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
+        table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
+        left = batch.fused_lists()[2]
+        if len(left):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._redo_generic(batch, left, d_src, t_int, bits, mask, labels, n_labels)
+        batch.vignette_stage(d_src, d_image, t_int, passes, bits, mask, labels, counts, staging, cap,
+                             high_order=self.high_order, props=True)
+        if len(left):
+            main.wait_stream(side)
+        batch.count_scan(n_labels, out=lab_off)
+        batch.props_finish_staged(staging, acc_base, lab_off, cap, True, self.high_order, table)
+        if len(left):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                batch.regionprops(lab_off, cap, labels=labels, bits=bits, image=d_image, high_order=self.high_order,
+                                  runs=True, table=table, acc_base=acc_base, tiles=batch.tiles_of(left))
+            main.wait_stream(side)
+        slot = self._readback[self._readback_i % len(self._readback)] if self._readback else None
+        if slot is None or slot.numel() < 3 * n + 1:
+            slot = torch.empty(3 * n + 1 + 256, dtype=torch.int32, pin_memory=True)
+            if len(self._readback) < 4:
+                self._readback.append(slot)
+            else:
+                self._readback[self._readback_i % 4] = slot
+        self._readback_i += 1
+        host = slot[:3 * n + 1]
+        host[:3 * n].copy_(counts, non_blocking=True)
+        host[3 * n:].copy_(lab_off[n:n + 1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        left_set = set(int(i) for i in left)
+
+        def pending(res):
+            done.synchronize()
+            h = host.numpy()
+            total = int(h[3 * n])
+            bad = np.nonzero((h[n:2 * n] != 0) | ((h[2 * n:3 * n] < 0) & (h[:n] > 0)))[0]
+            bad = [int(i) for i in bad if int(i) not in left_set]
+            if bad or total > cap:
+                # a vignette overflowed the fused kernel's tables (more word runs than union-find slots, or
+                # the staging rows ran out): redo the batch with the per-operator kernels
+                with torch.cuda.stream(main):
+                    b2, l2, off2, m2 = self._front_generic(batch, d_src, t_int, labels=labels, mask=mask)
+                    total = int(off2[-1].item())
+                    res.bits, res.lab_off = b2, off2
+                    res._table = batch.regionprops(off2, total, labels=l2, bits=b2, image=d_image,
+                                                   high_order=self.high_order, runs=True)
+            else:
+                res._table = table[:total]
+            res._n_obj = total
+
+        return DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
 
     def prepare(self, batch: DeviceBatch):
         """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
@@ -273,7 +360,7 @@ class LokiSegmentationStage:
                 h_pred = self._pool.get("pred", geom.total_px, torch.uint8)
                 geom.pack_host([np.asarray(p, dtype=bool) for p in foreground_pred], out=h_pred.numpy())
                 d_pred = h_pred.to(batch.device, non_blocking=True)
-            res = self.run_device(batch, d_image, d_pred)
+            res = self.run_device(batch, d_image, d_pred).finalize()
             mask_flat = labels_flat = None
             if want_mask:
                 h_mask = self._pool.get("mask", geom.total_px, torch.uint8)
