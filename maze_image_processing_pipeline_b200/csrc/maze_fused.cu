@@ -97,11 +97,24 @@ __device__ __forceinline__ int find16(const u16 *P, int n)
     return n;
 }
 
+// find with path halving (used while linking): a non-root's pointer may be replaced by any ancestor
+__device__ __forceinline__ int find16_halve(u16 *P, int n)
+{
+    int p = *(volatile u16 *)(P + n);
+    while (p != n) {
+        int g = *(volatile u16 *)(P + p);
+        if (g != p) *(volatile u16 *)(P + n) = (u16)g;
+        n = p;
+        p = g;
+    }
+    return n;
+}
+
 __device__ __forceinline__ void union16(u16 *P, int a, int b)
 {
     while (true) {
-        a = find16(P, a);
-        b = find16(P, b);
+        a = find16_halve(P, a);
+        b = find16_halve(P, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
         int old = atomicCAS(P + a, (u16)a, (u16)b); // a stays a root only while P[a] == a
@@ -208,15 +221,18 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     AccRow *ACC = (AccRow *)(s_mem + 2 * wcap);
     const int tid = threadIdx.x;
 
-    // ---- 0. zero-fill the mask and label image first: the stores drain while the CTA computes ----------
-    {
+    // ---- 0. zero-fill of the mask and label image: even CTAs issue it first (the stores drain while the
+    // CTA computes), odd CTAs after the labelling, so the CTAs of a wave do not hit HBM in one burst
+    auto zero_fill = [&]() {
         const int npx = H * W;
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *l4 = (uint4 *)(labels + v.pix_off);
         for (int i = tid; i < (npx + 3) / 4; i += T) l4[i] = z;
         uint4 *m4 = (uint4 *)(mask + v.pix_off);
         for (int i = tid; i < (npx + 15) / 16; i += T) m4[i] = z;
-    }
+    };
+    const bool fill_first = (blockIdx.x & 1) == 0;
+    if (fill_first) zero_fill();
     // word walk without divisions: thread t visits words t, t + T, ...; (y, k) advance by (T / wpr, T % wpr)
     const int step_y = T / wpr, step_k = T - step_y * wpr;
     const int y_first = tid / wpr, k_first = tid - y_first * wpr;
@@ -413,6 +429,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     }
 
     // ---- 4. outputs: final bit plane, then the foreground runs over the zero-filled mask / labels -----
+    if (!fill_first) zero_fill();
     {
         uint32_t *gb = bits_out + v.word_off;
         for (int w = tid; w < words; w += T) gb[w] = M[w];
@@ -468,23 +485,25 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     // consecutive runs in a column almost always carry the same label: the sums of the current label stay
     // in registers and are flushed (shared-memory atomics) only when the label changes.
     const uint8_t *gi = intensity ? intensity + v.pix_off : nullptr;
-    const int p_nstrip = max(1, min(H, (T + wpr - 1) / wpr));
-    const int p_S = (H + p_nstrip - 1) / p_nstrip;
+    // short strips (<= 16 rows) and several work items per thread even out the foreground between threads
+    const int p_S = max(1, min(16, (words + 2 * T - 1) / (2 * T)));
+    const int p_nstrip = (H + p_S - 1) / p_S;
     const int p_items = wpr * p_nstrip;
     for (int q = tid; q < p_items; q += T) {
         const int st = q / wpr, k = q - st * wpr;
         const int y0 = st * p_S, y1 = min(H, y0 + p_S);
         int cur = 0;
-        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
+        // moments of the current label in STRIP-LOCAL coordinates (row - y0 < 16, column - 32k < 32): 32 bits
+        // are enough; the shift to vignette coordinates happens once per flush
+        uint32_t aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
         uint32_t aV = 0, aZ = 0;
         int rmin = 0, rmax = 0, cmin = 0x7fffffff, cmax = -1;
         uint32_t vmn = FULL, vmx = 0u;
-        const u64 cb = 32 * (u64)k;
         for (int y = y0; y <= y1; y++) {
             const uint32_t m = y < y1 ? M[y * wpr + k] : 0u;
             uint32_t pend = m;
             int rid = m ? (int)RB[y * wpr + k] : 0;
-            bool last = (y == y1);
+            const bool last = (y == y1);
             while (pend || last) {
                 int L = 0, b0 = 0, len = 0;
                 if (!last) {
@@ -495,17 +514,27 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                     L = label_of(P, rid++);
                 }
                 if (L != cur) {
-                    if (cur) { // flush the finished label
+                    if (cur) { // flush the finished label: local -> vignette coordinates (r = y0 + r', c = cb + c')
+                        const u64 N = aN, oy = (u64)y0, ox = 32 * (u64)k;
+                        const u64 lR = aR, lC = aC, lRR = aRR, lRC = aRC, lCC = aCC;
+                        const u64 gRR = oy * oy * N + 2 * oy * lR + lRR;
+                        const u64 gCC = ox * ox * N + 2 * ox * lC + lCC;
                         u64 *Aa;
                         int *Ee;
                         if (cur <= FUSED_LCAP) { Aa = ACC[cur - 1].a; Ee = ACC[cur - 1].e; }
                         else { Aa = acc_stage + (i64)(base + cur - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + cur - 1) * MAZE_NEXT; }
-                        atomicAdd(Aa + A_N, aN); atomicAdd(Aa + A_R, aR); atomicAdd(Aa + A_C, aC);
-                        atomicAdd(Aa + A_RR, aRR); atomicAdd(Aa + A_RC, aRC); atomicAdd(Aa + A_CC, aCC);
-                        atomicAdd(Aa + A_RRR, aRRR); atomicAdd(Aa + A_RRC, aRRC); atomicAdd(Aa + A_RCC, aRCC);
-                        atomicAdd(Aa + A_CCC, aCCC);
+                        atomicAdd(Aa + A_N, N);
+                        atomicAdd(Aa + A_R, oy * N + lR);
+                        atomicAdd(Aa + A_C, ox * N + lC);
+                        atomicAdd(Aa + A_RR, gRR);
+                        atomicAdd(Aa + A_RC, oy * ox * N + oy * lC + ox * lR + lRC);
+                        atomicAdd(Aa + A_CC, gCC);
+                        atomicAdd(Aa + A_RRR, oy * oy * oy * N + 3 * oy * oy * lR + 3 * oy * lRR + (u64)aRRR);
+                        atomicAdd(Aa + A_RRC, ox * gRR + oy * oy * lC + 2 * oy * lRC + (u64)aRRC);
+                        atomicAdd(Aa + A_RCC, oy * gCC + ox * ox * lR + 2 * ox * lRC + (u64)aRCC);
+                        atomicAdd(Aa + A_CCC, ox * ox * ox * N + 3 * ox * ox * lC + 3 * ox * lCC + (u64)aCCC);
                         atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
-                        atomicMin(Ee + E_CMIN, cmin); atomicMax(Ee + E_CMAX, cmax);
+                        atomicMin(Ee + E_CMIN, 32 * k + cmin); atomicMax(Ee + E_CMAX, 32 * k + cmax);
                         if (gi) {
                             atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ);
                             vmn = __vminu4(vmn, vmn >> 16); vmn = __vminu4(vmn, vmn >> 8);
@@ -519,20 +548,17 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                     cur = L;
                 }
                 if (last) break;
-                // run [b0, b0 + len) of this word: column sums relative to the word, shifted to absolute columns
-                const uint32_t ja = b0, jb = b0 + len - 1, n = len;
+                // run [b0, b0 + len) of this word
+                const uint32_t ja = b0, jb = b0 + len - 1, n = len, yl = (uint32_t)(y - y0);
                 const uint32_t s1 = n * (ja + jb) / 2;
                 const uint32_t s2 = f_pow2sum(jb) - (ja ? f_pow2sum(ja - 1) : 0u);
                 const uint32_t t3b = jb * (jb + 1) / 2, t3a = ja ? (ja - 1) * ja / 2 : 0u;
                 const uint32_t s3 = t3b * t3b - t3a * t3a;
-                const u64 S1 = s1 + cb * n;
-                const u64 S2 = s2 + 2 * cb * s1 + cb * cb * n;
-                const u64 S3 = s3 + 3 * cb * s2 + 3 * cb * cb * s1 + cb * cb * cb * n;
-                const u64 yy = (u64)y;
-                aN += n; aR += yy * n; aC += S1; aRR += yy * yy * n; aRC += yy * S1; aCC += S2;
-                aRRR += yy * yy * yy * n; aRRC += yy * yy * S1; aRCC += yy * S2; aCCC += S3;
+                const uint32_t yn = yl * n, ys1 = yl * s1;
+                aN += n; aR += yn; aC += s1; aRR += yl * yn; aRC += ys1; aCC += s2;
+                aRRR += yl * yl * yn; aRRC += yl * ys1; aRCC += yl * s2; aCCC += s3;
                 rmax = y;
-                cmin = min(cmin, (int)cb + (int)ja); cmax = max(cmax, (int)cb + (int)jb);
+                cmin = min(cmin, (int)ja); cmax = max(cmax, (int)jb);
                 if (gi) { // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
                     const uint32_t runmask = (len == 32 ? FULL : ((1u << len) - 1u)) << b0;
                     const uint8_t *pw = gi + (size_t)y * W + 32 * (size_t)k;

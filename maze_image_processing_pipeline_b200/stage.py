@@ -145,6 +145,7 @@ class LokiSegmentationStage:
         self.high_order = high_order
         self._pool = _PinnedPool()
         self._ws = Workspace()
+        self._ws_ring, self._ws_i = [Workspace(), Workspace()], 0  # the async path alternates two workspaces
         self._side = None
         self._readback, self._readback_i = [], 0
 
@@ -241,12 +242,17 @@ class LokiSegmentationStage:
         vignette-resident kernel on the current stream, the few vignettes it cannot hold through the
         per-operator kernels on a forked stream, label offsets scanned on the device, counts read back
         asynchronously (DeviceResult.finalize)."""
-        g, ws, dev = batch.g, self._ws, batch.device
+        g, dev = batch.g, batch.device
+        ws = self._ws_ring[self._ws_i % 2]   # results stay valid until the call after the next one
+        self._ws_i += 1
         n = g.n_img
         main = torch.cuda.current_stream()
         if self._side is None or self._side.device != dev:
             self._side = torch.cuda.Stream(device=dev)
         side = self._side
+        if getattr(ws, "side_done", None) is not None:
+            main.wait_event(ws.side_done)  # trailing side-stream work of the batch that used this workspace
+            ws.side_done = None
         bits = ws.get("bits", max(g.total_words, 1), torch.int32, dev)
         mask = ws.get("mask", g.total_px, torch.uint8, dev)
         labels = ws.get("labels", g.total_px, torch.int32, dev)
@@ -270,12 +276,17 @@ class LokiSegmentationStage:
             main.wait_stream(side)
         batch.count_scan(n_labels, out=lab_off)
         batch.props_finish_staged(staging, acc_base, lab_off, cap, True, self.high_order, table)
+        side_done = None
         if len(left):
+            # the features of the oversize vignettes trail on the side stream; the next batch's fused kernel may
+            # start meanwhile (it joins the side stream before it touches the table again)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 batch.regionprops(lab_off, cap, labels=labels, bits=bits, image=d_image, high_order=self.high_order,
                                   runs=True, table=table, acc_base=acc_base, tiles=batch.tiles_of(left))
-            main.wait_stream(side)
+                side_done = torch.cuda.Event()
+                side_done.record(side)
+                ws.side_done = side_done
         slot = self._readback[self._readback_i % len(self._readback)] if self._readback else None
         if slot is None or slot.numel() < 3 * n + 1:
             slot = torch.empty(3 * n + 1 + 256, dtype=torch.int32, pin_memory=True)
@@ -293,6 +304,8 @@ class LokiSegmentationStage:
 
         def pending(res):
             done.synchronize()
+            if side_done is not None:
+                side_done.synchronize()
             h = host.numpy()
             total = int(h[3 * n])
             bad = np.nonzero((h[n:2 * n] != 0) | ((h[2 * n:3 * n] < 0) & (h[:n] > 0)))[0]

@@ -11,9 +11,9 @@ B = 2048
 pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
 st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
 batches = []
-for b in range(4):
+for b in range(6):
     g = BatchGeometry(hs[b * B:(b + 1) * B], ws[b * B:(b + 1) * B])
-    db = DeviceBatch(g)
+    db = st.prepare(DeviceBatch(g))
     batches.append((db, db.synth(1, b * B)))
 for db, img in batches:
     st.run_device(db, img)
@@ -22,12 +22,14 @@ t0 = time.perf_counter()
 for _ in range(3):
     for db, img in batches:
         st.run_device(db, img)
+t_host = time.perf_counter() - t0
 torch.cuda.synchronize()
-print("ms/step", (time.perf_counter() - t0) / 12 * 1e3)
+t_all = time.perf_counter() - t0
+print("host enqueue ms/step", t_host / 18 * 1e3, "total ms/step", t_all / 18 * 1e3)
 pr = cProfile.Profile()
 pr.enable()
 for db, img in batches:
     st.run_device(db, img)
-torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+torch.cuda.synchronize()
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
