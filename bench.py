@@ -59,8 +59,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, polled every 50 ms from before the warm-up until after the
+    timed region; the samples whose timestamps fall inside the timed region are reported (when the
+    region is shorter than the polling period: the samples nearest to it)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -72,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,33 +83,39 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for t, line in self.lines:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                rows.append((t, float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t_begin - 0.03 <= r[0] <= t_end + 0.08]
+        how = "inside the timed region"
+        if not inside and rows:
+            mid = 0.5 * (t_begin + t_end)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
+            how = "nearest to the timed region (region shorter than the 50 ms polling period)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None, "samples": len(sm),
+                "samples_total": len(rows), "which": how, "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,7 +239,11 @@ def run_b200(args):
         db = stage.prepare(DeviceBatch(geom))
         img = db.synth(PIXEL_SEED, lo)
         batches.append((db, img))
+    stage.reserve([b[0].g for b in batches])
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
 
     def step(i):
         db, img = batches[i]
@@ -241,12 +253,10 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record()
     n_vig = n_px = n_obj = 0
     prev = None
@@ -260,9 +270,10 @@ def run_b200(args):
     n_obj += prev.n_obj
     ev1.record()
     barrier()
+    t_end = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     # instrumented repeat of the same steps: per-kernel CUDA-event durations for the roofline
     _lib.prof_enable(True)
@@ -283,14 +294,14 @@ def run_b200(args):
         db, img = batches[i]
         flat = img.cpu().numpy()
         host_batches.append([db.g.view(flat, k) for k in range(db.g.n_img)])
-    stage(host_batches[0])  # warm the pinned pool
+    for r in stage.map(host_batches[:3]):  # warm the three pinned buffer sets
+        pass
     barrier()
     t0 = time.perf_counter()
     e2e_vig = e2e_px = 0
     h2d = d2h = 0
-    for hb in host_batches:
-        r = stage(hb)
-        e2e_vig += len(hb)
+    for r in stage.map(host_batches):  # the streaming call a user makes: numpy in, numpy out, copies inside
+        e2e_vig += len(r)
         e2e_px += r.geometry.pixels
         h2d += r.geometry.total_px
         d2h += r.geometry.total_px * 5 + r.table.nbytes + r.lab_off.nbytes
@@ -367,12 +378,12 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--merge", type=int, default=0, help="merge_segments_distance (0 = off, the schema default)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

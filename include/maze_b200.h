@@ -231,6 +231,11 @@ int maze_props_finish_staged(const unsigned long long *acc_stage, const double *
 /* lab_off[0..n_img] = exclusive prefix sum of n_labels[0..n_img). */
 int maze_count_scan(const int32_t *n_labels, int n_img, int32_t *lab_off, void *stream);
 
+/* HOST helper: copies n host arrays (srcs[i], nbytes[i] bytes) to dst + dst_off[i] with n_threads threads.
+ * Used to pack the vignettes of a batch into one pinned staging buffer (one upload per batch). */
+int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,
+                   void *dst_host, int n_threads);
+
 /* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
  * maze_launch_count: kernels launched by this library since load.  With maze_prof_enable(1) every
  * launch is bracketed by an event pair; maze_prof_collect waits for them and ADDS elapsed

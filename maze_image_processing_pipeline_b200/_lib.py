@@ -40,7 +40,7 @@ class MazeCudaError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".cpp", ".sh"))]
     srcs.append(os.path.join(_HERE, "..", "include", "maze_b200.h"))
     if not force and os.path.exists(SO_PATH):
         so_m = os.path.getmtime(SO_PATH)
@@ -77,6 +77,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
+    "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
 }
 OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",
                  "maze_prof_kernel_name", "maze_prof_enable", "maze_prof_collect"]

@@ -9,6 +9,7 @@ elements); binary images are bit planes with rows padded to 32-bit words; the ba
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -105,13 +106,28 @@ class BatchGeometry:
         o = int(self.pix_off[i])
         return flat[o:o + int(self.npx[i])].reshape(int(self.h[i]), int(self.w[i]))
 
-    def pack_host(self, images, out=None, dtype=np.uint8):
-        """Copy a list of (h, w) arrays into one flat host array laid out like the device batch."""
+    def pack_host(self, images, out=None, dtype=np.uint8, threads=None):
+        """Copy a list of (h, w) arrays into one flat host array laid out like the device batch
+        (multi-threaded memcpy in libmaze_b200.so when the arrays already have the right dtype)."""
+        dtype = np.dtype(dtype)
         if out is None:
             out = np.zeros(self.total_px, dtype)
-        for i, im in enumerate(images):
-            o = int(self.pix_off[i])
-            out[o:o + int(self.npx[i])] = np.asarray(im).reshape(-1)
+        arrs = []
+        for im in images:
+            a = np.asarray(im)
+            if a.dtype != dtype or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a, dtype=dtype)
+            arrs.append(a)
+        n = len(arrs)
+        if n == 0:
+            return out
+        ptrs = np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uint64, count=n)
+        nbytes = (self.npx * dtype.itemsize).astype(np.int64)
+        offs = (self.pix_off[:-1] * dtype.itemsize).astype(np.int64)
+        if threads is None:
+            threads = min(16, max(1, (os.cpu_count() or 2) // 2))
+        check(lib().maze_host_pack(ptrs.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, n,
+                                   out.__array_interface__["data"][0], int(threads)), "maze_host_pack")
         return out
 
 

@@ -63,6 +63,9 @@ class DeviceResult:
         self.keep = keep
         self.merge_status = merge_status
         self._pending = pending
+        # True when the table was produced by kernels on the main stream that no event has covered yet
+        # (every path except the asynchronous fused one, and the redo inside finalize)
+        self._sync_main = pending is None
 
     def finalize(self):
         if self._pending is not None:
@@ -147,6 +150,8 @@ class LokiSegmentationStage:
         self._ws = Workspace()
         self._ws_ring, self._ws_i = [Workspace(), Workspace()], 0  # the async path alternates two workspaces
         self._side = None
+        self._copy_stream = None
+        self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
@@ -287,14 +292,15 @@ class LokiSegmentationStage:
                 side_done = torch.cuda.Event()
                 side_done.record(side)
                 ws.side_done = side_done
-        slot = self._readback[self._readback_i % len(self._readback)] if self._readback else None
+        # four rotating pinned readback slots: a slot is reused only after its batch has been finalised
+        ri = self._readback_i % 4
+        self._readback_i += 1
+        while len(self._readback) < 4:
+            self._readback.append(None)
+        slot = self._readback[ri]
         if slot is None or slot.numel() < 3 * n + 1:
             slot = torch.empty(3 * n + 1 + 256, dtype=torch.int32, pin_memory=True)
-            if len(self._readback) < 4:
-                self._readback.append(slot)
-            else:
-                self._readback[self._readback_i % 4] = slot
-        self._readback_i += 1
+            self._readback[ri] = slot
         host = slot[:3 * n + 1]
         host[:3 * n].copy_(counts, non_blocking=True)
         host[3 * n:].copy_(lab_off[n:n + 1], non_blocking=True)
@@ -319,11 +325,28 @@ class LokiSegmentationStage:
                     res.bits, res.lab_off = b2, off2
                     res._table = batch.regionprops(off2, total, labels=l2, bits=b2, image=d_image,
                                                    high_order=self.high_order, runs=True)
+                    res._sync_main = True
             else:
                 res._table = table[:total]
             res._n_obj = total
 
         return DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
+
+    def reserve(self, geometries, device=None):
+        """Size both device workspaces for the largest of the given batch geometries, so that the steady
+        state makes no allocator call (cudaMalloc inside a step costs milliseconds)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        px = max(g.total_px for g in geometries)
+        words = max(max(g.total_words, 1) for g in geometries)
+        n = max(g.n_img for g in geometries)
+        cap = 16 * n + 1024
+        for ws in self._ws_ring + [self._ws]:
+            for key, size, dt in (("bits", words, torch.int32), ("mask", px, torch.uint8), ("labels", px, torch.int32),
+                                  ("counts", 3 * n, torch.int32), ("lab_off", n + 1, torch.int32),
+                                  ("acc", cap * NACC, torch.int64), ("hi", cap * 8, torch.float64),
+                                  ("ext", cap * NEXT, torch.int32), ("counter", 1, torch.int32),
+                                  ("table", cap * NFEAT, torch.float64)):
+                ws.get(key, size, dt, dev)
 
     def prepare(self, batch: DeviceBatch):
         """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
@@ -354,47 +377,97 @@ class LokiSegmentationStage:
         n_labels[idx] = slab_off[1:] - slab_off[:-1]
 
     # ---- host entry: numpy in, numpy out --------------------------------------------------------------
-    def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,
-                 want_mask=True, want_labels=True) -> StageResult:
+    def _enqueue(self, images, foreground_pred, pool, want_mask, want_labels):
+        """Pack + upload one batch, launch its kernels and start the download of the per-pixel outputs on the
+        copy stream; returns what _complete needs.  Nothing here waits for the GPU."""
         if self.threshold is None and foreground_pred is None:
             raise ValueError("postprocess-only stage needs foreground_pred")
         geom = BatchGeometry.from_images(images)
         if geom.n_img == 0:
+            return (geom, None, None, None, None, None, None)
+        dev = self.device
+        batch = DeviceBatch(geom, dev)
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None or self._copy_stream.device != batch.device:
+            self._copy_stream = torch.cuda.Stream(device=batch.device)
+        h_img = pool.get("img", geom.total_px, torch.uint8)
+        geom.pack_host(images, out=h_img.numpy())
+        d_image = h_img.to(batch.device, non_blocking=True)
+        d_pred = None
+        if self.threshold is None:
+            h_pred = pool.get("pred", geom.total_px, torch.uint8)
+            geom.pack_host([np.asarray(p, dtype=bool).view(np.uint8) for p in foreground_pred], out=h_pred.numpy())
+            d_pred = h_pred.to(batch.device, non_blocking=True)
+        res = self.run_device(batch, d_image, d_pred)
+        # the per-pixel outputs do not depend on the object counts: download them on the copy stream while
+        # the next batch is packed, uploaded and computed
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        h_mask = h_lab = None
+        with torch.cuda.stream(cs):
+            if want_mask:
+                h_mask = pool.get("mask", geom.total_px, torch.uint8)
+                h_mask.copy_(res.mask, non_blocking=True)
+            if want_labels and res.labels is not None:
+                h_lab = pool.get("labels", geom.total_px, torch.int32)
+                h_lab.copy_(res.labels, non_blocking=True)
+        return (geom, batch, res, h_mask, h_lab, pool, (d_image, d_pred))
+
+    def _complete(self, inflight) -> StageResult:
+        geom, batch, res, h_mask, h_lab, pool, _keepalive = inflight
+        if batch is None:
             return StageResult(geom, np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(1, np.int32),
                                np.zeros((0, NFEAT)))
-        dev = self.device
-        with torch.cuda.device(dev if dev is not None else torch.cuda.current_device()):
-            batch = DeviceBatch(geom, dev)
-            h_img = self._pool.get("img", geom.total_px, torch.uint8)
-            geom.pack_host(images, out=h_img.numpy())
-            d_image = h_img.to(batch.device, non_blocking=True)
-            d_pred = None
-            if self.threshold is None:
-                h_pred = self._pool.get("pred", geom.total_px, torch.uint8)
-                geom.pack_host([np.asarray(p, dtype=bool) for p in foreground_pred], out=h_pred.numpy())
-                d_pred = h_pred.to(batch.device, non_blocking=True)
-            res = self.run_device(batch, d_image, d_pred).finalize()
-            mask_flat = labels_flat = None
-            if want_mask:
-                h_mask = self._pool.get("mask", geom.total_px, torch.uint8)
-                h_mask.copy_(res.mask, non_blocking=True)
-                mask_flat = h_mask.numpy()
-            if want_labels and res.labels is not None:
-                h_lab = self._pool.get("labels", geom.total_px, torch.int32)
-                h_lab.copy_(res.labels, non_blocking=True)
-                labels_flat = h_lab.numpy()
-            h_tab = self._pool.get("table", res.table.numel(), torch.float64)
-            h_tab.copy_(res.table.reshape(-1), non_blocking=True)
-            h_off = self._pool.get("lab_off", geom.n_img + 1, torch.int32)
+        cs = self._copy_stream
+        main = torch.cuda.current_stream()
+        redone_bits = res.bits
+        res.finalize()  # waits for the counts; redoes the batch if a vignette overflowed the fused kernel
+        if res._sync_main:
+            cs.wait_stream(main)  # the table (and, after a redo, the per-pixel outputs) was produced synchronously on main
+        with torch.cuda.stream(cs):
+            if res.bits is not redone_bits:  # rare: the per-pixel outputs were rewritten by the per-operator path
+                if h_mask is not None:
+                    h_mask.copy_(res.mask, non_blocking=True)
+                if h_lab is not None:
+                    h_lab.copy_(res.labels, non_blocking=True)
+            table = res.table
+            h_tab = pool.get("table", max(table.numel(), 1), torch.float64)[:table.numel()]
+            h_tab.copy_(table.reshape(-1), non_blocking=True)
+            h_off = pool.get("lab_off", geom.n_img + 1, torch.int32)
             h_off.copy_(res.lab_off, non_blocking=True)
             keep = None if res.keep is None else res.keep.cpu().numpy()
             status = None if res.merge_status is None else res.merge_status.cpu().numpy()
-            torch.cuda.current_stream().synchronize()
+        cs.synchronize()
         if status is not None and (status == MAZE_ERR_TYPEERROR).any():
             # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
             raise TypeError("'NoneType' object is not iterable")
-        table = h_tab.numpy().reshape(-1, NFEAT)
-        return StageResult(geom, mask_flat, labels_flat, h_off.numpy(), table, keep=keep)
+        return StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
+                           h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
+
+    def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,
+                 want_mask=True, want_labels=True) -> StageResult:
+        """One batch: list of uint8 (h, w) vignettes in, masks / label images / object table out (numpy views of
+        pinned buffers that stay valid until the next call)."""
+        dev = self.device
+        with torch.cuda.device(dev if dev is not None else torch.cuda.current_device()):
+            return self._complete(self._enqueue(images, foreground_pred, self._pool, want_mask, want_labels))
+
+    def map(self, batches, want_mask=True, want_labels=True):
+        """Streaming form: ``for res in stage.map(iterable_of_image_lists)``.  Packing and upload of batch i+1
+        overlap the kernels and the download of batch i (three rotating pinned buffer sets, two device
+        workspaces, a separate copy stream).  A yielded result stays valid until the next-but-one is yielded.
+        Items may be image lists or (images, foreground_pred) pairs."""
+        dev = self.device
+        with torch.cuda.device(dev if dev is not None else torch.cuda.current_device()):
+            pending = None
+            for i, item in enumerate(batches):
+                images, pred = item if isinstance(item, tuple) else (item, None)
+                inflight = self._enqueue(images, pred, self._map_pools[i % 3], want_mask, want_labels)
+                if pending is not None:
+                    yield self._complete(pending)
+                pending = inflight
+            if pending is not None:
+                yield self._complete(pending)
 
 
 def shard_bounds(n_items: int, rank: int, world: int):

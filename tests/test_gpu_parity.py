@@ -404,3 +404,26 @@ def test_fused_and_generic_paths_agree_bitwise(mz):
     for i in range(len(imgs)):
         assert np.array_equal(am[i], b.mask(i)) and np.array_equal(al[i], b.labels(i))
     assert np.array_equal(np.nan_to_num(at, nan=-1.0)[:, :8], np.nan_to_num(b.table, nan=-1.0)[:, :8])
+
+
+def test_streaming_map_equals_single_calls(mz):
+    S = mz.stage
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+    batches = [mz.synth.synth_batch(300 + b, 5 + b, lo=64, hi=260) for b in range(5)]
+    batches.insert(2, [])  # an empty batch in the stream
+    got = []
+    for res in st.map(batches):
+        got.append(([res.mask(i).copy() for i in range(len(res))], [res.labels(i).copy() for i in range(len(res))],
+                    res.table.copy(), res.lab_off.copy()))
+    assert len(got) == len(batches)
+    for imgs, (masks, labels, table, off) in zip(batches, got):
+        assert len(masks) == len(imgs)
+        rows = 0
+        for i, im in enumerate(imgs):
+            m, l, t = scipy_chain.loki_chain(im, 40, 1, 2)
+            assert np.array_equal(masks[i], m) and np.array_equal(labels[i], l)
+            assert off[i + 1] - off[i] == len(t)
+            assert_tables_close(table[off[i]:off[i + 1]], t)
+            rows += len(t)
+        assert rows == len(table)
