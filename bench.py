@@ -63,63 +63,91 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, polled every 50 ms from before the warm-up until after the
-    timed region; the samples whose timestamps fall inside the timed region are reported (when the
-    region is shorter than the polling period: the samples nearest to it)."""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled every 20 ms DURING the timed region by a thread
+    that calls NVML directly (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    prints; spawning nvidia-smi itself every few ms stalls the driver and was measured to slow the timed
+    region by up to 2x).  Falls back to one nvidia-smi query before and after the region."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.rows = []
+        self.h = None
+        self.nv = None
+        self._stop = threading.Event()
+        self.t = None
+        try:
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def _smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            bits = 0
+            for bit, val in zip((0x8, 0x40, 0x20, 0x4), out[2:6]):
+                if val.strip().lower().startswith("active"):
+                    bits |= bit
+            self.max_mhz = float(out[1])
+            self.rows.append((time.time(), float(out[0]), bits))
+        except Exception:
+            pass
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+        if self.nv is None:
+            self._smi()
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        rows = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                rows.append((t, float(parts[1]), float(parts[2]),
-                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
-            except ValueError:
-                continue
-        inside = [r for r in rows if t_begin - 0.03 <= r[0] <= t_end + 0.08]
-        how = "inside the timed region"
-        if not inside and rows:
+        if self.nv is None:
+            self._smi()
+        else:
+            self._stop.set()
+            self.t.join(timeout=2)
+        rows = self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source available"]}
+        inside = [r for r in rows if t_begin <= r[0] <= t_end]
+        how = "NVML, every 20 ms inside the timed region" if self.nv is not None else "nvidia-smi before/after the timed region"
+        if not inside:
             mid = 0.5 * (t_begin + t_end)
             inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
-            how = "nearest to the timed region (region shorter than the 50 ms polling period)"
-        sm = [r[1] for r in inside]
-        reasons = sorted({x for r in inside for x in r[3]})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(r[2] for r in inside) if inside else None, "samples": len(sm),
-                "samples_total": len(rows), "which": how, "reasons": reasons}
+            how += " (nearest samples: region shorter than the polling period)"
+        bits = 0
+        for r in inside:
+            bits |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": getattr(self, "max_mhz", None),
+                "samples": len(inside), "source": how, "reasons": sorted(v for k, v in self.BITS.items() if bits & k)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,15 +291,17 @@ def run_b200(args):
     t_begin = time.time()
     ev0.record()
     n_vig = n_px = n_obj = 0
-    prev = None
+    inflight = []
     for i in range(args.warmup, need):
         res, _ = step(i)
-        if prev is not None:
-            n_obj += prev.n_obj  # readback check of the PREVIOUS step: the GPU is already busy with this one
-        prev = res
+        inflight.append(res)
+        if len(inflight) > 2:
+            n_obj += inflight.pop(0).n_obj  # readback check two steps behind (three rotating workspaces)
         n_vig += batches[i][0].g.n_img
         n_px += batches[i][0].g.pixels
-    n_obj += prev.n_obj
+    for r in inflight:
+        n_obj += r.n_obj
+    stage.join()
     ev1.record()
     barrier()
     t_end = time.time()
@@ -285,6 +315,7 @@ def run_b200(args):
     evp0.record()
     for i in range(args.warmup, need):
         step(i)
+    stage.join()
     evp1.record()
     torch.cuda.synchronize()
     _lib.prof_enable(False)

@@ -231,6 +231,16 @@ int maze_props_finish_staged(const unsigned long long *acc_stage, const double *
 /* lab_off[0..n_img] = exclusive prefix sum of n_labels[0..n_img). */
 int maze_count_scan(const int32_t *n_labels, int n_img, int32_t *lab_off, void *stream);
 
+/* threshold -> n_pass thresholded-EDT passes (d2 thresholds < 33^2) -> label -> mask bytes in one call, with
+ * the per-operator kernels above (for vignettes too large for maze_vignette_stage).  plane_a / plane_b:
+ * bit-plane scratch, flags_a / flags_b: n_img uint32 each; *final_plane_host receives the plane (a or b)
+ * that holds the final mask.  Other arguments as for maze_label / maze_unpack_mask. */
+int maze_front_chain(const uint8_t *image, const maze_vignette_t *vig, int n_img, const maze_tile_t *tiles,
+                     int n_tiles, int t_int, int n_pass, const int32_t *pass_t_host, const int32_t *pass_invert_host,
+                     uint32_t *plane_a, uint32_t *plane_b, uint32_t *flags_a, uint32_t *flags_b, int32_t *parent,
+                     int32_t *labels, int32_t *tile_scan, int32_t *lab_off, uint8_t *mask,
+                     uint32_t **final_plane_host, void *stream);
+
 /* HOST helper: copies n host arrays (srcs[i], nbytes[i] bytes) to dst + dst_off[i] with n_threads threads.
  * Used to pack the vignettes of a batch into one pinned staging buffer (one upload per batch). */
 int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,

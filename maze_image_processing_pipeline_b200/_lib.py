@@ -78,6 +78,7 @@ SIGNATURES = {
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
+    "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",
                  "maze_prof_kernel_name", "maze_prof_enable", "maze_prof_collect"]

@@ -138,6 +138,8 @@ __device__ __forceinline__ int label_of(const u16 *P, int rid)
     return p & 0x7fff;
 }
 
+__device__ __forceinline__ u64 pw2(u64 m) { return m * (m + 1) * (2 * m + 1) / 6; }   // sum_{i<=m} i^2, m < 2^16
+__device__ __forceinline__ u64 pw3(u64 m) { u64 t = m * (m + 1) / 2; return t * t; }      // sum_{i<=m} i^3
 // power sums of 0..m for m < 1024 (columns relative to a 1024-pixel chunk): 32-bit arithmetic suffices
 __device__ __forceinline__ uint32_t f_pow2sum(uint32_t m) { return m * (m + 1) / 2 * (2 * m + 1) / 3; }
 __device__ __forceinline__ u64 f_pow3sum(uint32_t m) { uint32_t t = m * (m + 1) / 2; return (u64)t * t; }
@@ -214,10 +216,13 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ int s_warp[34];
     __shared__ int s_base;
+    __shared__ int s_hist[FUSED_LCAP + 2];
     const int img = img_list[blockIdx.x];
     const maze_vignette_t v = vig[img];
     const int H = v.h, W = v.w, wpr = v.wpr, words = H * wpr;
-    uint32_t *A = s_mem, *B = s_mem + wcap;
+    // planes are laid out tightly (A = first `words` words, B = the next `words`); the pass sequence starts in
+    // the plane that makes the FINAL plane land in A, so that everything behind A is free for the run list
+    uint32_t *A = s_mem, *B = s_mem + words;
     AccRow *ACC = (AccRow *)(s_mem + 2 * wcap);
     const int tid = threadIdx.x;
 
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     const int y_first = tid / wpr, k_first = tid - y_first * wpr;
 
     // ---- 1. threshold + pack (loki/pipeline.py:649) -------------------------------------------------
+    uint32_t *T0 = (prm.n_pass & 1) ? B : A; // an odd number of passes must start in B to end in A
     {
         const uint8_t *base = image + v.pix_off;
         const int t = prm.t_int;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                     }
                 }
             }
-            A[w] = word & valid_mask(W, k);
+            T0[w] = word & valid_mask(W, k);
             y += step_y; k += step_k;
             if (k >= wpr) { k -= wpr; y++; }
         }
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     __syncthreads();
 
     // ---- 2. thresholded-EDT passes in shared memory (isotropic.py:35-36, 66-67) ----------------------
-    uint32_t *src = A, *dst = B;
+    uint32_t *src = T0, *dst = (T0 == A) ? B : A;
     for (int ps = 0; ps < prm.n_pass; ps++) {
         const int R = prm.pass[ps].R;
         const uint32_t inv = prm.pass[ps].invert ? FULL : 0u;
@@ -341,65 +347,77 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         __syncthreads();
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
-    const uint32_t *M = src;   // final plane
-    u16 *RB = (u16 *)dst;      // free plane: first run id of every word ...
-    u16 *P = RB + wcap;        // ... and the union-find over run ids
+    const uint32_t *M = src; // final plane
+    // The free plane now holds the RUN LIST: every maximal horizontal run of foreground pixels (y, x0, x1),
+    // its union-find slot, the label-sorted order and the first run of every row.  Everything after the
+    // morphology works on this compact list (thread per run, no divergence over empty words).
+    const int RC = max(0, (4 * (2 * wcap - words) - 2 * (H + 2)) / 10); // M == A: all words behind it are free
+    u16 *rY = (u16 *)(s_mem + words), *rX0 = rY + RC, *rX1 = rX0 + RC, *P = rX1 + RC, *rO = P + RC, *rowStart = rO + RC;
 
-    // ---- 3. labelling on word runs in shared memory (loki/pipeline.py:430-433) -----------------------
+    // ---- 3. run list + labelling (loki/pipeline.py:430-433) --------------------------------------------
     const int chunk = (words + T - 1) / T;
     const int lo = min(tid * chunk, words), hi = min(lo + chunk, words);
     int cnt = 0;
-    for (int w = lo; w < hi; w++) {
-        uint32_t m = M[w];
-        cnt += __popc(m & ~(m << 1));
+    {
+        int k = lo % wpr;
+        for (int w = lo; w < hi; w++) {
+            uint32_t m = M[w];
+            uint32_t prevbit = k > 0 ? (M[w - 1] >> 31) : 0u;
+            cnt += __popc(m & ~((m << 1) | prevbit));
+            if (++k == wpr) k = 0;
+        }
     }
     int n_runs;
     int run = block_exclusive_scan<T>(cnt, s_warp, &n_runs);
-    if (n_runs > wcap || n_runs >= 0x8000) { // more runs than union-find slots: per-operator kernels take over
+    if (n_runs > RC || n_runs >= 0x8000) { // more runs than slots (noise): the per-operator kernels take over
         if (tid == 0) { fallback[img] = 1; n_labels[img] = 0; acc_base[img] = -1; }
         return;
     }
-    for (int w = lo; w < hi; w++) {
-        uint32_t m = M[w];
-        RB[w] = (u16)run;
-        run += __popc(m & ~(m << 1));
+    {
+        int y = lo / wpr, k = lo - y * wpr;
+        for (int w = lo; w < hi; w++) {
+            if (k == 0) rowStart[y] = (u16)run;
+            uint32_t m = M[w];
+            uint32_t prevbit = k > 0 ? (M[w - 1] >> 31) : 0u;
+            uint32_t starts = m & ~((m << 1) | prevbit);
+            while (starts) {
+                int b0 = __ffs(starts) - 1;
+                starts &= starts - 1;
+                uint32_t rest = ~(m >> b0);
+                int x0 = 32 * k + b0, x1;
+                if ((rest & (b0 ? ((1u << (32 - b0)) - 1u) : FULL)) != 0u) {
+                    x1 = x0 + __ffs(rest) - 2; // the run ends inside this word
+                } else {                       // it reaches bit 31: follow it through the next words of the row
+                    x1 = 32 * k + 31;
+                    for (int kk = k + 1; kk < wpr; kk++) {
+                        uint32_t mm = M[w - k + kk];
+                        if (mm == FULL) { x1 += 32; continue; }
+                        x1 += __ffs(~mm) - 1;
+                        break;
+                    }
+                }
+                rY[run] = (u16)y; rX0[run] = (u16)x0; rX1[run] = (u16)x1; P[run] = (u16)run;
+                run++;
+            }
+            if (++k == wpr) { k = 0; y++; }
+        }
+        if (tid == 0) rowStart[H] = (u16)n_runs;
     }
-    for (int r = tid; r < n_runs; r += T) P[r] = (u16)r;
     __syncthreads();
-    for (int w = tid; w < words; w += T) {
-        uint32_t m = M[w];
-        if (!m) continue;
-        int y = w / wpr, k = w - y * wpr;
-        uint32_t prev = k > 0 ? M[w - 1] : 0u;
-        uint32_t next = k + 1 < wpr ? M[w + 1] : 0u;
-        if ((m & 1u) && (prev >> 31)) union16(P, RB[w], run_id(RB, w - 1, prev, 31));
+    // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1)
+    for (int i = tid; i < n_runs; i += T) {
+        const int y = rY[i];
         if (y == 0) continue;
-        uint32_t uc = M[w - wpr];
-        uint32_t ulw = k > 0 ? M[w - wpr - 1] : 0u;
-        uint32_t urw = k + 1 < wpr ? M[w - wpr + 1] : 0u;
-        if (!(uc | (ulw >> 31) | (urw & 1u))) continue;
-        uint32_t UL = (uc << 1) | (ulw >> 31), UR = (uc >> 1) | (urw << 31);
-        uint32_t left = (m << 1) | (prev >> 31), right = (m >> 1) | (next << 31);
-        uint32_t need_up = m & uc & ~(left & UL);
-        uint32_t need_ul = m & ~uc & UL & ~left;
-        uint32_t need_ur = m & ~uc & UR & ~right;
-        while (need_up) {
-            int b = __ffs(need_up) - 1;
-            need_up &= need_up - 1;
-            union16(P, run_id(RB, w, m, b), run_id(RB, w - wpr, uc, b));
+        int a = rowStart[y - 1];
+        const int bnd = rowStart[y];
+        if (a == bnd) continue;
+        const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
+        int e = bnd; // first run of the previous row whose end reaches lo0 (runs of a row are sorted by x)
+        while (a < e) {
+            int mid = (a + e) >> 1;
+            if ((int)rX1[mid] < lo0) a = mid + 1; else e = mid;
         }
-        while (need_ul) {
-            int b = __ffs(need_ul) - 1;
-            need_ul &= need_ul - 1;
-            int tgt = b > 0 ? run_id(RB, w - wpr, uc, b - 1) : run_id(RB, w - wpr - 1, ulw, 31);
-            union16(P, run_id(RB, w, m, b), tgt);
-        }
-        while (need_ur) {
-            int b = __ffs(need_ur) - 1;
-            need_ur &= need_ur - 1;
-            int tgt = b < 31 ? run_id(RB, w - wpr, uc, b + 1) : (int)RB[w - wpr + 1];
-            union16(P, run_id(RB, w, m, b), tgt);
-        }
+        for (int j = a; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
     }
     __syncthreads();
     for (int r = tid; r < n_runs; r += T) {
@@ -435,8 +453,9 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         for (int w = tid; w < words; w += T) gb[w] = M[w];
         const int nsm = min(n_lab, FUSED_LCAP);
         for (int i = tid; i < nsm * (int)(sizeof(AccRow) / 4); i += T) ((uint32_t *)ACC)[i] = 0;
+        if (tid <= FUSED_LCAP + 1) s_hist[tid] = 0;
     }
-    __syncthreads(); // labels in P are final; the zero-fill of step 0 is ordered before the stores below
+    __syncthreads(); // labels in P are final; the zero fill is ordered before the stores below
     const int base = s_base;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NWARP = T / 32;
@@ -458,133 +477,130 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             }
         int32_t *gl = labels + v.pix_off;
         uint8_t *gm = mask + v.pix_off;
-        // one warp per row, one lane per word: coalesced 4-byte label / 1-byte mask stores of set pixels
-        for (int y = warp; y < H; y += NWARP) {
-            for (int kc = 0; kc < wpr; kc += 32) {
-                int k = kc + lane;
-                uint32_t m = k < wpr ? M[y * wpr + k] : 0u;
-                uint32_t nz = __ballot_sync(FULL, m != 0u);
-                while (nz) {
-                    int j = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t mj = __shfl_sync(FULL, m, j);
-                    if ((mj >> lane) & 1u) {
-                        int o = y * W + 32 * (kc + j) + lane;
-                        gl[o] = label_of(P, run_id(RB, y * wpr + kc + j, mj, lane));
-                        gm[o] = 1;
-                    }
-                }
+        // one warp per run: coalesced 4-byte label / 1-byte mask stores
+        for (int i = warp; i < n_runs; i += NWARP) {
+            const int y = rY[i], x0 = rX0[i], x1 = rX1[i];
+            const int lab = label_of(P, i);
+            const int o = y * W;
+            for (int x = x0 + lane; x <= x1; x += 32) {
+                gl[o + x] = lab;
+                gm[o + x] = 1;
             }
         }
+        // histogram of the runs over the labels (bucket FUSED_LCAP: all labels beyond the shared table)
+        for (int i = tid; i < n_runs; i += T) atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1);
     }
     __syncthreads();
     if (base < 0) return;
 
     // ---- 5. per-label accumulators (loki/pipeline.py:589-625) -----------------------------------------
-    // COLUMN WALK: a thread owns word column k and a strip of rows.  Objects are vertically coherent, so
-    // consecutive runs in a column almost always carry the same label: the sums of the current label stay
-    // in registers and are flushed (shared-memory atomics) only when the label changes.
+    // Counting sort of the runs by label, then every thread walks a contiguous piece of the sorted list:
+    // the sums of the current label stay in registers and are flushed when the label changes.
+    if (tid == 0) {
+        int acc0 = 0;
+        for (int b = 0; b <= FUSED_LCAP; b++) { int c = s_hist[b]; s_hist[b] = acc0; acc0 += c; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) rO[atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1)] = (u16)i;
+    __syncthreads();
     const uint8_t *gi = intensity ? intensity + v.pix_off : nullptr;
-    // short strips (<= 16 rows) and several work items per thread even out the foreground between threads
-    const int p_S = max(1, min(16, (words + 2 * T - 1) / (2 * T)));
-    const int p_nstrip = (H + p_S - 1) / p_S;
-    const int p_items = wpr * p_nstrip;
-    for (int q = tid; q < p_items; q += T) {
-        const int st = q / wpr, k = q - st * wpr;
-        const int y0 = st * p_S, y1 = min(H, y0 + p_S);
+    const int p_chunk = (n_runs + T - 1) / T;
+    const int p_lo = min(tid * p_chunk, n_runs), p_hi = min(p_lo + p_chunk, n_runs);
+    {
         int cur = 0;
-        // moments of the current label in STRIP-LOCAL coordinates (row - y0 < 16, column - 32k < 32): 32 bits
-        // are enough; the shift to vignette coordinates happens once per flush
-        uint32_t aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
+        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
         uint32_t aV = 0, aZ = 0;
-        int rmin = 0, rmax = 0, cmin = 0x7fffffff, cmax = -1;
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1;
         uint32_t vmn = FULL, vmx = 0u;
-        for (int y = y0; y <= y1; y++) {
-            const uint32_t m = y < y1 ? M[y * wpr + k] : 0u;
-            uint32_t pend = m;
-            int rid = m ? (int)RB[y * wpr + k] : 0;
-            const bool last = (y == y1);
-            while (pend || last) {
-                int L = 0, b0 = 0, len = 0;
-                if (!last) {
-                    b0 = __ffs(pend) - 1;
-                    uint32_t rest = ~(pend >> b0);
-                    len = rest ? __ffs(rest) - 1 : 32 - b0;
-                    pend &= ~((len == 32 ? FULL : ((1u << len) - 1u)) << b0);
-                    L = label_of(P, rid++);
+        auto flush = [&](int lab) { // add the register sums of label `lab` to its accumulator row
+            u64 *Aa;
+            int *Ee;
+            if (lab <= FUSED_LCAP) { Aa = ACC[lab - 1].a; Ee = ACC[lab - 1].e; }
+            else { Aa = acc_stage + (i64)(base + lab - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + lab - 1) * MAZE_NEXT; }
+            atomicAdd(Aa + A_N, aN); atomicAdd(Aa + A_R, aR); atomicAdd(Aa + A_C, aC);
+            atomicAdd(Aa + A_RR, aRR); atomicAdd(Aa + A_RC, aRC); atomicAdd(Aa + A_CC, aCC);
+            atomicAdd(Aa + A_RRR, aRRR); atomicAdd(Aa + A_RRC, aRRC); atomicAdd(Aa + A_RCC, aRCC);
+            atomicAdd(Aa + A_CCC, aCCC);
+            atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
+            atomicMin(Ee + E_CMIN, cmin); atomicMax(Ee + E_CMAX, cmax);
+            if (gi) {
+                atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ);
+                uint32_t mn = __vminu4(vmn, vmn >> 16); mn = __vminu4(mn, mn >> 8);
+                uint32_t mx = __vmaxu4(vmx, vmx >> 16); mx = __vmaxu4(mx, mx >> 8);
+                atomicMin(Ee + E_VMIN, (int)(mn & 0xffu)); atomicMax(Ee + E_VMAX, (int)(mx & 0xffu));
+            }
+        };
+        for (int pos = p_lo; pos < p_hi; pos++) {
+            const int i = rO[pos];
+            const int L = label_of(P, i);
+            if (L != cur) {
+                if (cur) flush(cur); // label change inside a chunk: rare (the list is sorted by label)
+                aN = aR = aC = aRR = aRC = aCC = aRRR = aRRC = aRCC = aCCC = 0;
+                aV = aZ = 0; rmin = 0x7fffffff; rmax = -1; cmin = 0x7fffffff; cmax = -1; vmn = FULL; vmx = 0u;
+                cur = L;
+            }
+            const u64 y = rY[i], a = rX0[i], b = rX1[i], n = b - a + 1;
+            const u64 S1 = n * (a + b) / 2;
+            const u64 S2 = pw2(b) - (a ? pw2(a - 1) : 0);
+            const u64 S3 = pw3(b) - (a ? pw3(a - 1) : 0);
+            aN += n; aR += y * n; aC += S1; aRR += y * y * n; aRC += y * S1; aCC += S2;
+            aRRR += y * y * y * n; aRRC += y * y * S1; aRCC += y * S2; aCCC += S3;
+            rmin = min(rmin, (int)y); rmax = max(rmax, (int)y); cmin = min(cmin, (int)a); cmax = max(cmax, (int)b);
+            if (gi) { // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
+                const uint8_t *prow = gi + (size_t)y * W;
+                const uint32_t al = (uint32_t)((uintptr_t)prow & 3u);   // row start relative to 4-byte alignment
+                const uint32_t *qq = (const uint32_t *)(prow - al);     // word g holds row bytes 4g-al .. 4g-al+3
+                const int ga = ((int)a + (int)al) >> 2, gb = ((int)b + (int)al) >> 2;
+                for (int g = ga; g <= gb; g++) {
+                    uint32_t px = __ldg(qq + g);
+                    const int c0 = 4 * g - (int)al;                     // column of byte 0 of this word
+                    uint32_t nib = 0xfu;
+                    if (c0 < (int)a) nib &= 0xfu << ((int)a - c0);
+                    if (c0 + 3 > (int)b) nib &= 0xfu >> (c0 + 3 - (int)b);
+                    uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                    aV += __vsadu4(px & bm, 0u);
+                    aZ += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
+                    vmn = __vminu4(vmn, px | ~bm);
+                    vmx = __vmaxu4(vmx, px & bm);
                 }
-                if (L != cur) {
-                    if (cur) { // flush the finished label: local -> vignette coordinates (r = y0 + r', c = cb + c')
-                        const u64 N = aN, oy = (u64)y0, ox = 32 * (u64)k;
-                        const u64 lR = aR, lC = aC, lRR = aRR, lRC = aRC, lCC = aCC;
-                        const u64 gRR = oy * oy * N + 2 * oy * lR + lRR;
-                        const u64 gCC = ox * ox * N + 2 * ox * lC + lCC;
-                        u64 *Aa;
-                        int *Ee;
-                        if (cur <= FUSED_LCAP) { Aa = ACC[cur - 1].a; Ee = ACC[cur - 1].e; }
-                        else { Aa = acc_stage + (i64)(base + cur - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + cur - 1) * MAZE_NEXT; }
-                        atomicAdd(Aa + A_N, N);
-                        atomicAdd(Aa + A_R, oy * N + lR);
-                        atomicAdd(Aa + A_C, ox * N + lC);
-                        atomicAdd(Aa + A_RR, gRR);
-                        atomicAdd(Aa + A_RC, oy * ox * N + oy * lC + ox * lR + lRC);
-                        atomicAdd(Aa + A_CC, gCC);
-                        atomicAdd(Aa + A_RRR, oy * oy * oy * N + 3 * oy * oy * lR + 3 * oy * lRR + (u64)aRRR);
-                        atomicAdd(Aa + A_RRC, ox * gRR + oy * oy * lC + 2 * oy * lRC + (u64)aRRC);
-                        atomicAdd(Aa + A_RCC, oy * gCC + ox * ox * lR + 2 * ox * lRC + (u64)aRCC);
-                        atomicAdd(Aa + A_CCC, ox * ox * ox * N + 3 * ox * ox * lC + 3 * ox * lCC + (u64)aCCC);
-                        atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
-                        atomicMin(Ee + E_CMIN, 32 * k + cmin); atomicMax(Ee + E_CMAX, 32 * k + cmax);
-                        if (gi) {
-                            atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ);
-                            vmn = __vminu4(vmn, vmn >> 16); vmn = __vminu4(vmn, vmn >> 8);
-                            vmx = __vmaxu4(vmx, vmx >> 16); vmx = __vmaxu4(vmx, vmx >> 8);
-                            atomicMin(Ee + E_VMIN, (int)(vmn & 0xffu)); atomicMax(Ee + E_VMAX, (int)(vmx & 0xffu));
-                        }
-                    }
-                    aN = aR = aC = aRR = aRC = aCC = aRRR = aRRC = aRCC = aCCC = 0;
-                    aV = aZ = 0; cmin = 0x7fffffff; cmax = -1; vmn = FULL; vmx = 0u;
-                    rmin = y;
-                    cur = L;
-                }
-                if (last) break;
-                // run [b0, b0 + len) of this word
-                const uint32_t ja = b0, jb = b0 + len - 1, n = len, yl = (uint32_t)(y - y0);
-                const uint32_t s1 = n * (ja + jb) / 2;
-                const uint32_t s2 = f_pow2sum(jb) - (ja ? f_pow2sum(ja - 1) : 0u);
-                const uint32_t t3b = jb * (jb + 1) / 2, t3a = ja ? (ja - 1) * ja / 2 : 0u;
-                const uint32_t s3 = t3b * t3b - t3a * t3a;
-                const uint32_t yn = yl * n, ys1 = yl * s1;
-                aN += n; aR += yn; aC += s1; aRR += yl * yn; aRC += ys1; aCC += s2;
-                aRRR += yl * yl * yn; aRRC += yl * ys1; aRCC += yl * s2; aCCC += s3;
-                rmax = y;
-                cmin = min(cmin, (int)ja); cmax = max(cmax, (int)jb);
-                if (gi) { // intensity of the run's pixels, four at a time (byte-SIMD on aligned words)
-                    const uint32_t runmask = (len == 32 ? FULL : ((1u << len) - 1u)) << b0;
-                    const uint8_t *pw = gi + (size_t)y * W + 32 * (size_t)k;
-                    const uint32_t al = (uint32_t)((uintptr_t)pw & 3u);
-                    const uint32_t *qq = (const uint32_t *)(pw - al);
-                    const int g0 = b0 >> 2, g1 = (b0 + len - 1) >> 2;
-                    uint32_t lo32 = __ldg(qq + g0);
-                    for (int g = g0; g <= g1; g++) {
-                        uint32_t hi32 = __ldg(qq + g + 1); // <= 4 bytes past the row: inside the padded slot
-                        uint32_t px = __funnelshift_r(lo32, hi32, 8 * al);
-                        lo32 = hi32;
-                        uint32_t nib = (runmask >> (4 * g)) & 0xfu;
-                        uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                        aV += __vsadu4(px & bm, 0u);
-                        aZ += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
-                        vmn = __vminu4(vmn, px | ~bm);
-                        vmx = __vmaxu4(vmx, px & bm);
-                    }
-                }
+            }
+        }
+        // end of chunk: neighbouring threads mostly hold the SAME label -> reduce across the warp, one flush per
+        // label and warp (all 32 lanes take part; lanes without work carry label 0)
+        uint32_t todo = __ballot_sync(FULL, cur != 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int lab = __shfl_sync(FULL, cur, leader);
+            const bool in = (cur == lab);
+            todo &= ~__ballot_sync(FULL, in);
+            u64 v[10] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC};
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                u64 x = in ? v[j] : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                v[j] = x;
+            }
+            uint32_t sV = __reduce_add_sync(FULL, in ? aV : 0u), sZ = __reduce_add_sync(FULL, in ? aZ : 0u);
+            int r0 = __reduce_min_sync(FULL, in ? rmin : 0x7fffffff), r1 = __reduce_max_sync(FULL, in ? rmax : -1);
+            int c0 = __reduce_min_sync(FULL, in ? cmin : 0x7fffffff), c1 = __reduce_max_sync(FULL, in ? cmax : -1);
+            uint32_t mn = in ? vmn : FULL, mx = in ? vmx : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                mn = __vminu4(mn, __shfl_xor_sync(FULL, mn, d));
+                mx = __vmaxu4(mx, __shfl_xor_sync(FULL, mx, d));
+            }
+            if (lane == leader) {
+                aN = v[0]; aR = v[1]; aC = v[2]; aRR = v[3]; aRC = v[4]; aCC = v[5]; aRRR = v[6]; aRRC = v[7];
+                aRCC = v[8]; aCCC = v[9]; aV = sV; aZ = sZ; rmin = r0; rmax = r1; cmin = c0; cmax = c1; vmn = mn; vmx = mx;
+                flush(lab);
             }
         }
     }
     __syncthreads();
     if (prm.high_order) {
-        // float64 central moments with p + q > 3 about the exact centroid: sum_c (c - cc)^q over a run
-        // follows from its n, S1, S2, S3; same column walk, six doubles per current label in registers
+        // float64 central moments with p + q > 3 about the exact centroid: sum_c (c - cc)^q over a run follows
+        // from its n, S1, S2, S3 (columns taken relative to the run start); same walk over the sorted runs
         for (int l = tid; l < n_lab; l += T) {
             const u64 *Aa = l < FUSED_LCAP ? ACC[l].a : acc_stage + (i64)(base + l) * MAZE_NACC;
             double *Hh = l < FUSED_LCAP ? ACC[l].h : hi_stage + (i64)(base + l) * 8;
@@ -593,53 +609,56 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             Hh[H_CC] = (double)*(const volatile u64 *)(Aa + A_C) / dn;
         }
         __syncthreads();
-        for (int q = tid; q < p_items; q += T) {
-            const int st = q / wpr, k = q - st * wpr;
-            const int y0 = st * p_S, y1 = min(H, y0 + p_S);
-            int cur = 0;
-            double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0, cr = 0, o = 0;
-            double *Hh = nullptr;
-            for (int y = y0; y <= y1; y++) {
-                const uint32_t m = y < y1 ? M[y * wpr + k] : 0u;
-                uint32_t pend = m;
-                int rid = m ? (int)RB[y * wpr + k] : 0;
-                bool last = (y == y1);
-                while (pend || last) {
-                    int L = 0, b0 = 0, len = 0;
-                    if (!last) {
-                        b0 = __ffs(pend) - 1;
-                        uint32_t rest = ~(pend >> b0);
-                        len = rest ? __ffs(rest) - 1 : 32 - b0;
-                        pend &= ~((len == 32 ? FULL : ((1u << len) - 1u)) << b0);
-                        L = label_of(P, rid++);
-                    }
-                    if (L != cur) {
-                        if (cur) {
-                            atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
-                            atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
-                        }
-                        h13 = h22 = h31 = h23 = h32 = h33 = 0;
-                        cur = L;
-                        if (L) {
-                            Hh = L <= FUSED_LCAP ? ACC[L - 1].h : hi_stage + (i64)(base + L - 1) * 8;
-                            cr = *(volatile double *)(Hh + H_CR);
-                            o = *(volatile double *)(Hh + H_CC) - 32.0 * k; // centroid column relative to the word
-                        }
-                    }
-                    if (last) break;
-                    const uint32_t ja = b0, jb = b0 + len - 1, n = len;
-                    const uint32_t s1 = n * (ja + jb) / 2;
-                    const uint32_t s2 = f_pow2sum(jb) - (ja ? f_pow2sum(ja - 1) : 0u);
-                    const uint32_t t3b = jb * (jb + 1) / 2, t3a = ja ? (ja - 1) * ja / 2 : 0u;
-                    const uint32_t s3 = t3b * t3b - t3a * t3a;
-                    const double dn = (double)n, S1 = (double)s1, S2 = (double)s2, S3 = (double)s3;
-                    const double T1 = S1 - dn * o;
-                    const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
-                    const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
-                    const double dr = (double)y - cr, dr2 = dr * dr, dr3 = dr2 * dr;
-                    h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
-                    h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+        int cur = 0;
+        double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0, cr = 0, cc = 0;
+        auto hrow = [&](int lab) { return lab <= FUSED_LCAP ? ACC[lab - 1].h : hi_stage + (i64)(base + lab - 1) * 8; };
+        for (int pos = p_lo; pos < p_hi; pos++) {
+            const int i = rO[pos];
+            const int L = label_of(P, i);
+            if (L != cur) {
+                if (cur) {
+                    double *Hh = hrow(cur);
+                    atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
+                    atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
                 }
+                h13 = h22 = h31 = h23 = h32 = h33 = 0;
+                cur = L;
+                const double *Hc = hrow(L);
+                cr = *(const volatile double *)(Hc + H_CR);
+                cc = *(const volatile double *)(Hc + H_CC);
+            }
+            // columns relative to the run start: j = 0 .. n-1, u = j - o with o = cc - x0
+            const int nn = (int)rX1[i] - (int)rX0[i] + 1;
+            const double dn = (double)nn, m1 = (double)(nn - 1);
+            const double S1 = dn * m1 * 0.5;                          // sum j
+            const double S2 = m1 * dn * (2.0 * m1 + 1.0) / 6.0;       // sum j^2
+            const double S3 = S1 * S1;                                // sum j^3
+            const double o = cc - (double)rX0[i];
+            const double T1 = S1 - dn * o;
+            const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
+            const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+            const double dr = (double)rY[i] - cr, dr2 = dr * dr, dr3 = dr2 * dr;
+            h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
+            h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+        }
+        uint32_t todo = __ballot_sync(FULL, cur != 0);
+        while (todo) { // one flush per label and warp
+            const int leader = __ffs(todo) - 1;
+            const int lab = __shfl_sync(FULL, cur, leader);
+            const bool in = (cur == lab);
+            todo &= ~__ballot_sync(FULL, in);
+            double v[6] = {h13, h22, h31, h23, h32, h33};
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double x = in ? v[j] : 0.0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                v[j] = x;
+            }
+            if (lane == leader) {
+                double *Hh = hrow(lab);
+                atomicAdd(Hh + H_13, v[0]); atomicAdd(Hh + H_22, v[1]); atomicAdd(Hh + H_31, v[2]);
+                atomicAdd(Hh + H_23, v[3]); atomicAdd(Hh + H_32, v[4]); atomicAdd(Hh + H_33, v[5]);
             }
         }
         __syncthreads();

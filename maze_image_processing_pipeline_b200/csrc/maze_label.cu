@@ -380,3 +380,30 @@ extern "C" int maze_max_label(const int32_t *labels, const maze_vignette_t *vig,
     MAZE_KERNEL(KID_MAX_LABEL, s, k_max_label<<<n_tiles, MAZE_CTA, 0, s>>>(labels, vig, tiles, max_label));
     return MAZE_OK;
 }
+
+
+// threshold -> thresholded-EDT passes -> label -> mask bytes in ONE call (the per-operator chain for the
+// vignettes the fused kernel cannot hold; saves a dozen host round trips through the binding)
+extern "C" int maze_front_chain(const uint8_t *image, const maze_vignette_t *vig, int n_img, const maze_tile_t *tiles,
+                                int n_tiles, int t_int, int n_pass, const int32_t *pass_t_host,
+                                const int32_t *pass_invert_host, uint32_t *plane_a, uint32_t *plane_b,
+                                uint32_t *flags_a, uint32_t *flags_b, int32_t *parent, int32_t *labels,
+                                int32_t *tile_scan, int32_t *lab_off, uint8_t *mask, uint32_t **final_plane_host,
+                                void *stream)
+{
+    if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
+    int rc = maze_threshold_pack(image, vig, n_img, tiles, n_tiles, t_int, plane_a, flags_a, stream);
+    if (rc != MAZE_OK) return rc;
+    uint32_t *src = plane_a, *dst = plane_b, *fs = flags_a, *fd = flags_b;
+    for (int p = 0; p < n_pass; p++) {
+        rc = maze_morph_pass(src, dst, vig, n_img, tiles, n_tiles, pass_t_host[p], pass_invert_host[p], fs, fd, stream);
+        if (rc != MAZE_OK) return rc;
+        uint32_t *t = src; src = dst; dst = t;
+        t = fs; fs = fd; fd = t;
+    }
+    rc = maze_label(src, vig, n_img, tiles, n_tiles, parent, labels, tile_scan, lab_off, stream);
+    if (rc != MAZE_OK) return rc;
+    rc = maze_unpack_mask(src, vig, n_img, tiles, n_tiles, mask, stream);
+    if (final_plane_host) *final_plane_host = src;
+    return rc;
+}

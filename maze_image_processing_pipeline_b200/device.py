@@ -88,13 +88,14 @@ class BatchGeometry:
         maze_vignette_stage (largest first inside a class), and the ones too large for it."""
         order, off = [], [0]
         lo = 0
+        small = (self.h < 65536) & (self.w < 65536)  # the fused kernel keeps run coordinates in 16 bits
         for cap in FUSED_CAPS:
-            sel = np.nonzero((self.nwords > lo) & (self.nwords <= cap))[0]
+            sel = np.nonzero((self.nwords > lo) & (self.nwords <= cap) & small)[0]
             sel = sel[np.argsort(-self.nwords[sel], kind="stable")]
             order.append(sel)
             off.append(off[-1] + len(sel))
             lo = cap
-        left = np.nonzero(self.nwords > FUSED_CAPS[-1])[0]
+        left = np.nonzero((self.nwords > FUSED_CAPS[-1]) | ~small)[0]
         return np.concatenate(order).astype(np.int32), np.asarray(off, np.int32), left
 
     @classmethod
@@ -179,8 +180,43 @@ def fold_threshold(thr) -> int:
     return int(min(255, max(-1, math.floor(t))))
 
 
+_ITEMSIZE = {torch.uint8: 1, torch.int32: 4, torch.int64: 8, torch.float64: 8, torch.float32: 4, torch.int16: 2}
+
+
+class Arena:
+    """Bump allocator over one device buffer, reset once per step: the per-operator kernels need a dozen
+    scratch arrays per call and a cudaMalloc inside a step costs milliseconds.  Grows (once) on demand."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf = None
+        self.off = 0
+        self.need = 0
+
+    def reserve(self, nbytes):
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.off = 0
+
+    def reset(self):
+        if self.buf is None or self.need > self.buf.numel():
+            self.reserve(int(self.need * 1.2) + (1 << 20))
+        self.off = 0
+        self.need = 0
+
+    def take(self, n, dtype):
+        nbytes = (int(n) * _ITEMSIZE[dtype] + 255) // 256 * 256
+        self.need += nbytes
+        if self.buf is None or self.off + nbytes > self.buf.numel():
+            return torch.empty(int(n), dtype=dtype, device=self.device)  # overflow: plain allocation this once
+        t = self.buf[self.off:self.off + nbytes].view(dtype)[:int(n)]
+        self.off += nbytes
+        return t
+
+
 class DeviceBatch:
     """A packed batch resident on one GPU plus the operators that act on it."""
+    arena = None  # optional Arena for the scratch / output arrays of the per-operator kernels
 
     def __init__(self, geometry: BatchGeometry, device=None):
         if not torch.cuda.is_available():
@@ -193,14 +229,19 @@ class DeviceBatch:
             self.d_tiles = torch.from_numpy(geometry.tiles.view(np.uint8).copy()).to(self.device, non_blocking=False)
 
     # ---- buffers -------------------------------------------------------------------------------
+    def _new(self, n, dtype):
+        if self.arena is not None:
+            return self.arena.take(n, dtype)
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
     def empty_px(self, dtype):
-        return torch.empty(self.g.total_px, dtype=dtype, device=self.device)
+        return self._new(self.g.total_px, dtype)
 
     def empty_plane(self):
-        return torch.empty(max(self.g.total_words, 1), dtype=torch.int32, device=self.device)
+        return self._new(max(self.g.total_words, 1), torch.int32)
 
     def empty_flags(self):
-        return torch.empty(max(self.g.n_img, 1), dtype=torch.int32, device=self.device)
+        return self._new(max(self.g.n_img, 1), torch.int32)
 
     def upload(self, host_flat):
         t = torch.from_numpy(host_flat) if isinstance(host_flat, np.ndarray) else host_flat
@@ -277,8 +318,8 @@ class DeviceBatch:
         if labels is None:
             labels = self.empty_px(torch.int32)
         parent = self.empty_px(torch.int32)
-        tile_scan = torch.empty(self.g.n_tiles + 1, dtype=torch.int32, device=self.device)
-        lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device)
+        tile_scan = self._new(self.g.n_tiles + 1, torch.int32)
+        lab_off = self._new(self.g.n_img + 1, torch.int32)
         check(lib().maze_label(bits.data_ptr(), vig, n, tiles, nt, parent.data_ptr(), labels.data_ptr(),
                                tile_scan.data_ptr(), lab_off.data_ptr(), _stream()), "maze_label")
         return labels, lab_off
@@ -327,8 +368,8 @@ class DeviceBatch:
             table = torch.empty((max(n_obj, 0), NFEAT), dtype=torch.float64, device=self.device)
         if n_obj <= 0 or nt == 0:
             return table
-        acc = torch.empty(n_obj * NACC, dtype=torch.int64, device=self.device)
-        ext = torch.empty(n_obj * NEXT, dtype=torch.int32, device=self.device)
+        acc = self._new(n_obj * NACC, torch.int64)
+        ext = self._new(n_obj * NEXT, torch.int32)
         check(lib().maze_regionprops(_ptr(labels), _ptr(bits), _ptr(image), vig, n, d_tiles, nt, lab_off.data_ptr(),
                                      int(n_obj), acc.data_ptr(), ext.data_ptr(), table.data_ptr(),
                                      (RP_HIGH_ORDER if high_order else 0) | (RP_RUNS if runs else 0),
@@ -355,6 +396,25 @@ class DeviceBatch:
                                       merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
                                       status.data_ptr(), _stream()), "maze_merge_labels")
         return merge_dist, n_merge, index_state, status, obj_scratch
+
+    def front_chain(self, d_src, t_int, passes, labels, mask):
+        """threshold -> passes -> label -> mask with the per-operator kernels in one C call.
+        Returns (final bit plane, lab_off)."""
+        import ctypes
+        vig, n, tiles, nt = self._geo()
+        pa, pb = self.empty_plane(), self.empty_plane()
+        fa, fb = self.empty_flags(), self.empty_flags()
+        parent = self.empty_px(torch.int32)
+        tile_scan = self._new(self.g.n_tiles + 1, torch.int32)
+        lab_off = self._new(self.g.n_img + 1, torch.int32)
+        pt = np.asarray([p[0] for p in passes] + [0], np.int32)
+        pi = np.asarray([p[1] for p in passes] + [0], np.int32)
+        final = ctypes.c_void_p(0)
+        check(lib().maze_front_chain(d_src.data_ptr(), vig, n, tiles, nt, int(t_int), len(passes), pt.ctypes.data,
+                                     pi.ctypes.data, pa.data_ptr(), pb.data_ptr(), fa.data_ptr(), fb.data_ptr(),
+                                     parent.data_ptr(), labels.data_ptr(), tile_scan.data_ptr(), lab_off.data_ptr(),
+                                     mask.data_ptr(), ctypes.addressof(final), _stream()), "maze_front_chain")
+        return (pa if final.value == pa.data_ptr() else pb), lab_off
 
     def fused_lists(self):
         if not hasattr(self, "_fused"):

@@ -25,7 +25,7 @@ import torch
 
 from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT
 from ._lib import MAX_DISK_RADIUS
-from .device import (BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
+from .device import (Arena, BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
 
 @dataclass
@@ -66,6 +66,8 @@ class DeviceResult:
         # True when the table was produced by kernels on the main stream that no event has covered yet
         # (every path except the asynchronous fused one, and the redo inside finalize)
         self._sync_main = pending is None
+        self.redone = False
+        self.ready = None  # event after which mask / labels / bits are complete (None: stream order of the caller)
 
     def finalize(self):
         if self._pending is not None:
@@ -148,13 +150,25 @@ class LokiSegmentationStage:
         self.high_order = high_order
         self._pool = _PinnedPool()
         self._ws = Workspace()
-        self._ws_ring, self._ws_i = [Workspace(), Workspace()], 0  # the async path alternates two workspaces
+        self._ws_ring, self._ws_i = [Workspace(), Workspace(), Workspace()], 0  # the async path rotates three workspaces
         self._side = None
         self._copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
+    def _passes_all(self):
+        """All passes incl. identities (t == 0), for maze_front_chain; None if a radius needs the exact EDT."""
+        pp = self.postprocess
+        out = []
+        if pp.opening_radius > 0:
+            out += [(fold_erosion_radius(pp.opening_radius), 0), (fold_dilation_radius(pp.opening_radius), 1)]
+        if pp.closing_radius > 0:
+            out += [(fold_dilation_radius(pp.closing_radius), 1), (fold_erosion_radius(pp.closing_radius), 0)]
+        if any(t >= (MAX_DISK_RADIUS + 1) ** 2 for t, _ in out):
+            return None
+        return [(t, inv) for t, inv in out if t != 0]
+
     def _passes(self):
         """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path."""
         pp = self.postprocess
@@ -243,18 +257,43 @@ class LokiSegmentationStage:
         return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
 
     def _run_fused_async(self, batch, d_src, d_image, t_int, passes) -> DeviceResult:
+        """Three workspaces, each with its own LANE stream, rotate: batch i+1 starts on the next lane while
+        the tail of batch i (label offsets, feature rows, stragglers of the big size class) still runs, so the
+        GPU never drains between batches.  The caller's stream is joined at the start (inputs) only; the
+        result carries a `ready` event and DeviceResult.finalize() waits for it."""
+        dev = batch.device
+        ws = self._ws_ring[self._ws_i % 3]   # results stay valid for the next two calls
+        self._ws_i += 1
+        if getattr(ws, "lane", None) is None or ws.lane.device != dev:
+            ws.lane = torch.cuda.Stream(device=dev)
+            ws.side = torch.cuda.Stream(device=dev)
+        caller = torch.cuda.current_stream()
+        ws.lane.wait_stream(caller)
+        with torch.cuda.stream(ws.lane):
+            res = self._run_fused_lane(batch, d_src, d_image, t_int, passes, ws)
+        return res
+
+    def join(self):
+        """Make the current stream wait for everything the stage has in flight on its lanes."""
+        cur = torch.cuda.current_stream()
+        for ws in self._ws_ring:
+            if getattr(ws, "lane", None) is not None:
+                cur.wait_stream(ws.lane)
+                cur.wait_stream(ws.side)
+
+    def _run_fused_lane(self, batch, d_src, d_image, t_int, passes, ws) -> DeviceResult:
         """threshold -> morphology -> label -> regionprops with no host synchronisation: the
         vignette-resident kernel on the current stream, the few vignettes it cannot hold through the
         per-operator kernels on a forked stream, label offsets scanned on the device, counts read back
         asynchronously (DeviceResult.finalize)."""
         g, dev = batch.g, batch.device
-        ws = self._ws_ring[self._ws_i % 2]   # results stay valid until the call after the next one
-        self._ws_i += 1
         n = g.n_img
-        main = torch.cuda.current_stream()
-        if self._side is None or self._side.device != dev:
-            self._side = torch.cuda.Stream(device=dev)
-        side = self._side
+        if getattr(ws, "arena", None) is None or ws.arena.device != dev:
+            ws.arena = Arena(dev)
+        ws.arena.reset()
+        batch.arena = ws.arena
+        main = torch.cuda.current_stream()  # == the lane stream of this workspace
+        side = ws.side
         if getattr(ws, "side_done", None) is not None:
             main.wait_event(ws.side_done)  # trailing side-stream work of the batch that used this workspace
             ws.side_done = None
@@ -317,20 +356,39 @@ class LokiSegmentationStage:
             bad = np.nonzero((h[n:2 * n] != 0) | ((h[2 * n:3 * n] < 0) & (h[:n] > 0)))[0]
             bad = [int(i) for i in bad if int(i) not in left_set]
             if bad or total > cap:
-                # a vignette overflowed the fused kernel's tables (more word runs than union-find slots, or
-                # the staging rows ran out): redo the batch with the per-operator kernels
+                # some vignettes overflowed the fused kernel's tables (more runs than slots, or the staging rows
+                # ran out): the per-operator kernels redo just those, then offsets and features are re-derived
                 with torch.cuda.stream(main):
-                    b2, l2, off2, m2 = self._front_generic(batch, d_src, t_int, labels=labels, mask=mask)
-                    total = int(off2[-1].item())
-                    res.bits, res.lab_off = b2, off2
-                    res._table = batch.regionprops(off2, total, labels=l2, bits=b2, image=d_image,
-                                                   high_order=self.high_order, runs=True)
+                    res.redone = True
+                    total2 = cap + 1
+                    if total <= cap and len(bad) <= 256:
+                        self._redo_generic(batch, bad, d_src, t_int, bits, mask, labels, n_labels)
+                        batch.count_scan(n_labels, out=lab_off)
+                        total2 = int(lab_off[n].item())
+                    if total2 <= cap:
+                        batch.props_finish_staged(staging, acc_base, lab_off, cap, True, self.high_order, table)
+                        todo = sorted(left_set | set(bad))
+                        batch.regionprops(lab_off, cap, labels=labels, bits=bits, image=d_image,
+                                          high_order=self.high_order, runs=True, table=table, acc_base=acc_base,
+                                          tiles=batch.tiles_of(todo))
+                        total = total2
+                        res._table = table[:total]
+                    else:  # the whole batch through the per-operator kernels
+                        b2, l2, off2, m2 = self._front_generic(batch, d_src, t_int, labels=labels, mask=mask)
+                        total = int(off2[-1].item())
+                        res.bits, res.lab_off = b2, off2
+                        res._table = batch.regionprops(off2, total, labels=l2, bits=b2, image=d_image,
+                                                       high_order=self.high_order, runs=True)
                     res._sync_main = True
+                    res.ready = torch.cuda.Event()
+                    res.ready.record(main)  # the redo ran on the lane stream
             else:
                 res._table = table[:total]
             res._n_obj = total
 
-        return DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
+        res = DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
+        res.ready = done
+        return res
 
     def reserve(self, geometries, device=None):
         """Size both device workspaces for the largest of the given batch geometries, so that the steady
@@ -347,6 +405,11 @@ class LokiSegmentationStage:
                                   ("ext", cap * NEXT, torch.int32), ("counter", 1, torch.int32),
                                   ("table", cap * NFEAT, torch.float64)):
                 ws.get(key, size, dt, dev)
+            if getattr(ws, "arena", None) is None or ws.arena.device != dev:
+                ws.arena = Arena(dev)
+            # scratch of the per-operator path for the oversize vignettes: ~8 planes, parent + misc per pixel
+            # (twice: a redo of overflowed vignettes in finalize() takes a second set)
+            ws.arena.reserve(int(2.2 * (8 * 4 * words + 5 * px + cap * (NACC * 8 + NEXT * 4))) + (8 << 20))
 
     def prepare(self, batch: DeviceBatch):
         """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
@@ -372,7 +435,12 @@ class LokiSegmentationStage:
     def _redo_generic(self, batch, indices, d_src, t_int, bits, mask, labels, n_labels):
         """Run the per-operator kernels on a few vignettes of the batch, in place in the batch buffers."""
         sub, word_idx, idx = self._sub(batch, indices)
-        sbits, _, slab_off, _ = self._front_generic(sub, d_src, t_int, labels=labels, mask=mask)
+        sub.arena = batch.arena
+        passes = self._passes_all()
+        if passes is not None:
+            sbits, slab_off = sub.front_chain(d_src, t_int, passes, labels, mask)
+        else:
+            sbits, _, slab_off, _ = self._front_generic(sub, d_src, t_int, labels=labels, mask=mask)
         bits[word_idx] = sbits[word_idx]
         n_labels[idx] = slab_off[1:] - slab_off[:-1]
 
@@ -402,7 +470,10 @@ class LokiSegmentationStage:
         # the per-pixel outputs do not depend on the object counts: download them on the copy stream while
         # the next batch is packed, uploaded and computed
         cs = self._copy_stream
-        cs.wait_stream(main)
+        if res.ready is not None:
+            cs.wait_event(res.ready)
+        else:
+            cs.wait_stream(main)
         h_mask = h_lab = None
         with torch.cuda.stream(cs):
             if want_mask:
@@ -420,12 +491,14 @@ class LokiSegmentationStage:
                                np.zeros((0, NFEAT)))
         cs = self._copy_stream
         main = torch.cuda.current_stream()
-        redone_bits = res.bits
-        res.finalize()  # waits for the counts; redoes the batch if a vignette overflowed the fused kernel
-        if res._sync_main:
-            cs.wait_stream(main)  # the table (and, after a redo, the per-pixel outputs) was produced synchronously on main
+        res.finalize()  # waits for the counts; redoes the vignettes that overflowed the fused kernel
+        if res._sync_main:  # the table (and, after a redo, the per-pixel outputs) came from kernels no host sync covered
+            if res.ready is not None:
+                cs.wait_event(res.ready)
+            else:
+                cs.wait_stream(main)
         with torch.cuda.stream(cs):
-            if res.bits is not redone_bits:  # rare: the per-pixel outputs were rewritten by the per-operator path
+            if res.redone:  # rare: per-pixel outputs were rewritten by the per-operator path
                 if h_mask is not None:
                     h_mask.copy_(res.mask, non_blocking=True)
                 if h_lab is not None:
