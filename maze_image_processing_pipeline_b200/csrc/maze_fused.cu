@@ -147,14 +147,22 @@ __device__ __forceinline__ u64 f_pow3sum(uint32_t m) { uint32_t t = m * (m + 1) 
 // One thresholded-EDT pass as a COLUMN WALK: a thread owns word column k and a strip of rows and slides
 // down, keeping for the last 2R+1 rows the chord tests at the R+1 chord widths in registers, so every
 // word is loaded once and every chord test is computed once (instead of 2R+1 times).
-template <int R, int T>
+struct WRuntime { // chord half-widths read from the pass table
+    const int *p;
+    __device__ __forceinline__ int w(int j) const { return p[j]; }
+};
+template <int A, int B, int C, int D>
+struct WFixed { // compile-time chord half-widths of the common small disks: the chord loops unroll completely
+    __device__ __forceinline__ constexpr int w(int j) const { return j == 0 ? A : j == 1 ? B : j == 2 ? C : D; }
+};
+
+template <int R, int T, typename WT>
 __device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int H, int W,
-                                              int wpr, const int *__restrict__ wtab, uint32_t inv, bool phantom,
-                                              int nstrip, int S)
+                                              int wpr, const WT wt, uint32_t inv, bool phantom, int nstrip, int S)
 {
     int wd[R + 1];
 #pragma unroll
-    for (int j = 0; j <= R; j++) wd[j] = wtab[j];
+    for (int j = 0; j <= R; j++) wd[j] = wt.w(j);
     const int nitems = wpr * nstrip;
     for (int q = threadIdx.x; q < nitems; q += T) {
         const int s = q / wpr, k = q - s * wpr;
@@ -298,10 +306,19 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             const int nstrip = max(1, min(H, (T + wpr - 1) / wpr));
             const int S = (H + nstrip - 1) / nstrip;
             const int *wt = prm.pass[ps].w;
-            if (R == 0) morph_columns<0, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
-            else if (R == 1) morph_columns<1, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
-            else if (R == 2) morph_columns<2, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
-            else morph_columns<3, T>(src, dst, H, W, wpr, wt, inv, phantom, nstrip, S);
+            const int pat = R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
+            switch (pat) { // d2 thresholds 1, 2-3, 4, 5-7, 8 get fully unrolled code
+            case 1100: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 0, 0, 0>(), inv, phantom, nstrip, S); break;
+            case 1110: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 1, 0, 0>(), inv, phantom, nstrip, S); break;
+            case 2210: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 1, 0, 0>(), inv, phantom, nstrip, S); break;
+            case 2221: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 1, 0>(), inv, phantom, nstrip, S); break;
+            case 2222: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 2, 0>(), inv, phantom, nstrip, S); break;
+            default:
+                if (R == 0) morph_columns<0, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
+                else if (R == 1) morph_columns<1, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
+                else if (R == 2) morph_columns<2, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
+                else morph_columns<3, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
+            }
         } else {
             int y = y_first, k = k_first;
             for (int w = tid; w < words; w += T) {

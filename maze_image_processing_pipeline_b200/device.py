@@ -86,16 +86,24 @@ class BatchGeometry:
     def fused_classes(self):
         """(img_list, class_off[4], leftovers): vignette indices grouped by the size classes of
         maze_vignette_stage (largest first inside a class), and the ones too large for it."""
-        order, off = [], [0]
-        lo = 0
         small = (self.h < 65536) & (self.w < 65536)  # the fused kernel keeps run coordinates in 16 bits
-        for cap in FUSED_CAPS:
-            sel = np.nonzero((self.nwords > lo) & (self.nwords <= cap) & small)[0]
+        # smallest class whose shared memory holds the planes AND a run list of at least two runs per row
+        # (tall narrow vignettes have few words but one run per row)
+        cls = np.full(self.n_img, len(FUSED_CAPS), np.int64)
+        for c in range(len(FUSED_CAPS) - 1, -1, -1):
+            cap = FUSED_CAPS[c]
+            rc = (4 * (2 * cap - self.nwords) - 2 * (self.h + 2)) // 10
+            ok = (self.nwords <= cap) & (rc >= 2 * self.h + 64) & small
+            cls[ok] = c
+        # the last class takes whatever fits its planes (an overflowing run list falls back at run time)
+        cls[(cls == len(FUSED_CAPS)) & (self.nwords <= FUSED_CAPS[-1]) & small] = len(FUSED_CAPS) - 1
+        order, off = [], [0]
+        for c in range(len(FUSED_CAPS)):
+            sel = np.nonzero(cls == c)[0]
             sel = sel[np.argsort(-self.nwords[sel], kind="stable")]
             order.append(sel)
             off.append(off[-1] + len(sel))
-            lo = cap
-        left = np.nonzero((self.nwords > FUSED_CAPS[-1]) | ~small)[0]
+        left = np.nonzero(cls == len(FUSED_CAPS))[0]
         return np.concatenate(order).astype(np.int32), np.asarray(off, np.int32), left
 
     @classmethod
