@@ -241,6 +241,42 @@ int maze_front_chain(const uint8_t *image, const maze_vignette_t *vig, int n_img
                      int32_t *labels, int32_t *tile_scan, int32_t *lab_off, uint8_t *mask,
                      uint32_t **final_plane_host, void *stream);
 
+/* One asynchronous step of the fused stage in a single call (what stage.LokiSegmentationStage issues per
+ * batch): counters zeroed, maze_vignette_stage on `lane_stream`, maze_front_chain for the left_n vignettes
+ * that are too large for it on `side_stream` (forked / joined with events), maze_count_scan,
+ * maze_props_finish_staged, maze_regionprops for the oversize vignettes (trailing on the side stream), and
+ * the copy of counts[3*n_img] (n_labels | fallback | acc_base) and of the object total into pinned
+ * counts_host[3*n_img + 1].  left_vig / left_tiles describe the oversize vignettes as their own batch (same
+ * offsets), left_idx (device) holds their indices in the full batch, left_tiles_full their tiles with
+ * full-batch vignette indices.  pass_t / pass_invert: as for maze_vignette_stage (no t == 0 passes).
+ * scratch_*: plane (total words), flags (2*left_n), parent (per pixel), tile_scan (left_n_tiles+1),
+ * lab_off (left_n+1), acc / ext (stage_cap rows). */
+typedef struct maze_step_args {
+    const maze_vignette_t *vig;
+    const int32_t *img_list;
+    const maze_vignette_t *left_vig;
+    const maze_tile_t *left_tiles;
+    const int32_t *left_idx;
+    const maze_tile_t *left_tiles_full;
+    const uint8_t *image, *intensity;
+    uint32_t *bits;
+    uint8_t *mask;
+    int32_t *labels, *counts, *lab_off, *stage_counter;
+    unsigned long long *acc_stage;
+    double *hi_stage;
+    int32_t *ext_stage;
+    double *table;
+    uint32_t *scratch_plane, *scratch_flags;
+    int32_t *scratch_parent, *scratch_tile_scan, *scratch_lab_off;
+    unsigned long long *scratch_acc;
+    int32_t *scratch_ext;
+    int32_t *counts_host;
+    int32_t class_off[MAZE_FUSED_CLASSES + 1];
+    int32_t pass_t[4], pass_invert[4];
+    int32_t n_img, left_n, left_n_tiles, left_n_tiles_full, t_int, n_pass, flags, stage_cap;
+} maze_step_args_t;
+int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);
+
 /* HOST helper: copies n host arrays (srcs[i], nbytes[i] bytes) to dst + dst_off[i] with n_threads threads.
  * Used to pack the vignettes of a batch into one pinned staging buffer (one upload per batch). */
 int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,

@@ -30,6 +30,18 @@ FUSED_CAPS = (1024, 4096, 12288, 28320)
 FUSED_NO_PROPS = 4
 
 
+class StepArgs(ctypes.Structure):
+    """maze_step_args_t of include/maze_b200.h."""
+    _fields_ = ([(k, ctypes.c_void_p) for k in (
+        "vig", "img_list", "left_vig", "left_tiles", "left_idx", "left_tiles_full", "image", "intensity", "bits",
+        "mask", "labels", "counts", "lab_off", "stage_counter", "acc_stage", "hi_stage", "ext_stage", "table",
+        "scratch_plane", "scratch_flags", "scratch_parent", "scratch_tile_scan", "scratch_lab_off", "scratch_acc",
+        "scratch_ext", "counts_host")]
+        + [("class_off", ctypes.c_int32 * 5), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
+        + [(k, ctypes.c_int32) for k in ("n_img", "left_n", "left_n_tiles", "left_n_tiles_full", "t_int", "n_pass",
+                                         "flags", "stage_cap")])
+
+
 class MazeLibraryError(RuntimeError):
     pass
 
@@ -78,6 +90,7 @@ SIGNATURES = {
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
+    "maze_stage_step": [_vp, _vp, _vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",

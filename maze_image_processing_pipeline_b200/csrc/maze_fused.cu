@@ -234,18 +234,24 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     AccRow *ACC = (AccRow *)(s_mem + 2 * wcap);
     const int tid = threadIdx.x;
 
-    // ---- 0. zero-fill of the mask and label image: even CTAs issue it first (the stores drain while the
-    // CTA computes), odd CTAs after the labelling, so the CTAs of a wave do not hit HBM in one burst
-    auto zero_fill = [&]() {
+    // ---- 0. zero-fill of the mask and label image, in ZF_PARTS slices issued between the compute phases: the
+    // stores drain in the background instead of blocking every warp at the store queue in one burst
+    constexpr int ZF_PARTS = 8;
+    int zf_next = 0;
+    auto zero_fill = [&](int upto) { // issue slices zf_next .. upto-1
         const int npx = H * W;
-        uint4 z = make_uint4(0, 0, 0, 0);
+        const int nl = (npx + 3) / 4, nm = (npx + 15) / 16;
+        const uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *l4 = (uint4 *)(labels + v.pix_off);
-        for (int i = tid; i < (npx + 3) / 4; i += T) l4[i] = z;
         uint4 *m4 = (uint4 *)(mask + v.pix_off);
-        for (int i = tid; i < (npx + 15) / 16; i += T) m4[i] = z;
+        for (; zf_next < upto; zf_next++) {
+            const int l0 = (int)((i64)nl * zf_next / ZF_PARTS), l1 = (int)((i64)nl * (zf_next + 1) / ZF_PARTS);
+            for (int i = l0 + tid; i < l1; i += T) l4[i] = z;
+            const int m0 = (int)((i64)nm * zf_next / ZF_PARTS), m1 = (int)((i64)nm * (zf_next + 1) / ZF_PARTS);
+            for (int i = m0 + tid; i < m1; i += T) m4[i] = z;
+        }
     };
-    const bool fill_first = (blockIdx.x & 1) == 0;
-    if (fill_first) zero_fill();
+    zero_fill(1);
     // word walk without divisions: thread t visits words t, t + T, ...; (y, k) advance by (T / wpr, T % wpr)
     const int step_y = T / wpr, step_k = T - step_y * wpr;
     const int y_first = tid / wpr, k_first = tid - y_first * wpr;
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             if (k >= wpr) { k -= wpr; y++; }
         }
     }
+    zero_fill(2);
     __syncthreads();
 
     // ---- 2. thresholded-EDT passes in shared memory (isotropic.py:35-36, 66-67) ----------------------
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                 if (k >= wpr) { k -= wpr; y++; }
             }
         }
+        zero_fill(min(3 + ps, 5));
         __syncthreads();
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
@@ -420,6 +428,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         }
         if (tid == 0) rowStart[H] = (u16)n_runs;
     }
+    zero_fill(6);
     __syncthreads();
     // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1)
     for (int i = tid; i < n_runs; i += T) {
@@ -436,6 +445,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         }
         for (int j = a; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
     }
+    zero_fill(7);
     __syncthreads();
     for (int r = tid; r < n_runs; r += T) {
         int root = find16(P, r);
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     }
 
     // ---- 4. outputs: final bit plane, then the foreground runs over the zero-filled mask / labels -----
-    if (!fill_first) zero_fill();
+    zero_fill(ZF_PARTS);
     {
         uint32_t *gb = bits_out + v.word_off;
         for (int w = tid; w < words; w += T) gb[w] = M[w];

@@ -23,7 +23,9 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT
+import ctypes
+
+from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, RP_HIGH_ORDER, StepArgs, check, lib
 from ._lib import MAX_DISK_RADIUS
 from .device import (Arena, BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
@@ -302,35 +304,12 @@ class LokiSegmentationStage:
         labels = ws.get("labels", g.total_px, torch.int32, dev)
         counts = ws.get("counts", 3 * n, torch.int32, dev)
         lab_off = ws.get("lab_off", n + 1, torch.int32, dev)
-        counts[:2 * n].zero_()
-        counts[2 * n:].fill_(-1)
         n_labels, acc_base = counts[:n], counts[2 * n:]
         cap = 16 * n + 1024
         staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
                    ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
         table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
-        left = batch.fused_lists()[2]
-        if len(left):
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                self._redo_generic(batch, left, d_src, t_int, bits, mask, labels, n_labels)
-        batch.vignette_stage(d_src, d_image, t_int, passes, bits, mask, labels, counts, staging, cap,
-                             high_order=self.high_order, props=True)
-        if len(left):
-            main.wait_stream(side)
-        batch.count_scan(n_labels, out=lab_off)
-        batch.props_finish_staged(staging, acc_base, lab_off, cap, True, self.high_order, table)
-        side_done = None
-        if len(left):
-            # the features of the oversize vignettes trail on the side stream; the next batch's fused kernel may
-            # start meanwhile (it joins the side stream before it touches the table again)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                batch.regionprops(lab_off, cap, labels=labels, bits=bits, image=d_image, high_order=self.high_order,
-                                  runs=True, table=table, acc_base=acc_base, tiles=batch.tiles_of(left))
-                side_done = torch.cuda.Event()
-                side_done.record(side)
-                ws.side_done = side_done
+        d_list, class_off, left = batch.fused_lists()
         # four rotating pinned readback slots: a slot is reused only after its batch has been finalised
         ri = self._readback_i % 4
         self._readback_i += 1
@@ -341,8 +320,41 @@ class LokiSegmentationStage:
             slot = torch.empty(3 * n + 1 + 256, dtype=torch.int32, pin_memory=True)
             self._readback[ri] = slot
         host = slot[:3 * n + 1]
-        host[:3 * n].copy_(counts, non_blocking=True)
-        host[3 * n:].copy_(lab_off[n:n + 1], non_blocking=True)
+        # the whole step is ONE call into the library (maze_stage_step): fused kernel on the lane stream, the
+        # oversize vignettes through the per-operator chain on the side stream, offsets, feature rows, readback
+        a = StepArgs()
+        a.vig, a.img_list = batch.d_vig.data_ptr(), d_list.data_ptr()
+        a.image, a.intensity = d_src.data_ptr(), d_image.data_ptr()
+        a.bits, a.mask, a.labels = bits.data_ptr(), mask.data_ptr(), labels.data_ptr()
+        a.counts, a.lab_off, a.stage_counter = counts.data_ptr(), lab_off.data_ptr(), staging[3].data_ptr()
+        a.acc_stage, a.hi_stage, a.ext_stage = staging[0].data_ptr(), staging[1].data_ptr(), staging[2].data_ptr()
+        a.table, a.counts_host = table.data_ptr(), host.data_ptr()
+        for c in range(5):
+            a.class_off[c] = int(class_off[c])
+        for k, (t, inv) in enumerate(passes):
+            a.pass_t[k], a.pass_invert[k] = int(t), int(inv)
+        a.n_img, a.t_int, a.n_pass, a.stage_cap = n, int(t_int), len(passes), cap
+        a.flags = RP_HIGH_ORDER if self.high_order else 0
+        a.left_n = len(left)
+        keep = None
+        if len(left):
+            sub, _, idx = self._sub(batch, left)
+            tiles_full = batch.tiles_of(left)
+            ar = ws.arena
+            keep = (ar.take(max(g.total_words, 1), torch.int32), ar.take(2 * len(left), torch.int32),
+                    ar.take(g.total_px, torch.int32), ar.take(sub.g.n_tiles + 1, torch.int32),
+                    ar.take(len(left) + 1, torch.int32), ar.take(cap * NACC, torch.int64), ar.take(cap * NEXT, torch.int32))
+            a.left_vig, a.left_tiles, a.left_idx = sub.d_vig.data_ptr(), sub.d_tiles.data_ptr(), idx.data_ptr()
+            a.left_tiles_full = tiles_full.data_ptr()
+            a.left_n_tiles, a.left_n_tiles_full = sub.g.n_tiles, tiles_full.numel() // 8
+            (a.scratch_plane, a.scratch_flags, a.scratch_parent, a.scratch_tile_scan, a.scratch_lab_off, a.scratch_acc,
+             a.scratch_ext) = (t.data_ptr() for t in keep)
+        check(lib().maze_stage_step(ctypes.byref(a), main.cuda_stream, side.cuda_stream), "maze_stage_step")
+        side_done = None
+        if len(left):
+            side_done = torch.cuda.Event()
+            side_done.record(side)
+            ws.side_done = side_done
         done = torch.cuda.Event()
         done.record(main)
         left_set = set(int(i) for i in left)
@@ -429,7 +441,7 @@ class LokiSegmentationStage:
             sub = DeviceBatch(g.subset(indices), batch.device)
             word_idx = np.concatenate([np.arange(g.word_off[i], g.word_off[i] + g.nwords[i]) for i in indices])
             cache[key] = (sub, torch.from_numpy(word_idx).to(batch.device),
-                          torch.as_tensor(np.asarray(indices, np.int64), device=batch.device))
+                          torch.as_tensor(np.asarray(indices, np.int32), device=batch.device))
         return cache[key]
 
     def _redo_generic(self, batch, indices, d_src, t_int, bits, mask, labels, n_labels):
@@ -442,7 +454,7 @@ class LokiSegmentationStage:
         else:
             sbits, _, slab_off, _ = self._front_generic(sub, d_src, t_int, labels=labels, mask=mask)
         bits[word_idx] = sbits[word_idx]
-        n_labels[idx] = slab_off[1:] - slab_off[:-1]
+        n_labels[idx.long()] = slab_off[1:] - slab_off[:-1]
 
     # ---- host entry: numpy in, numpy out --------------------------------------------------------------
     def _enqueue(self, images, foreground_pred, pool, want_mask, want_labels):
