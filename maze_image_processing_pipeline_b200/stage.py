@@ -128,10 +128,19 @@ class Workspace:
 
 
 class _PinnedPool:
-    """Reusable pinned host staging buffers (one per purpose), grown on demand."""
+    """Reusable pinned host staging buffers and device input buffers (one per purpose), grown on demand."""
 
     def __init__(self):
         self._bufs = {}
+        self._dev = {}
+
+    def dev(self, key, n, dtype, device):
+        """Device buffer for an upload: a fresh torch allocation per batch costs milliseconds (cudaMalloc)."""
+        t = self._dev.get(key)
+        if t is None or t.numel() < n or t.dtype != dtype or t.device != device:
+            t = torch.empty(int(max(n, 1) * 1.3) + 64, dtype=dtype, device=device)
+            self._dev[key] = t
+        return t[:n]
 
     def get(self, key, n, dtype):
         t = self._bufs.get(key)
@@ -155,6 +164,7 @@ class LokiSegmentationStage:
         self._ws_ring, self._ws_i = [Workspace(), Workspace(), Workspace()], 0  # the async path rotates three workspaces
         self._side = None
         self._copy_stream = None
+        self._small_copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._readback, self._readback_i = [], 0
 
@@ -472,12 +482,14 @@ class LokiSegmentationStage:
             self._copy_stream = torch.cuda.Stream(device=batch.device)
         h_img = pool.get("img", geom.total_px, torch.uint8)
         geom.pack_host(images, out=h_img.numpy())
-        d_image = h_img.to(batch.device, non_blocking=True)
+        d_image = pool.dev("img", geom.total_px, torch.uint8, batch.device)
+        d_image.copy_(h_img, non_blocking=True)
         d_pred = None
         if self.threshold is None:
             h_pred = pool.get("pred", geom.total_px, torch.uint8)
             geom.pack_host([np.asarray(p, dtype=bool).view(np.uint8) for p in foreground_pred], out=h_pred.numpy())
-            d_pred = h_pred.to(batch.device, non_blocking=True)
+            d_pred = pool.dev("pred", geom.total_px, torch.uint8, batch.device)
+            d_pred.copy_(h_pred, non_blocking=True)
         res = self.run_device(batch, d_image, d_pred)
         # the per-pixel outputs do not depend on the object counts: download them on the copy stream while
         # the next batch is packed, uploaded and computed
@@ -494,7 +506,9 @@ class LokiSegmentationStage:
             if want_labels and res.labels is not None:
                 h_lab = pool.get("labels", geom.total_px, torch.int32)
                 h_lab.copy_(res.labels, non_blocking=True)
-        return (geom, batch, res, h_mask, h_lab, pool, (d_image, d_pred))
+            copied = torch.cuda.Event()
+            copied.record(cs)
+        return (geom, batch, res, h_mask, h_lab, pool, (d_image, d_pred, copied))
 
     def _complete(self, inflight) -> StageResult:
         geom, batch, res, h_mask, h_lab, pool, _keepalive = inflight
@@ -502,15 +516,20 @@ class LokiSegmentationStage:
             return StageResult(geom, np.zeros(0, np.uint8), np.zeros(0, np.int32), np.zeros(1, np.int32),
                                np.zeros((0, NFEAT)))
         cs = self._copy_stream
+        if self._small_copy_stream is None or self._small_copy_stream.device != batch.device:
+            self._small_copy_stream = torch.cuda.Stream(device=batch.device)
+        ss = self._small_copy_stream  # table / offsets must not queue behind the NEXT batch's big downloads on cs
         main = torch.cuda.current_stream()
+        copied = _keepalive[2]
         res.finalize()  # waits for the counts; redoes the vignettes that overflowed the fused kernel
         if res._sync_main:  # the table (and, after a redo, the per-pixel outputs) came from kernels no host sync covered
             if res.ready is not None:
-                cs.wait_event(res.ready)
+                ss.wait_event(res.ready)
             else:
-                cs.wait_stream(main)
-        with torch.cuda.stream(cs):
+                ss.wait_stream(main)
+        with torch.cuda.stream(ss):
             if res.redone:  # rare: per-pixel outputs were rewritten by the per-operator path
+                ss.wait_event(copied)
                 if h_mask is not None:
                     h_mask.copy_(res.mask, non_blocking=True)
                 if h_lab is not None:
@@ -522,7 +541,8 @@ class LokiSegmentationStage:
             h_off.copy_(res.lab_off, non_blocking=True)
             keep = None if res.keep is None else res.keep.cpu().numpy()
             status = None if res.merge_status is None else res.merge_status.cpu().numpy()
-        cs.synchronize()
+        ss.synchronize()
+        copied.synchronize()
         if status is not None and (status == MAZE_ERR_TYPEERROR).any():
             # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
             raise TypeError("'NoneType' object is not iterable")
