@@ -42,9 +42,9 @@ KERNEL_BYTES_PER_PX = {
 }
 STAGE_BYTES_PER_PX = 6.0  # 1 R image + 1 W mask + 4 W labels
 # dram__bytes_read.sum + dram__bytes_write.sum of the four k_vignette_fused launches of one step divided by their
-# algorithmic bytes, from the ncu --set full capture summarised in profiles/ncu_fused_r1_v4_metrics.txt
-# (1.398 GB moved for 1.405 GB algorithmic: the intensity re-read hits L2, sparse label stores merge in L2)
-MEASURED_TRAFFIC_RATIO = {"k_vignette_fused": 0.995}
+# algorithmic bytes, from the ncu --set full capture summarised in profiles/ncu_fused_r1_final_metrics.txt
+# (1.428 GB moved for 1.405 GB algorithmic: the intensity re-read hits L2, sparse label stores merge in L2)
+MEASURED_TRAFFIC_RATIO = {"k_vignette_fused": 1.016}
 
 
 def job_sizes():
@@ -370,7 +370,7 @@ def run_b200(args):
     ratio = MEASURED_TRAFFIC_RATIO.get(top_name)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None if ratio is None else ratio * alg_bytes,
-                "traffic_source": "ncu --set full capture, profiles/ncu_fused_r1_v4_metrics.txt", "peak_source": peak_src,
+                "traffic_source": "ncu --set full capture, profiles/ncu_fused_r1_final_metrics.txt", "peak_source": peak_src,
                 "algorithmic_bytes_per_px": bpp, "avg_launch_ms": top_ms / top_cnt,
                 "share_of_step": top_ms / ms_instr}
     stage_gbs = STAGE_BYTES_PER_PX * n_px / (ms / 1e3) / 1e9
