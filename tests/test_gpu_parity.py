@@ -427,3 +427,35 @@ def test_streaming_map_equals_single_calls(mz):
             assert_tables_close(table[off[i]:off[i + 1]], t)
             rows += len(t)
         assert rows == len(table)
+
+
+def test_config3_radius_sweep_on_2048_frame(mz):
+    """BASELINE.json configs[2]: isotropic closing / opening on a 2048 x 2048 frame (bit-plane disk path up to
+    r = 32, exact-EDT path beyond)."""
+    rng = np.random.default_rng(3)
+    frame = mz.synth.synth_dense_frame(7, size=2048, n_blobs=60)
+    frame = np.maximum(frame, (rng.random(frame.shape) < 0.002).astype(np.uint8) * 255)  # specks for the opening
+    mask = frame > 40
+    for r in (1, 5, 32, 40):
+        for op in ("opening", "closing"):
+            want = getattr(oracle, f"isotropic_{op}")(mask, r)
+            got = getattr(mz.isotropic, f"isotropic_{op}")(mask, r)
+            assert np.array_equal(got, want), (op, r)
+
+
+def test_config4_dense_4096_frame_label_and_regionprops(mz):
+    """BASELINE.json configs[3]: a 4096 x 4096 frame with thousands of labels through the stage (too large for
+    the vignette-resident kernel: per-operator kernels) and through the per-image drop-ins."""
+    S = mz.stage
+    frame = mz.synth.synth_dense_frame(11, size=4096, n_blobs=3000)
+    want_lab, n = oracle.label(frame > 40)
+    assert n > 2000
+    want_tab = oracle.regionprops_table(want_lab, frame)
+    pp = S.SegmentationPostprocessingConfig()  # no morphology, no filters
+    res = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)([frame])
+    assert np.array_equal(res.labels(0), want_lab)
+    assert np.array_equal(res.mask(0), frame > 40)
+    assert len(res.table) == n
+    assert_tables_close(res.table, want_tab)
+    lab2, n2 = mz.measure.label(frame > 40, return_num=True)
+    assert n2 == n and np.array_equal(lab2, want_lab)

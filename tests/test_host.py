@@ -156,3 +156,44 @@ def test_sharded_tables_are_concatenated_in_image_order_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK 10" in outs[0]
+
+
+def test_regions_find_regions_recalc_metadata_and_features():
+    """Host-side tail of the stage (loki/pipeline.py:589-625) on a table produced by the oracle."""
+    import oracle
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    from maze_image_processing_pipeline_b200.regions import find_regions, objects_of, recalc_metadata
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    lab = np.zeros((40, 60), np.int32)
+    lab[5:15, 10:30] = 1          # 10 x 20 block
+    lab[20:23, 50:58] = 2         # small block near the right edge
+    lab[30:35, 2:6] = 4           # label 3 absent (removed by a filter): its row has area 0
+    img = np.full(lab.shape, 7, np.uint8)
+    img[lab == 2] = 200
+    img[6, 11] = 0
+    table = oracle.regionprops_table(lab, img)
+    g = BatchGeometry([40], [60])
+    res = StageResult(g, g.pack_host([(lab > 0).view(np.uint8)]), g.pack_host([lab], dtype=np.int32),
+                      np.array([0, 4], np.int32), table)
+    regs = list(find_regions(res, 0, padding=75, image=img))
+    assert [r.label for r in regs] == [1, 2, 4]
+    # padded slice: start clipped at 0, stop unclipped (FindRegions / _enlarge_slice semantics)
+    assert regs[0].bbox == (0, 0, 15 + 75, 30 + 75)
+    assert regs[0].image.shape == (40, 60) and regs[0].image.sum() == 200
+    m = recalc_metadata(regs[1], {"sample": "s"}, "{sample}_{object_sequence}")
+    # the reference unpacks bbox as (y0, x0, x1, y1): width = max_row - min_col, height = max_col - min_row
+    y0, x0, x1, y1 = regs[1].bbox
+    assert (m["object_posx"], m["object_posy"]) == (x0, y0)
+    assert m["object_width"] == x1 - x0 and m["object_height"] == y1 - y0
+    assert m["object_width"] == (23 + 75) - 0 and m["object_id"] == "s_2"
+    assert recalc_metadata(regs[0], {})["object_frac_invalid"] == 1 / 200
+    # min_intensity drops regions whose brightest pixel is darker
+    assert [r.label for r in find_regions(res, 0, min_intensity=100)] == [2]
+    objs = objects_of(res, 0, meta={"frame": 3}, padding=0, image=img)
+    assert len(objs) == 3 and objs[0]["frame"] == 3
+    o = objs[0]
+    assert o["object_area"] == 200 and o["object_bx"] == 10 and o["object_by"] == 5
+    assert o["object_width"] == 20 and o["object_height"] == 10   # ZooProcess overrides the swapped values
+    assert abs(o["object_x"] - 19.5) < 1e-12 and abs(o["object_y"] - 9.5) < 1e-12
+    assert abs(o["object_angle"] - (table[0, oracle.F_ORIENT] / np.pi * 180 + 90)) < 1e-12
+    assert o["object_intden"] == 200 * o["object_mean"] and o["object_range"] == 7.0
