@@ -224,6 +224,31 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa(local_rank, world):
+    """Multi-rank runs: pin this rank (and the packing threads it spawns) to the CPUs of the NUMA node its GPU
+    hangs off, so that pinned staging buffers, the pack memcpy and the PCIe DMA stay on one socket."""
+    if world <= 1:
+        return None
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def workload_config(args, batch):
     return {"workload": "configs[1]: 100k synthetic variable-size vignettes (64-1024 px, log-uniform), "
                         f"batches of {batch}", "batch_vignettes": batch, "threshold_brighter": THRESHOLD,
@@ -244,8 +269,11 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # share the host cores between the ranks for the packing threads
+        os.environ.setdefault("MAZE_PACK_THREADS", str(max(2, min(8, host_cores() // max(1, world // 2)))))
     _lib.lib()
 
     def barrier():

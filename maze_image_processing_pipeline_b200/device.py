@@ -134,7 +134,12 @@ class BatchGeometry:
         nbytes = (self.npx * dtype.itemsize).astype(np.int64)
         offs = (self.pix_off[:-1] * dtype.itemsize).astype(np.int64)
         if threads is None:
-            threads = min(16, max(1, (os.cpu_count() or 2) // 2))
+            env = os.environ.get("MAZE_PACK_THREADS")
+            try:
+                avail = len(os.sched_getaffinity(0))
+            except Exception:
+                avail = os.cpu_count() or 2
+            threads = int(env) if env else min(16, max(1, avail // 2))
         check(lib().maze_host_pack(ptrs.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, n,
                                    out.__array_interface__["data"][0], int(threads)), "maze_host_pack")
         return out
