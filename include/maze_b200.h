@@ -200,7 +200,7 @@ int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,
  * image: bytes that are thresholded (pixel > t_int); intensity: bytes the intensity features are
  * taken from (may be the same pointer, or NULL).
  * img_list (device) holds the vignette indices grouped into MAZE_FUSED_CLASSES size classes (h*wpr
- * words <= MAZE_FUSED_CAP0..3); class c is img_list[class_off_host[c] .. class_off_host[c+1]).
+ * words <= MAZE_FUSED_CAPS[c]); class c is img_list[class_off_host[c] .. class_off_host[c+1]).
  * Larger vignettes must go through the per-operator entry points above.  pass_t_host /
  * pass_invert_host: the d2 threshold and erosion(0)/dilation(1) flag of every pass, as for
  * maze_morph_pass.  flags: MAZE_RP_HIGH_ORDER, MAZE_FUSED_NO_PROPS.
@@ -210,11 +210,8 @@ int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,
  * stage_cap rows of acc_stage [MAZE_NACC u64 each] / hi_stage [8 doubles] / ext_stage [MAZE_NEXT
  * int32] were used up: use maze_regionprops for those).  stage_counter: one int32 of scratch. */
 #define MAZE_FUSED_NO_PROPS 4 /* flag: labels only, no accumulators are staged (acc_base[i] = -1) */
-#define MAZE_FUSED_CLASSES 4
-#define MAZE_FUSED_CAP0 1024
-#define MAZE_FUSED_CAP1 4096
-#define MAZE_FUSED_CAP2 12288
-#define MAZE_FUSED_CAP3 28320
+#define MAZE_FUSED_CLASSES 8
+#define MAZE_FUSED_CAPS {1024, 2560, 4096, 6144, 9216, 13312, 19456, 28320}
 int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig,
                         const int32_t *img_list, const int32_t *class_off_host, int t_int, int n_pass,
                         const int32_t *pass_t_host, const int32_t *pass_invert_host, int flags,

@@ -26,7 +26,7 @@ NACC = 12
 NEXT = 8
 RP_HIGH_ORDER = 1
 RP_RUNS = 2
-FUSED_CAPS = (1024, 4096, 12288, 28320)
+FUSED_CAPS = (1024, 2560, 4096, 6144, 9216, 13312, 19456, 28320)  # MAZE_FUSED_CAPS of include/maze_b200.h
 FUSED_NO_PROPS = 4
 
 
@@ -37,7 +37,7 @@ class StepArgs(ctypes.Structure):
         "mask", "labels", "counts", "lab_off", "stage_counter", "acc_stage", "hi_stage", "ext_stage", "table",
         "scratch_plane", "scratch_flags", "scratch_parent", "scratch_tile_scan", "scratch_lab_off", "scratch_acc",
         "scratch_ext", "counts_host")]
-        + [("class_off", ctypes.c_int32 * 5), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
+        + [("class_off", ctypes.c_int32 * (len(FUSED_CAPS) + 1)), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
         + [(k, ctypes.c_int32) for k in ("n_img", "left_n", "left_n_tiles", "left_n_tiles_full", "t_int", "n_pass",
                                          "flags", "stage_cap")])
 

@@ -817,7 +817,7 @@ extern "C" int maze_vignette_stage(const uint8_t *image, const uint8_t *intensit
     MAZE_CUDA(cudaMemsetAsync(stage_counter, 0, sizeof(int32_t), s), "stage counter");
     FusedArgs a = {image, intensity, vig, bits, mask, labels, n_labels, fallback, acc_base, stage_counter,
                    (u64 *)acc_stage, hi_stage, ext_stage};
-    const int caps[MAZE_FUSED_CLASSES] = {MAZE_FUSED_CAP0, MAZE_FUSED_CAP1, MAZE_FUSED_CAP2, MAZE_FUSED_CAP3};
+    const int caps[MAZE_FUSED_CLASSES] = MAZE_FUSED_CAPS;
     // The size classes touch disjoint vignettes, so their kernels run CONCURRENTLY: the class of the
     // largest vignettes (one long CTA per SM) goes to the caller's stream, the others to forked streams,
     // and the small CTAs fill the SMs the big ones leave idle.
@@ -834,9 +834,10 @@ extern "C" int maze_vignette_stage(const uint8_t *image, const uint8_t *intensit
             MAZE_CUDA(cudaStreamWaitEvent(sc, fk->fork, 0), "fork wait");
         }
         int rc;
-        if (c == 0) rc = launch_class<128>(n, caps[c], sc, list, prm, a);
-        else if (c == 1) rc = launch_class<256>(n, caps[c], sc, list, prm, a);
-        else if (c == 2) rc = launch_class<512>(n, caps[c], sc, list, prm, a);
+        // threads per CTA by class: finer shared-memory classes let CTAs of different sizes share an SM
+        if (caps[c] <= 1024) rc = launch_class<128>(n, caps[c], sc, list, prm, a);
+        else if (caps[c] <= 4096) rc = launch_class<256>(n, caps[c], sc, list, prm, a);
+        else if (caps[c] <= 19456) rc = launch_class<512>(n, caps[c], sc, list, prm, a);
         else rc = launch_class<1024>(n, caps[c], sc, list, prm, a);
         if (rc != MAZE_OK) return rc;
         if (sc != s) {

@@ -339,7 +339,7 @@ class LokiSegmentationStage:
         a.counts, a.lab_off, a.stage_counter = counts.data_ptr(), lab_off.data_ptr(), staging[3].data_ptr()
         a.acc_stage, a.hi_stage, a.ext_stage = staging[0].data_ptr(), staging[1].data_ptr(), staging[2].data_ptr()
         a.table, a.counts_host = table.data_ptr(), host.data_ptr()
-        for c in range(5):
+        for c in range(len(class_off)):
             a.class_off[c] = int(class_off[c])
         for k, (t, inv) in enumerate(passes):
             a.pass_t[k], a.pass_invert[k] = int(t), int(inv)
