@@ -153,14 +153,22 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's scipy restatement of the reference chain on host cores
 # ------------------------------------------------------------------------------------------------
+_CPU_MERGE = 0
+
+
 def _cpu_one(img):
     from oracle import scipy_chain
-    mask, labels, table = scipy_chain.loki_chain(img, THRESHOLD, R_OPEN, R_CLOSE)
+    try:
+        mask, labels, table = scipy_chain.loki_chain(img, THRESHOLD, R_OPEN, R_CLOSE, merge_segments_distance=_CPU_MERGE)
+    except TypeError:  # the reference's merge_labels raises when a bridge swallows a label (merge_labels.py:19-20)
+        return 0, 0
     return int(labels.max()), int(mask.sum())
 
 
-def _cpu_pool(cores):
+def _cpu_pool(cores, merge=0):
     import multiprocessing as mp
+    global _CPU_MERGE
+    _CPU_MERGE = merge  # inherited by the forked workers
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     import oracle
     oracle.build()
@@ -198,7 +206,7 @@ def run_reference(args):
         return 0
     cores = host_cores()
     per_step = max(cores, min(4 * cores, 256))
-    pool = _cpu_pool(cores)
+    pool = _cpu_pool(cores, args.merge)
     imgs = cpu_sample_images(per_step)
     px = sum(int(i.size) for i in imgs)
     for _ in range(args.warmup):
@@ -287,7 +295,7 @@ def run_b200(args):
     need = args.steps + args.warmup
     pp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN,
                                             merge_segments_distance=args.merge)
-    stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp)
+    stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore")
 
     # resident inputs: the batches this rank will touch, generated on the device
     batches = []
@@ -409,7 +417,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         n_s = max(cores, min(4 * cores, 256))
-        pool = _cpu_pool(cores)
+        pool = _cpu_pool(cores, args.merge)
         imgs = host_batches[0][:n_s]
         time_cpu(pool, imgs[: max(1, len(imgs) // 4)])
         dt, _ = time_cpu(pool, imgs)

@@ -96,6 +96,7 @@ class StageResult:
         self.lab_off = lab_off
         self.table = table
         self.keep = keep  # threshold branch: vignettes that survive the empty-mask filter
+        self.merge_failed = None  # merge_errors="ignore": vignettes where merge_labels hit the reference's TypeError
 
     def __len__(self):
         return self.geometry.n_img
@@ -151,8 +152,13 @@ class _PinnedPool:
 
 
 class LokiSegmentationStage:
-    def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True):
+    def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True,
+                 merge_errors="raise"):
+        """merge_errors: "raise" (the reference's behaviour: merge_labels raises TypeError when a bridge
+        swallows a label, merge_labels.py:19-20, and the run aborts) or "ignore" (keep the labels as the loop
+        left them for those vignettes and list them in StageResult.merge_failed)."""
         self.fused = fused
+        self.merge_errors = merge_errors
         if threshold is None and postprocess is None:
             raise ValueError("exactly one of threshold / postprocess (or both, for the composite stage) is required")
         self.threshold = threshold
@@ -543,11 +549,16 @@ class LokiSegmentationStage:
             status = None if res.merge_status is None else res.merge_status.cpu().numpy()
         ss.synchronize()
         copied.synchronize()
+        failed = None
         if status is not None and (status == MAZE_ERR_TYPEERROR).any():
-            # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
-            raise TypeError("'NoneType' object is not iterable")
-        return StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
-                           h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
+            if self.merge_errors == "raise":
+                # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
+                raise TypeError("'NoneType' object is not iterable")
+            failed = np.nonzero(status == MAZE_ERR_TYPEERROR)[0]
+        out = StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
+                          h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
+        out.merge_failed = failed
+        return out
 
     def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,
                  want_mask=True, want_labels=True) -> StageResult:
