@@ -10,7 +10,7 @@ independently log-uniform in [64, 1024]), processed in batches of --batch vignet
 pass of the whole chain (threshold 40 -> isotropic opening r=1 -> isotropic closing r=2 -> 8-connected
 labelling -> regionprops, mask bytes written) over one batch.  Batch b holds vignettes
 [b*B, (b+1)*B) of the job; rank r of N works on batches r, r+N, ... (weak scaling, no collective on
-the data path).  Every batch is > L2 (about 250 MB of pixels), so no L2 flush is needed.
+the data path).  Every batch is > L2 (about 490 MB of pixels at the default 4096 vignettes), so no L2 flush is needed.
 """
 from __future__ import annotations
 
@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--merge", type=int, default=0, help="merge_segments_distance (0 = off, the schema default)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
