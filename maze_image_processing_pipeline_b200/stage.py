@@ -113,9 +113,9 @@ class StageResult:
 
 
 class Workspace:
-    """Device buffers of the fused path, allocated once and grown on demand so that the steady state
-    makes no allocator calls.  Results of run_device alias these buffers and stay valid until the
-    next run_device on the same stage."""
+    """Device buffers of the fused path, allocated once and grown on demand so that the steady state makes
+    no allocator calls.  The stage rotates three of them (each with its own lane / side stream and scratch
+    arena); results of run_device alias one and stay valid for the next two run_device calls."""
 
     def __init__(self):
         self._t = {}
@@ -168,25 +168,12 @@ class LokiSegmentationStage:
         self._pool = _PinnedPool()
         self._ws = Workspace()
         self._ws_ring, self._ws_i = [Workspace(), Workspace(), Workspace()], 0  # the async path rotates three workspaces
-        self._side = None
         self._copy_stream = None
         self._small_copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
-    def _passes_all(self):
-        """All passes incl. identities (t == 0), for maze_front_chain; None if a radius needs the exact EDT."""
-        pp = self.postprocess
-        out = []
-        if pp.opening_radius > 0:
-            out += [(fold_erosion_radius(pp.opening_radius), 0), (fold_dilation_radius(pp.opening_radius), 1)]
-        if pp.closing_radius > 0:
-            out += [(fold_dilation_radius(pp.closing_radius), 1), (fold_erosion_radius(pp.closing_radius), 0)]
-        if any(t >= (MAX_DISK_RADIUS + 1) ** 2 for t, _ in out):
-            return None
-        return [(t, inv) for t, inv in out if t != 0]
-
     def _passes(self):
         """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path."""
         pp = self.postprocess
@@ -233,7 +220,6 @@ class LokiSegmentationStage:
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
         if passes is not None and not filters:
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
-        staged = None
         if passes is None:
             bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
             n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
@@ -464,7 +450,7 @@ class LokiSegmentationStage:
         """Run the per-operator kernels on a few vignettes of the batch, in place in the batch buffers."""
         sub, word_idx, idx = self._sub(batch, indices)
         sub.arena = batch.arena
-        passes = self._passes_all()
+        passes = self._passes()
         if passes is not None:
             sbits, slab_off = sub.front_chain(d_src, t_int, passes, labels, mask)
         else:
