@@ -180,12 +180,14 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
  * the distances at which labels were merged.  index_state (2 * n_img int32): the length of the
  * label list the loop started from and how many entries it popped (the list itself, popped entries
  * first, is left in obj_scratch + 2 * lab_off[i]).  status (n_img int32): MAZE_OK or
- * MAZE_ERR_TYPEERROR per vignette. */
+ * MAZE_ERR_TYPEERROR per vignette.  order (optional, n_img int32): CTA b works on vignette order[b] (put the
+ * largest vignettes first: one CTA per vignette, the longest ones decide the makespan). */
 int maze_merge_labels(const int32_t *labels, int32_t *labels_out, const maze_vignette_t *vig, int n_img,
                       const int32_t *lab_off, int n_obj_cap, const int32_t *index, const int32_t *index_off,
                       int have_max, double max_distance, double path_tolerance,
                       int32_t *d2a, int32_t *d2b, int32_t *d2c, int32_t *obj_scratch,
-                      double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status, void *stream);
+                      double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status,
+                      const int32_t *order, void *stream);
 
 /* Synthetic LOKI-shaped vignettes for the benchmark: dark noisy background plus
  * 1-6 anisotropic Gaussian blobs per vignette, counter-based RNG keyed by (seed, vignette, pixel). */

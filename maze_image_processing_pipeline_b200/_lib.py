@@ -83,7 +83,8 @@ SIGNATURES = {
     "maze_remove_small_objects": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i64, _vp],
     "maze_max_label": [_vp, _vp, _i, _vp, _i, _vp, _vp],
     "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
-    "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                          _vp],
     "maze_synth_vignettes": [_vp, _vp, _i, _vp, _i, _u64, _i64, _vp],
     "maze_vignette_stage": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
                             _vp, _vp, _vp, _vp],

@@ -12,7 +12,7 @@
 
 #include "maze_common.cuh"
 
-#define MG_CTA 512
+#define MG_CTA 1024
 #define MG_INF (1 << 24)
 
 struct MgShared {
@@ -29,11 +29,21 @@ __device__ __forceinline__ void mg_bbox(MgShared &S, const int32_t *L, int H, in
 {
     int r0 = 0x7fffffff, r1 = -1, c0 = 0x7fffffff, c1 = -1;
     int n = H * W;
-    for (int p = threadIdx.x; p < n; p += MG_CTA)
-        if (L[p] == l) {
-            int y = p / W, x = p - y * W;
-            r0 = min(r0, y); r1 = max(r1, y); c0 = min(c0, x); c1 = max(c1, x);
+    {
+        const int sy = MG_CTA / W, sx = MG_CTA - sy * W;
+        int y = threadIdx.x / W, x = threadIdx.x - y * W;
+        for (int p0 = threadIdx.x; p0 < n; p0 += 4 * MG_CTA) { // four independent loads in flight
+            int v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (p0 + u * MG_CTA < n) ? L[p0 + u * MG_CTA] : l - 1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (v[u] == l) { r0 = min(r0, y); r1 = max(r1, y); c0 = min(c0, x); c1 = max(c1, x); }
+                y += sy; x += sx;
+                if (x >= W) { x -= W; y++; }
+            }
         }
+    }
     r0 = __reduce_min_sync(FULL, r0); r1 = __reduce_max_sync(FULL, r1);
     c0 = __reduce_min_sync(FULL, c0); c1 = __reduce_max_sync(FULL, c1);
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,11 +186,12 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
                                                          const int32_t *__restrict__ index_off, int have_max,
                                                          double max_distance, double path_tolerance, int32_t *d2a,
                                                          int32_t *d2b, int32_t *gbuf, int32_t *obj_scratch,
-                                                         double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status)
+                                                         double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status,
+                                                         const int32_t *__restrict__ order)
 {
     __shared__ MgShared S;
     __shared__ int s_scan[MG_CTA / 32 + 2];
-    const int img = blockIdx.x;
+    const int img = order ? order[blockIdx.x] : blockIdx.x; // longest vignettes first when an order is given
     maze_vignette_t v = vig[img];
     const int H = v.h, W = v.w, npx = H * W;
     const int32_t *L = labels + v.pix_off;
@@ -258,9 +269,17 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
         // :83 per-label minimum of distmap, initial = max_dist
         for (int j = threadIdx.x; j < bound; j += MG_CTA) mintab[j] = 0xffffffffu;
         __syncthreads();
-        for (int p = threadIdx.x; p < npx; p += MG_CTA) {
-            int l = L[p];
-            if (l > 0 && l <= bound) atomicMin(mintab + (l - 1), (uint32_t)A[p]);
+        for (int p0 = threadIdx.x; p0 < npx; p0 += 4 * MG_CTA) { // four independent pixels per thread in flight
+            int l[4], a[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int p = p0 + u * MG_CTA;
+                l[u] = p < npx ? L[p] : 0;
+                a[u] = (l[u] > 0 && l[u] <= bound) ? A[p] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (l[u] > 0 && l[u] <= bound) atomicMin(mintab + (l[u] - 1), (uint32_t)a[u]);
         }
         __syncthreads();
         u64 best = ~0ull;
@@ -295,26 +314,66 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
         }
         const double sfillB = sqrt((double)fillB);
         double md = INFINITY;
-        for (int p = threadIdx.x; p < npx; p += MG_CTA) { // :90-92
-            int y = p / W, x = p - y * W;
-            bool inb = !(y < winB[0] || y >= winB[1] || x < winB[2] || x >= winB[3]);
-            double sb = inb ? sqrt((double)B[p]) : sfillB;
-            double s = sqrt((double)A[p]) + sb;
-            md = s < md ? s : md;
+        // :90-92 min over all pixels of sqrt(A) + sqrt(B).  sqrt(a) + sqrt(b) >= sqrt(a + b), so a pixel whose
+        // a + b is clearly above the running minimum squared cannot lower it: most pixels need no sqrt at all
+        const int sy = MG_CTA / W, sx = MG_CTA - sy * W;
+        {
+            int y = threadIdx.x / W, x = threadIdx.x - y * W;
+            for (int p0 = threadIdx.x; p0 < npx; p0 += 4 * MG_CTA) {
+                int a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int p = p0 + u * MG_CTA;
+                    bool inb = !(y < winB[0] || y >= winB[1] || x < winB[2] || x >= winB[3]);
+                    a[u] = p < npx ? A[p] : 0x3fffffff;
+                    b[u] = (p < npx && inb) ? B[p] : fillB;
+                    y += sy; x += sx;
+                    if (x >= W) { x -= W; y++; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if ((double)a[u] + (double)b[u] > md * md * (1.0 + 1e-12)) continue;
+                    double s = sqrt((double)a[u]) + sqrt((double)b[u]);
+                    md = s < md ? s : md;
+                }
+            }
         }
         md = mg_min_double(S, md);
         if (have_max && md > max_distance) break; // :94-96
         const double lim = md + path_tolerance;
         if (threadIdx.x == 0 && merge_dist) merge_dist[obj0 + nm] = md; // :100
         nm++;
-        for (int p = threadIdx.x; p < npx; p += MG_CTA) {
-            int y = p / W, x = p - y * W;
-            bool inb = !(y < winB[0] || y >= winB[1] || x < winB[2] || x >= winB[3]);
-            int b2 = inb ? B[p] : fillB;
-            int a2 = A[p];
-            double s = sqrt((double)a2) + sqrt((double)b2);
-            if (L[p] == cur_l || s <= lim) O[p] = l0; // :98, :103-106 (labelmap only ever holds l0)
-            if (b2 < a2) A[p] = b2;                   // :109-111
+        {
+            // :98, :103-106 (labelmap only ever holds l0) and :109-111.  sqrt(a+b) <= sqrt(a)+sqrt(b) <= sqrt(2(a+b))
+            // decides most pixels on the integers; the float64 compare runs only in the narrow band between
+            const double lim2 = lim * lim;
+            int y = threadIdx.x / W, x = threadIdx.x - y * W;
+            for (int p0 = threadIdx.x; p0 < npx; p0 += 4 * MG_CTA) {
+                int a[4], b[4], l[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int p = p0 + u * MG_CTA;
+                    bool inb = !(y < winB[0] || y >= winB[1] || x < winB[2] || x >= winB[3]);
+                    a[u] = p < npx ? A[p] : 0;
+                    b[u] = (p < npx && inb) ? B[p] : fillB;
+                    l[u] = p < npx ? L[p] : 0;
+                    y += sy; x += sx;
+                    if (x >= W) { x -= W; y++; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    int p = p0 + u * MG_CTA;
+                    if (p >= npx) continue;
+                    const double ab = (double)a[u] + (double)b[u];
+                    bool fill = l[u] == cur_l;
+                    if (!fill && !(ab > lim2 * (1.0 + 1e-12))) {
+                        if (2.0 * ab < lim2 * (1.0 - 1e-12)) fill = true;
+                        else fill = sqrt((double)a[u]) + sqrt((double)b[u]) <= lim;
+                    }
+                    if (fill) O[p] = l0;
+                    if (b[u] < a[u]) A[p] = b[u];
+                }
+            }
         }
         __syncthreads();
     }
@@ -325,13 +384,14 @@ extern "C" int maze_merge_labels(const int32_t *labels, int32_t *labels_out, con
                                  const int32_t *lab_off, int n_obj_cap, const int32_t *index,
                                  const int32_t *index_off, int have_max, double max_distance, double path_tolerance,
                                  int32_t *d2a, int32_t *d2b, int32_t *gbuf, int32_t *obj_scratch, double *merge_dist,
-                                 int32_t *n_merge, int32_t *index_state, int32_t *status, void *stream)
+                                 int32_t *n_merge, int32_t *index_state, int32_t *status, const int32_t *order,
+                                 void *stream)
 {
     if (n_img <= 0) return MAZE_OK;
     if (index && !index_off) return MAZE_ERR_BADARG;
     MAZE_KERNEL(KID_MERGE_LABELS, (cudaStream_t)stream, k_merge_labels<<<n_img, MG_CTA, 0, (cudaStream_t)stream>>>(labels, labels_out, vig, lab_off, n_obj_cap, index,
                                                                 index_off, have_max, max_distance, path_tolerance,
                                                                 d2a, d2b, gbuf, obj_scratch, merge_dist, n_merge,
-                                                                index_state, status));
+                                                                index_state, status, order));
     return MAZE_OK;
 }

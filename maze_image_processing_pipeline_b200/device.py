@@ -402,12 +402,14 @@ class DeviceBatch:
         index_state = torch.zeros(2 * g.n_img, dtype=torch.int32, device=self.device)
         status = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
         have_max = max_distance is not None
+        if not hasattr(self, "_merge_order"):  # largest vignettes first
+            self._merge_order = torch.from_numpy(np.argsort(-g.npx, kind="stable").astype(np.int32)).to(self.device)
         check(lib().maze_merge_labels(labels.data_ptr(), labels_out.data_ptr(), self.d_vig.data_ptr(), g.n_img,
                                       lab_off.data_ptr(), n_obj, _ptr(index), _ptr(index_off), int(have_max),
                                       float(max_distance) if have_max else 0.0, float(path_tolerance),
                                       d2a.data_ptr(), d2b.data_ptr(), d2c.data_ptr(), obj_scratch.data_ptr(),
                                       merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
-                                      status.data_ptr(), _stream()), "maze_merge_labels")
+                                      status.data_ptr(), self._merge_order.data_ptr(), _stream()), "maze_merge_labels")
         return merge_dist, n_merge, index_state, status, obj_scratch
 
     def front_chain(self, d_src, t_int, passes, labels, mask):
