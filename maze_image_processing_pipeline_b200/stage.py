@@ -572,6 +572,46 @@ class LokiSegmentationStage:
                 yield self._complete(pending)
 
 
+def stream_objects(stage: "LokiSegmentationStage", objects, batch_size: int = 2048, image_key: str = "image",
+                   meta_key: str = "meta", padding: int = 75, min_intensity=None, object_id_fmt=None):
+    """Adapter for a morphocut-style object stream (the place of the `Call` chain of
+    maze_ipp/loki/pipeline.py:396-459 and the FindRegions / recalc_metadata / CalculateZooProcessFeatures tail,
+    :589-625): consumes an iterable of dict-like stream objects that carry a uint8 vignette or frame under
+    `image_key`, buffers `batch_size` of them, runs the stage once per buffer (pipelined over buffers) and yields,
+    in input order, one dict per input object with the keys of the input plus `mask`, `labels` and `objects` (a
+    list of metadata dicts, one per segmented object, see regions.objects_of)."""
+    from .regions import objects_of
+
+    def buffers():
+        buf = []
+        for obj in objects:
+            buf.append(obj)
+            if len(buf) == batch_size:
+                yield buf
+                buf = []
+        if buf:
+            yield buf
+
+    pending = []
+
+    def images():
+        for buf in buffers():
+            pending.append(buf)
+            yield [np.ascontiguousarray(o[image_key], dtype=np.uint8) for o in buf]
+
+    for res in stage.map(images()):
+        buf = pending.pop(0)
+        for i, obj in enumerate(buf):
+            out = dict(obj)
+            out["mask"] = res.mask(i).copy()
+            lab = res.labels(i)
+            out["labels"] = None if lab is None else lab.copy()
+            out["objects"] = objects_of(res, i, meta=obj.get(meta_key, {}) if hasattr(obj, "get") else {},
+                                        padding=padding, min_intensity=min_intensity, image=obj[image_key],
+                                        object_id_fmt=object_id_fmt) if lab is not None else []
+            yield out
+
+
 def shard_bounds(n_items: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of n_items for `rank` of `world` (images are independent)."""
     base, rem = divmod(n_items, world)

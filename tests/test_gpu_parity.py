@@ -459,3 +459,25 @@ def test_config4_dense_4096_frame_label_and_regionprops(mz):
     assert_tables_close(res.table, want_tab)
     lab2, n2 = mz.measure.label(frame > 40, return_num=True)
     assert n2 == n and np.array_equal(lab2, want_lab)
+
+
+def test_stream_objects_adapter_and_odd_geometries(mz):
+    """The stream adapter (input order, per-object metadata) and vignettes the fused kernel must hand to the
+    per-operator path: wider than 65535 px, one-pixel rows / columns."""
+    S = mz.stage
+    rng = np.random.default_rng(2)
+    imgs = mz.synth.synth_batch(77, 5, lo=64, hi=160)
+    wide = (rng.random((3, 70000)) < 0.3).astype(np.uint8) * 200
+    imgs += [wide, np.full((1, 300), 90, np.uint8), np.full((257, 1), 90, np.uint8)]
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+    objs = [{"image": im, "meta": {"object_id": f"v{k}"}, "k": k} for k, im in enumerate(imgs)]
+    out = list(S.stream_objects(st, objs, batch_size=3, padding=0))
+    assert [o["k"] for o in out] == list(range(len(imgs)))
+    for o, im in zip(out, imgs):
+        mask, labels, table = scipy_chain.loki_chain(im, 40, 1, 2)
+        assert np.array_equal(o["mask"], mask) and np.array_equal(o["labels"], labels)
+        live = table[table[:, oracle.F_AREA] > 0]
+        assert [d["object_sequence"] for d in o["objects"]] == [int(v) for v in live[:, oracle.F_LABEL]]
+        assert [d["object_area"] for d in o["objects"]] == [float(v) for v in live[:, oracle.F_AREA]]
+        assert all(d["object_id"] == f"v{o['k']}" for d in o["objects"])
