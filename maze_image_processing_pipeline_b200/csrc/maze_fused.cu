@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     {
         const uint8_t *base = image + v.pix_off;
         const int t = prm.t_int;
-        const uint32_t t4 = (uint32_t)(t & 0xff) * 0x01010101u;
+        // byte-wise "pixel > t" on four pixels with three integer ops instead of the emulated SIMD compare:
+        // t < 128: px > t  <=>  msb(px) | msb(low7(px) + 127 - t);  t >= 128: msb(px) & msb(low7(px) + 255 - t)
+        const uint32_t addc = (uint32_t)((t < 128 ? 127 - t : 255 - t) & 0x7f) * 0x01010101u;
+        const bool hi_t = t >= 128;
         int y = y_first, k = k_first;
         for (int w = tid; w < words; w += T) {
             int nvalid = min(32, W - 32 * k);
@@ -278,8 +281,9 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                     if (4 * i < nvalid) {
                         uint32_t hi = __ldg(q + i + 1); // at most 4 bytes past the row: inside the padded slot
                         uint32_t px = __funnelshift_r(lo, hi, 8 * a);
-                        uint32_t cmp = __vcmpgtu4(px, t4) & 0x01010101u;
-                        word |= ((cmp * 0x01020408u) >> 24 & 0xfu) << (4 * i);
+                        uint32_t s7 = (px & 0x7f7f7f7fu) + addc;          // no carry across bytes
+                        uint32_t m = (hi_t ? (s7 & px) : (s7 | px)) & 0x80808080u;
+                        word += (((m >> 7) * 0x01020408u) >> 24) << (4 * i); // gather the four msbs into a nibble
                         lo = hi;
                     }
                 }
