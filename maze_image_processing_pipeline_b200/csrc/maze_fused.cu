@@ -589,8 +589,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                     if (c0 < (int)a) nib &= 0xfu << ((int)a - c0);
                     if (c0 + 3 > (int)b) nib &= 0xfu >> (c0 + 3 - (int)b);
                     uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                    aV += __vsadu4(px & bm, 0u);
-                    aZ += __popc(__vcmpeq4(px, 0u) & bm & 0x01010101u);
+                    aV = __dp4a(px & bm, 0x01010101u, aV);                              // sum of the four masked bytes
+                    aZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u); // bytes equal to 0
                     vmn = __vminu4(vmn, px | ~bm);
                     vmx = __vmaxu4(vmx, px & bm);
                 }
