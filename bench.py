@@ -223,7 +223,7 @@ def run_reference(args):
         "mpix_per_s": px * args.steps / total / 1e6, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, per_step),
+        "config": dict(workload_config(args, args.batch), reference_sample_per_step=per_step),
         "cpu_baseline": {"value": v, "unit": "vignettes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "vignettes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,8 +333,8 @@ def run_b200(args):
     for i in range(args.warmup, need):
         res, _ = step(i)
         inflight.append(res)
-        if len(inflight) > 2:
-            n_obj += inflight.pop(0).n_obj  # readback check two steps behind (three rotating workspaces)
+        if len(inflight) > stage.n_lanes - 1:
+            n_obj += inflight.pop(0).n_obj  # readback check n_lanes - 1 steps behind (rotating workspaces)
         n_vig += batches[i][0].g.n_img
         n_px += batches[i][0].g.pixels
     for r in inflight:

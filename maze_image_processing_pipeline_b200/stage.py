@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 import ctypes
+import os
 
 from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, RP_HIGH_ORDER, StepArgs, check, lib
 from ._lib import MAX_DISK_RADIUS
@@ -114,7 +115,7 @@ class StageResult:
 
 class Workspace:
     """Device buffers of the fused path, allocated once and grown on demand so that the steady state makes
-    no allocator calls.  The stage rotates three of them (each with its own lane / side stream and scratch
+    no allocator calls.  The stage rotates n_lanes (default four) of them (each with its own lane / side stream and scratch
     arena); results of run_device alias one and stay valid for the next two run_device calls."""
 
     def __init__(self):
@@ -167,7 +168,8 @@ class LokiSegmentationStage:
         self.high_order = high_order
         self._pool = _PinnedPool()
         self._ws = Workspace()
-        self._ws_ring, self._ws_i = [Workspace(), Workspace(), Workspace()], 0  # the async path rotates three workspaces
+        self.n_lanes = int(os.environ.get("MAZE_LANES", "4"))  # workspaces (each with its own lane stream) in rotation
+        self._ws_ring, self._ws_i = [Workspace() for _ in range(self.n_lanes)], 0
         self._copy_stream = None
         self._small_copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
@@ -266,7 +268,7 @@ class LokiSegmentationStage:
         GPU never drains between batches.  The caller's stream is joined at the start (inputs) only; the
         result carries a `ready` event and DeviceResult.finalize() waits for it."""
         dev = batch.device
-        ws = self._ws_ring[self._ws_i % 3]   # results stay valid for the next two calls
+        ws = self._ws_ring[self._ws_i % self.n_lanes]   # results stay valid for the next n_lanes - 1 calls
         self._ws_i += 1
         if getattr(ws, "lane", None) is None or ws.lane.device != dev:
             ws.lane = torch.cuda.Stream(device=dev)
@@ -312,10 +314,11 @@ class LokiSegmentationStage:
                    ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
         table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
         d_list, class_off, left = batch.fused_lists()
-        # four rotating pinned readback slots: a slot is reused only after its batch has been finalised
-        ri = self._readback_i % 4
+        # rotating pinned readback slots (one more than lanes): a slot is reused only after its batch was finalised
+        nslot = self.n_lanes + 1
+        ri = self._readback_i % nslot
         self._readback_i += 1
-        while len(self._readback) < 4:
+        while len(self._readback) < nslot:
             self._readback.append(None)
         slot = self._readback[ri]
         if slot is None or slot.numel() < 3 * n + 1:
@@ -556,7 +559,7 @@ class LokiSegmentationStage:
 
     def map(self, batches, want_mask=True, want_labels=True):
         """Streaming form: ``for res in stage.map(iterable_of_image_lists)``.  Packing and upload of batch i+1
-        overlap the kernels and the download of batch i (three rotating pinned buffer sets, two device
+        overlap the kernels and the download of batch i (three rotating pinned buffer sets, rotating device
         workspaces, a separate copy stream).  A yielded result stays valid until the next-but-one is yielded.
         Items may be image lists or (images, foreground_pred) pairs."""
         dev = self.device

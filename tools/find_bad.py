@@ -16,7 +16,7 @@ for b in range(0, 48):
     r = st.run_device(db, img)
     torch.cuda.synchronize()
     n = g.n_img
-    ws_ = st._ws_ring[(st._ws_i - 1) % 3]
+    ws_ = st._ws_ring[(st._ws_i - 1) % st.n_lanes]
     c = ws_._t["counts"][:3 * n].cpu().numpy()
     bad = np.nonzero(c[n:2 * n])[0]
     for i in bad:
