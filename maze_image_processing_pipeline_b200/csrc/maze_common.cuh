@@ -125,6 +125,35 @@ __device__ __forceinline__ int cta_exclusive_scan(int v, int *smem, int *total)
     return res;
 }
 
+// bits of "pixel > t" for the 32 pixels of word k of row y (row-major uint8 image of width W): nine aligned
+// 32-bit loads, byte alignment by funnel shift, byte-wise compare as three integer ops on four pixels
+// (t < 128: px > t <=> msb(px) | msb(low7(px) + 127 - t); t >= 128: msb(px) & msb(low7(px) + 255 - t)), the
+// four msbs gathered into a nibble by a multiply.  Never reads past the aligned word holding the row's last pixel.
+__device__ __forceinline__ uint32_t threshold_word32(const uint8_t *base, int y, int k, int W, int t)
+{
+    if (t < 0) return valid_mask(W, k);
+    if (t >= 255) return 0u;
+    const uint32_t addc = (uint32_t)((t < 128 ? 127 - t : 255 - t) & 0x7f) * 0x01010101u;
+    const bool hi_t = t >= 128;
+    const int nvalid = min(32, W - 32 * k);
+    const uint8_t *p = base + (size_t)y * W + 32 * k;
+    const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t *q = (const uint32_t *)(p - a);
+    uint32_t word = 0, lo = __ldg(q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (4 * i < nvalid) {
+            uint32_t hi = (4 * (i + 1) < (int)a + nvalid) ? __ldg(q + i + 1) : 0u;  // never past the last pixel's word
+            uint32_t px = __funnelshift_r(lo, hi, 8 * a);
+            uint32_t s7 = (px & 0x7f7f7f7fu) + addc;
+            uint32_t m = (hi_t ? (s7 & px) : (s7 | px)) & 0x80808080u;
+            word += (((m >> 7) * 0x01020408u) >> 24) << (4 * i);
+            lo = hi;
+        }
+    }
+    return word & valid_mask(W, k);
+}
+
 struct TileCtx {
     maze_vignette_t v;
     int img;

@@ -203,6 +203,33 @@ __global__ void __launch_bounds__(MAZE_CTA) k_ccl_write(const uint32_t *__restri
     const int32_t *P = parent + c.v.pix_off;
     int32_t *L = labels + c.v.pix_off;
     int wbase = c.word0 + warp * 32;
+    if ((c.v.w & 3) == 0) {
+        // rows start 16-byte aligned in the int32 image: a warp writes FOUR words (128 pixels) per step, one
+        // 16-byte store per lane; background quads need no lookups at all
+        for (int i = 0; i < 32; i += 4) {
+            int widx = wbase + i + (lane >> 3);
+            if (wbase + i >= c.nwords) break;
+            bool ok = widx < c.nwords;
+            uint32_t m = ok ? __ldg(bits + c.v.word_off + widx) : 0u;
+            int y = ok ? widx / c.v.wpr : 0, k = ok ? widx - y * c.v.wpr : 0;
+            int x = 32 * k + 4 * (lane & 7);
+            if (!ok || x >= c.v.w) continue;
+            int base = y * c.v.w + 32 * k;
+            uint32_t nib = (m >> (4 * (lane & 7))) & 0xfu;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (nib) {
+                int lab[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int b = 4 * (lane & 7) + j;
+                    if ((m >> b) & 1u) lab[j] = ld_volatile(L + P[base + run_start_in_word(m, b)]);
+                }
+                v = make_int4(lab[0], lab[1], lab[2], lab[3]);
+            }
+            *(int4 *)(L + base + 4 * (lane & 7)) = v;
+        }
+        return;
+    }
     int y = wbase / c.v.wpr, k = wbase - y * c.v.wpr;
     for (int i = 0; i < 32; i++) {
         int widx = wbase + i;

@@ -17,34 +17,30 @@ extern "C" const char *maze_error_string(void) { return maze_err_buf; }
 extern "C" int maze_version(void) { return 100; }
 
 // ---------------------------------------------------------------------------------------------
-// threshold + pack: one warp per word, one lane per pixel (v1; see DESIGN.md for the traffic)
+// threshold + pack: one thread per 32-pixel word (aligned 32-bit loads + byte-SIMD compare, maze_common.cuh)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MAZE_CTA) k_threshold_pack(const uint8_t *__restrict__ image,
                                                              const maze_vignette_t *__restrict__ vig,
                                                              const maze_tile_t *__restrict__ tiles, int t_int,
                                                              uint32_t *__restrict__ bits, uint32_t *flags)
 {
+    __shared__ uint32_t s_fl;
     TileCtx c = load_tile(vig, tiles);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint8_t *img = image + c.v.pix_off;
+    if (threadIdx.x == 0) s_fl = 0;
+    __syncthreads();
+    const int widx = c.word0 + threadIdx.x;
     uint32_t fl = 0;
-    int wbase = c.word0 + warp * 32;
-    int y = wbase / c.v.wpr, k = wbase - y * c.v.wpr;
-    for (int i = 0; i < 32; i++) {
-        int widx = wbase + i;
-        if (widx >= c.nwords) break;
-        int x = 32 * k + lane;
-        bool p = false;
-        if (x < c.v.w) p = (int)__ldg(img + (i64)y * c.v.w + x) > t_int;
-        uint32_t word = __ballot_sync(FULL, p);
-        if (lane == 0) {
-            bits[c.v.word_off + widx] = word;
-            uint32_t vm = valid_mask(c.v.w, k);
-            fl |= (word ? 1u : 0u) | ((word ^ vm) ? 2u : 0u);
-        }
-        if (++k == c.v.wpr) { k = 0; y++; }
+    if (widx < c.nwords) {
+        const int y = widx / c.v.wpr, k = widx - y * c.v.wpr;
+        const uint32_t word = threshold_word32(image + c.v.pix_off, y, k, c.v.w, t_int);
+        bits[c.v.word_off + widx] = word;
+        const uint32_t vm = valid_mask(c.v.w, k);
+        fl = (word ? 1u : 0u) | ((word ^ vm) ? 2u : 0u);
     }
-    if (lane == 0 && fl) atomicOr(flags + c.img, fl);
+    fl = __reduce_or_sync(FULL, fl);
+    if ((threadIdx.x & 31) == 0 && fl) atomicOr(&s_fl, fl);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_fl) atomicOr(flags + c.img, s_fl);
 }
 
 extern "C" int maze_threshold_pack(const uint8_t *image, const maze_vignette_t *vig, int n_img,
@@ -110,8 +106,21 @@ __global__ void __launch_bounds__(MAZE_CTA) k_unpack_mask(const uint32_t *__rest
                                                           uint8_t *__restrict__ mask)
 {
     TileCtx c = load_tile(vig, tiles);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *dst = mask + c.v.pix_off;
+    if ((c.v.w & 3) == 0) {
+        // rows start 4-byte aligned: one thread per word, each nibble expanded to four 0/1 bytes by a multiply
+        const int widx = c.word0 + threadIdx.x;
+        if (widx >= c.nwords) return;
+        const int y = widx / c.v.wpr, k = widx - y * c.v.wpr;
+        const uint32_t word = __ldg(bits + c.v.word_off + widx);
+        uint32_t *d4 = (uint32_t *)(dst + (size_t)y * c.v.w + 32 * k);
+        const int n4 = min(8, (c.v.w - 32 * k) >> 2);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < n4) d4[i] = (((word >> (4 * i)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        return;
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int wbase = c.word0 + warp * 32;
     int y = wbase / c.v.wpr, k = wbase - y * c.v.wpr;
     for (int i = 0; i < 32; i++) {
