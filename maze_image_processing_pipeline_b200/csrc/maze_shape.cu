@@ -1,0 +1,283 @@
+// Per-label shape features that need the pixel neighbourhood: the numbers
+// skimage's RegionProperties hands to morphocut's CalculateZooProcessFeatures (loki/pipeline.py:625, 654) as
+// `perimeter`, `euler_number` and `filled_area`.
+//
+//   perimeter     skimage.measure.perimeter(region.image, neighborhood=4): border = image minus its erosion by
+//                 the 4-neighbourhood cross (outside the crop counts as background); every border pixel gets the
+//                 code 1 + 2 * (#4-neighbours on the border) + 10 * (#diagonal neighbours on the border); codes
+//                 5, 7, 15, 17, 25, 27 weigh 1, codes 21, 33 weigh sqrt(2), codes 13, 23 weigh (1 + sqrt(2)) / 2.
+//   euler_number  skimage.measure.euler_number(region.image, connectivity=2): over all 2x2 windows of the
+//                 zero-padded crop, +1 for "only the top-left pixel set", -1 for "top-right and bottom-left set,
+//                 the other two clear", -1 for "all but the bottom-right set".
+//   filled_area   region.image with its holes filled by scipy.ndimage.binary_fill_holes(image, ones((3, 3))): the
+//                 complement is flooded from outside the crop with 8-CONNECTED steps; what the flood does not
+//                 reach is object or hole.
+//
+// One CTA takes one object at a time from a work counter: it builds the object's own bit plane P (label == l
+// inside the bounding box, one zero pixel of frame around it) from the label image, derives the border plane,
+// the three perimeter class counts and the Euler sum with 32-pixel word operations, then floods the complement
+// from the frame by row sweeps (in-word Kogge-Stone fill, carries across the words of a row resolved with one
+// ballot + add per direction) until a whole round changes nothing.  Planes of small crops live in shared
+// memory, the others in the CTA's slab of a caller-provided pool.  All counts are exact integers; the only
+// floating-point step is the final weighted sum of the perimeter.
+#include "maze_common.cuh"
+
+#define SH_T 128           /* threads per CTA */
+#define SH_SMEM_WORDS 4096 /* both planes of a crop of up to 2048 words stay in shared memory */
+#define SH_MAX_CHUNKS 5    /* 32-word chunks per framed row: (4096 + 2 + 31) / 32 = 129 words */
+
+// seeds spread along the runs of m, both directions, inside one word
+__device__ __forceinline__ uint32_t fill_in_word(uint32_t seeds, uint32_t m)
+{
+    uint32_t s = seeds & m, p = m;
+    s |= p & (s << 1); p &= p << 1;
+    s |= p & (s << 2); p &= p << 2;
+    s |= p & (s << 4); p &= p << 4;
+    s |= p & (s << 8); p &= p << 8;
+    s |= p & (s << 16);
+    p = m;
+    s |= p & (s >> 1); p &= p >> 1;
+    s |= p & (s >> 2); p &= p >> 2;
+    s |= p & (s >> 4); p &= p >> 4;
+    s |= p & (s >> 8); p &= p >> 8;
+    s |= p & (s >> 16);
+    return s;
+}
+
+__device__ __forceinline__ uint32_t trailing_ones(uint32_t m)
+{
+    int tz = __ffs(~m) - 1;  // position of the lowest zero; -1 when m is all ones
+    return tz < 0 ? FULL : ((1u << tz) - 1u);
+}
+
+__device__ __forceinline__ uint32_t leading_ones(uint32_t m)
+{
+    int lz = __clz(~m);  // number of leading ones of m (32 when m is all ones)
+    return lz ? (FULL << (32 - lz)) : 0u;
+}
+
+__device__ __forceinline__ uint32_t ldv(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+
+// bit-sliced count of four one-bit planes: c0, c1, c2 = bits of x1 + x2 + x3 + x4
+__device__ __forceinline__ void count4(uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t &c0, uint32_t &c1,
+                                       uint32_t &c2)
+{
+    uint32_t p1 = x1 ^ x2, h1 = x1 & x2, p2 = x3 ^ x4, h2 = x3 & x4;
+    c0 = p1 ^ p2;
+    uint32_t carry = p1 & p2;
+    c1 = h1 ^ h2 ^ carry;
+    c2 = h1 & h2;
+}
+
+__global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict__ labels,
+                                                      const uint32_t *__restrict__ bits,
+                                                      const maze_vignette_t *__restrict__ vig,
+                                                      const double *__restrict__ table, int n_obj, uint32_t *pool,
+                                                      i64 slab_words, int *work_counter, double *__restrict__ shape)
+{
+    __shared__ uint32_t s_planes[SH_SMEM_WORDS];
+    __shared__ int s_job;
+    __shared__ int s_acc[5];  // n1, n2, n3, euler, reached
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SH_T / 32;
+    uint32_t *slab = pool + (i64)blockIdx.x * slab_words;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_job = atomicAdd(work_counter, 1);
+        if (tid < 5) s_acc[tid] = 0;
+        __syncthreads();
+        const int o = s_job;
+        if (o >= n_obj) return;
+        const double *row = table + (i64)o * MAZE_NFEAT;
+        double *out = shape + (i64)o * MAZE_NSHAPE;
+        const double area = row[MAZE_F_AREA];
+        if (!(area > 0)) {  // label removed by a filter, or absent
+            if (tid < MAZE_NSHAPE) out[tid] = nan("");
+            continue;
+        }
+        const int r0 = (int)row[MAZE_F_BBOX], c0 = (int)row[MAZE_F_BBOX + 1];
+        const int h = (int)row[MAZE_F_BBOX + 2] - r0, w = (int)row[MAZE_F_BBOX + 3] - c0;
+        const int label = (int)row[MAZE_F_LABEL];
+        const maze_vignette_t v = vig[(int)row[MAZE_F_IMAGE]];
+        const int rows = h + 2, fw = w + 2, cw = (fw + 31) >> 5, nwords = rows * cw;
+        if ((i64)2 * nwords > slab_words && 2 * nwords > SH_SMEM_WORDS) {  // cannot happen with a slab sized by the caller
+            if (tid < MAZE_NSHAPE) out[tid] = nan("");
+            continue;
+        }
+        uint32_t *P = (2 * nwords <= SH_SMEM_WORDS) ? s_planes : slab;
+        uint32_t *R = P + nwords;
+
+        // ---- A. the object's own plane, framed by one zero pixel --------------------------------------------
+        for (int fy = warp; fy < rows; fy += nwarp) {
+            const bool inside = fy >= 1 && fy <= h;
+            const int y = r0 + fy - 1;
+            for (int k = 0; k < cw; k++) {
+                const int fx = 32 * k + lane, x = c0 - 1 + fx;
+                bool b = false;
+                if (inside && fx >= 1 && fx <= w) {
+                    if (labels) b = __ldg(labels + v.pix_off + (i64)y * v.w + x) == label;
+                    else b = (__ldg(bits + v.word_off + (i64)y * v.wpr + (x >> 5)) >> (x & 31)) & 1u;
+                }
+                const uint32_t word = __ballot_sync(FULL, b);
+                if (lane == 0) P[fy * cw + k] = word;
+            }
+        }
+        __syncthreads();
+
+        // ---- B. border plane (into R) and the Euler sum ------------------------------------------------------
+        int euler = 0;
+        for (int i = tid; i < nwords; i += SH_T) {
+            const int fy = i / cw, k = i - fy * cw;
+            const uint32_t C = P[i];
+            const uint32_t U = fy > 0 ? P[i - cw] : 0u, D = fy < rows - 1 ? P[i + cw] : 0u;
+            const uint32_t Lw = k > 0 ? P[i - 1] : 0u, Rw = k < cw - 1 ? P[i + 1] : 0u;
+            const uint32_t ULw = (fy > 0 && k > 0) ? P[i - cw - 1] : 0u;
+            const uint32_t Cl = (C << 1) | (Lw >> 31), Cr = (C >> 1) | (Rw << 31);  // pixel x-1 / x+1 at bit x
+            R[i] = C & ~(U & D & Cl & Cr);
+            // window a = (y-1, x-1), b = (y-1, x), c = (y, x-1), d = (y, x)
+            const uint32_t Ul = (U << 1) | (ULw >> 31);
+            euler += __popc(Ul & ~U & ~Cl & ~C) - __popc(~Ul & U & Cl & ~C) - __popc(Ul & U & Cl & ~C);
+        }
+        __syncthreads();
+
+        // ---- C. perimeter classes ----------------------------------------------------------------------------
+        int n1 = 0, n2 = 0, n3 = 0;
+        for (int i = tid; i < nwords; i += SH_T) {
+            const uint32_t B = R[i];
+            if (!B) continue;  // border pixels exist only in rows 1..h
+            const int fy = i / cw, k = i - fy * cw;
+            const bool hl = k > 0, hr = k < cw - 1;
+            const uint32_t Bu = R[i - cw], Bd = R[i + cw];
+            const uint32_t Bl = hl ? R[i - 1] : 0u, Br = hr ? R[i + 1] : 0u;
+            const uint32_t Bul = hl ? R[i - cw - 1] : 0u, Bur = hr ? R[i - cw + 1] : 0u;
+            const uint32_t Bdl = hl ? R[i + cw - 1] : 0u, Bdr = hr ? R[i + cw + 1] : 0u;
+            uint32_t a0, a1, a2, b0, b1, b2;
+            count4(Bu, Bd, (B << 1) | (Bl >> 31), (B >> 1) | (Br << 31), a0, a1, a2);
+            count4((Bu << 1) | (Bul >> 31), (Bu >> 1) | (Bur << 31), (Bd << 1) | (Bdl >> 31), (Bd >> 1) | (Bdr << 31), b0,
+                   b1, b2);
+            const uint32_t a_is0 = ~(a0 | a1 | a2), a_is1 = a0 & ~a1, a_is23 = a1;  // a1 set <=> count 2 or 3
+            const uint32_t b_le2 = ~((b1 & b0) | b2), b_is1 = b0 & ~b1, b_is2 = b1 & ~b0, b_is3 = b1 & b0;
+            n1 += __popc(B & a_is23 & b_le2);                           // codes 5, 7, 15, 17, 25, 27
+            n2 += __popc(B & ((a_is0 & b_is2) | (a_is1 & b_is3)));      // codes 21, 33
+            n3 += __popc(B & a_is1 & (b_is1 | b_is2));                  // codes 13, 23
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            n1 += __shfl_xor_sync(FULL, n1, d);
+            n2 += __shfl_xor_sync(FULL, n2, d);
+            n3 += __shfl_xor_sync(FULL, n3, d);
+            euler += __shfl_xor_sync(FULL, euler, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&s_acc[0], n1);
+            atomicAdd(&s_acc[1], n2);
+            atomicAdd(&s_acc[2], n3);
+            atomicAdd(&s_acc[3], euler);
+        }
+        __syncthreads();
+
+        // ---- D. flood of the complement from the frame (8-connected) ------------------------------------------
+        for (int i = tid; i < nwords; i += SH_T) {
+            const int fy = i / cw, k = i - fy * cw;
+            uint32_t s = 0;
+            if (fy == 0 || fy == rows - 1) s = valid_mask(fw, k);
+            else {
+                if (k == 0) s |= 1u;
+                if (k == (fw - 1) >> 5) s |= 1u << ((fw - 1) & 31);
+            }
+            R[i] = s;
+        }
+        __syncthreads();
+        const int band = (rows + nwarp - 1) / nwarp;
+        const int b_lo = max(1, warp * band), b_hi = min(rows - 1, (warp + 1) * band);  // frame rows are complete
+        const int nchunk = (cw + 31) >> 5;
+        for (;;) {
+            int changed = 0;
+            for (int dir = 0; dir < 2; dir++) {
+                for (int step = 0; step < b_hi - b_lo; step++) {
+                    const int fy = dir == 0 ? b_lo + step : b_hi - 1 - step;
+                    uint32_t s[SH_MAX_CHUNKS], M[SH_MAX_CHUNKS], old[SH_MAX_CHUNKS];
+                    uint32_t cin = 0;
+#pragma unroll
+                    for (int c = 0; c < SH_MAX_CHUNKS; c++) {  // local fill, then carries towards larger x
+                        if (c < nchunk) {
+                            const int k = 32 * c + lane;
+                            const bool ok = k < cw;
+                            const int i = fy * cw + k;
+                            M[c] = ok ? (~P[i] & valid_mask(fw, k)) : 0u;
+                            old[c] = ok ? ldv(R + i) : 0u;
+                            uint32_t V = 0, VL = 0, VR = 0;
+                            if (ok) {
+                                V = ldv(R + i - cw) | ldv(R + i + cw);
+                                if (k > 0) VL = ldv(R + i - cw - 1) | ldv(R + i + cw - 1);
+                                if (k < cw - 1) VR = ldv(R + i - cw + 1) | ldv(R + i + cw + 1);
+                            }
+                            const uint32_t spread = V | (V << 1) | (VL >> 31) | (V >> 1) | (VR << 31);
+                            s[c] = fill_in_word(old[c] | spread, M[c]);
+                            const uint32_t G = __ballot_sync(FULL, s[c] >> 31), Pm = __ballot_sync(FULL, M[c] == FULL);
+                            const uint32_t A = G | Pm;
+                            const u64 S = (u64)A + G + cin;
+                            const uint32_t Cin = (uint32_t)S ^ A ^ G;
+                            cin = (uint32_t)(S >> 32);
+                            if ((Cin >> lane) & 1u) s[c] |= trailing_ones(M[c]);
+                        }
+                    }
+                    cin = 0;
+#pragma unroll
+                    for (int c = SH_MAX_CHUNKS - 1; c >= 0; c--) {  // carries towards smaller x
+                        if (c < nchunk) {
+                            const uint32_t G = __brev(__ballot_sync(FULL, s[c] & 1u));
+                            const uint32_t Pm = __brev(__ballot_sync(FULL, M[c] == FULL));
+                            const uint32_t A = G | Pm;
+                            const u64 S = (u64)A + G + cin;
+                            const uint32_t Cin = (uint32_t)S ^ A ^ G;
+                            cin = (uint32_t)(S >> 32);
+                            if ((Cin >> (31 - lane)) & 1u) s[c] |= leading_ones(M[c]);
+                            const int k = 32 * c + lane;
+                            if (k < cw && s[c] != old[c]) {
+                                R[fy * cw + k] = s[c];
+                                changed = 1;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        int reached = 0;
+        for (int i = tid; i < nwords; i += SH_T) reached += __popc(R[i]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) reached += __shfl_xor_sync(FULL, reached, d);
+        if (lane == 0) atomicAdd(&s_acc[4], reached);
+        __syncthreads();
+        if (tid == 0) {
+            const double SQ2 = 1.4142135623730951;
+            const int m1 = s_acc[0], m2 = s_acc[1], m3 = s_acc[2];
+            out[MAZE_S_PERIMETER] = (double)m1 + (double)m2 * SQ2 + (double)m3 * ((1.0 + SQ2) / 2.0);
+            out[MAZE_S_FILLED_AREA] = (double)((i64)rows * fw - s_acc[4]);
+            out[MAZE_S_EULER] = (double)s_acc[3];
+            out[MAZE_S_N1] = (double)m1;
+            out[MAZE_S_N2] = (double)m2;
+            out[MAZE_S_N3] = (double)m3;
+            out[6] = nan("");
+            out[7] = nan("");
+        }
+    }
+}
+
+extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
+                                const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
+                                int32_t *work_counter, double *shape, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_obj <= 0) return MAZE_OK;
+    if ((!labels && !bits) || !vig || !table || !shape || !work_counter || n_slabs <= 0 || slab_words < 0 ||
+        (slab_words > 0 && !pool))
+        return MAZE_ERR_BADARG;
+    MAZE_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), s), "label_shape counter");
+    const int grid = n_slabs < n_obj ? n_slabs : n_obj;
+    MAZE_KERNEL(KID_LABEL_SHAPE, s,
+                k_label_shape<<<grid, SH_T, 0, s>>>(labels, bits, vig, table, n_obj, pool, slab_words, work_counter,
+                                                    shape));
+    return MAZE_OK;
+}

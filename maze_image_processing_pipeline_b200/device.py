@@ -476,6 +476,33 @@ class DeviceBatch:
               "maze_props_finish_staged")
         return table
 
+    _shape_pool = None  # scratch of label_shape, shared by the batches of one device (grown on demand)
+
+    def label_shape(self, table, labels=None, bits=None, out=None, pool_bytes=1 << 30):
+        """perimeter / filled_area / euler_number per row of the finished feature table (maze_label_shape): the
+        RegionProperties values CalculateZooProcessFeatures reads besides the moments (loki/pipeline.py:625, 654).
+        Returns an (n_obj, NSHAPE) float64 tensor."""
+        from ._lib import NSHAPE
+        n_obj = int(table.shape[0])
+        shape = torch.empty((n_obj, NSHAPE), dtype=torch.float64, device=self.device) if out is None else out
+        if n_obj == 0:
+            return shape
+        g = self.g
+        slab_words = 2 * (int(g.h.max()) + 2) * ((int(g.w.max()) + 2 + 31) // 32)
+        n_slabs = max(1, min(n_obj, 148 * 8, pool_bytes // (4 * slab_words)))
+        need = n_slabs * slab_words + 64
+        key = (str(self.device), _stream())  # one pool per stream: calls on one stream are ordered
+        pools = DeviceBatch._shape_pool = DeviceBatch._shape_pool or {}
+        if key not in pools or pools[key].numel() < need:
+            pools[key] = torch.empty(need, dtype=torch.int32, device=self.device)
+        pool = pools[key]
+        counter = pool[n_slabs * slab_words:]  # one int32 behind the slabs
+        check(lib().maze_label_shape(None if labels is None else labels.data_ptr(),
+                                     None if bits is None else bits.data_ptr(), self.d_vig.data_ptr(),
+                                     table.data_ptr(), n_obj, pool.data_ptr(), slab_words, n_slabs, counter.data_ptr(),
+                                     shape.data_ptr(), _stream()), "maze_label_shape")
+        return shape
+
     def count_scan(self, n_labels, out=None):
         lab_off = torch.empty(self.g.n_img + 1, dtype=torch.int32, device=self.device) if out is None else out
         check(lib().maze_count_scan(n_labels.data_ptr(), self.g.n_img, lab_off.data_ptr(), _stream()),

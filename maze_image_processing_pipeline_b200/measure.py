@@ -8,13 +8,17 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ._lib import NFEAT
+from ._lib import NFEAT, NSHAPE
 from .device import BatchGeometry, DeviceBatch
 
 # column layout of the feature table (include/maze_b200.h, MAZE_F_*)
 F_LABEL, F_AREA, F_BBOX, F_CENTROID, F_MU, F_NU, F_HU, F_EIG = 0, 1, 2, 6, 8, 24, 40, 47
 F_AXIS_MAJOR, F_AXIS_MINOR, F_ECC, F_ORIENT = 49, 50, 51, 52
 F_IMIN, F_IMAX, F_IMEAN, F_FRAC_INVALID, F_IMAGE, F_T00, F_T01, F_T11 = 53, 54, 55, 56, 57, 58, 59, 60
+
+
+# column layout of the shape table (MAZE_S_*)
+S_PERIMETER, S_FILLED_AREA, S_EULER, S_N1, S_N2, S_N3 = 0, 1, 2, 3, 4, 5
 
 
 def _single(arr, dtype):
@@ -94,3 +98,28 @@ def mask_properties(mask, intensity_image=None, high_order=True):
         d_img = batch.upload(geom.pack_host([np.ascontiguousarray(intensity_image, dtype=np.uint8)]))
     lab_off, n_obj = batch.lab_off_from_bounds([1])
     return batch.regionprops(lab_off, n_obj, bits=bits, image=d_img, high_order=high_order).cpu().numpy()
+
+
+def regionprops_shape(labels):
+    """(max_label, NSHAPE) float64 table of the RegionProperties values that need the pixel neighbourhood --
+    ``perimeter`` (4-neighbourhood), ``filled_area`` (holes filled with the full 3x3 structure) and
+    ``euler_number`` (8-connectivity), each taken from the label's own bounding-box crop -- as read by
+    ``CalculateZooProcessFeatures`` (loki/pipeline.py:625).  Row l-1 describes label l (NaN when absent)."""
+    lab = np.asarray(labels)
+    if lab.size == 0:
+        return np.zeros((0, NSHAPE))
+    geom, batch, d_lab = _single(lab, np.int32)
+    bound = int(batch.max_label(d_lab).cpu()[0])
+    lab_off, n_obj = batch.lab_off_from_bounds([bound])
+    table = batch.regionprops(lab_off, n_obj, labels=d_lab, high_order=False)
+    return batch.label_shape(table, labels=d_lab).cpu().numpy()
+
+
+def mask_shape(mask):
+    """The same three values for the whole mask as one region (``ImageProperties``, loki/pipeline.py:653-654)."""
+    m = np.asarray(mask)
+    geom, batch, d_m = _single((m != 0).view(np.uint8), np.uint8)
+    bits, _ = batch.threshold_pack(d_m, 0)
+    lab_off, n_obj = batch.lab_off_from_bounds([1])
+    table = batch.regionprops(lab_off, n_obj, bits=bits, high_order=False)
+    return batch.label_shape(table, bits=bits).cpu().numpy()

@@ -8,8 +8,11 @@ prefix="object_")`` (:625).  Here the numbers come from the feature table the GP
 (``StageResult.features(i)``, columns ``MAZE_F_*`` of include/maze_b200.h); nothing is recomputed from pixels.
 
 Restated, not executed: morphocut and scikit-image are not available offline, so the
-key names follow morphocut's ZooProcess feature set as far as the stage's table carries the numbers; features
-that need perimeter / convex hull / hole filling are not produced yet.
+key names follow morphocut's ZooProcess feature set (``morphocut/contrib/zooprocess.py`` at the pinned commit
+03dbc6b, requirements.txt:1) as remembered: there ``area`` is the FILLED area and ``area_exc`` the pixel count.
+With the stage's shape table (``LokiSegmentationStage(shape_features=True)``: perimeter, filled_area,
+euler_number from maze_label_shape) every key of that set is produced except ``convex_area`` / ``solidity``
+(convex hull raster); without it, only the keys that follow from the moment table.
 """
 from __future__ import annotations
 
@@ -18,16 +21,20 @@ from typing import Dict, Iterator, List, Optional
 
 import numpy as np
 
-from .measure import (F_AREA, F_AXIS_MAJOR, F_AXIS_MINOR, F_BBOX, F_CENTROID, F_ECC, F_FRAC_INVALID, F_HU, F_IMAX,
-                      F_IMEAN, F_IMIN, F_LABEL, F_ORIENT)
+# column layouts (include/maze_b200.h, MAZE_F_* / MAZE_S_*); kept literal so that this module imports without CUDA
+F_LABEL, F_AREA, F_BBOX, F_CENTROID, F_HU = 0, 1, 2, 6, 40
+F_AXIS_MAJOR, F_AXIS_MINOR, F_ECC, F_ORIENT = 49, 50, 51, 52
+F_IMIN, F_IMAX, F_IMEAN, F_FRAC_INVALID = 53, 54, 55, 56
+S_PERIMETER, S_FILLED_AREA, S_EULER = 0, 1, 2
 
 
 class Region:
     """The part of skimage's RegionProperties the LOKI pipeline reads, backed by one row of the table."""
 
     def __init__(self, row: np.ndarray, shape, padding: int = 0, labels: Optional[np.ndarray] = None,
-                 intensity: Optional[np.ndarray] = None):
+                 intensity: Optional[np.ndarray] = None, shape_row: Optional[np.ndarray] = None):
         self._row = row
+        self._shape_row = shape_row
         self._shape = shape
         self._labels = labels
         self._intensity = intensity
@@ -47,6 +54,23 @@ class Region:
     @property
     def area(self) -> float:
         return float(self._row[F_AREA])
+
+    @property
+    def perimeter(self) -> float:
+        return float(self._need_shape()[S_PERIMETER])
+
+    @property
+    def filled_area(self) -> float:
+        return float(self._need_shape()[S_FILLED_AREA])
+
+    @property
+    def euler_number(self) -> int:
+        return int(self._need_shape()[S_EULER])
+
+    def _need_shape(self):
+        if self._shape_row is None:
+            raise ValueError("shape table not attached (LokiSegmentationStage(shape_features=True))")
+        return self._shape_row
 
     @property
     def centroid(self):
@@ -79,14 +103,15 @@ def find_regions(result, i: int, padding: int = 0, min_intensity: Optional[float
     (loki/pipeline.py:589-594): one Region per label that still has pixels, in label order; regions whose
     maximum intensity is below ``min_intensity`` are skipped."""
     feats = result.features(i)
+    shapes = result.shape_features(i) if hasattr(result, "shape_features") else None
     labels = result.labels(i)
     shape = (int(result.geometry.h[i]), int(result.geometry.w[i]))
-    for row in feats:
+    for j, row in enumerate(feats):
         if not row[F_AREA] > 0:  # label removed by clear_border / remove_small_objects / merge_labels
             continue
         if min_intensity is not None and row[F_IMAX] < min_intensity:
             continue
-        yield Region(row, shape, padding, labels, image)
+        yield Region(row, shape, padding, labels, image, None if shapes is None else shapes[j])
 
 
 def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = None) -> Dict:
@@ -108,33 +133,57 @@ def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = N
 
 
 def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str = "object_") -> Dict:
-    """The subset of ``CalculateZooProcessFeatures(region, meta, prefix)`` (loki/pipeline.py:625, 654) that
-    follows from the stage's table: area, intensity statistics, centroid, bounding box, ellipse axes, angle and
-    ratios derived from them.  Keys follow morphocut's ZooProcess names."""
+    """``CalculateZooProcessFeatures(region, meta, prefix)`` (loki/pipeline.py:625, 654) from the stage's tables.
+    Keys follow morphocut's ZooProcess names.  With a shape row: ``area`` = filled area, ``area_exc`` = pixel
+    count, ``%area``, ``perim.``, ``circ.``, ``circex``, ``perimareaexc``, ``perimmajor``, ``euler_number`` as
+    well; without one ``area`` falls back to the pixel count and the perimeter-based keys are absent."""
     out = dict(meta) if meta is not None else {}
     row = region._row
     r0, c0, r1, c1 = (int(v) for v in row[F_BBOX:F_BBOX + 4])
     area = float(row[F_AREA])
     major, minor = float(row[F_AXIS_MAJOR]), float(row[F_AXIS_MINOR])
+    mean = float(row[F_IMEAN])
+    has_shape = region._shape_row is not None
+    filled = region.filled_area if has_shape else area
+    bbox_area = float((r1 - r0) * (c1 - c0))
     feats = {
-        "area": area,
-        "mean": float(row[F_IMEAN]),
-        "min": float(row[F_IMIN]),
-        "max": float(row[F_IMAX]),
-        "x": float(row[F_CENTROID + 1]),
-        "y": float(row[F_CENTROID]),
-        "bx": c0,
-        "by": r0,
+        "label": region.label,
         "width": c1 - c0,
         "height": r1 - r0,
+        "bx": c0,
+        "by": r0,
+        "area_exc": area,
+        "area": filled,
+        "%area": 1.0 - area / filled,
         "major": major,
         "minor": minor,
-        "angle": float(row[F_ORIENT]) / math.pi * 180.0 + 90.0,
-        "intden": area * float(row[F_IMEAN]),
-        "range": float(row[F_IMAX]) - float(row[F_IMIN]),
+        "y": float(row[F_CENTROID]),
+        "x": float(row[F_CENTROID + 1]),
+        "min": float(row[F_IMIN]),
+        "max": float(row[F_IMAX]),
+        "mean": mean,
+        "intden": filled * mean,
         "elongation": (major / minor) if minor > 0 else float("inf"),
+        "range": float(row[F_IMAX]) - float(row[F_IMIN]),
+        "angle": float(row[F_ORIENT]) / math.pi * 180.0 + 90.0,
+        "bounding_box_area": bbox_area,
         "eccentricity": float(row[F_ECC]),
+        "equivalent_diameter": math.sqrt(4.0 * area / math.pi),
+        "extent": area / bbox_area,
+        "local_centroid_row": float(row[F_CENTROID]) - r0,
+        "local_centroid_col": float(row[F_CENTROID + 1]) - c0,
     }
+    if has_shape:
+        perim = region.perimeter
+        sq = perim * perim
+        feats.update({
+            "perim.": perim,
+            "circ.": (4.0 * math.pi * filled / sq) if sq > 0 else float("inf"),
+            "circex": (4.0 * math.pi * area / sq) if sq > 0 else float("inf"),
+            "perimareaexc": perim / area,
+            "perimmajor": (perim / major) if major > 0 else float("nan" if perim == 0 else "inf"),
+            "euler_number": region.euler_number,
+        })
     for k, v in feats.items():
         out[prefix + k] = v
     for j in range(7):

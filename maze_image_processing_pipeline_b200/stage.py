@@ -26,7 +26,7 @@ import torch
 import ctypes
 import os
 
-from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, RP_HIGH_ORDER, StepArgs, check, lib
+from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, StepArgs, check, lib
 from ._lib import MAX_DISK_RADIUS
 from .device import (Arena, BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
@@ -97,6 +97,7 @@ class StageResult:
         self.lab_off = lab_off
         self.table = table
         self.keep = keep  # threshold branch: vignettes that survive the empty-mask filter
+        self.shape_table = None  # shape_features=True: (n_obj, NSHAPE) perimeter / filled_area / euler_number rows
         self.merge_failed = None  # merge_errors="ignore": vignettes where merge_labels hit the reference's TypeError
 
     def __len__(self):
@@ -111,6 +112,12 @@ class StageResult:
     def features(self, i) -> np.ndarray:
         """Rows of the object table that belong to vignette i (row k = label k + 1)."""
         return self.table[int(self.lab_off[i]):int(self.lab_off[i + 1])]
+
+    def shape_features(self, i) -> Optional[np.ndarray]:
+        """Rows of the shape table (perimeter, filled_area, euler_number, ...) that belong to vignette i."""
+        if self.shape_table is None:
+            return None
+        return self.shape_table[int(self.lab_off[i]):int(self.lab_off[i + 1])]
 
 
 class Workspace:
@@ -154,12 +161,16 @@ class _PinnedPool:
 
 class LokiSegmentationStage:
     def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True,
-                 merge_errors="raise"):
-        """merge_errors: "raise" (the reference's behaviour: merge_labels raises TypeError when a bridge
+                 merge_errors="raise", shape_features=False):
+        """shape_features: also produce, per object, the RegionProperties values CalculateZooProcessFeatures reads
+        besides the moments -- perimeter, filled_area, euler_number (StageResult.shape_table; one more kernel over
+        the label image per batch).
+        merge_errors: "raise" (the reference's behaviour: merge_labels raises TypeError when a bridge
         swallows a label, merge_labels.py:19-20, and the run aborts) or "ignore" (keep the labels as the loop
         left them for those vignettes and list them in StageResult.merge_failed)."""
         self.fused = fused
         self.merge_errors = merge_errors
+        self.shape_features = shape_features
         if threshold is None and postprocess is None:
             raise ValueError("exactly one of threshold / postprocess (or both, for the composite stage) is required")
         self.threshold = threshold
@@ -534,6 +545,11 @@ class LokiSegmentationStage:
             h_tab.copy_(table.reshape(-1), non_blocking=True)
             h_off = pool.get("lab_off", geom.n_img + 1, torch.int32)
             h_off.copy_(res.lab_off, non_blocking=True)
+            h_shape = None
+            if self.shape_features:
+                d_shape = batch.label_shape(table, labels=res.labels, bits=res.bits if res.labels is None else None)
+                h_shape = pool.get("shape", max(d_shape.numel(), 1), torch.float64)[:d_shape.numel()]
+                h_shape.copy_(d_shape.reshape(-1), non_blocking=True)
             keep = None if res.keep is None else res.keep.cpu().numpy()
             status = None if res.merge_status is None else res.merge_status.cpu().numpy()
         ss.synchronize()
@@ -547,6 +563,8 @@ class LokiSegmentationStage:
         out = StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
                           h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
         out.merge_failed = failed
+        if self.shape_features:
+            out.shape_table = h_shape.numpy().reshape(-1, NSHAPE)
         return out
 
     def __call__(self, images: Sequence[np.ndarray], foreground_pred: Optional[Sequence[np.ndarray]] = None,

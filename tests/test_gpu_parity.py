@@ -511,3 +511,88 @@ def test_config1_thousand_256x256_vignettes(mz):
                 assert np.array_equal(lab > 0, res.mask(i))
             total_area += int((lab > 0).sum())
         assert res.table[:, oracle.F_AREA].sum() == total_area
+
+
+# ---- shape features: perimeter / filled_area / euler_number -------------
+def assert_shape_equal(got, want):
+    assert got.shape == want.shape
+    absent = np.isnan(want[:, 0])
+    assert np.array_equal(np.isnan(got[:, 0]), absent)
+    g, w = got[~absent], want[~absent]
+    assert np.array_equal(g[:, 1:6], w[:, 1:6])          # filled_area, euler_number, n1, n2, n3: exact integers
+    assert np.allclose(g[:, 0], w[:, 0], rtol=1e-12, atol=0)
+
+
+def test_label_shape_special_cases(mz):
+    from oracle import shape as oshape
+    ring = np.ones((7, 7), np.int32)
+    ring[2:5, 2:5] = 0
+    leak = ring.copy()
+    leak[0, 0] = leak[0, 1] = leak[1, 0] = leak[1, 1] = 0    # hole 8-connected to the outside: not filled
+    nested = np.zeros((40, 70), np.int32)                     # island (label 2) with its own hole inside a hole of 1
+    nested[2:38, 3:60] = 1
+    nested[6:34, 8:55] = 0
+    nested[10:30, 12:50] = 2
+    nested[14:26, 20:40] = 0
+    nested[18:22, 25:30] = 5                                  # labels 3, 4 absent
+    spiral = np.zeros((33, 33), np.int32)                     # the flood has to wind inwards
+    for k in range(0, 16, 2):
+        spiral[k, k:33 - k] = 1
+        spiral[k:33 - k, 32 - k] = 1
+        spiral[32 - k, k:33 - k] = 1
+        spiral[k + 2:33 - k, k] = 1
+    wide = np.zeros((9, 1500), np.int32)                      # rows of more than 32 words: carries across chunks
+    wide[1, 1:1499] = 1
+    wide[7, 1:1499] = 1
+    wide[1:8, 1] = 1
+    wide[1:8, 1498] = 1
+    wide[3:6, 700:900] = 2
+    for lab in (ring, leak, nested, spiral, wide, np.eye(6, dtype=np.int32), np.ones((1, 1), np.int32),
+                np.ones((1, 40), np.int32), np.ones((300, 2), np.int32)):
+        assert_shape_equal(mz.measure.regionprops_shape(lab), oshape.label_shape(lab))
+    # ImageProperties semantics: the whole mask is one region
+    m = nested > 0
+    assert_shape_equal(mz.measure.mask_shape(m), oshape.label_shape(m.astype(np.int32)))
+
+
+def test_label_shape_random_and_large(mz):
+    from oracle import shape as oshape
+    rng = np.random.default_rng(21)
+    for shape, p in (((70, 101), 0.5), ((200, 333), 0.62), ((64, 64), 0.9), ((31, 257), 0.3)):
+        lab, _ = oracle.label(rng.random(shape) < p)          # noise near the percolation threshold: many holes
+        assert_shape_equal(mz.measure.regionprops_shape(lab), oshape.label_shape(lab))
+    lab = rng.integers(0, 6, size=(90, 120)).astype(np.int32)  # arbitrary label image: labels touch each other
+    assert_shape_equal(mz.measure.regionprops_shape(lab), oshape.label_shape(lab))
+    # crops too large for shared memory (planes in the CTA's slab), thousands of labels
+    img = mz.synth.synth_dense_frame(3, size=1536, n_blobs=400)
+    lab, _ = oracle.label(img > 40)
+    assert_shape_equal(mz.measure.regionprops_shape(lab), oshape.label_shape(lab))
+    big = np.zeros((1024, 1024), np.int32)
+    big[rng.random(big.shape) < 0.6] = 1                       # one label whose crop is the whole 1024^2 vignette
+    assert_shape_equal(mz.measure.regionprops_shape(big), oshape.label_shape(big))
+
+
+def test_stage_shape_features_and_zooprocess_keys(mz):
+    from oracle import shape as oshape
+    from maze_image_processing_pipeline_b200.regions import objects_of
+    S = mz.stage
+    imgs = mz.synth.synth_batch(77, 24, lo=64, hi=400)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, shape_features=True)
+    outs = list(st.map([imgs[:12], imgs[12:]]))
+    k = 0
+    for res in outs:
+        for i in range(len(res)):
+            _, labels, table = scipy_chain.loki_chain(imgs[k], 40, 1, 2)
+            want = oshape.label_shape(labels, max_label=len(res.features(i)))
+            assert_shape_equal(res.shape_features(i), want)
+            for o, row in zip(objects_of(res, i, image=imgs[k]), want[~np.isnan(want[:, 0])]):
+                assert o["object_area"] == row[1] and o["object_perim."] == pytest.approx(row[0], rel=1e-12)
+                assert o["object_euler_number"] == row[2] and o["object_area_exc"] <= o["object_area"]
+            k += 1
+    assert k == 24
+    # threshold branch: one region per vignette, taken from the bit plane
+    st = S.LokiSegmentationStage(threshold=S.ThresholdSegmentationConfig(35.5), shape_features=True)
+    res = st(imgs[:6])
+    for i in range(6):
+        assert_shape_equal(res.shape_features(i), oshape.label_shape((imgs[i] > 35.5).astype(np.int32), max_label=1))

@@ -164,3 +164,60 @@ def test_chain_c_oracle_equals_scipy_chain():
         if k % 2:
             lab = oracle.merge_labels(lab, max_distance=10, labels_out=lab)
         assert np.array_equal(lab, labels)
+
+
+# ---- shape features ---------------------------------------------------
+def _shape_cases():
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(5)
+    cases = []
+    for t in range(120):
+        h, w = rng.integers(1, 48, 2)
+        img = rng.random((h, w)) < rng.choice([0.2, 0.5, 0.8, 0.95])
+        if t % 3 == 0:
+            img = ndi.binary_opening(ndi.binary_dilation(img, iterations=2))
+        cases.append(np.asarray(img, bool))
+    return cases
+
+
+def test_shape_oracle_euler_and_fill_match_independent_definitions():
+    """euler_number (quad counting) == #8-connected components - #4-connected holes; filled_area == everything the
+    8-connected flood of the complement from outside does not reach -- both counted with ndi.label."""
+    from scipy import ndimage as ndi
+    from oracle import shape as S
+    eight = np.ones((3, 3))
+    for img in _shape_cases():
+        n8 = ndi.label(img, structure=eight)[1]
+        holes4 = ndi.label(np.pad(img, 1) == 0)[1] - 1
+        assert S.euler_number(img) == n8 - holes4
+        comp = np.pad(img, 1) == 0
+        lab, _ = ndi.label(comp, structure=eight)
+        assert S.filled_area(img) == comp.size - int((lab == lab[0, 0]).sum())
+
+
+def test_shape_oracle_known_answers():
+    from oracle import shape as S
+    one = np.ones((1, 1), bool)
+    assert S.perimeter(one) == 0 and S.euler_number(one) == 1 and S.filled_area(one) == 1
+    for k in (2, 3, 7, 20):                              # k x k square: 4 (k - 1)
+        assert S.perimeter(np.ones((k, k), bool)) == 4 * (k - 1)
+    assert S.perimeter(np.ones((5, 9), bool)) == 2 * (4 + 8)
+    assert S.perimeter(np.ones((1, 10), bool)) == 8      # a line: end pixels weigh 0, inner ones 1
+    diag = np.eye(6, dtype=bool)                         # diagonal line: inner pixels weigh sqrt(2)
+    assert abs(S.perimeter(diag) - 4 * np.sqrt(2)) < 1e-12 and S.euler_number(diag) == 1
+    ring = np.ones((7, 7), bool)
+    ring[2:5, 2:5] = False
+    assert S.euler_number(ring) == 0 and S.filled_area(ring) == 49
+    leak = ring.copy()                                   # the hole touches the outside through a diagonal step:
+    leak[0, 0] = leak[0, 1] = leak[1, 0] = False         # ... not yet
+    assert S.filled_area(leak) == 46
+    leak[1, 1] = False                                   # now (1,1)-(2,2) connects hole and outside 8-wise
+    assert S.filled_area(leak) == int(leak.sum())
+    assert S.euler_number(leak) == 0                     # the 4-connected background of euler_number still sees a hole
+    two = np.zeros((5, 9), np.int32)                     # label_shape works on each label's own crop
+    two[1:4, 1:4] = 1
+    two[2, 2] = 0
+    two[0:5, 6:9] = 3
+    t = S.label_shape(two)
+    assert t.shape == (3, 8) and np.isnan(t[1]).all()
+    assert list(t[0, :3]) == [8.0, 9.0, 0.0] and list(t[2, :3]) == [2 * (2 + 4), 15.0, 1.0]
