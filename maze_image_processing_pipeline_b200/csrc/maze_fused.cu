@@ -158,7 +158,8 @@ struct WFixed { // compile-time chord half-widths of the common small disks: the
 
 template <int R, int T, typename WT>
 __device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int H, int W,
-                                              int wpr, const WT wt, uint32_t inv, bool phantom, int nstrip, int S)
+                                              int wpr, const WT wt, uint32_t inv, bool phantom, int nstrip, int S,
+                                              uint32_t inv_next, bool &hz_next)
 {
     int wd[R + 1];
 #pragma unroll
@@ -207,10 +208,34 @@ __device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, 
                 uint32_t acc = FULL;
 #pragma unroll
                 for (int i = 0; i < 2 * R + 1; i++) acc &= win[i][i < R ? R - i : i - R];
-                dst[y * wpr + k] = (acc ^ inv) & ~padC;
+                const uint32_t o = (acc ^ inv) & ~padC;
+                dst[y * wpr + k] = o;
+                hz_next |= ((o ^ inv_next) | padC) != FULL;  // the next pass's input plane has a 0 (phantom test)
             }
         }
     }
+}
+
+// "pixel > t" for 32 pixels held in nine aligned 32-bit words (row misaligned by `a` bytes).  Byte-wise compare in
+// three integer ops per four pixels (LOW, t < 128: msb(px) | msb(low7(px) + 127 - t); else msb(px) & msb(low7(px) +
+// 255 - t)); the msbs of two groups are interleaved (bits 0, 4, 8, ...) and gathered into one byte of the plane
+// by ONE multiply: bit b lands at b + {24, 17, 10, 3}, and no two partial products meet in the top byte.
+template <bool LOW>
+__device__ __forceinline__ uint32_t threshold32(const uint32_t (&raw)[9], uint32_t a, uint32_t addc)
+{
+    uint32_t byte4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t m[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t px = __funnelshift_r(raw[2 * j + h], raw[2 * j + h + 1], 8 * a);
+            const uint32_t s7 = (px & 0x7f7f7f7fu) + addc;  // no carry across bytes
+            m[h] = (LOW ? (s7 | px) : (s7 & px)) & 0x80808080u;
+        }
+        byte4[j] = ((m[0] >> 7) | (m[1] >> 3)) * 0x01020408u;  // top byte = pixels 8j .. 8j+7
+    }
+    return __byte_perm(__byte_perm(byte4[0], byte4[1], 0x0073), __byte_perm(byte4[2], byte4[3], 0x7300), 0x7610);
 }
 
 template <int T>
@@ -246,8 +271,10 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         uint4 *m4 = (uint4 *)(mask + v.pix_off);
         for (; zf_next < upto; zf_next++) {
             const int l0 = (int)((i64)nl * zf_next / ZF_PARTS), l1 = (int)((i64)nl * (zf_next + 1) / ZF_PARTS);
+#pragma unroll 4
             for (int i = l0 + tid; i < l1; i += T) l4[i] = z;
             const int m0 = (int)((i64)nm * zf_next / ZF_PARTS), m1 = (int)((i64)nm * (zf_next + 1) / ZF_PARTS);
+#pragma unroll 2
             for (int i = m0 + tid; i < m1; i += T) m4[i] = z;
         }
     };
@@ -258,60 +285,46 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
 
     // ---- 1. threshold + pack (loki/pipeline.py:649) -------------------------------------------------
     uint32_t *T0 = (prm.n_pass & 1) ? B : A; // an odd number of passes must start in B to end in A
+    bool hz = false;
     {
         const uint8_t *base = image + v.pix_off;
         const int t = prm.t_int;
         // byte-wise "pixel > t" on four pixels with three integer ops instead of the emulated SIMD compare:
-        // t < 128: px > t  <=>  msb(px) | msb(low7(px) + 127 - t);  t >= 128: msb(px) & msb(low7(px) + 255 - t)
+        // (threshold32 above)
         const uint32_t addc = (uint32_t)((t < 128 ? 127 - t : 255 - t) & 0x7f) * 0x01010101u;
-        const bool hi_t = t >= 128;
+        const bool lowmode = t < 128;
+        const uint32_t force = t < 0 ? FULL : 0u, kill = t >= 255 ? 0u : FULL;
+        const uint32_t inv0 = (prm.n_pass > 0 && prm.pass[0].invert) ? FULL : 0u;
         int y = y_first, k = k_first;
         for (int w = tid; w < words; w += T) {
-            int nvalid = min(32, W - 32 * k);
+            const int nvalid = min(32, W - 32 * k);
             const uint8_t *p = base + (size_t)y * W + 32 * k;
-            uint32_t a = (uint32_t)((uintptr_t)p & 3u);
+            const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
             const uint32_t *q = (const uint32_t *)(p - a);
-            uint32_t word = 0;
-            if (t < 0) {
-                word = FULL;
-            } else if (t < 255) {
-                uint32_t lo = __ldg(q);
+            const int last = (int)(a + nvalid - 1) >> 2;  // aligned word holding the row's last pixel of this word
+            uint32_t raw[9];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (4 * i < nvalid) {
-                        uint32_t hi = __ldg(q + i + 1); // at most 4 bytes past the row: inside the padded slot
-                        uint32_t px = __funnelshift_r(lo, hi, 8 * a);
-                        uint32_t s7 = (px & 0x7f7f7f7fu) + addc;          // no carry across bytes
-                        uint32_t m = (hi_t ? (s7 & px) : (s7 | px)) & 0x80808080u;
-                        word += (((m >> 7) * 0x01020408u) >> 24) << (4 * i); // gather the four msbs into a nibble
-                        lo = hi;
-                    }
-                }
-            }
-            T0[w] = word & valid_mask(W, k);
+            for (int i = 0; i < 9; i++) raw[i] = (i <= last) ? __ldg(q + i) : 0u;
+            const uint32_t word = lowmode ? threshold32<true>(raw, a, addc) : threshold32<false>(raw, a, addc);
+            const uint32_t vm = valid_mask(W, k), o = ((word | force) & kill) & vm;
+            T0[w] = o;
+            hz |= ((o ^ inv0) | ~vm) != FULL;  // the first pass's input plane has a 0 (scipy's phantom pixel otherwise)
             y += step_y; k += step_k;
             if (k >= wpr) { k -= wpr; y++; }
         }
     }
     zero_fill(2);
-    __syncthreads();
+    // scipy's phantom background pixel: the (inverted) input plane of a pass has no 0 at all.  Every producer of a
+    // plane (threshold, previous pass) tracks that while it writes, so the barrier between phases carries it.
+    bool phantom = !__syncthreads_or(hz);
 
     // ---- 2. thresholded-EDT passes in shared memory (isotropic.py:35-36, 66-67) ----------------------
     uint32_t *src = T0, *dst = (T0 == A) ? B : A;
     for (int ps = 0; ps < prm.n_pass; ps++) {
         const int R = prm.pass[ps].R;
         const uint32_t inv = prm.pass[ps].invert ? FULL : 0u;
-        // scipy's phantom background pixel: the (inverted) plane has no 0 at all
-        bool has_zero = false;
-        {
-            int k = k_first;
-            for (int w = tid; w < words; w += T) {
-                has_zero |= ((src[w] ^ inv) | ~valid_mask(W, k)) != FULL;
-                k += step_k;
-                if (k >= wpr) k -= wpr;
-            }
-        }
-        const bool phantom = !__syncthreads_or(has_zero);
+        const uint32_t inv_next = (ps + 1 < prm.n_pass && prm.pass[ps + 1].invert) ? FULL : 0u;
+        hz = false;
         if (R >= 0 && R <= 3) {
             // strips of S rows x word columns: about one work item per thread
             const int nstrip = max(1, min(H, (T + wpr - 1) / wpr));
@@ -319,16 +332,16 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             const int *wt = prm.pass[ps].w;
             const int pat = R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
             switch (pat) { // d2 thresholds 1, 2-3, 4, 5-7, 8 get fully unrolled code
-            case 1100: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 0, 0, 0>(), inv, phantom, nstrip, S); break;
-            case 1110: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 1, 0, 0>(), inv, phantom, nstrip, S); break;
-            case 2210: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 1, 0, 0>(), inv, phantom, nstrip, S); break;
-            case 2221: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 1, 0>(), inv, phantom, nstrip, S); break;
-            case 2222: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 2, 0>(), inv, phantom, nstrip, S); break;
+            case 1100: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 0, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
+            case 1110: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 1, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
+            case 2210: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 1, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
+            case 2221: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 1, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
+            case 2222: morph_columns<2, T>(src, dst, H, W, wpr, WFixed<2, 2, 2, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
             default:
-                if (R == 0) morph_columns<0, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
-                else if (R == 1) morph_columns<1, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
-                else if (R == 2) morph_columns<2, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
-                else morph_columns<3, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S);
+                if (R == 0) morph_columns<0, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz);
+                else if (R == 1) morph_columns<1, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz);
+                else if (R == 2) morph_columns<2, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz);
+                else morph_columns<3, T>(src, dst, H, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz);
             }
         } else {
             int y = y_first, k = k_first;
@@ -367,13 +380,15 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                         acc &= h;
                     }
                 }
-                dst[w] = (acc ^ inv) & valid_mask(W, k);
+                const uint32_t vm = valid_mask(W, k), o = (acc ^ inv) & vm;
+                dst[w] = o;
+                hz |= ((o ^ inv_next) | ~vm) != FULL;
                 y += step_y; k += step_k;
                 if (k >= wpr) { k -= wpr; y++; }
             }
         }
         zero_fill(min(3 + ps, 5));
-        __syncthreads();
+        phantom = !__syncthreads_or(hz);
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
     const uint32_t *M = src; // final plane
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     u16 *rY = (u16 *)(s_mem + words), *rX0 = rY + RC, *rX1 = rX0 + RC, *P = rX1 + RC, *rO = P + RC, *rowStart = rO + RC;
 
     // ---- 3. run list + labelling (loki/pipeline.py:430-433) --------------------------------------------
-    const int chunk = (words + T - 1) / T;
+    const int chunk = ((words + T - 1) / T) | 1;  // odd: lanes start in different banks
     const int lo = min(tid * chunk, words), hi = min(lo + chunk, words);
     int cnt = 0;
     {
