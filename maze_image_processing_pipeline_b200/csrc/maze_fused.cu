@@ -165,34 +165,27 @@ __device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, 
 #pragma unroll
     for (int j = 0; j <= R; j++) wd[j] = wt.w(j);
     const int nitems = wpr * nstrip;
+    uint32_t hzacc = 0;  // valid bits of the output that are 0 after the NEXT pass's inversion (phantom test)
     for (int q = threadIdx.x; q < nitems; q += T) {
         const int s = q / wpr, k = q - s * wpr;
         const int y0 = s * S, y1 = min(H, y0 + S);
         if (y0 >= y1) continue;
+        // neighbour words without branches: a missing neighbour is read from the word itself and forced to ones
+        const bool hasL = k > 0, hasR = k + 1 < wpr;
         const uint32_t padC = ~valid_mask(W, k);
-        const uint32_t padR = (k + 1 < wpr) ? ~valid_mask(W, k + 1) : 0u;
+        const uint32_t mL = hasL ? 0u : FULL, mR = hasR ? ~valid_mask(W, k + 1) : FULL;
+        const int oL = hasL ? -1 : 0, oR = hasR ? 1 : 0;
         uint32_t win[2 * R + 1][R + 1]; // win[i][j]: row (y - R + i) of the current output row y, chord width wd[j]
 #pragma unroll
         for (int i = 0; i < 2 * R + 1; i++)
 #pragma unroll
             for (int j = 0; j <= R; j++) win[i][j] = FULL;
-        for (int r = y0 - R; r < y1 + R; r++) {
-            uint32_t L = FULL, C = FULL, Rw = FULL;
-            if (r >= 0 && r < H) {
-                const uint32_t *row = src + r * wpr + k;
-                C = (row[0] ^ inv) | padC;
-                if (k > 0) L = row[-1] ^ inv;
-                if (k + 1 < wpr) Rw = (row[1] ^ inv) | padR;
-            } else if (phantom && r == -1) {
-                if (k == 0) C = 0xfffffffeu;
-                if (k == 1) L = 0xfffffffeu;
-            }
-            // slide the window up by one row
+        auto feed = [&](uint32_t C, uint32_t L, uint32_t Rw) {
+            // slide the window up by one row, then the chord tests of the new row, narrow to wide
 #pragma unroll
             for (int i = 0; i < 2 * R; i++)
 #pragma unroll
                 for (int j = 0; j <= R; j++) win[i][j] = win[i + 1][j];
-            // chord tests of the new row, narrow to wide (wd[j] is non-increasing in j)
             uint32_t cur = C;
             int d = 0;
 #pragma unroll
@@ -203,17 +196,41 @@ __device__ __forceinline__ void morph_columns(const uint32_t *__restrict__ src, 
                 }
                 win[2 * R][j] = cur;
             }
-            const int y = r - R;
-            if (y >= y0) {
-                uint32_t acc = FULL;
+        };
+        auto emit = [&](uint32_t *out) {
+            uint32_t acc = FULL;
 #pragma unroll
-                for (int i = 0; i < 2 * R + 1; i++) acc &= win[i][i < R ? R - i : i - R];
-                const uint32_t o = (acc ^ inv) & ~padC;
-                dst[y * wpr + k] = o;
-                hz_next |= ((o ^ inv_next) | padC) != FULL;  // the next pass's input plane has a 0 (phantom test)
+            for (int i = 0; i < 2 * R + 1; i++) acc &= win[i][i < R ? R - i : i - R];
+            const uint32_t o = (acc ^ inv) & ~padC;
+            *out = o;
+            hzacc |= ~((o ^ inv_next) | padC);
+        };
+        // rows fed: [y0 - R, y1 + R); rows outside the image are all ones (the border is not background), except
+        // scipy's phantom pixel at (-1, 0) of a plane without any 0
+        const int r_hi = y1 + R;
+        for (int r = y0 - R; r < 0; r++) {
+            uint32_t C = FULL, L = FULL;
+            if (phantom && r == -1) {
+                if (k == 0) C = 0xfffffffeu;
+                if (k == 1) L = 0xfffffffeu;
             }
+            feed(C, L, FULL);
+        }
+        const int ra = max(y0 - R, 0), rb = min(r_hi, H);    // rows that exist
+        const int rm = min(max(y0 + R, ra), rb);             // first row whose feed completes an output row
+        const uint32_t *row = src + ra * wpr + k;
+        for (int r = ra; r < rm; r++, row += wpr) feed((row[0] ^ inv) | padC, (row[oL] ^ inv) | mL, (row[oR] ^ inv) | mR);
+        uint32_t *out = dst + (rm - R) * wpr + k;
+        for (int r = rm; r < rb; r++, row += wpr, out += wpr) {
+            feed((row[0] ^ inv) | padC, (row[oL] ^ inv) | mL, (row[oR] ^ inv) | mR);
+            emit(out);
+        }
+        for (int r = rb; r < r_hi; r++) { // below the image (last strip only)
+            feed(FULL, FULL, FULL);
+            if (r - R >= y0) emit(dst + (r - R) * wpr + k);
         }
     }
+    hz_next |= hzacc != 0u;
 }
 
 // "pixel > t" for 32 pixels held in nine aligned 32-bit words (row misaligned by `a` bytes).  Byte-wise compare in
