@@ -312,22 +312,33 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         const bool lowmode = t < 128;
         const uint32_t force = t < 0 ? FULL : 0u, kill = t >= 255 ? 0u : FULL;
         const uint32_t inv0 = (prm.n_pass > 0 && prm.pass[0].invert) ? FULL : 0u;
+        // two words per trip: all 18 loads are issued before the first compare (the phase is bound by HBM latency)
         int y = y_first, k = k_first;
-        for (int w = tid; w < words; w += T) {
-            const int nvalid = min(32, W - 32 * k);
-            const uint8_t *p = base + (size_t)y * W + 32 * k;
-            const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
-            const uint32_t *q = (const uint32_t *)(p - a);
-            const int last = (int)(a + nvalid - 1) >> 2;  // aligned word holding the row's last pixel of this word
-            uint32_t raw[9];
+        for (int w = tid; w < words; w += 2 * T) {
+            uint32_t raw[2][9], al[2], vmk[2];
 #pragma unroll
-            for (int i = 0; i < 9; i++) raw[i] = (i <= last) ? __ldg(q + i) : 0u;
-            const uint32_t word = lowmode ? threshold32<true>(raw, a, addc) : threshold32<false>(raw, a, addc);
-            const uint32_t vm = valid_mask(W, k), o = ((word | force) & kill) & vm;
-            T0[w] = o;
-            hz |= ((o ^ inv0) | ~vm) != FULL;  // the first pass's input plane has a 0 (scipy's phantom pixel otherwise)
-            y += step_y; k += step_k;
-            if (k >= wpr) { k -= wpr; y++; }
+            for (int u = 0; u < 2; u++) {
+                const bool on = w + u * T < words;
+                const int nvalid = min(32, W - 32 * k);
+                const uint8_t *p = base + (size_t)y * W + 32 * k;
+                al[u] = (uint32_t)((uintptr_t)p & 3u);
+                const uint32_t *q = (const uint32_t *)(p - al[u]);
+                const int last = on ? (int)(al[u] + nvalid - 1) >> 2 : -1; // aligned word holding the last pixel
+                vmk[u] = valid_mask(W, k);
+#pragma unroll
+                for (int i = 0; i < 9; i++) raw[u][i] = (i <= last) ? __ldg(q + i) : 0u;
+                y += step_y; k += step_k;
+                if (k >= wpr) { k -= wpr; y++; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (w + u * T < words) {
+                    const uint32_t word = lowmode ? threshold32<true>(raw[u], al[u], addc) : threshold32<false>(raw[u], al[u], addc);
+                    const uint32_t o = ((word | force) & kill) & vmk[u];
+                    T0[w + u * T] = o;
+                    hz |= ((o ^ inv0) | ~vmk[u]) != FULL;  // the first pass's input plane has a 0 (scipy's phantom pixel otherwise)
+                }
+            }
         }
     }
     zero_fill(2);
@@ -614,17 +625,24 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
                 const uint32_t al = (uint32_t)((uintptr_t)prow & 3u);   // row start relative to 4-byte alignment
                 const uint32_t *qq = (const uint32_t *)(prow - al);     // word g holds row bytes 4g-al .. 4g-al+3
                 const int ga = ((int)a + (int)al) >> 2, gb = ((int)b + (int)al) >> 2;
-                for (int g = ga; g <= gb; g++) {
-                    uint32_t px = __ldg(qq + g);
-                    const int c0 = 4 * g - (int)al;                     // column of byte 0 of this word
-                    uint32_t nib = 0xfu;
-                    if (c0 < (int)a) nib &= 0xfu << ((int)a - c0);
-                    if (c0 + 3 > (int)b) nib &= 0xfu >> (c0 + 3 - (int)b);
-                    uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                    aV = __dp4a(px & bm, 0x01010101u, aV);                              // sum of the four masked bytes
-                    aZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u); // bytes equal to 0
-                    vmn = __vminu4(vmn, px | ~bm);
-                    vmx = __vmaxu4(vmx, px & bm);
+                for (int g0 = ga; g0 <= gb; g0 += 4) { // four loads in flight: the loop is bound by L2 latency
+                    uint32_t pxs[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) pxs[u] = __ldg(qq + min(g0 + u, gb));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int g = g0 + u;
+                        const uint32_t px = pxs[u];
+                        const int c0 = 4 * g - (int)al;                 // column of byte 0 of this word
+                        uint32_t nib = g <= gb ? 0xfu : 0u;             // words past the run contribute nothing
+                        if (c0 < (int)a) nib &= 0xfu << ((int)a - c0);
+                        if (c0 + 3 > (int)b) nib &= 0xfu >> min(c0 + 3 - (int)b, 31);
+                        uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                        aV = __dp4a(px & bm, 0x01010101u, aV);                              // sum of the four masked bytes
+                        aZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u); // bytes equal to 0
+                        vmn = __vminu4(vmn, px | ~bm);
+                        vmx = __vmaxu4(vmx, px & bm);
+                    }
                 }
             }
         }
