@@ -316,6 +316,18 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         int y = y_first, k = k_first;
         for (int w = tid; w < words; w += 2 * T) {
             uint32_t raw[2][9], al[2], vmk[2];
+            { // L2 prefetch of the NEXT trip's two words (every 32-byte sector of the image holds one word start)
+                int yn = y + 2 * step_y, kn = k + 2 * step_k;
+                if (kn >= wpr) { kn -= wpr; yn++; }
+                if (kn >= wpr) { kn -= wpr; yn++; }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (w + (2 + u) * T < words)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)yn * W + 32 * kn));
+                    yn += step_y; kn += step_k;
+                    if (kn >= wpr) { kn -= wpr; yn++; }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const bool on = w + u * T < words;
