@@ -314,15 +314,28 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         const uint32_t inv0 = (prm.n_pass > 0 && prm.pass[0].invert) ? FULL : 0u;
         // two words per trip: all 18 loads are issued before the first compare (the phase is bound by HBM latency)
         int y = y_first, k = k_first;
+        {
+            int yn = y + 2 * step_y, kn = k + 2 * step_k;
+            if (kn >= wpr) { kn -= wpr; yn++; }
+            if (kn >= wpr) { kn -= wpr; yn++; }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (tid + (2 + u) * T < words)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)yn * W + 32 * kn));
+                yn += step_y; kn += step_k;
+                if (kn >= wpr) { kn -= wpr; yn++; }
+            }
+        }
         for (int w = tid; w < words; w += 2 * T) {
             uint32_t raw[2][9], al[2], vmk[2];
-            { // L2 prefetch of the NEXT trip's two words (every 32-byte sector of the image holds one word start)
-                int yn = y + 2 * step_y, kn = k + 2 * step_k;
-                if (kn >= wpr) { kn -= wpr; yn++; }
-                if (kn >= wpr) { kn -= wpr; yn++; }
+            { // L2 prefetch two trips ahead (every 32-byte sector of the image holds one word start)
+                int yn = y + 4 * step_y, kn = k + 4 * step_k; // two trips ahead
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (kn >= wpr) { kn -= wpr; yn++; }
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
-                    if (w + (2 + u) * T < words)
+                    if (w + (4 + u) * T < words)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)yn * W + 32 * kn));
                     yn += step_y; kn += step_k;
                     if (kn >= wpr) { kn -= wpr; yn++; }
