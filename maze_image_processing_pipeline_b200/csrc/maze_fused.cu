@@ -37,6 +37,18 @@ struct FusedParams {
     FusedPass pass[4];
 };
 
+// 64-bit add to a shared-memory slot as one or two NATIVE 32-bit atomics (a 64-bit shared atomicAdd is a
+// compare-and-swap loop, and all warps of the CTA flush into the same few rows at the same moment): the low half
+// accumulates modulo 2^32, the carry of each add follows from the value the atomic returns.
+__device__ __forceinline__ void shared_add64(u64 *slot, u64 v)
+{
+    uint32_t *w = (uint32_t *)slot;
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t old = atomicAdd(w, lo);
+    const uint32_t up = hi + ((old + lo) < old ? 1u : 0u);
+    if (up) atomicAdd(w + 1, up);
+}
+
 struct AccRow { // shared-memory accumulator of one label
     u64 a[MAZE_NACC];
     double h[8];
@@ -614,16 +626,21 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
         auto flush = [&](int lab) { // add the register sums of label `lab` to its accumulator row
             u64 *Aa;
             int *Ee;
-            if (lab <= FUSED_LCAP) { Aa = ACC[lab - 1].a; Ee = ACC[lab - 1].e; }
-            else { Aa = acc_stage + (i64)(base + lab - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + lab - 1) * MAZE_NEXT; }
-            atomicAdd(Aa + A_N, aN); atomicAdd(Aa + A_R, aR); atomicAdd(Aa + A_C, aC);
-            atomicAdd(Aa + A_RR, aRR); atomicAdd(Aa + A_RC, aRC); atomicAdd(Aa + A_CC, aCC);
-            atomicAdd(Aa + A_RRR, aRRR); atomicAdd(Aa + A_RRC, aRRC); atomicAdd(Aa + A_RCC, aRCC);
-            atomicAdd(Aa + A_CCC, aCCC);
+            const u64 sums[10] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC};
+            if (lab <= FUSED_LCAP) {
+                Aa = ACC[lab - 1].a; Ee = ACC[lab - 1].e;
+#pragma unroll
+                for (int j = 0; j < 10; j++) shared_add64(Aa + j, sums[j]);
+                if (gi) { shared_add64(Aa + A_V, (u64)aV); if (aZ) shared_add64(Aa + A_Z, (u64)aZ); }
+            } else {
+                Aa = acc_stage + (i64)(base + lab - 1) * MAZE_NACC; Ee = ext_stage + (i64)(base + lab - 1) * MAZE_NEXT;
+#pragma unroll
+                for (int j = 0; j < 10; j++) atomicAdd(Aa + j, sums[j]);
+                if (gi) { atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ); }
+            }
             atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
             atomicMin(Ee + E_CMIN, cmin); atomicMax(Ee + E_CMAX, cmax);
             if (gi) {
-                atomicAdd(Aa + A_V, (u64)aV); atomicAdd(Aa + A_Z, (u64)aZ);
                 uint32_t mn = __vminu4(vmn, vmn >> 16); mn = __vminu4(mn, mn >> 8);
                 uint32_t mx = __vmaxu4(vmx, vmx >> 16); mx = __vmaxu4(mx, mx >> 8);
                 atomicMin(Ee + E_VMIN, (int)(mn & 0xffu)); atomicMax(Ee + E_VMAX, (int)(mx & 0xffu));
