@@ -186,7 +186,8 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
  * maze_props_finish_staged, which supplies label, vignette and bounding box); rows with area 0 get NaN.
  * labels may be NULL: `bits` is then the single region (ImageProperties semantics, loki/pipeline.py:653).
  * pool: n_slabs slabs of slab_words uint32 scratch, slab_words >= 2 * (max_h + 2) * ceil((max_w + 2) / 32) for the
- * tallest / widest bounding box of the batch; one CTA per slab.  work_counter: one int32 (cleared by the call). */
+ * tallest / widest bounding box of the batch (used by the objects whose planes exceed shared memory, one CTA per
+ * slab).  work_counter: two int32 (cleared by the call). */
 int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                      const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
                      int32_t *work_counter, double *shape, void *stream);

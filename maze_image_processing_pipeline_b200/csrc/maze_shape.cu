@@ -16,14 +16,18 @@
 // One CTA takes one object at a time from a work counter: it builds the object's own bit plane P (label == l
 // inside the bounding box, one zero pixel of frame around it) from the label image, derives the border plane,
 // the three perimeter class counts and the Euler sum with 32-pixel word operations, then floods the complement
-// from the frame by row sweeps (in-word Kogge-Stone fill, carries across the words of a row resolved with one
-// ballot + add per direction) until a whole round changes nothing.  Planes of small crops live in shared
+// from the frame: one row-parallel pass (in-word Kogge-Stone fill, carries across the words of a row resolved
+// with one ballot + add per direction), then sweeps down and up that only touch rows whose neighbours bring new
+// seeds, until a whole round changes nothing (a convex object is done after the first pass).  Planes of small crops live in shared
 // memory, the others in the CTA's slab of a caller-provided pool.  All counts are exact integers; the only
 // floating-point step is the final weighted sum of the perimeter.
 #include "maze_common.cuh"
 
-#define SH_T 128           /* threads per CTA */
-#define SH_SMEM_WORDS 4096 /* both planes of a crop of up to 2048 words stay in shared memory */
+#define SH_T 128           /* threads per CTA, crops whose planes fit shared memory */
+#define SH_T_BIG 512       /* threads per CTA for the others (planes in the CTA's slab): 16 bands of rows flood at once */
+#define SH_SMEM_WORDS 14000 /* both planes of a crop of up to 7000 words (~470 x 470 px) stay in shared memory:
+                               56 KB per CTA, four CTAs per SM; a row step on shared planes costs tens of cycles, on
+                               the global slab an L2 round trip */
 #define SH_MAX_CHUNKS 5    /* 32-word chunks per framed row: (4096 + 2 + 31) / 32 = 129 words */
 
 // seeds spread along the runs of m, both directions, inside one word
@@ -69,16 +73,17 @@ __device__ __forceinline__ void count4(uint32_t x1, uint32_t x2, uint32_t x3, ui
     c2 = h1 & h2;
 }
 
-__global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict__ labels,
+template <int T, bool BIG>
+__global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ labels,
                                                       const uint32_t *__restrict__ bits,
                                                       const maze_vignette_t *__restrict__ vig,
                                                       const double *__restrict__ table, int n_obj, uint32_t *pool,
                                                       i64 slab_words, int *work_counter, double *__restrict__ shape)
 {
-    __shared__ uint32_t s_planes[SH_SMEM_WORDS];
+    extern __shared__ uint32_t s_planes[];
     __shared__ int s_job;
     __shared__ int s_acc[5];  // n1, n2, n3, euler, reached
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = SH_T / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T / 32;
     uint32_t *slab = pool + (i64)blockIdx.x * slab_words;
     for (;;) {
         __syncthreads();
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
         double *out = shape + (i64)o * MAZE_NSHAPE;
         const double area = row[MAZE_F_AREA];
         if (!(area > 0)) {  // label removed by a filter, or absent
-            if (tid < MAZE_NSHAPE) out[tid] = nan("");
+            if (!BIG && tid < MAZE_NSHAPE) out[tid] = nan("");
             continue;
         }
         const int r0 = (int)row[MAZE_F_BBOX], c0 = (int)row[MAZE_F_BBOX + 1];
@@ -99,33 +104,56 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
         const int label = (int)row[MAZE_F_LABEL];
         const maze_vignette_t v = vig[(int)row[MAZE_F_IMAGE]];
         const int rows = h + 2, fw = w + 2, cw = (fw + 31) >> 5, nwords = rows * cw;
-        if ((i64)2 * nwords > slab_words && 2 * nwords > SH_SMEM_WORDS) {  // cannot happen with a slab sized by the caller
+        if ((2 * nwords > SH_SMEM_WORDS) != BIG) continue;  // the other launch takes this object
+        if (BIG && (i64)2 * nwords > slab_words) {          // cannot happen with a slab sized by the caller
             if (tid < MAZE_NSHAPE) out[tid] = nan("");
             continue;
         }
-        uint32_t *P = (2 * nwords <= SH_SMEM_WORDS) ? s_planes : slab;
+        uint32_t *P = BIG ? slab : s_planes;
         uint32_t *R = P + nwords;
 
         // ---- A. the object's own plane, framed by one zero pixel --------------------------------------------
-        for (int fy = warp; fy < rows; fy += nwarp) {
-            const bool inside = fy >= 1 && fy <= h;
-            const int y = r0 + fy - 1;
-            for (int k = 0; k < cw; k++) {
-                const int fx = 32 * k + lane, x = c0 - 1 + fx;
-                bool b = false;
-                if (inside && fx >= 1 && fx <= w) {
-                    if (labels) b = __ldg(labels + v.pix_off + (i64)y * v.w + x) == label;
-                    else b = (__ldg(bits + v.word_off + (i64)y * v.wpr + (x >> 5)) >> (x & 31)) & 1u;
+        // work items of (row, group of eight words); four items = 32 loads per lane are in flight, the loop is bound
+        // by memory latency
+        {
+            const int ngrp = (cw + 7) >> 3, nitem = rows * ngrp;
+            for (int it0 = warp * 4; it0 < nitem; it0 += nwarp * 4) {
+                uint32_t cmp[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int it = it0 + q;
+                    const int fy = it / ngrp, k0 = (it - fy * ngrp) * 8;
+                    const bool inside = it < nitem && fy >= 1 && fy <= h;
+                    const int y = r0 + fy - 1;
+                    cmp[q] = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int fx = 32 * (k0 + u) + lane, x = c0 - 1 + fx;
+                        bool b = false;
+                        if (inside && fx >= 1 && fx <= w) {
+                            if (labels) b = __ldg(labels + v.pix_off + (i64)y * v.w + x) == label;
+                            else b = (__ldg(bits + v.word_off + (i64)y * v.wpr + (x >> 5)) >> (x & 31)) & 1u;
+                        }
+                        cmp[q] |= (b ? 1u : 0u) << u;
+                    }
                 }
-                const uint32_t word = __ballot_sync(FULL, b);
-                if (lane == 0) P[fy * cw + k] = word;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int it = it0 + q;
+                    const int fy = it / ngrp, k0 = (it - fy * ngrp) * 8;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const uint32_t word = __ballot_sync(FULL, (cmp[q] >> u) & 1u);
+                        if (lane == u && it < nitem && k0 + u < cw) P[fy * cw + k0 + u] = word;
+                    }
+                }
             }
         }
         __syncthreads();
 
         // ---- B. border plane (into R) and the Euler sum ------------------------------------------------------
         int euler = 0;
-        for (int i = tid; i < nwords; i += SH_T) {
+        for (int i = tid; i < nwords; i += T) {
             const int fy = i / cw, k = i - fy * cw;
             const uint32_t C = P[i];
             const uint32_t U = fy > 0 ? P[i - cw] : 0u, D = fy < rows - 1 ? P[i + cw] : 0u;
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
 
         // ---- C. perimeter classes ----------------------------------------------------------------------------
         int n1 = 0, n2 = 0, n3 = 0;
-        for (int i = tid; i < nwords; i += SH_T) {
+        for (int i = tid; i < nwords; i += T) {
             const uint32_t B = R[i];
             if (!B) continue;  // border pixels exist only in rows 1..h
             const int fy = i / cw, k = i - fy * cw;
@@ -176,7 +204,7 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
         __syncthreads();
 
         // ---- D. flood of the complement from the frame (8-connected) ------------------------------------------
-        for (int i = tid; i < nwords; i += SH_T) {
+        for (int i = tid; i < nwords; i += T) {
             const int fy = i / cw, k = i - fy * cw;
             uint32_t s = 0;
             if (fy == 0 || fy == rows - 1) s = valid_mask(fw, k);
@@ -187,65 +215,83 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
             R[i] = s;
         }
         __syncthreads();
-        const int band = (rows + nwarp - 1) / nwarp;
-        const int b_lo = max(1, warp * band), b_hi = min(rows - 1, (warp + 1) * band);  // frame rows are complete
+        // one row: seeds = what the row already holds plus the 8-neighbour spread of the rows above and below;
+        // in-word fill, then the carries across the words of the row.  `lazy` skips rows the neighbours add nothing
+        // to (every row is closed under its own fill after the first, row-parallel pass).  Returns "row changed".
         const int nchunk = (cw + 31) >> 5;
-        for (;;) {
-            int changed = 0;
-            for (int dir = 0; dir < 2; dir++) {
-                for (int step = 0; step < b_hi - b_lo; step++) {
-                    const int fy = dir == 0 ? b_lo + step : b_hi - 1 - step;
-                    uint32_t s[SH_MAX_CHUNKS], M[SH_MAX_CHUNKS], old[SH_MAX_CHUNKS];
-                    uint32_t cin = 0;
+        auto flood_row = [&](int fy, bool lazy) -> int {
+            uint32_t s[SH_MAX_CHUNKS], M[SH_MAX_CHUNKS], old[SH_MAX_CHUNKS];
+            bool fresh = false;
 #pragma unroll
-                    for (int c = 0; c < SH_MAX_CHUNKS; c++) {  // local fill, then carries towards larger x
-                        if (c < nchunk) {
-                            const int k = 32 * c + lane;
-                            const bool ok = k < cw;
-                            const int i = fy * cw + k;
-                            M[c] = ok ? (~P[i] & valid_mask(fw, k)) : 0u;
-                            old[c] = ok ? ldv(R + i) : 0u;
-                            uint32_t V = 0, VL = 0, VR = 0;
-                            if (ok) {
-                                V = ldv(R + i - cw) | ldv(R + i + cw);
-                                if (k > 0) VL = ldv(R + i - cw - 1) | ldv(R + i + cw - 1);
-                                if (k < cw - 1) VR = ldv(R + i - cw + 1) | ldv(R + i + cw + 1);
-                            }
-                            const uint32_t spread = V | (V << 1) | (VL >> 31) | (V >> 1) | (VR << 31);
-                            s[c] = fill_in_word(old[c] | spread, M[c]);
-                            const uint32_t G = __ballot_sync(FULL, s[c] >> 31), Pm = __ballot_sync(FULL, M[c] == FULL);
-                            const uint32_t A = G | Pm;
-                            const u64 S = (u64)A + G + cin;
-                            const uint32_t Cin = (uint32_t)S ^ A ^ G;
-                            cin = (uint32_t)(S >> 32);
-                            if ((Cin >> lane) & 1u) s[c] |= trailing_ones(M[c]);
-                        }
+            for (int c = 0; c < SH_MAX_CHUNKS; c++) {
+                if (c < nchunk) {
+                    const int k = 32 * c + lane;
+                    const bool ok = k < cw;
+                    const int i = fy * cw + k;
+                    M[c] = ok ? (~P[i] & valid_mask(fw, k)) : 0u;
+                    old[c] = ok ? ldv(R + i) : 0u;
+                    uint32_t V = 0, VL = 0, VR = 0;
+                    if (ok) {
+                        V = ldv(R + i - cw) | ldv(R + i + cw);
+                        if (k > 0) VL = ldv(R + i - cw - 1) | ldv(R + i + cw - 1);
+                        if (k < cw - 1) VR = ldv(R + i - cw + 1) | ldv(R + i + cw + 1);
                     }
-                    cin = 0;
-#pragma unroll
-                    for (int c = SH_MAX_CHUNKS - 1; c >= 0; c--) {  // carries towards smaller x
-                        if (c < nchunk) {
-                            const uint32_t G = __brev(__ballot_sync(FULL, s[c] & 1u));
-                            const uint32_t Pm = __brev(__ballot_sync(FULL, M[c] == FULL));
-                            const uint32_t A = G | Pm;
-                            const u64 S = (u64)A + G + cin;
-                            const uint32_t Cin = (uint32_t)S ^ A ^ G;
-                            cin = (uint32_t)(S >> 32);
-                            if ((Cin >> (31 - lane)) & 1u) s[c] |= leading_ones(M[c]);
-                            const int k = 32 * c + lane;
-                            if (k < cw && s[c] != old[c]) {
-                                R[fy * cw + k] = s[c];
-                                changed = 1;
-                            }
-                        }
-                    }
-                    __syncwarp();
+                    const uint32_t spread = (V | (V << 1) | (VL >> 31) | (V >> 1) | (VR << 31)) & M[c];
+                    fresh |= (spread & ~old[c]) != 0u;
+                    s[c] = old[c] | spread;
                 }
             }
+            if (lazy && !__any_sync(FULL, fresh)) return 0;
+            uint32_t cin = 0;
+#pragma unroll
+            for (int c = 0; c < SH_MAX_CHUNKS; c++) {  // local fill, then carries towards larger x
+                if (c < nchunk) {
+                    s[c] = fill_in_word(s[c], M[c]);
+                    const uint32_t G = __ballot_sync(FULL, s[c] >> 31), Pm = __ballot_sync(FULL, M[c] == FULL);
+                    const uint32_t A = G | Pm;
+                    const u64 S = (u64)A + G + cin;
+                    const uint32_t Cin = (uint32_t)S ^ A ^ G;
+                    cin = (uint32_t)(S >> 32);
+                    if ((Cin >> lane) & 1u) s[c] |= trailing_ones(M[c]);
+                }
+            }
+            cin = 0;
+            int changed = 0;
+#pragma unroll
+            for (int c = SH_MAX_CHUNKS - 1; c >= 0; c--) {  // carries towards smaller x
+                if (c < nchunk) {
+                    const uint32_t G = __brev(__ballot_sync(FULL, s[c] & 1u));
+                    const uint32_t Pm = __brev(__ballot_sync(FULL, M[c] == FULL));
+                    const uint32_t A = G | Pm;
+                    const u64 S = (u64)A + G + cin;
+                    const uint32_t Cin = (uint32_t)S ^ A ^ G;
+                    cin = (uint32_t)(S >> 32);
+                    if ((Cin >> (31 - lane)) & 1u) s[c] |= leading_ones(M[c]);
+                    const int k = 32 * c + lane;
+                    if (k < cw && s[c] != old[c]) {
+                        R[fy * cw + k] = s[c];
+                        changed = 1;
+                    }
+                }
+            }
+            __syncwarp();
+            return changed;
+        };
+        // first pass, all rows in parallel: from the frame columns (and whatever the neighbours already hold)
+        for (int fy = 1 + warp; fy < rows - 1; fy += nwarp) flood_row(fy, false);
+        __syncthreads();
+        // then sweeps down and up over bands of rows (one band per warp) until a whole round changes nothing;
+        // for a convex object the first pass has reached everything and the sweeps only look
+        const int band = (rows + nwarp - 1) / nwarp;
+        const int b_lo = max(1, warp * band), b_hi = min(rows - 1, (warp + 1) * band);  // frame rows are complete
+        for (;;) {
+            int changed = 0;
+            for (int fy = b_lo; fy < b_hi; fy++) changed |= flood_row(fy, true);
+            for (int fy = b_hi - 1; fy >= b_lo; fy--) changed |= flood_row(fy, true);
             if (!__syncthreads_or(changed)) break;
         }
         int reached = 0;
-        for (int i = tid; i < nwords; i += SH_T) reached += __popc(R[i]);
+        for (int i = tid; i < nwords; i += T) reached += __popc(R[i]);
 #pragma unroll
         for (int d = 16; d; d >>= 1) reached += __shfl_xor_sync(FULL, reached, d);
         if (lane == 0) atomicAdd(&s_acc[4], reached);
@@ -265,6 +311,33 @@ __global__ void __launch_bounds__(SH_T) k_label_shape(const int32_t *__restrict_
     }
 }
 
+struct ShapeFork {  // side stream for the launch of the large crops (per host thread and device)
+    int device;
+    cudaStream_t aux;
+    cudaEvent_t fork, join;
+};
+
+static ShapeFork *shape_fork()
+{
+    static thread_local ShapeFork pool[16];
+    static thread_local int n_pool = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < n_pool; i++)
+        if (pool[i].device == dev) return &pool[i];
+    if (n_pool >= 16) return nullptr;
+    ShapeFork *f = &pool[n_pool];
+    f->device = dev;
+    if (cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaFuncSetAttribute(k_label_shape<SH_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SH_SMEM_WORDS * (int)sizeof(uint32_t)) != cudaSuccess)
+        return nullptr;
+    n_pool++;
+    return f;
+}
+
 extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                                 const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
                                 int32_t *work_counter, double *shape, void *stream)
@@ -274,10 +347,24 @@ extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, con
     if ((!labels && !bits) || !vig || !table || !shape || !work_counter || n_slabs <= 0 || slab_words < 0 ||
         (slab_words > 0 && !pool))
         return MAZE_ERR_BADARG;
-    MAZE_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), s), "label_shape counter");
-    const int grid = n_slabs < n_obj ? n_slabs : n_obj;
+    MAZE_CUDA(cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), s), "label_shape counter");
+    ShapeFork *fk = shape_fork();
+    if (!fk) return MAZE_ERR_CUDA;
+    // the few objects whose planes do not fit shared memory (they take longest: 512 threads each on a slab of the
+    // pool) run on a side stream next to everything else (four CTAs of 128 threads per SM, planes in shared memory)
+    if (slab_words > 0) {
+        MAZE_CUDA(cudaEventRecord(fk->fork, s), "label_shape fork");
+        MAZE_CUDA(cudaStreamWaitEvent(fk->aux, fk->fork, 0), "label_shape fork wait");
+        const int grid_big = n_slabs < n_obj ? n_slabs : n_obj;
+        MAZE_KERNEL(KID_LABEL_SHAPE, fk->aux,
+                    (k_label_shape<SH_T_BIG, true><<<grid_big, SH_T_BIG, 0, fk->aux>>>(
+                        labels, bits, vig, table, n_obj, pool, slab_words, work_counter, shape)));
+        MAZE_CUDA(cudaEventRecord(fk->join, fk->aux), "label_shape join");
+    }
+    const int grid = n_obj < 148 * 8 ? n_obj : 148 * 8;
     MAZE_KERNEL(KID_LABEL_SHAPE, s,
-                k_label_shape<<<grid, SH_T, 0, s>>>(labels, bits, vig, table, n_obj, pool, slab_words, work_counter,
-                                                    shape));
+                (k_label_shape<SH_T, false><<<grid, SH_T, SH_SMEM_WORDS * sizeof(uint32_t), s>>>(
+                    labels, bits, vig, table, n_obj, pool, slab_words, work_counter + 1, shape)));
+    if (slab_words > 0) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "label_shape join wait");
     return MAZE_OK;
 }

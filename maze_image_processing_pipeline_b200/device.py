@@ -489,7 +489,7 @@ class DeviceBatch:
             return shape
         g = self.g
         slab_words = 2 * (int(g.h.max()) + 2) * ((int(g.w.max()) + 2 + 31) // 32)
-        n_slabs = max(1, min(n_obj, 148 * 8, pool_bytes // (4 * slab_words)))
+        n_slabs = max(1, min(n_obj, 148, pool_bytes // (4 * slab_words)))  # one 512-thread CTA per SM
         need = n_slabs * slab_words + 64
         key = (str(self.device), _stream())  # one pool per stream: calls on one stream are ordered
         pools = DeviceBatch._shape_pool = DeviceBatch._shape_pool or {}
