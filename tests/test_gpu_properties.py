@@ -66,3 +66,22 @@ def test_stage_random_batches(ms, r_open, r_close, thr):
         assert np.array_equal(feats[:, oracle.F_IMIN:oracle.F_IMAX + 1], table[:, oracle.F_IMIN:oracle.F_IMAX + 1])
         np.testing.assert_allclose(feats[:, oracle.F_CENTROID:oracle.F_CENTROID + 2],
                                    table[:, oracle.F_CENTROID:oracle.F_CENTROID + 2], rtol=1e-13)
+
+
+@settings(**SET)
+@given(m=masks(max_side=90), as_labels=st.booleans())
+def test_label_shape_random(m, as_labels):
+    """perimeter class counts, euler_number and filled_area of arbitrary masks: per 8-connected label, or the whole
+    mask as one region (ImageProperties semantics; the region may then be disconnected)."""
+    from oracle import shape as oshape
+    from maze_image_processing_pipeline_b200 import measure
+    if as_labels:
+        lab, _ = oracle.label(m)
+        got, want = measure.regionprops_shape(lab), oshape.label_shape(lab)
+    else:
+        got, want = measure.mask_shape(m), oshape.label_shape(m.astype(np.int32), max_label=1)
+    assert got.shape == want.shape
+    absent = np.isnan(want[:, 0])
+    assert np.array_equal(np.isnan(got[:, 0]), absent)
+    assert np.array_equal(got[~absent, 1:6], want[~absent, 1:6])
+    np.testing.assert_allclose(got[~absent, 0], want[~absent, 0], rtol=1e-12)
