@@ -98,6 +98,7 @@ typedef struct maze_tile {
 #define MAZE_S_N1 3          /* border pixels of weight 1, sqrt(2), (1 + sqrt(2)) / 2: the exact integers behind */
 #define MAZE_S_N2 4          /*   the perimeter */
 #define MAZE_S_N3 5
+#define MAZE_S_CONVEX_AREA 6 /* np.sum(skimage.morphology.convex_hull_image(region.image)) */
 
 /* Per-object integer accumulators (regionprops pass 1): MAZE_NACC uint64 per object followed,
  * in a second array, by MAZE_NEXT int32 extrema per object. */
@@ -181,16 +182,18 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
                      double *table, int flags, const int32_t *acc_base, void *stream);
 
 /* Shape features read by CalculateZooProcessFeatures(region, meta, prefix="object_") (loki/pipeline.py:625, 654)
- * through skimage's RegionProperties: perimeter, euler_number, filled_area.
+ * through skimage's RegionProperties: perimeter, euler_number, filled_area, convex_area (SURVEY.md section 8, rows
+ * a10 / f1).
  * One row of MAZE_NSHAPE doubles per row of `table` (the finished feature table of maze_regionprops /
  * maze_props_finish_staged, which supplies label, vignette and bounding box); rows with area 0 get NaN.
  * labels may be NULL: `bits` is then the single region (ImageProperties semantics, loki/pipeline.py:653).
  * pool: n_slabs slabs of slab_words uint32 scratch, slab_words >= 2 * (max_h + 2) * ceil((max_w + 2) / 32) for the
  * tallest / widest bounding box of the batch (used by the objects whose planes exceed shared memory, one CTA per
- * slab).  work_counter: two int32 (cleared by the call). */
+ * slab).  max_h: tallest vignette of the batch (sizes the hull storage of those objects).  work_counter: two int32
+ * (cleared by the call). */
 int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                      const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
-                     int32_t *work_counter, double *shape, void *stream);
+                     int max_h, int32_t *work_counter, double *shape, void *stream);
 
 /* maze_ipp/merge_labels.py:29-113 for every vignette of the batch, one CTA per vignette.
  * labels: read by the loop; labels_out: written (pass the same pointer for the pipeline's aliased

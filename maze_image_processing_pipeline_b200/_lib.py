@@ -24,7 +24,7 @@ MAX_DISK_RADIUS = 32
 NFEAT = 64
 NACC = 12
 NEXT = 8
-NSHAPE = 8  # MAZE_NSHAPE: perimeter, filled_area, euler_number, n1, n2, n3, -, -
+NSHAPE = 8  # MAZE_NSHAPE: perimeter, filled_area, euler_number, n1, n2, n3, convex_area, -
 RP_HIGH_ORDER = 1
 RP_RUNS = 2
 FUSED_CAPS = (1024, 2560, 4096, 6144, 9216, 13312, 19456, 28320)  # MAZE_FUSED_CAPS of include/maze_b200.h
@@ -91,7 +91,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
-    "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _vp, _vp, _vp],
+    "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
     "maze_stage_step": [_vp, _vp, _vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -9,6 +9,8 @@
 //   euler_number  skimage.measure.euler_number(region.image, connectivity=2): over all 2x2 windows of the
 //                 zero-padded crop, +1 for "only the top-left pixel set", -1 for "top-right and bottom-left set,
 //                 the other two clear", -1 for "all but the bottom-right set".
+//   convex_area   np.sum(skimage.morphology.convex_hull_image(region.image)): hull of the four edge midpoints of every
+//                 pixel, pixel centres inside or on the hull count.
 //   filled_area   region.image with its holes filled by scipy.ndimage.binary_fill_holes(image, ones((3, 3))): the
 //                 complement is flooded from outside the crop with 8-CONNECTED steps; what the flood does not
 //                 reach is object or hole.
@@ -19,7 +21,8 @@
 // from the frame: one row-parallel pass (in-word Kogge-Stone fill, carries across the words of a row resolved
 // with one ballot + add per direction), then sweeps down and up that only touch rows whose neighbours bring new
 // seeds, until a whole round changes nothing (a convex object is done after the first pass).  Planes of small crops live in shared
-// memory, the others in the CTA's slab of a caller-provided pool.  All counts are exact integers; the only
+// memory, the others in the CTA's slab of a caller-provided pool.  The convex hull area follows from the row
+// extremes of the plane (monotone chain + exact rasterisation).  All counts are exact integers; the only
 // floating-point step is the final weighted sum of the perimeter.
 #include "maze_common.cuh"
 
@@ -78,17 +81,19 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
                                                       const uint32_t *__restrict__ bits,
                                                       const maze_vignette_t *__restrict__ vig,
                                                       const double *__restrict__ table, int n_obj, uint32_t *pool,
-                                                      i64 slab_words, int *work_counter, double *__restrict__ shape)
+                                                      i64 slab_words, int big_chain_words, int *work_counter,
+                                                      double *__restrict__ shape)
 {
     extern __shared__ uint32_t s_planes[];
     __shared__ int s_job;
-    __shared__ int s_acc[5];  // n1, n2, n3, euler, reached
+    __shared__ int s_acc[6];  // n1, n2, n3, euler, reached, convex
+    __shared__ int s_nchain[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T / 32;
     uint32_t *slab = pool + (i64)blockIdx.x * slab_words;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_job = atomicAdd(work_counter, 1);
-        if (tid < 5) s_acc[tid] = 0;
+        if (tid < 6) s_acc[tid] = 0;
         __syncthreads();
         const int o = s_job;
         if (o >= n_obj) return;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
         const int label = (int)row[MAZE_F_LABEL];
         const maze_vignette_t v = vig[(int)row[MAZE_F_IMAGE]];
         const int rows = h + 2, fw = w + 2, cw = (fw + 31) >> 5, nwords = rows * cw;
-        if ((2 * nwords > SH_SMEM_WORDS) != BIG) continue;  // the other launch takes this object
+        if ((2 * nwords + 4 * h + 2 > SH_SMEM_WORDS) != BIG) continue;  // the other launch takes this object
         if (BIG && (i64)2 * nwords > slab_words) {          // cannot happen with a slab sized by the caller
             if (tid < MAZE_NSHAPE) out[tid] = nan("");
             continue;
@@ -296,6 +301,100 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
         for (int d = 16; d; d >>= 1) reached += __shfl_xor_sync(FULL, reached, d);
         if (lane == 0) atomicAdd(&s_acc[4], reached);
         __syncthreads();
+
+        // ---- E. area of the convex hull image (skimage.morphology.convex_hull_image: every pixel contributes the
+        // midpoints of its four edges; a pixel is in when its centre lies in or on the hull) --------------------------
+        // Doubled coordinates (row y <-> Y = 2y): per level Y = -1 .. 2h-1 the leftmost / rightmost hull candidate
+        // follows from the row extremes; two threads run the monotone chain in place; every row then counts the
+        // pixel centres between the two chains in exact integer arithmetic.
+        uint32_t *CL = BIG ? s_planes : s_planes + 2 * nwords, *CR = CL + (2 * h + 1);
+        const bool hull_ok = BIG ? (4 * h + 2 <= big_chain_words) : true;
+        if (hull_ok) {
+            for (int y = tid; y < h; y += T) {  // row extremes (pixel columns) into the now idle plane R
+                const uint32_t *prow = P + (y + 1) * cw;
+                int xl = -1, xr = -1;
+                for (int k = 0; k < cw; k++) {
+                    const uint32_t m = prow[k];
+                    if (m) { xl = 32 * k + __ffs(m) - 2; break; }
+                }
+                for (int k = cw - 1; k >= 0 && xl >= 0; k--) {
+                    const uint32_t m = prow[k];
+                    if (m) { xr = 32 * k + 30 - __clz(m); break; }
+                }
+                R[y] = xl < 0 ? FULL : (((uint32_t)xl << 16) | (uint32_t)xr);
+            }
+            __syncthreads();
+            for (int j = tid; j <= 2 * h; j += T) {  // level Y = j - 1, stored as (Y + 1) << 16 | (X + 1)
+                int l = 0x7fffffff, r = -0x7fffffff;
+                if (j & 1) {  // pixel row: (y, xl - 1/2), (y, xr + 1/2)
+                    const uint32_t e = R[j >> 1];
+                    if (e != FULL) { l = 2 * (int)(e >> 16) - 1; r = 2 * (int)(e & 0xffffu) + 1; }
+                } else {      // between rows: (y + 1/2, x) of the row above, (y - 1/2, x) of the row below
+                    const int ya = (j >> 1) - 1, yb = j >> 1;
+                    if (ya >= 0) {
+                        const uint32_t e = R[ya];
+                        if (e != FULL) { l = min(l, 2 * (int)(e >> 16)); r = max(r, 2 * (int)(e & 0xffffu)); }
+                    }
+                    if (yb < h) {
+                        const uint32_t e = R[yb];
+                        if (e != FULL) { l = min(l, 2 * (int)(e >> 16)); r = max(r, 2 * (int)(e & 0xffffu)); }
+                    }
+                }
+                const bool has = r >= l;
+                CL[j] = has ? (((uint32_t)j << 16) | (uint32_t)(l + 1)) : FULL;
+                CR[j] = has ? (((uint32_t)j << 16) | (uint32_t)(r + 1)) : FULL;
+            }
+            __syncthreads();
+            if (tid == 0 || tid == 32) {  // monotone chain, in place (the stack never passes the read position)
+                uint32_t *C = tid == 0 ? CL : CR;
+                const bool left = tid == 0;
+                int n = 0;
+                for (int j = 0; j <= 2 * h; j++) {
+                    const uint32_t c = C[j];
+                    if (c == FULL) continue;
+                    const int cy = (int)(c >> 16), cx = (int)(c & 0xffffu);
+                    while (n >= 2) {
+                        const uint32_t a = C[n - 2], b = C[n - 1];
+                        const int ay = (int)(a >> 16), ax = (int)(a & 0xffffu), by = (int)(b >> 16), bx = (int)(b & 0xffffu);
+                        const int cr = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay);
+                        if (left ? cr >= 0 : cr <= 0) n--; else break;
+                    }
+                    C[n++] = c;
+                }
+                s_nchain[left ? 0 : 1] = n;
+            }
+            __syncthreads();
+            int cnt = 0;
+            const int nl = s_nchain[0], nr = s_nchain[1];
+            for (int y = tid; y < h; y += T) {
+                const int Yp = 2 * y + 1;  // stored level of the row
+                if (nl < 2 || nr < 2 || Yp < (int)(CL[0] >> 16) || Yp > (int)(CL[nl - 1] >> 16)) continue;
+                int bound[2];
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const uint32_t *C = side ? CR : CL;
+                    const int n = side ? nr : nl;
+                    int lo = 0, hi = n - 2;  // last segment start with level <= Yp
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if ((int)(C[mid] >> 16) <= Yp) lo = mid; else hi = mid - 1;
+                    }
+                    const uint32_t a = C[lo], b = C[lo + 1];
+                    const int y1 = (int)(a >> 16), x1 = (int)(a & 0xffffu) - 1, y2 = (int)(b >> 16), x2 = (int)(b & 0xffffu) - 1;
+                    const int D = y2 - y1, N = x1 * D + (x2 - x1) * (Yp - y1);  // hull abscissa (doubled) = N / D
+                    const int q = 2 * D;
+                    // left: smallest x with 2x >= N / D; right: largest x with 2x <= N / D
+                    if (side == 0) bound[0] = N >= 0 ? (N + q - 1) / q : -((-N) / q);
+                    else bound[1] = N >= 0 ? N / q : -((-N + q - 1) / q);
+                }
+                const int xa = max(bound[0], 0), xb = min(bound[1], w - 1);
+                cnt += max(0, xb - xa + 1);
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+            if (lane == 0) atomicAdd(&s_acc[5], cnt);
+            __syncthreads();
+        }
         if (tid == 0) {
             const double SQ2 = 1.4142135623730951;
             const int m1 = s_acc[0], m2 = s_acc[1], m3 = s_acc[2];
@@ -305,7 +404,7 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
             out[MAZE_S_N1] = (double)m1;
             out[MAZE_S_N2] = (double)m2;
             out[MAZE_S_N3] = (double)m3;
-            out[6] = nan("");
+            out[MAZE_S_CONVEX_AREA] = hull_ok ? (double)s_acc[5] : nan("");
             out[7] = nan("");
         }
     }
@@ -315,6 +414,7 @@ struct ShapeFork {  // side stream for the launch of the large crops (per host t
     int device;
     cudaStream_t aux;
     cudaEvent_t fork, join;
+    int big_smem;  // dynamic shared memory the large-crop kernel is configured for
 };
 
 static ShapeFork *shape_fork()
@@ -328,6 +428,7 @@ static ShapeFork *shape_fork()
     if (n_pool >= 16) return nullptr;
     ShapeFork *f = &pool[n_pool];
     f->device = dev;
+    f->big_smem = 48 * 1024;
     if (cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -340,7 +441,7 @@ static ShapeFork *shape_fork()
 
 extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                                 const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
-                                int32_t *work_counter, double *shape, void *stream)
+                                int max_h, int32_t *work_counter, double *shape, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_obj <= 0) return MAZE_OK;
@@ -356,15 +457,24 @@ extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, con
         MAZE_CUDA(cudaEventRecord(fk->fork, s), "label_shape fork");
         MAZE_CUDA(cudaStreamWaitEvent(fk->aux, fk->fork, 0), "label_shape fork wait");
         const int grid_big = n_slabs < n_obj ? n_slabs : n_obj;
+        // chain storage of the convex hull step: 2 * (2 * max_h + 1) words of shared memory (objects taller than
+        // what 200 KB hold get NaN for the convex area)
+        int chain_words = 4 * (max_h > 0 ? max_h : 0) + 8;
+        if (chain_words > 50000) chain_words = 50000;
+        if (chain_words * (int)sizeof(uint32_t) > fk->big_smem) {
+            MAZE_CUDA(cudaFuncSetAttribute(k_label_shape<SH_T_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           chain_words * (int)sizeof(uint32_t)), "label_shape chain smem");
+            fk->big_smem = chain_words * (int)sizeof(uint32_t);
+        }
         MAZE_KERNEL(KID_LABEL_SHAPE, fk->aux,
-                    (k_label_shape<SH_T_BIG, true><<<grid_big, SH_T_BIG, 0, fk->aux>>>(
-                        labels, bits, vig, table, n_obj, pool, slab_words, work_counter, shape)));
+                    (k_label_shape<SH_T_BIG, true><<<grid_big, SH_T_BIG, chain_words * sizeof(uint32_t), fk->aux>>>(
+                        labels, bits, vig, table, n_obj, pool, slab_words, chain_words, work_counter, shape)));
         MAZE_CUDA(cudaEventRecord(fk->join, fk->aux), "label_shape join");
     }
     const int grid = n_obj < 148 * 8 ? n_obj : 148 * 8;
     MAZE_KERNEL(KID_LABEL_SHAPE, s,
                 (k_label_shape<SH_T, false><<<grid, SH_T, SH_SMEM_WORDS * sizeof(uint32_t), s>>>(
-                    labels, bits, vig, table, n_obj, pool, slab_words, work_counter + 1, shape)));
+                    labels, bits, vig, table, n_obj, pool, slab_words, 0, work_counter + 1, shape)));
     if (slab_words > 0) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "label_shape join wait");
     return MAZE_OK;
 }

@@ -499,7 +499,8 @@ class DeviceBatch:
         counter = pool[n_slabs * slab_words:]  # one int32 behind the slabs
         check(lib().maze_label_shape(None if labels is None else labels.data_ptr(),
                                      None if bits is None else bits.data_ptr(), self.d_vig.data_ptr(),
-                                     table.data_ptr(), n_obj, pool.data_ptr(), slab_words, n_slabs, counter.data_ptr(),
+                                     table.data_ptr(), n_obj, pool.data_ptr(), slab_words, n_slabs, int(g.h.max()),
+                                     counter.data_ptr(),
                                      shape.data_ptr(), _stream()), "maze_label_shape")
         return shape
 

@@ -18,7 +18,7 @@ F_IMIN, F_IMAX, F_IMEAN, F_FRAC_INVALID, F_IMAGE, F_T00, F_T01, F_T11 = 53, 54, 
 
 
 # column layout of the shape table (MAZE_S_*)
-S_PERIMETER, S_FILLED_AREA, S_EULER, S_N1, S_N2, S_N3 = 0, 1, 2, 3, 4, 5
+S_PERIMETER, S_FILLED_AREA, S_EULER, S_N1, S_N2, S_N3, S_CONVEX_AREA = 0, 1, 2, 3, 4, 5, 6
 
 
 def _single(arr, dtype):
@@ -102,8 +102,8 @@ def mask_properties(mask, intensity_image=None, high_order=True):
 
 def regionprops_shape(labels):
     """(max_label, NSHAPE) float64 table of the RegionProperties values that need the pixel neighbourhood --
-    ``perimeter`` (4-neighbourhood), ``filled_area`` (holes filled with the full 3x3 structure) and
-    ``euler_number`` (8-connectivity), each taken from the label's own bounding-box crop -- as read by
+    ``perimeter`` (4-neighbourhood), ``filled_area`` (holes filled with the full 3x3 structure),
+    ``euler_number`` (8-connectivity) and ``convex_area`` (convex hull image), each taken from the label's own bounding-box crop -- as read by
     ``CalculateZooProcessFeatures`` (loki/pipeline.py:625).  Row l-1 describes label l (NaN when absent)."""
     lab = np.asarray(labels)
     if lab.size == 0:

@@ -11,8 +11,8 @@ Restated, not executed: morphocut and scikit-image are not available offline (DE
 key names follow morphocut's ZooProcess feature set (``morphocut/contrib/zooprocess.py`` at the pinned commit
 03dbc6b, requirements.txt:1) as remembered: there ``area`` is the FILLED area and ``area_exc`` the pixel count.
 With the stage's shape table (``LokiSegmentationStage(shape_features=True)``: perimeter, filled_area,
-euler_number from maze_label_shape) every key of that set is produced except ``convex_area`` / ``solidity``
-(convex hull raster); without it, only the keys that follow from the moment table.
+euler_number, convex_area from maze_label_shape) every key of that set is produced; without it, only the keys
+that follow from the moment table.
 """
 from __future__ import annotations
 
@@ -25,7 +25,7 @@ import numpy as np
 F_LABEL, F_AREA, F_BBOX, F_CENTROID, F_HU = 0, 1, 2, 6, 40
 F_AXIS_MAJOR, F_AXIS_MINOR, F_ECC, F_ORIENT = 49, 50, 51, 52
 F_IMIN, F_IMAX, F_IMEAN, F_FRAC_INVALID = 53, 54, 55, 56
-S_PERIMETER, S_FILLED_AREA, S_EULER = 0, 1, 2
+S_PERIMETER, S_FILLED_AREA, S_EULER, S_CONVEX_AREA = 0, 1, 2, 6
 
 
 class Region:
@@ -66,6 +66,10 @@ class Region:
     @property
     def euler_number(self) -> int:
         return int(self._need_shape()[S_EULER])
+
+    @property
+    def convex_area(self) -> float:
+        return float(self._need_shape()[S_CONVEX_AREA])
 
     def _need_shape(self):
         if self._shape_row is None:
@@ -135,8 +139,8 @@ def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = N
 def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str = "object_") -> Dict:
     """``CalculateZooProcessFeatures(region, meta, prefix)`` (loki/pipeline.py:625, 654) from the stage's tables.
     Keys follow morphocut's ZooProcess names.  With a shape row: ``area`` = filled area, ``area_exc`` = pixel
-    count, ``%area``, ``perim.``, ``circ.``, ``circex``, ``perimareaexc``, ``perimmajor``, ``euler_number`` as
-    well; without one ``area`` falls back to the pixel count and the perimeter-based keys are absent."""
+    count, ``%area``, ``perim.``, ``circ.``, ``circex``, ``perimareaexc``, ``perimmajor``, ``euler_number``,
+    ``convex_area``, ``solidity`` as well; without one ``area`` falls back to the pixel count and the perimeter-based keys are absent."""
     out = dict(meta) if meta is not None else {}
     row = region._row
     r0, c0, r1, c1 = (int(v) for v in row[F_BBOX:F_BBOX + 4])
@@ -184,6 +188,9 @@ def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str
             "perimmajor": (perim / major) if major > 0 else float("nan" if perim == 0 else "inf"),
             "euler_number": region.euler_number,
         })
+        convex = region.convex_area
+        if convex == convex:  # NaN only for objects taller than the hull storage of the kernel
+            feats.update({"convex_area": convex, "solidity": area / convex})
     for k, v in feats.items():
         out[prefix + k] = v
     for j in range(7):

@@ -5,10 +5,11 @@ These are the values morphocut's ``CalculateZooProcessFeatures(region, meta, pre
 maze_ipp/loki/pipeline.py:625 and :654 besides the moments.
 
 PARITY UNPINNED for the skimage formulas: scikit-image is not installed here and is not vendored under
-/root/reference (environment.yaml:11 lists it without a version), so ``perimeter`` and ``euler_number`` below
-restate the published algorithms of ``skimage.measure.perimeter`` / ``skimage.measure.euler_number`` (0.19-0.25)
-around the SAME scipy.ndimage primitives skimage calls (``binary_erosion``, ``convolve``, ``binary_fill_holes``,
-``find_objects``), which are executed, not restated.  tests/test_oracle.py additionally pins them to independent
+/root/reference (environment.yaml:11 lists it without a version), so ``perimeter``, ``euler_number`` and
+``convex_area`` below restate the published algorithms of ``skimage.measure.perimeter`` /
+``skimage.measure.euler_number`` / ``skimage.morphology.convex_hull_image`` (0.19-0.25) around the SAME scipy
+primitives skimage calls (``ndimage.binary_erosion``, ``convolve``, ``binary_fill_holes``, ``find_objects``,
+``spatial.ConvexHull``), which are executed, not restated.  tests/test_oracle.py additionally pins them to independent
 definitions: the Euler number to (#8-connected components - #4-connected holes) counted with ``ndi.label``, the
 perimeter to closed forms for rectangles, lines and single pixels.
 """
@@ -64,7 +65,7 @@ def filled_area(image) -> int:
 
 
 def label_shape(labels, max_label=None) -> np.ndarray:
-    """One row per label 1..max_label: perimeter, filled_area, euler_number, n1, n2, n3 (NaN for absent labels),
+    """One row per label 1..max_label: perimeter, filled_area, euler_number, n1, n2, n3, convex_area (NaN for absent labels),
     each taken from the label's own bounding-box crop ``labels[slice] == label`` as RegionProperties does."""
     labels = np.asarray(labels)
     n = int(labels.max()) if max_label is None else int(max_label)
@@ -74,5 +75,33 @@ def label_shape(labels, max_label=None) -> np.ndarray:
             continue
         img = labels[sl] == lab
         n1, n2, n3 = perimeter_classes(img)
-        out[lab - 1, :6] = (perimeter(img), filled_area(img), euler_number(img), n1, n2, n3)
+        out[lab - 1, :7] = (perimeter(img), filled_area(img), euler_number(img), n1, n2, n3, convex_area(img))
     return out
+
+
+def convex_area(image) -> int:
+    """RegionProperties.convex_area: np.sum(skimage.morphology.convex_hull_image(region.image)) as published for
+    scikit-image >= 0.19 (offset_coordinates=True, include_borders=True): every object pixel contributes the four
+    midpoints of its edges, scipy.spatial.ConvexHull (Qhull, executed) gives the hull, and a pixel belongs to the hull
+    image when its centre lies inside the polygon or on its border.  Vertex coordinates are multiples of 1/2, so the
+    cross products below are exact in float64."""
+    from scipy.spatial import ConvexHull
+    img = np.asarray(image) != 0
+    if not img.any():
+        return 0
+    coords = np.argwhere(img).astype(np.float64)
+    offsets = np.array([[0.5, 0.0], [-0.5, 0.0], [0.0, 0.5], [0.0, -0.5]])
+    pts = np.unique((coords[:, None, :] + offsets[None, :, :]).reshape(-1, 2), axis=0)
+    hull = ConvexHull(pts)
+    v = pts[hull.vertices]                       # counter-clockwise in 2-D
+    nxt = np.roll(v, -1, axis=0)
+    e = (nxt - v)[None, :, :]
+    total = 0
+    step = max(1, (1 << 22) // max(1, img.shape[1] * len(v)))   # rows per chunk: bounded temporaries
+    for y0 in range(0, img.shape[0], step):
+        yy, xx = np.mgrid[y0:min(y0 + step, img.shape[0]), 0:img.shape[1]]
+        p = np.stack([yy.ravel(), xx.ravel()], axis=1).astype(np.float64)
+        d = p[:, None, :] - v[None, :, :]
+        cross = e[:, :, 0] * d[:, :, 1] - e[:, :, 1] * d[:, :, 0]
+        total += int(((cross >= 0).all(axis=1) | (cross <= 0).all(axis=1)).sum())
+    return total

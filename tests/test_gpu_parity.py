@@ -519,7 +519,7 @@ def assert_shape_equal(got, want):
     absent = np.isnan(want[:, 0])
     assert np.array_equal(np.isnan(got[:, 0]), absent)
     g, w = got[~absent], want[~absent]
-    assert np.array_equal(g[:, 1:6], w[:, 1:6])          # filled_area, euler_number, n1, n2, n3: exact integers
+    assert np.array_equal(g[:, 1:7], w[:, 1:7])          # filled_area, euler_number, n1, n2, n3, convex_area: exact integers
     assert np.allclose(g[:, 0], w[:, 0], rtol=1e-12, atol=0)
 
 
@@ -589,6 +589,7 @@ def test_stage_shape_features_and_zooprocess_keys(mz):
             for o, row in zip(objects_of(res, i, image=imgs[k]), want[~np.isnan(want[:, 0])]):
                 assert o["object_area"] == row[1] and o["object_perim."] == pytest.approx(row[0], rel=1e-12)
                 assert o["object_euler_number"] == row[2] and o["object_area_exc"] <= o["object_area"]
+                assert o["object_convex_area"] == row[6] and o["object_solidity"] == o["object_area_exc"] / row[6]
             k += 1
     assert k == 24
     # threshold branch: one region per vignette, taken from the bit plane

@@ -83,5 +83,5 @@ def test_label_shape_random(m, as_labels):
     assert got.shape == want.shape
     absent = np.isnan(want[:, 0])
     assert np.array_equal(np.isnan(got[:, 0]), absent)
-    assert np.array_equal(got[~absent, 1:6], want[~absent, 1:6])
+    assert np.array_equal(got[~absent, 1:7], want[~absent, 1:7])
     np.testing.assert_allclose(got[~absent, 0], want[~absent, 0], rtol=1e-12)

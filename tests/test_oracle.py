@@ -221,3 +221,14 @@ def test_shape_oracle_known_answers():
     t = S.label_shape(two)
     assert t.shape == (3, 8) and np.isnan(t[1]).all()
     assert list(t[0, :3]) == [8.0, 9.0, 0.0] and list(t[2, :3]) == [2 * (2 + 4), 15.0, 1.0]
+    assert t[0, 6] == 9 and t[2, 6] == 15
+    # convex hull image: hull of the edge midpoints of the pixels, centres in or on it
+    assert S.convex_area(one) == 1 and S.convex_area(np.ones((4, 7), bool)) == 28
+    assert S.convex_area(diag) == 6                      # the band around a diagonal line holds no other centre
+    plus = np.zeros((3, 3), bool)
+    plus[1, :] = plus[:, 1] = True
+    assert S.convex_area(plus) == 5                      # the corners' centres lie outside the octagon
+    ell = np.zeros((6, 6), bool)
+    ell[:, 0] = ell[5, :] = True                         # an L: hull = triangle over the two arms
+    assert S.convex_area(ell) == 21
+    assert S.convex_area(ring) == 49 and S.convex_area(np.zeros((3, 3), bool)) == 0
