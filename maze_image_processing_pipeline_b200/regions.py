@@ -198,6 +198,20 @@ def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str
     return out
 
 
+def extract_roi(image: np.ndarray, region: Region, alpha: float = 0, bg_color=0) -> np.ndarray:
+    """``ExtractROI(image, region, alpha=1 if config.apply_mask else 0, bg_color=...)`` (loki/pipeline.py:596-602):
+    the padded crop ``image[region.slice]``; with ``alpha`` = 1 everything outside the object is painted with the
+    scalar ``bg_color``.  ``apply_mask`` defaults to False (config_schema.py:97-100), i.e. the plain crop; the
+    ``keep_background`` variant and colour names / quantiles of ``background_color`` are morphocut internals that
+    cannot be restated offline and raise NotImplementedError."""
+    crop = np.asarray(image)[region.slice]
+    if alpha == 0:
+        return crop
+    if alpha != 1 or not np.isscalar(bg_color):
+        raise NotImplementedError("only alpha in {0, 1} with a scalar background colour")
+    return np.where(region.image, crop, np.asarray(bg_color, dtype=crop.dtype))
+
+
 def objects_of(result, i: int, meta: Optional[Dict] = None, padding: int = 75, min_intensity: Optional[float] = None,
                image: Optional[np.ndarray] = None, object_id_fmt: Optional[str] = None) -> List[Dict]:
     """All objects of vignette / frame ``i`` as metadata dicts: FindRegions -> recalc_metadata ->

@@ -197,3 +197,42 @@ def test_regions_find_regions_recalc_metadata_and_features():
     assert abs(o["object_x"] - 19.5) < 1e-12 and abs(o["object_y"] - 9.5) < 1e-12
     assert abs(o["object_angle"] - (table[0, oracle.F_ORIENT] / np.pi * 180 + 90)) < 1e-12
     assert o["object_intden"] == 200 * o["object_mean"] and o["object_range"] == 7.0
+
+
+def test_regions_zooprocess_keys_with_shape_table():
+    """The full ZooProcess key set from the moment table + the shape table (both produced by the oracle here)."""
+    import oracle
+    from oracle import shape as oshape
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    from maze_image_processing_pipeline_b200.regions import extract_roi, find_regions, objects_of
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    lab = np.zeros((30, 40), np.int32)
+    lab[4:14, 5:25] = 1
+    lab[7:10, 9:15] = 0                 # a hole of 18 pixels
+    lab[20:25, 30:33] = 2
+    img = np.full(lab.shape, 50, np.uint8)
+    table = oracle.regionprops_table(lab, img)
+    g = BatchGeometry([30], [40])
+    res = StageResult(g, g.pack_host([(lab > 0).view(np.uint8)]), g.pack_host([lab], dtype=np.int32),
+                      np.array([0, 2], np.int32), table)
+    res.shape_table = oshape.label_shape(lab)
+    o1, o2 = objects_of(res, 0, padding=0, image=img)
+    assert o1["object_area_exc"] == 200 - 18 and o1["object_area"] == 200 and o1["object_convex_area"] == 200
+    assert abs(o1["object_%area"] - 18 / 200) < 1e-15 and o1["object_euler_number"] == 0
+    assert o1["object_perim."] == oshape.perimeter(lab[4:14, 5:25] == 1)
+    assert abs(o1["object_circ."] - 4 * np.pi * 200 / o1["object_perim."] ** 2) < 1e-12
+    assert o1["object_solidity"] == 182 / 200 and o1["object_extent"] == 182 / 200
+    assert o1["object_bounding_box_area"] == 200 and o1["object_intden"] == 200 * 50.0
+    assert abs(o1["object_equivalent_diameter"] - np.sqrt(4 * 182 / np.pi)) < 1e-12
+    assert o2["object_area"] == 15 and o2["object_euler_number"] == 1 and o2["object_solidity"] == 1.0
+    assert abs(o2["object_local_centroid_row"] - 2.0) < 1e-12 and abs(o2["object_local_centroid_col"] - 1.0) < 1e-12
+    # without the shape table the perimeter-based keys are absent and area falls back to the pixel count
+    res.shape_table = None
+    p1 = objects_of(res, 0, padding=0, image=img)[0]
+    assert "object_perim." not in p1 and p1["object_area"] == 182
+    # ExtractROI with apply_mask = False (the schema default) is the padded crop; alpha = 1 paints the rest
+    reg = list(find_regions(res, 0, padding=3, image=img))[1]
+    crop = extract_roi(img, reg)
+    assert crop.shape == (5 + 6, 3 + 6) and crop.base is not None
+    masked = extract_roi(img, reg, alpha=1, bg_color=7)
+    assert (masked[reg.image] == 50).all() and (masked[~reg.image] == 7).all()
