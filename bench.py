@@ -282,7 +282,18 @@ def run_b200(args):
     cores_before = host_cores()
     numa = bind_to_gpu_numa(local_rank, world)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when NCCL_DEBUG asks for it: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         # share the host cores between the ranks for the packing threads
         os.environ.setdefault("MAZE_PACK_THREADS", str(max(1, min(8, cores_before // world))))
     _lib.lib()
