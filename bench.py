@@ -377,10 +377,12 @@ def run_b200(args):
     host_batches = []
     for i in range(args.warmup, args.warmup + e2e_steps):
         db, img = batches[i]
-        flat = img.cpu().numpy()
         # the end-to-end call uses batches of --e2e-batch vignettes (three pinned buffer sets per rank: smaller
         # batches keep the pinned working set of 8 ranks on one host in check; measured 2.4x faster at N = 8)
-        host_batches.append([db.g.view(flat, k) for k in range(min(db.g.n_img, args.e2e_batch))])
+        n_k = min(db.g.n_img, args.e2e_batch)
+        end = int(db.g.pix_off[n_k - 1]) + int(db.g.h[n_k - 1]) * int(db.g.w[n_k - 1])
+        flat = img[:end].cpu().numpy()  # only the pixels of the vignettes the leg uses stay on the host
+        host_batches.append([db.g.view(flat, k) for k in range(n_k)])
     for r in stage.map(host_batches[:3]):  # warm the three pinned buffer sets
         pass
     barrier()
@@ -472,7 +474,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--merge", type=int, default=0, help="merge_segments_distance (0 = off, the schema default)")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=16,
+                    help="batches of the streaming end-to-end leg (a 100k-vignette job is 49 batches of 2048)")
     ap.add_argument("--e2e-batch", type=int, default=2048, help="vignettes per stage.map batch in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -483,6 +483,9 @@ class LokiSegmentationStage:
             return (geom, None, None, None, None, None, None)
         dev = self.device
         batch = DeviceBatch(geom, dev)
+        # descriptors and launch plan go up BEFORE the image: their (small, blocking) uploads would otherwise queue
+        # behind the image copy on the same stream and cost the host several milliseconds per batch
+        self.prepare(batch)
         main = torch.cuda.current_stream()
         if self._copy_stream is None or self._copy_stream.device != batch.device:
             self._copy_stream = torch.cuda.Stream(device=batch.device)
