@@ -4,7 +4,13 @@ import json, os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
-bench.bind_to_gpu_numa(0, 1)
+import torch.distributed as dist
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(LOCAL)
+bench.bind_to_gpu_numa(LOCAL, WORLD)
+if WORLD > 1:  # all ranks copy at the same time: the aggregate ceiling of the host (torchrun --nproc-per-node N)
+    dist.init_process_group("gloo")
 n = 245_000_000
 d_lab = torch.empty(n, dtype=torch.int32, device="cuda"); d_mask = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_img = torch.empty(n, dtype=torch.uint8, device="cuda")
@@ -18,6 +24,8 @@ def run(h2d, pack, reps=5):
     src = np.empty(n, np.uint8)
     for _ in range(reps):
         torch.cuda.synchronize()
+        if WORLD > 1:
+            dist.barrier()
         stop = []
         th = None
         if pack:
@@ -43,5 +51,11 @@ def run(h2d, pack, reps=5):
 
 for h2d, pack in ((False, False), (True, False), (True, True)):
     dt = run(h2d, pack)
-    print(json.dumps({"d2h_GBps": round(5 * n / dt / 1e9, 1), "ms": round(dt * 1e3, 2), "with_h2d": h2d, "with_host_memcpy": pack,
-                      "vignettes_per_s_ceiling": round(2048 / dt)}))
+    if WORLD > 1:
+        t = torch.tensor([dt], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+        if dist.get_rank() != 0:
+            continue
+    print(json.dumps({"ranks": WORLD, "aggregate_d2h_GBps": round(WORLD * 5 * n / dt / 1e9, 1),"d2h_GBps": round(5 * n / dt / 1e9, 1), "ms": round(dt * 1e3, 2), "with_h2d": h2d, "with_host_memcpy": pack,
+                      "vignettes_per_s_ceiling": round(WORLD * 2048 / dt)}))
