@@ -189,7 +189,8 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
  * labels may be NULL: `bits` is then the single region (ImageProperties semantics, loki/pipeline.py:653).
  * pool: n_slabs slabs of slab_words uint32 scratch, slab_words >= 2 * (max_h + 2) * ceil((max_w + 2) / 32) for the
  * tallest / widest bounding box of the batch (used by the objects whose planes exceed shared memory, one CTA per
- * slab).  max_h: tallest vignette of the batch (sizes the hull storage of those objects).  work_counter: two int32
+ * slab; required).  max_h: tallest vignette of the batch (sizes the hull storage of those objects; objects taller
+ * than 12 499 rows get NaN for the convex area).  Coordinates are packed in 16 bits: sides up to 32 767 pixels.  work_counter: two int32
  * (cleared by the call). */
 int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                      const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,

@@ -445,15 +445,15 @@ extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, con
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_obj <= 0) return MAZE_OK;
-    if ((!labels && !bits) || !vig || !table || !shape || !work_counter || n_slabs <= 0 || slab_words < 0 ||
-        (slab_words > 0 && !pool))
+    // every object needs a home: the ones whose planes exceed shared memory live in the slabs
+    if ((!labels && !bits) || !vig || !table || !shape || !work_counter || n_slabs <= 0 || slab_words <= 0 || !pool)
         return MAZE_ERR_BADARG;
     MAZE_CUDA(cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), s), "label_shape counter");
     ShapeFork *fk = shape_fork();
     if (!fk) return MAZE_ERR_CUDA;
     // the few objects whose planes do not fit shared memory (they take longest: 512 threads each on a slab of the
     // pool) run on a side stream next to everything else (four CTAs of 128 threads per SM, planes in shared memory)
-    if (slab_words > 0) {
+    {
         MAZE_CUDA(cudaEventRecord(fk->fork, s), "label_shape fork");
         MAZE_CUDA(cudaStreamWaitEvent(fk->aux, fk->fork, 0), "label_shape fork wait");
         const int grid_big = n_slabs < n_obj ? n_slabs : n_obj;
@@ -475,6 +475,6 @@ extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, con
     MAZE_KERNEL(KID_LABEL_SHAPE, s,
                 (k_label_shape<SH_T, false><<<grid, SH_T, SH_SMEM_WORDS * sizeof(uint32_t), s>>>(
                     labels, bits, vig, table, n_obj, pool, slab_words, 0, work_counter + 1, shape)));
-    if (slab_words > 0) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "label_shape join wait");
+    MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "label_shape join wait");
     return MAZE_OK;
 }

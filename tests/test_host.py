@@ -236,3 +236,14 @@ def test_regions_zooprocess_keys_with_shape_table():
     assert crop.shape == (5 + 6, 3 + 6) and crop.base is not None
     masked = extract_roi(img, reg, alpha=1, bg_color=7)
     assert (masked[reg.image] == 50).all() and (masked[~reg.image] == 7).all()
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    """Entry points validate their arguments first (no CUDA call is made for a rejected request)."""
+    from maze_image_processing_pipeline_b200 import _lib
+    lib = _lib.lib()
+    assert lib.maze_label_shape(None, None, None, None, 0, None, 0, 0, 0, None, None, None) == _lib.MAZE_OK  # nothing to do
+    assert lib.maze_label_shape(None, None, None, None, 5, None, 0, 0, 0, None, None, None) == _lib.MAZE_ERR_BADARG
+    with pytest.raises(ValueError):
+        _lib.check(_lib.MAZE_ERR_BADARG, "maze_label_shape")
+    assert lib.maze_count_scan(None, -1, None, None) == _lib.MAZE_ERR_BADARG
