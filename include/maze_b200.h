@@ -129,6 +129,18 @@ int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vignette_t *vi
                     const maze_tile_t *tiles, int n_tiles, int t, int invert,
                     const uint32_t *flags_in, uint32_t *flags_out, void *stream);
 
+/* Plain binary morphology with a footprint (skimage.morphology.binary_erosion / binary_dilation as called through
+ * binary_opening / binary_closing at loki/pipeline.py:408-427): the footprint is symmetric and row-convex, given as
+ * half chords w[|dy|] for |dy| <= R (row dy holds the pixels |dx| <= w[|dy|]); w must not increase with |dy|.
+ * disk(r) and disk(r, decomposition="crosses") both collapse to one such footprint (erosion by a sequence of
+ * elements is the erosion by their Minkowski sum).  maze_footprint_register returns an id >= 0 (the same id for the
+ * same table; negative = error); pass MAZE_FOOTPRINT_T(id) wherever a pass threshold `t` is expected
+ * (maze_morph_pass, the pass tables of maze_front_chain / maze_vignette_stage / maze_stage_step): invert = 0 is then
+ * the erosion (pixels outside the image count as foreground, skimage's border_value=True), invert = 1 the dilation
+ * (outside = background); scipy's EDT phantom pixel does not apply. */
+#define MAZE_FOOTPRINT_T(id) (-2 - (id))
+int maze_footprint_register(int R, const int32_t *w);
+
 /* bit plane -> one byte per pixel (numpy bool). */
 int maze_unpack_mask(const uint32_t *bits, const maze_vignette_t *vig, int n_img,
                      const maze_tile_t *tiles, int n_tiles, uint8_t *mask, void *stream);

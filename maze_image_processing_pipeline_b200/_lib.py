@@ -77,6 +77,7 @@ SIGNATURES = {
     "maze_threshold_pack": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "maze_morph_pass": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "maze_unpack_mask": [_vp, _vp, _i, _vp, _i, _vp, _vp],
+    "maze_footprint_register": [_i, _vp],
     "maze_edt_sq": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "maze_compare_pack": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "maze_label": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp],

@@ -52,6 +52,12 @@ void maze_prof_end(int kid, cudaStream_t s);
         }                                             \
     } while (0)
 
+// Chord table of one morphology pass from its threshold code (maze_morph.cu): t >= 0 is the squared-distance
+// threshold of the EDT compare (closed disk of d2 <= t, scipy's phantom pixel applies); t = MAZE_FOOTPRINT_T(id)
+// selects a footprint registered with maze_footprint_register (plain binary erosion / dilation, no phantom).
+// Returns false for an invalid code.
+bool maze_pass_table(int t, int *R, int *w /* MAZE_MAX_DISK_RADIUS + 1 */, int *use_phantom);
+
 // bits of word k of a row of width w that are real pixels
 __device__ __forceinline__ uint32_t valid_mask(int w, int k)
 {

@@ -26,6 +26,7 @@ enum { H_13 = 0, H_22, H_31, H_23, H_32, H_33, H_CR, H_CC };
 struct FusedPass {
     int R;
     int invert;
+    int use_phantom; // EDT pass (scipy's phantom pixel applies) or plain binary morphology with a registered footprint
     int w[MAZE_MAX_DISK_RADIUS + 1];
 };
 struct FusedParams {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     zero_fill(2);
     // scipy's phantom background pixel: the (inverted) input plane of a pass has no 0 at all.  Every producer of a
     // plane (threshold, previous pass) tracks that while it writes, so the barrier between phases carries it.
-    bool phantom = !__syncthreads_or(hz);
+    bool phantom = !__syncthreads_or(hz) && prm.n_pass > 0 && prm.pass[0].use_phantom;
 
     // ---- 2. thresholded-EDT passes in shared memory (isotropic.py:35-36, 66-67) ----------------------
     uint32_t *src = T0, *dst = (T0 == A) ? B : A;
@@ -395,7 +396,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             const int nstrip = max(1, min(H, (T + wpr - 1) / wpr));
             const int S = (H + nstrip - 1) / nstrip;
             const int *wt = prm.pass[ps].w;
-            const int pat = R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
+            // (registered footprints may have chords wider than R: they take the run-time table)
+            const int pat = wt[0] != R ? -1 : R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
             switch (pat) { // d2 thresholds 1, 2-3, 4, 5-7, 8 get fully unrolled code
             case 1100: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 0, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
             case 1110: morph_columns<1, T>(src, dst, H, W, wpr, WFixed<1, 1, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz); break;
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
             }
         }
         zero_fill(min(3 + ps, 5));
-        phantom = !__syncthreads_or(hz);
+        phantom = !__syncthreads_or(hz) && ps + 1 < prm.n_pass && prm.pass[ps + 1].use_phantom;
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
     const uint32_t *M = src; // final plane
@@ -819,13 +821,6 @@ __global__ void __launch_bounds__(1024) k_count_scan(const int32_t *__restrict__
     if (t == 0) lab_off[n_img] = total;
 }
 
-static int isqrt_i(int v)
-{
-    int r = 0;
-    while ((r + 1) * (r + 1) <= v) r++;
-    return r;
-}
-
 struct FusedArgs {
     const uint8_t *image, *intensity;
     const maze_vignette_t *vig;
@@ -899,16 +894,12 @@ extern "C" int maze_vignette_stage(const uint8_t *image, const uint8_t *intensit
     for (int p = 0; p < 4; p++) {
         prm.pass[p].R = -1;
         prm.pass[p].invert = 0;
+        prm.pass[p].use_phantom = 1;
         for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) prm.pass[p].w[i] = 0;
     }
     for (int p = 0; p < n_pass; p++) {
-        int t = pass_t_host[p];
-        if (t >= (MAZE_MAX_DISK_RADIUS + 1) * (MAZE_MAX_DISK_RADIUS + 1)) return MAZE_ERR_BADARG;
         prm.pass[p].invert = pass_invert_host[p] ? 1 : 0;
-        if (t >= 0) {
-            prm.pass[p].R = isqrt_i(t);
-            for (int dy = 0; dy <= prm.pass[p].R; dy++) prm.pass[p].w[dy] = isqrt_i(t - dy * dy);
-        }
+        if (!maze_pass_table(pass_t_host[p], &prm.pass[p].R, prm.pass[p].w, &prm.pass[p].use_phantom)) return MAZE_ERR_BADARG;
     }
     MAZE_CUDA(cudaMemsetAsync(stage_counter, 0, sizeof(int32_t), s), "stage counter");
     FusedArgs a = {image, intensity, vig, bits, mask, labels, n_labels, fallback, acc_base, stage_counter,

@@ -156,7 +156,64 @@ extern "C" int maze_unpack_mask(const uint32_t *bits, const maze_vignette_t *vig
 struct DiskTab {
     int R;                              // isqrt(t), or -1 for the empty disk
     int w[MAZE_MAX_DISK_RADIUS + 1];    // half chord per |dy|
+    int use_phantom;                    // EDT semantics (scipy's phantom pixel) or plain binary morphology
 };
+
+// ---- footprint registry: symmetric, row-convex footprints given as half chords per |dy| (skimage.morphology.disk
+// with or without decomposition="crosses" collapses to one such footprint, loki/pipeline.py:408-427) ------------
+#include <mutex>
+#define MAZE_MAX_FOOTPRINTS 256
+static std::mutex g_fp_mutex;
+static int g_fp_count = 0;
+static int g_fp_R[MAZE_MAX_FOOTPRINTS];
+static int g_fp_w[MAZE_MAX_FOOTPRINTS][MAZE_MAX_DISK_RADIUS + 1];
+
+extern "C" int maze_footprint_register(int R, const int32_t *w)
+{
+    if (R < 0 || R > MAZE_MAX_DISK_RADIUS || !w) return MAZE_ERR_BADARG;
+    for (int i = 0; i <= R; i++)
+        if (w[i] < 0 || w[i] > MAZE_MAX_DISK_RADIUS) return MAZE_ERR_BADARG;
+    std::lock_guard<std::mutex> lock(g_fp_mutex);
+    for (int id = 0; id < g_fp_count; id++) {
+        if (g_fp_R[id] != R) continue;
+        bool same = true;
+        for (int i = 0; i <= R && same; i++) same = g_fp_w[id][i] == w[i];
+        if (same) return id;
+    }
+    if (g_fp_count >= MAZE_MAX_FOOTPRINTS) return MAZE_ERR_CAPACITY;
+    const int id = g_fp_count;
+    g_fp_R[id] = R;
+    for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) g_fp_w[id][i] = i <= R ? w[i] : 0;
+    g_fp_count = id + 1;  // published last: readers only look below the count
+    return id;
+}
+
+static int isqrt_tab(int v)
+{
+    int r = 0;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+
+bool maze_pass_table(int t, int *R, int *w, int *use_phantom)
+{
+    for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) w[i] = 0;
+    *use_phantom = 1;
+    if (t == -1) { *R = -1; return true; }
+    if (t >= 0) {
+        if (t >= (MAZE_MAX_DISK_RADIUS + 1) * (MAZE_MAX_DISK_RADIUS + 1)) return false;
+        *R = isqrt_tab(t);
+        for (int dy = 0; dy <= *R; dy++) w[dy] = isqrt_tab(t - dy * dy);
+        return true;
+    }
+    const int id = -2 - t;  // MAZE_FOOTPRINT_T
+    std::lock_guard<std::mutex> lock(g_fp_mutex);
+    if (id < 0 || id >= g_fp_count) return false;
+    *R = g_fp_R[id];
+    for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) w[i] = g_fp_w[id][i];
+    *use_phantom = 0;
+    return true;
+}
 
 __device__ __forceinline__ uint32_t morph_load(const uint32_t *plane, int H, int W, int wpr, int yy, int kk,
                                                uint32_t inv, bool phantom)
@@ -184,8 +241,11 @@ __global__ void __launch_bounds__(MAZE_CTA) k_morph_pass(const uint32_t *__restr
         const uint32_t *plane = in + c.v.word_off;
         int y = widx / wpr, k = widx - y * wpr;
         uint32_t inv = invert ? FULL : 0u;
-        uint32_t fin = flags_in[c.img];
-        bool phantom = invert ? !(fin & 1u) : !(fin & 2u);
+        bool phantom = false;
+        if (disk.use_phantom) {
+            uint32_t fin = flags_in[c.img];
+            phantom = invert ? !(fin & 1u) : !(fin & 2u);
+        }
         uint32_t acc = FULL;
         for (int dy = -disk.R; dy <= disk.R; dy++) {
             int yy = y + dy;
@@ -213,13 +273,6 @@ __global__ void __launch_bounds__(MAZE_CTA) k_morph_pass(const uint32_t *__restr
     if (threadIdx.x == 0 && s_fl) atomicOr(flags_out + c.img, s_fl);
 }
 
-static int isqrt_host(int v)
-{
-    int r = 0;
-    while ((r + 1) * (r + 1) <= v) r++;
-    return r;
-}
-
 extern "C" int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vignette_t *vig, int n_img,
                                const maze_tile_t *tiles, int n_tiles, int t, int invert, const uint32_t *flags_in,
                                uint32_t *flags_out, void *stream)
@@ -228,14 +281,7 @@ extern "C" int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vig
     if (n_img <= 0 || n_tiles <= 0) return MAZE_OK;
     if (in == out) return MAZE_ERR_BADARG;
     DiskTab disk;
-    for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) disk.w[i] = 0;
-    if (t < 0) {
-        disk.R = -1;
-    } else {
-        if (t >= (MAZE_MAX_DISK_RADIUS + 1) * (MAZE_MAX_DISK_RADIUS + 1)) return MAZE_ERR_BADARG;
-        disk.R = isqrt_host(t);
-        for (int dy = 0; dy <= disk.R; dy++) disk.w[dy] = isqrt_host(t - dy * dy);
-    }
+    if (!maze_pass_table(t, &disk.R, disk.w, &disk.use_phantom)) return MAZE_ERR_BADARG;
     MAZE_CUDA(cudaMemsetAsync(flags_out, 0, sizeof(uint32_t) * (size_t)n_img, s), "morph flags");
     MAZE_KERNEL(KID_MORPH_PASS, s, k_morph_pass<<<n_tiles, MAZE_CTA, 0, s>>>(in, out, vig, tiles, disk, invert, flags_in, flags_out));
     return MAZE_OK;

@@ -161,8 +161,11 @@ class _PinnedPool:
 
 class LokiSegmentationStage:
     def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True,
-                 merge_errors="raise", shape_features=False):
-        """shape_features: also produce, per object, the RegionProperties values CalculateZooProcessFeatures reads
+                 merge_errors="raise", shape_features=False, morphology="isotropic"):
+        """morphology: "isotropic" (maze_ipp/isotropic.py, the EDT-based operators of the north-star contract) or
+        "crosses" (what the live pipeline calls: skimage binary_opening / binary_closing with
+        disk(radius, decomposition="crosses"), loki/pipeline.py:408-427).
+        shape_features: also produce, per object, the RegionProperties values CalculateZooProcessFeatures reads
         besides the moments -- perimeter, filled_area, euler_number (StageResult.shape_table; one more kernel over
         the label image per batch).
         merge_errors: "raise" (the reference's behaviour: merge_labels raises TypeError when a bridge
@@ -171,6 +174,9 @@ class LokiSegmentationStage:
         self.fused = fused
         self.merge_errors = merge_errors
         self.shape_features = shape_features
+        if morphology not in ("isotropic", "crosses"):
+            raise ValueError("morphology must be 'isotropic' or 'crosses'")
+        self.morphology = morphology
         if threshold is None and postprocess is None:
             raise ValueError("exactly one of threshold / postprocess (or both, for the composite stage) is required")
         self.threshold = threshold
@@ -191,6 +197,17 @@ class LokiSegmentationStage:
         """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path."""
         pp = self.postprocess
         out = []
+        if self.morphology == "crosses":  # loki/pipeline.py:408-427: erosion + dilation / dilation + erosion
+            from .morphology import disk, footprint_pass_code
+            if max(pp.opening_radius, pp.closing_radius) > MAX_DISK_RADIUS:
+                raise NotImplementedError(f"footprint radii up to {MAX_DISK_RADIUS}")
+            if pp.opening_radius > 0:
+                code = footprint_pass_code(disk(int(pp.opening_radius), decomposition="crosses"))
+                out += [(code, 0), (code, 1)]
+            if pp.closing_radius > 0:
+                code = footprint_pass_code(disk(int(pp.closing_radius), decomposition="crosses"))
+                out += [(code, 1), (code, 0)]
+            return out
         if pp.opening_radius > 0:   # isotropic.py:97-98
             out += [(fold_erosion_radius(pp.opening_radius), 0), (fold_dilation_radius(pp.opening_radius), 1)]
         if pp.closing_radius > 0:   # isotropic.py:128-129
@@ -205,10 +222,14 @@ class LokiSegmentationStage:
         """Per-operator kernels: threshold -> opening -> closing -> label (any size, any radius)."""
         pp = self.postprocess
         bits, flags = batch.threshold_pack(d_src, t_int)
-        if pp.opening_radius > 0:
-            bits, flags = batch.opening(bits, flags, pp.opening_radius)
-        if pp.closing_radius > 0:
-            bits, flags = batch.closing(bits, flags, pp.closing_radius)
+        if self.morphology == "crosses":
+            for code, inv in self._passes():
+                bits, flags = batch.morph_pass(bits, flags, code, inv)
+        else:
+            if pp.opening_radius > 0:
+                bits, flags = batch.opening(bits, flags, pp.opening_radius)
+            if pp.closing_radius > 0:
+                bits, flags = batch.closing(bits, flags, pp.closing_radius)
         labels, lab_off = batch.label(bits, labels=labels)
         mask = batch.unpack_mask(bits, out=mask)
         return bits, labels, lab_off, mask

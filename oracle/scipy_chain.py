@@ -43,6 +43,34 @@ def closing(mask, radius, out=None):  # isotropic.py:128-129
     return erosion(dilation(mask, radius, out=out), radius, out=out)
 
 
+def _apply_footprint(op, img, footprint, **kw):
+    # skimage applies a footprint sequence element by element, each n times
+    if isinstance(footprint, np.ndarray):
+        return op(img, structure=footprint, **kw)
+    for fp, n in footprint:
+        for _ in range(int(n)):
+            img = op(img, structure=fp, **kw)
+    return img
+
+
+def binary_erosion(mask, footprint):
+    """skimage.morphology.binary_erosion: ndi.binary_erosion(..., border_value=True)."""
+    return _apply_footprint(ndi.binary_erosion, np.asarray(mask) != 0, footprint, border_value=True)
+
+
+def binary_dilation(mask, footprint):
+    """skimage.morphology.binary_dilation: ndi.binary_dilation (outside = background)."""
+    return _apply_footprint(ndi.binary_dilation, np.asarray(mask) != 0, footprint)
+
+
+def binary_opening(mask, footprint):  # loki/pipeline.py:408-416
+    return binary_dilation(binary_erosion(mask, footprint), footprint)
+
+
+def binary_closing(mask, footprint):  # loki/pipeline.py:419-427
+    return binary_erosion(binary_dilation(mask, footprint), footprint)
+
+
 def label(mask):
     """loki/pipeline.py:430-433: skimage.measure.label(bool) == ndi.label with the full 3x3."""
     lab, n = ndi.label(mask, structure=_EIGHT)

@@ -597,3 +597,49 @@ def test_stage_shape_features_and_zooprocess_keys(mz):
     res = st(imgs[:6])
     for i in range(6):
         assert_shape_equal(res.shape_features(i), oshape.label_shape((imgs[i] > 35.5).astype(np.int32), max_label=1))
+
+
+# ---- footprint morphology: what the live pipeline calls (loki/pipeline.py:408-427) -----------
+def test_binary_morphology_with_footprints_vs_scipy(mz):
+    from maze_image_processing_pipeline_b200 import morphology as M
+    rng = np.random.default_rng(31)
+    masks = [rng.random((61, 97)) < 0.55, rng.random((40, 40)) < 0.9, rng.random((1, 70)) < 0.8,
+             rng.random((50, 1)) < 0.8, np.ones((20, 33), bool), np.zeros((7, 9), bool),
+             mz.synth.synth_batch(3, 1, size=(150, 131))[0] > 40]
+    fps = [None, M.disk(1), M.disk(2), M.disk(5), M.disk(9), np.ones((3, 3), np.uint8), np.ones((3, 7), np.uint8),
+           M.disk(1, decomposition="crosses"), M.disk(3, decomposition="crosses"), M.disk(13, decomposition="crosses")]
+    default = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8)
+    for m in masks:
+        for fp in fps:
+            ofp = default if fp is None else fp
+            for op in ("erosion", "dilation", "opening", "closing"):
+                want = getattr(scipy_chain, f"binary_{op}")(m, ofp)
+                got = getattr(M, f"binary_{op}")(m, fp)
+                assert got.dtype == bool and np.array_equal(got, want), (m.shape, op)
+    buf = np.zeros(masks[0].shape, bool)
+    assert M.binary_opening(masks[0].astype(np.uint8) * 255, M.disk(2), out=buf) is buf
+    assert np.array_equal(buf, scipy_chain.binary_opening(masks[0], M.disk(2)))
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_stage_crosses_mode_vs_live_pipeline_chain(mz, fused):
+    """LokiSegmentationStage(morphology="crosses"): threshold -> binary_opening(disk(r, "crosses")) ->
+    binary_closing(disk(r, "crosses")) -> label, in the fused kernel and through the per-operator kernels."""
+    from maze_image_processing_pipeline_b200 import morphology as M
+    S = mz.stage
+    imgs = mz.synth.synth_batch(55, 14, lo=64, hi=300)
+    imgs.append(np.full((70, 90), 255, np.uint8))   # all foreground: no phantom pixel in this mode
+    for r_open, r_close in ((1, 2), (3, 13), (0, 4)):
+        pp = S.SegmentationPostprocessingConfig(closing_radius=r_close, opening_radius=r_open)
+        st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, morphology="crosses", fused=fused)
+        res = st(imgs)
+        for i, im in enumerate(imgs):
+            m = im > 40
+            if r_open:
+                m = scipy_chain.binary_opening(m, M.disk(r_open, decomposition="crosses"))
+            if r_close:
+                m = scipy_chain.binary_closing(m, M.disk(r_close, decomposition="crosses"))
+            lab, _ = scipy_chain.label(m)
+            assert np.array_equal(res.mask(i), m), (r_open, r_close, i)
+            assert np.array_equal(res.labels(i), lab), (r_open, r_close, i)
+            assert_tables_close(res.features(i), oracle.regionprops_table(lab, im, max_label=len(res.features(i))))

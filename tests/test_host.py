@@ -247,3 +247,33 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     with pytest.raises(ValueError):
         _lib.check(_lib.MAZE_ERR_BADARG, "maze_label_shape")
     assert lib.maze_count_scan(None, -1, None, None) == _lib.MAZE_ERR_BADARG
+
+
+def test_crosses_footprints_and_minkowski_collapse():
+    """disk(r, decomposition="crosses") as the live pipeline passes it (loki/pipeline.py:408-427): its expansion is
+    the closed disk exactly for the radii SURVEY.md section 0.3 lists; a footprint sequence applied element by
+    element (what skimage does) equals ONE pass with the collapsed footprint, borders included (scipy both)."""
+    from scipy import ndimage as ndi
+    from oracle import scipy_chain
+    from maze_image_processing_pipeline_b200 import morphology as M
+    diff = {}
+    for r in range(1, 21):
+        F, D = M.collapse(M.disk(r, decomposition="crosses")), M.disk(r).astype(bool)
+        assert F.shape == D.shape
+        diff[r] = int((F ^ D).sum())
+    assert [r for r in diff if diff[r] == 0] == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 19, 20]
+    assert (diff[13], diff[17], diff[18]) == (8, 16, 8)
+    assert M.chord_table(M.disk(2, decomposition="crosses")).tolist() == [2, 1, 0]
+    assert M.chord_table(np.ones((3, 7), np.uint8)).tolist() == [3, 3]
+    for bad in (np.array([[1, 0, 1], [0, 1, 0], [1, 0, 1]], np.uint8), np.ones((2, 3), np.uint8),
+                np.array([[0, 1, 0], [0, 1, 0], [1, 1, 1]], np.uint8)):
+        with pytest.raises(NotImplementedError):
+            M.chord_table(bad)
+    rng = np.random.default_rng(4)
+    for r in (1, 2, 3, 5, 13):
+        seq = M.disk(r, decomposition="crosses")
+        fp = M.collapse(seq)
+        for shape, p in (((40, 57), 0.5), ((9, 64), 0.9), ((33, 5), 0.97)):
+            m = rng.random(shape) < p
+            assert np.array_equal(scipy_chain.binary_erosion(m, seq), ndi.binary_erosion(m, structure=fp, border_value=1))
+            assert np.array_equal(scipy_chain.binary_dilation(m, seq), ndi.binary_dilation(m, structure=fp))
