@@ -263,6 +263,7 @@ def workload_config(args, batch):
                         f"batches of {batch}", "batch_vignettes": batch, "threshold_brighter": THRESHOLD,
             "opening_radius": R_OPEN, "closing_radius": R_CLOSE, "merge_segments_distance": args.merge,
             "min_area": 0, "clear_border": False, "regionprops": "full table incl. high-order moments",
+            "morphology": getattr(args, "morphology", "isotropic"),
             "e2e_batch_vignettes": getattr(args, "e2e_batch", batch),
             "l2": "each batch is larger than L2 (no flush needed)", "parallelism": f"images sharded over {args.gpus} GPU(s)"}
 
@@ -309,7 +310,8 @@ def run_b200(args):
     need = args.steps + args.warmup
     pp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN,
                                             merge_segments_distance=args.merge)
-    stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore")
+    stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore",
+                                    morphology=args.morphology)
 
     # resident inputs: the batches this rank will touch, generated on the device
     batches = []
@@ -475,6 +477,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--merge", type=int, default=0, help="merge_segments_distance (0 = off, the schema default)")
+    ap.add_argument("--morphology", default="isotropic", choices=["isotropic", "crosses"],
+                    help="isotropic = maze_ipp/isotropic.py (north star); crosses = the live pipeline's "
+                         "binary_opening / binary_closing with disk(r, decomposition='crosses')")
     ap.add_argument("--e2e-steps", type=int, default=16,
                     help="batches of the streaming end-to-end leg (a 100k-vignette job is 49 batches of 2048)")
     ap.add_argument("--e2e-batch", type=int, default=2048, help="vignettes per stage.map batch in the e2e leg")
