@@ -85,3 +85,16 @@ def test_label_shape_random(m, as_labels):
     assert np.array_equal(np.isnan(got[:, 0]), absent)
     assert np.array_equal(got[~absent, 1:7], want[~absent, 1:7])
     np.testing.assert_allclose(got[~absent, 0], want[~absent, 0], rtol=1e-12)
+
+
+@settings(**SET)
+@given(m=masks(max_side=80), r=st.integers(1, 14), crosses=st.booleans(),
+       op=st.sampled_from(["erosion", "dilation", "opening", "closing"]))
+def test_binary_morphology_random(m, r, crosses, op):
+    """skimage-style binary morphology with disk(r) / disk(r, decomposition="crosses") on arbitrary masks."""
+    from oracle import scipy_chain
+    from maze_image_processing_pipeline_b200 import morphology as M
+    fp = M.disk(r, decomposition="crosses" if crosses else None)
+    want = getattr(scipy_chain, f"binary_{op}")(m, fp)
+    got = getattr(M, f"binary_{op}")(m, fp)
+    assert np.array_equal(got, want)
