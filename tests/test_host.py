@@ -1,5 +1,6 @@
 """Host-side logic and the C-ABI surface (CPU only; no kernel is launched)."""
 import ctypes
+import io
 import math
 import os
 import re
@@ -277,3 +278,33 @@ def test_crosses_footprints_and_minkowski_collapse():
             m = rng.random(shape) < p
             assert np.array_equal(scipy_chain.binary_erosion(m, seq), ndi.binary_erosion(m, structure=fp, border_value=1))
             assert np.array_equal(scipy_chain.binary_dilation(m, seq), ndi.binary_dilation(m, structure=fp))
+
+
+def test_ecotaxa_writer_and_rescale_max_intensity(tmp_path):
+    """Archive layout of the output stage (loki/pipeline.py:1225-1236) and rescale_max_intensity (:382-383)."""
+    import zipfile
+    from PIL import Image
+    from maze_image_processing_pipeline_b200.ecotaxa import EcotaxaWriter, rescale_max_intensity
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 120, size=(20, 30), dtype=np.uint8)
+    out = rescale_max_intensity(img)
+    assert out.dtype == np.uint8 and out.max() == 255 and out.min() == 0 * img.min()
+    assert np.array_equal(out, np.asarray(img / img.max() * 255, dtype=np.uint8))
+    assert np.array_equal(rescale_max_intensity(np.zeros((3, 3), np.uint8)), np.zeros((3, 3), np.uint8))
+    fn = str(tmp_path / "export.zip")
+    mask = img > 60
+    with EcotaxaWriter(fn, store_types=True) as w:
+        w.add([("obj_1.png", img), ("obj_1_mask.png", mask)], {"object_id": "obj_1", "object_area": 12.0, "object_label": 1})
+        w.add([("obj_2.png", out)], {"object_id": "obj_2", "object_area": 7.5, "object_label": 2, "object_note": "x"})
+    with zipfile.ZipFile(fn) as z:
+        assert sorted(z.namelist()) == ["ecotaxa_export.tsv", "obj_1.png", "obj_1_mask.png", "obj_2.png"]
+        rows = z.read("ecotaxa_export.tsv").decode().rstrip("\n").split("\n")
+        assert rows[0].split("\t") == ["img_file_name", "img_rank", "object_id", "object_area", "object_label", "object_note"]
+        assert rows[1].split("\t") == ["[t]", "[f]", "[t]", "[f]", "[f]", "[t]"]
+        assert rows[2].split("\t") == ["obj_1.png", "1", "obj_1", "12.0", "1", ""]
+        assert rows[3].split("\t")[:2] == ["obj_1_mask.png", "2"] and rows[4].split("\t")[-1] == "x"
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(z.read("obj_1.png")))), img)
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(z.read("obj_1_mask.png")))) > 0, mask)
+    with pytest.raises(ValueError):
+        with EcotaxaWriter(str(tmp_path / "bad.zip")) as w:
+            w.add([("obj.xyz", img)], {})
