@@ -232,3 +232,67 @@ def test_shape_oracle_known_answers():
     ell[:, 0] = ell[5, :] = True                         # an L: hull = triangle over the two arms
     assert S.convex_area(ell) == 21
     assert S.convex_area(ring) == 49 and S.convex_area(np.zeros((3, 3), bool)) == 0
+
+
+def _convex_area_integer(img):
+    """The algorithm of maze_label_shape's hull step, restated in Python: row extremes -> leftmost / rightmost
+    candidate per half-row level in doubled coordinates -> monotone chains -> exact per-row counts."""
+    h, w = img.shape
+    ext = []
+    for y in range(h):
+        xs = np.nonzero(img[y])[0]
+        ext.append((int(xs[0]), int(xs[-1])) if len(xs) else None)
+    L, R = [], []
+    for Y in range(-1, 2 * (h - 1) + 2):       # row y <-> Y = 2y; odd levels lie between two rows
+        if Y % 2 == 0:
+            e = ext[Y // 2]
+            if e is not None:
+                L.append((Y, 2 * e[0] - 1)); R.append((Y, 2 * e[1] + 1))
+        else:
+            c = [ext[y] for y in ((Y - 1) // 2, (Y + 1) // 2) if 0 <= y < h and ext[y] is not None]
+            if c:
+                L.append((Y, min(2 * e[0] for e in c))); R.append((Y, max(2 * e[1] for e in c)))
+
+    def chain(pts, left):
+        st = []
+        for C in pts:
+            while len(st) >= 2:
+                A, B = st[-2], st[-1]
+                cr = (B[1] - A[1]) * (C[0] - A[0]) - (C[1] - A[1]) * (B[0] - A[0])
+                if (cr >= 0) if left else (cr <= 0):
+                    st.pop()
+                else:
+                    break
+            st.append(C)
+        return st
+
+    def at(ch, Y):
+        for (Y1, X1), (Y2, X2) in zip(ch[:-1], ch[1:]):
+            if Y1 <= Y <= Y2:
+                return X1 * (Y2 - Y1) + (X2 - X1) * (Y - Y1), Y2 - Y1
+        return None
+
+    cl, cr = chain(L, True), chain(R, False)
+    total = 0
+    for y in range(h):
+        a, b = at(cl, 2 * y), at(cr, 2 * y)
+        if a is None or b is None:
+            continue
+        xmin, xmax = max(-((-a[0]) // (2 * a[1])), 0), min(b[0] // (2 * b[1]), w - 1)
+        total += max(0, xmax - xmin + 1)
+    return total
+
+
+def test_convex_area_integer_algorithm_equals_qhull_oracle():
+    """The exact-integer hull rasterisation the CUDA kernel implements against the Qhull-based oracle, on crops that
+    include disconnected masks, lines and single pixels."""
+    from oracle import shape as S
+    n = 0
+    for img in _shape_cases():
+        if not img.any():
+            continue
+        ys, xs = np.nonzero(img)
+        crop = img[ys.min():ys.max() + 1, xs.min():xs.max() + 1]
+        assert _convex_area_integer(crop) == S.convex_area(crop)
+        n += 1
+    assert n > 100
