@@ -199,6 +199,8 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
  * One row of MAZE_NSHAPE doubles per row of `table` (the finished feature table of maze_regionprops /
  * maze_props_finish_staged, which supplies label, vignette and bounding box); rows with area 0 get NaN.
  * labels may be NULL: `bits` is then the single region (ImageProperties semantics, loki/pipeline.py:653).
+ * runs = 1: labels AND bits given and the labels are constant along the runs of bits (as for MAZE_RP_RUNS): the
+ * object planes are then cut from the bit plane, a fraction of the loads.
  * pool: n_slabs slabs of slab_words uint32 scratch, slab_words >= 2 * (max_h + 2) * ceil((max_w + 2) / 32) for the
  * tallest / widest bounding box of the batch (used by the objects whose planes exceed shared memory, one CTA per
  * slab; required).  max_h: tallest vignette of the batch (sizes the hull storage of those objects; objects taller
@@ -206,7 +208,7 @@ int maze_regionprops(const int32_t *labels, const uint32_t *bits, const uint8_t 
  * (cleared by the call). */
 int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                      const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
-                     int max_h, int32_t *work_counter, double *shape, void *stream);
+                     int max_h, int runs, int32_t *work_counter, double *shape, void *stream);
 
 /* maze_ipp/merge_labels.py:29-113 for every vignette of the batch, one CTA per vignette.
  * labels: read by the loop; labels_out: written (pass the same pointer for the pipeline's aliased

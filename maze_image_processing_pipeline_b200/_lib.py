@@ -92,7 +92,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
-    "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp],
+    "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
     "maze_stage_step": [_vp, _vp, _vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
                                                       const uint32_t *__restrict__ bits,
                                                       const maze_vignette_t *__restrict__ vig,
                                                       const double *__restrict__ table, int n_obj, uint32_t *pool,
-                                                      i64 slab_words, int big_chain_words, int *work_counter,
+                                                      i64 slab_words, int big_chain_words, int runs, int *work_counter,
                                                       double *__restrict__ shape)
 {
     extern __shared__ uint32_t s_planes[];
@@ -120,7 +120,39 @@ __global__ void __launch_bounds__(T) k_label_shape(const int32_t *__restrict__ l
         // ---- A. the object's own plane, framed by one zero pixel --------------------------------------------
         // work items of (row, group of eight words); four items = 32 loads per lane are in flight, the loop is bound
         // by memory latency
-        {
+        if (runs) {
+            // labels are constant along the runs of `bits` (output of maze_label / the fused kernel, also after the
+            // label filters): one thread per word takes the 32 bits of the bit plane and keeps the runs whose first
+            // pixel carries this label -- one or two 4-byte loads per word instead of 32
+            for (int i = tid; i < nwords; i += T) {
+                const int fy = i / cw, k = i - fy * cw;
+                uint32_t word = 0;
+                if (fy >= 1 && fy <= h) {
+                    const int y = r0 + fy - 1;
+                    const int x0 = c0 - 1 + 32 * k;                       // pixel column of bit 0 (may be -1)
+                    const uint32_t *brow = bits + v.word_off + (i64)y * v.wpr;
+                    const int wi = x0 >> 5, sh = x0 & 31;                 // arithmetic shift: x0 = -1 -> wi = -1, sh = 31
+                    const uint32_t lo = (wi >= 0 && wi < v.wpr) ? __ldg(brow + wi) : 0u;
+                    const uint32_t hi = (wi + 1 >= 0 && wi + 1 < v.wpr) ? __ldg(brow + wi + 1) : 0u;
+                    uint32_t m = __funnelshift_r(lo, hi, sh);
+                    // crop: framed columns 1 .. w
+                    const int f_lo = max(1 - 32 * k, 0), f_hi = min(w - 32 * k, 31);  // bit range inside this word
+                    if (f_hi < f_lo) m = 0;
+                    else m &= (f_hi == 31 ? FULL : ((2u << f_hi) - 1u)) & ~((1u << f_lo) - 1u);
+                    const int32_t *lrow = labels + v.pix_off + (i64)y * v.w;
+                    uint32_t rest = m;
+                    while (rest) {
+                        const int b = __ffs(rest) - 1;                     // first pixel of the next run in the word
+                        const uint32_t from_b = rest >> b;                 // run = the ones from bit b up to the next zero
+                        const int len = (~from_b == 0u) ? 32 - b : __ffs(~from_b) - 1;
+                        const uint32_t run = (len >= 32 ? FULL : ((1u << len) - 1u)) << b;
+                        if (__ldg(lrow + x0 + b) == label) word |= run;
+                        rest &= ~run;
+                    }
+                }
+                P[i] = word;
+            }
+        } else {
             const int ngrp = (cw + 7) >> 3, nitem = rows * ngrp;
             for (int it0 = warp * 4; it0 < nitem; it0 += nwarp * 4) {
                 uint32_t cmp[4];
@@ -441,13 +473,14 @@ static ShapeFork *shape_fork()
 
 extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vignette_t *vig,
                                 const double *table, int n_obj, uint32_t *pool, long long slab_words, int n_slabs,
-                                int max_h, int32_t *work_counter, double *shape, void *stream)
+                                int max_h, int runs, int32_t *work_counter, double *shape, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_obj <= 0) return MAZE_OK;
     // every object needs a home: the ones whose planes exceed shared memory live in the slabs
     if ((!labels && !bits) || !vig || !table || !shape || !work_counter || n_slabs <= 0 || slab_words <= 0 || !pool)
         return MAZE_ERR_BADARG;
+    if (runs && (!labels || !bits)) return MAZE_ERR_BADARG;
     MAZE_CUDA(cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), s), "label_shape counter");
     ShapeFork *fk = shape_fork();
     if (!fk) return MAZE_ERR_CUDA;
@@ -468,13 +501,13 @@ extern "C" int maze_label_shape(const int32_t *labels, const uint32_t *bits, con
         }
         MAZE_KERNEL(KID_LABEL_SHAPE, fk->aux,
                     (k_label_shape<SH_T_BIG, true><<<grid_big, SH_T_BIG, chain_words * sizeof(uint32_t), fk->aux>>>(
-                        labels, bits, vig, table, n_obj, pool, slab_words, chain_words, work_counter, shape)));
+                        labels, bits, vig, table, n_obj, pool, slab_words, chain_words, runs ? 1 : 0, work_counter, shape)));
         MAZE_CUDA(cudaEventRecord(fk->join, fk->aux), "label_shape join");
     }
     const int grid = n_obj < 148 * 8 ? n_obj : 148 * 8;
     MAZE_KERNEL(KID_LABEL_SHAPE, s,
                 (k_label_shape<SH_T, false><<<grid, SH_T, SH_SMEM_WORDS * sizeof(uint32_t), s>>>(
-                    labels, bits, vig, table, n_obj, pool, slab_words, 0, work_counter + 1, shape)));
+                    labels, bits, vig, table, n_obj, pool, slab_words, 0, runs ? 1 : 0, work_counter + 1, shape)));
     MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "label_shape join wait");
     return MAZE_OK;
 }

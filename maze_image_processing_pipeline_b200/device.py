@@ -478,9 +478,11 @@ class DeviceBatch:
 
     _shape_pool = None  # scratch of label_shape, shared by the batches of one device (grown on demand)
 
-    def label_shape(self, table, labels=None, bits=None, out=None, pool_bytes=1 << 30):
+    def label_shape(self, table, labels=None, bits=None, out=None, pool_bytes=1 << 30, runs=False):
         """perimeter / filled_area / euler_number per row of the finished feature table (maze_label_shape): the
         RegionProperties values CalculateZooProcessFeatures reads besides the moments (loki/pipeline.py:625, 654).
+        runs=True: labels are constant along the runs of bits (output of label() / the fused kernel, also after the
+        label filters, NOT after merge_labels): the object planes are cut from the bit plane.
         Returns an (n_obj, NSHAPE) float64 tensor."""
         from ._lib import NSHAPE
         n_obj = int(table.shape[0])
@@ -500,7 +502,7 @@ class DeviceBatch:
         check(lib().maze_label_shape(None if labels is None else labels.data_ptr(),
                                      None if bits is None else bits.data_ptr(), self.d_vig.data_ptr(),
                                      table.data_ptr(), n_obj, pool.data_ptr(), slab_words, n_slabs, int(g.h.max()),
-                                     counter.data_ptr(),
+                                     1 if (runs and labels is not None and bits is not None) else 0, counter.data_ptr(),
                                      shape.data_ptr(), _stream()), "maze_label_shape")
         return shape
 

@@ -571,7 +571,8 @@ class LokiSegmentationStage:
             h_off.copy_(res.lab_off, non_blocking=True)
             h_shape = None
             if self.shape_features:
-                d_shape = batch.label_shape(table, labels=res.labels, bits=res.bits if res.labels is None else None)
+                # (after merge_labels the labels leave the runs of the bit plane: per-pixel plane build)
+                d_shape = batch.label_shape(table, labels=res.labels, bits=res.bits, runs=res.merge_status is None)
                 h_shape = pool.get("shape", max(d_shape.numel(), 1), torch.float64)[:d_shape.numel()]
                 h_shape.copy_(d_shape.reshape(-1), non_blocking=True)
             keep = None if res.keep is None else res.keep.cpu().numpy()

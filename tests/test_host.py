@@ -243,8 +243,8 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     """Entry points validate their arguments first (no CUDA call is made for a rejected request)."""
     from maze_image_processing_pipeline_b200 import _lib
     lib = _lib.lib()
-    assert lib.maze_label_shape(None, None, None, None, 0, None, 0, 0, 0, None, None, None) == _lib.MAZE_OK  # nothing to do
-    assert lib.maze_label_shape(None, None, None, None, 5, None, 0, 0, 0, None, None, None) == _lib.MAZE_ERR_BADARG
+    assert lib.maze_label_shape(None, None, None, None, 0, None, 0, 0, 0, 0, None, None, None) == _lib.MAZE_OK  # nothing to do
+    assert lib.maze_label_shape(None, None, None, None, 5, None, 0, 0, 0, 0, None, None, None) == _lib.MAZE_ERR_BADARG
     with pytest.raises(ValueError):
         _lib.check(_lib.MAZE_ERR_BADARG, "maze_label_shape")
     assert lib.maze_count_scan(None, -1, None, None) == _lib.MAZE_ERR_BADARG

@@ -30,11 +30,13 @@ res = st.run_device(db, img)
 table = res.table
 torch.cuda.synchronize()
 ms_stage, _ = timed(lambda: (st.run_device(db, img).table, st.join()))
-ms, shape = timed(lambda: db.label_shape(table, labels=res.labels))
+ms_px, shape_px = timed(lambda: db.label_shape(table, labels=res.labels))
+ms, shape = timed(lambda: db.label_shape(table, labels=res.labels, bits=res.bits, runs=True))
+assert torch.equal(torch.nan_to_num(shape), torch.nan_to_num(shape_px))
 sh = shape.cpu().numpy()
 ok = ~np.isnan(sh[:, 0])
 print(json.dumps({"config": "configs[1] batch", "vignettes": B, "mpix": round(g.total_px / 1e6, 1), "objects": int(ok.sum()),
-                  "ms_label_shape": round(ms, 4), "ms_stage_step_alone": round(ms_stage, 4),
+                  "ms_label_shape": round(ms, 4), "ms_label_shape_per_pixel_planes": round(ms_px, 4),
                   "objects_with_holes": int((sh[ok, 1] > table.cpu().numpy()[ok, 1]).sum()),
                   "mean_perimeter": round(float(sh[ok, 0].mean()), 2)}))
 
@@ -45,7 +47,7 @@ bits, flags = b.threshold_pack(d, 40)
 labels, lab_off = b.label(bits)
 n = int(lab_off[-1].item())
 table = b.regionprops(lab_off, n, labels=labels, bits=bits, image=d, runs=True)
-ms, shape = timed(lambda: b.label_shape(table, labels=labels))
+ms, shape = timed(lambda: b.label_shape(table, labels=labels, bits=bits, runs=True))
 print(json.dumps({"config": "configs[3]", "frame": "4096x4096", "labels": n, "ms_label_shape": round(ms, 4)}))
 
 # where does the time go: the largest bounding boxes vs the rest (configs[1] batch)
@@ -64,6 +66,6 @@ for name, keep in (("largest 16", order[:16]), ("largest 128", order[:128]), ("a
     mask = np.ones(len(t), bool); mask[keep] = False
     t2[mask, 1] = 0
     d2 = torch.from_numpy(t2).to(table.device)
-    ms, _ = timed(lambda: db.label_shape(d2, labels=res.labels))
+    ms, _ = timed(lambda: db.label_shape(d2, labels=res.labels, bits=res.bits, runs=True))
     print(json.dumps({"subset": name, "objects": int((t2[:, 1] > 0).sum()), "ms_label_shape": round(ms, 4),
                       "max_bbox": [int(np.sqrt(area[keep].max()))] if len(keep) else None}))
