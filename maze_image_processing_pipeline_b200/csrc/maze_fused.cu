@@ -516,20 +516,44 @@ __global__ void __launch_bounds__(T, 1024 / T) k_vignette_fused(
     }
     zero_fill(6);
     __syncthreads();
-    // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1)
+    // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1), in three steps
+    // that keep the union-find chains short: (a) a plain store links the run to the FIRST run it touches (nobody
+    // else writes that slot yet), (b) every run jumps its own pointer up to its root (concurrent pointer doubling;
+    // only the owner writes a slot, and it always writes an ancestor), (c) the further runs it touches -- the places
+    // where components merge -- are united with the lock-free union on chains of length one or two.
     for (int i = tid; i < n_runs; i += T) {
         const int y = rY[i];
-        if (y == 0) continue;
-        int a = rowStart[y - 1];
-        const int bnd = rowStart[y];
-        if (a == bnd) continue;
-        const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
-        int e = bnd; // first run of the previous row whose end reaches lo0 (runs of a row are sorted by x)
-        while (a < e) {
-            int mid = (a + e) >> 1;
-            if ((int)rX1[mid] < lo0) a = mid + 1; else e = mid;
+        int first = 0xffff;
+        if (y > 0) {
+            int a = rowStart[y - 1];
+            const int bnd = rowStart[y];
+            const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
+            int e = bnd; // first run of the previous row whose end reaches lo0 (runs of a row are sorted by x)
+            while (a < e) {
+                int mid = (a + e) >> 1;
+                if ((int)rX1[mid] < lo0) a = mid + 1; else e = mid;
+            }
+            if (a < bnd && (int)rX0[a] <= hi0) { first = a; P[i] = (u16)a; }
         }
-        for (int j = a; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
+        rO[i] = (u16)first; // (the sort order is built much later)
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) {
+        int p = *(volatile u16 *)(P + i);
+        for (;;) {
+            const int g = *(volatile u16 *)(P + p);
+            if (g == p) break;
+            *(volatile u16 *)(P + i) = (u16)g;
+            p = g;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) {
+        const int first = rO[i];
+        if (first == 0xffff) continue;
+        const int bnd = rowStart[rY[i]];
+        const int hi0 = (int)rX1[i] + 1;
+        for (int j = first + 1; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
     }
     zero_fill(7);
     __syncthreads();
