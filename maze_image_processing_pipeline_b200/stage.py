@@ -295,7 +295,7 @@ class LokiSegmentationStage:
         return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
 
     def _run_fused_async(self, batch, d_src, d_image, t_int, passes) -> DeviceResult:
-        """Three workspaces, each with its own LANE stream, rotate: batch i+1 starts on the next lane while
+        """n_lanes workspaces (default four), each with its own LANE stream, rotate: batch i+1 starts on the next lane while
         the tail of batch i (label offsets, feature rows, stragglers of the big size class) still runs, so the
         GPU never drains between batches.  The caller's stream is joined at the start (inputs) only; the
         result carries a `ready` event and DeviceResult.finalize() waits for it."""
