@@ -260,6 +260,35 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
                         int32_t *acc_base, int32_t *stage_counter, int stage_cap,
                         unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, void *stream);
 
+/* ---- Band pipeline (maze_bands.cu): the same chain as maze_vignette_stage, cut into uniform pieces ----------
+ * A BAND is a group of consecutive rows [y0, y1) of one vignette; together with the halo rows it recomputes
+ * (halo = sum of the pass radii on each side, none when the band is the whole vignette) it holds at most
+ * MAZE_BAND_PLANE_WORDS words.  All bands of a vignette have rpb rows (the last one may be shorter) and are
+ * consecutive in the band list; band_off[i] .. band_off[i+1] are the bands of vignette i (none: the vignette is
+ * not handled by this entry point -- a row plus halo does not fit, or a side >= 65536).
+ * Results: the final bit plane; the RUN LIST -- every maximal horizontal run of foreground pixels as
+ * {y, x0, x1 (inclusive), label}, the runs of a band contiguous and in raster order at runs[band_out[b].base ..
+ * + n_runs) -- which is also the compact form of the label image that crosses PCIe; n_labels / fallback /
+ * acc_base / staged accumulators exactly as for maze_vignette_stage; and, when mask and labels are given, the
+ * dense bool mask and int32 label image (every pixel written once, zeros included).
+ * counters: 4 int32 (cleared by the call): [0] staging rows used, [1] runs used (may exceed run_cap: the bands
+ * that did not fit are flagged), [2] vignettes that needed the large run table.  big_list: n_img int32 scratch.
+ * run_base: one uint16 per bit-plane word (index of the first run starting in the word, band-relative).
+ * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
+ * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
+#define MAZE_BAND_PLANE_WORDS 6144
+typedef struct maze_band { int32_t img, y0, y1, rpb; } maze_band_t;
+typedef struct maze_band_out { int32_t base, n_runs, zflags, reserved; } maze_band_out_t;
+typedef struct maze_run { uint16_t y, x0, x1, label; } maze_run_t;
+typedef struct maze_run_stat { uint32_t isum; uint16_t zeros; uint8_t vmin, vmax; } maze_run_stat_t;
+int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig, int n_img,
+                    const maze_band_t *bands, int n_bands, const int32_t *band_off, int t_int, int n_pass,
+                    const int32_t *pass_t_host, const int32_t *pass_invert_host, int halo, int flags,
+                    uint32_t *bits, uint16_t *run_base, maze_run_t *runs, maze_run_stat_t *run_stats, int run_cap,
+                    maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
+                    int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list, int stage_cap,
+                    unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, void *stream);
+
 /* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
  * acc_base[i] >= 0 (the others are left to maze_regionprops). */
 int maze_props_finish_staged(const unsigned long long *acc_stage, const double *hi_stage, const int32_t *ext_stage,
@@ -283,8 +312,8 @@ int maze_front_chain(const uint8_t *image, const maze_vignette_t *vig, int n_img
  * batch): counters zeroed, maze_vignette_stage on `lane_stream`, maze_front_chain for the left_n vignettes
  * that are too large for it on `side_stream` (forked / joined with events), maze_count_scan,
  * maze_props_finish_staged, maze_regionprops for the oversize vignettes (trailing on the side stream), and
- * the copy of counts[3*n_img] (n_labels | fallback | acc_base) and of the object total into pinned
- * counts_host[3*n_img + 1].  left_vig / left_tiles describe the oversize vignettes as their own batch (same
+ * the copy of counts[3*n_img] (n_labels | fallback | acc_base), of the object total and (band pipeline) of the
+ * number of runs used into pinned counts_host[3*n_img + 2].  left_vig / left_tiles describe the oversize vignettes as their own batch (same
  * offsets), left_idx (device) holds their indices in the full batch, left_tiles_full their tiles with
  * full-batch vignette indices.  pass_t / pass_invert: as for maze_vignette_stage (no t == 0 passes).
  * scratch_*: plane (total words), flags (2*left_n), parent (per pixel), tile_scan (left_n_tiles+1),
@@ -309,10 +338,21 @@ typedef struct maze_step_args {
     unsigned long long *scratch_acc;
     int32_t *scratch_ext;
     int32_t *counts_host;
+    /* band pipeline (bands != NULL: maze_band_stage runs in place of maze_vignette_stage) */
+    const maze_band_t *bands;
+    const int32_t *band_off;
+    uint16_t *run_base;
+    maze_run_t *runs;
+    maze_run_stat_t *run_stats;
+    maze_band_out_t *band_out;
+    int32_t *band_counters; /* 4 int32 */
+    int32_t *big_list;      /* n_img int32 */
     int32_t class_off[MAZE_FUSED_CLASSES + 1];
     int32_t pass_t[4], pass_invert[4];
     int32_t n_img, left_n, left_n_tiles, left_n_tiles_full, t_int, n_pass, flags, stage_cap;
+    int32_t n_bands, halo, run_cap, step_flags; /* step_flags: MAZE_STEP_COMPACT */
 } maze_step_args_t;
+#define MAZE_STEP_COMPACT 1 /* band pipeline: no dense mask / label image for the band vignettes (run list only) */
 int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);
 
 /* HOST helper: copies n host arrays (srcs[i], nbytes[i] bytes) to dst + dst_off[i] with n_threads threads.

@@ -29,6 +29,8 @@ RP_HIGH_ORDER = 1
 RP_RUNS = 2
 FUSED_CAPS = (1024, 2560, 4096, 6144, 9216, 13312, 19456, 28320)  # MAZE_FUSED_CAPS of include/maze_b200.h
 FUSED_NO_PROPS = 4
+BAND_PLANE_WORDS = 6144  # MAZE_BAND_PLANE_WORDS
+STEP_COMPACT = 1         # MAZE_STEP_COMPACT
 
 
 class StepArgs(ctypes.Structure):
@@ -37,10 +39,11 @@ class StepArgs(ctypes.Structure):
         "vig", "img_list", "left_vig", "left_tiles", "left_idx", "left_tiles_full", "image", "intensity", "bits",
         "mask", "labels", "counts", "lab_off", "stage_counter", "acc_stage", "hi_stage", "ext_stage", "table",
         "scratch_plane", "scratch_flags", "scratch_parent", "scratch_tile_scan", "scratch_lab_off", "scratch_acc",
-        "scratch_ext", "counts_host")]
+        "scratch_ext", "counts_host", "bands", "band_off", "run_base", "runs", "run_stats", "band_out", "band_counters",
+        "big_list")]
         + [("class_off", ctypes.c_int32 * (len(FUSED_CAPS) + 1)), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
         + [(k, ctypes.c_int32) for k in ("n_img", "left_n", "left_n_tiles", "left_n_tiles_full", "t_int", "n_pass",
-                                         "flags", "stage_cap")])
+                                         "flags", "stage_cap", "n_bands", "halo", "run_cap", "step_flags")])
 
 
 class MazeLibraryError(RuntimeError):
@@ -92,6 +95,8 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp],
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
+    "maze_band_stage": [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
     "maze_stage_step": [_vp, _vp, _vp],

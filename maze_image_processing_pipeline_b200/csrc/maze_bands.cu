@@ -1,0 +1,826 @@
+// Band pipeline of the LOKI stage: the same chain as maze_fused.cu (threshold -> thresholded-EDT passes ->
+// label -> regionprops accumulators), cut so that every CTA is small and uniform and the per-pixel work never
+// waits for the per-vignette work.  sm_100a.
+//
+//   K1 k_band_front   one CTA per BAND (a group of consecutive rows of one vignette, at most
+//                     MAZE_BAND_PLANE_WORDS words including the halo rows it recomputes): threshold + pack,
+//                     the morphology passes in shared memory, final bit plane -> HBM, the band's horizontal
+//                     runs (y, x0, x1) in raster order + per-run intensity statistics -> HBM run list,
+//                     per-word run index (for the dense writer).  Touches every pixel once (1 B/px read).
+//   K2 k_band_label   one CTA per VIGNETTE, works on the run list only (a few thousand runs per megapixel):
+//                     links the runs across rows (and thereby across bands), union-find, raster-order ranking
+//                     = the labels of scipy.ndimage.label / skimage.measure.label, per-label accumulators from
+//                     the run end points and the per-run statistics, label of every run -> HBM.
+//   K3 k_band_write   one CTA per band again: dense outputs (bool mask byte + int32 label per pixel) composed
+//                     from bit plane + run labels and streamed out with full 16-byte stores, zeros included
+//                     (5 B/px written once, nothing is zero-filled first).  Skipped in COMPACT mode, where the
+//                     run list {y, x0, x1, label} (8 B per run) IS the result that crosses PCIe.
+//
+// Reference behaviour restated (paths relative to the reference root):
+//   maze_ipp/loki/pipeline.py:649 / :405      threshold / bool cast
+//   maze_ipp/isotropic.py:35-36, 66-67        erosion / dilation compares on the EDT.  scipy's phantom
+//                                             background pixel (plane without any 0) is exact for one-band
+//                                             vignettes; a multi-band vignette whose pass input has no 0 is
+//                                             flagged (fallback) and redone by the per-operator kernels
+//   maze_ipp/loki/pipeline.py:430-433         label(): raster-order labels, 8-connectivity
+//   maze_ipp/loki/pipeline.py:589-625         per-label RegionProperties reads (accumulators)
+#include "maze_fused.cuh"
+
+constexpr int PW = MAZE_BAND_PLANE_WORDS;
+
+struct BandParams {
+    int t_int, n_pass, halo, high_order, stage_cap, do_props, phantom_mask, has_intensity;
+    FusedPass pass[4];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: band front
+// ---------------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_band_front(
+    const uint8_t *__restrict__ image, const uint8_t *__restrict__ intensity, const maze_vignette_t *__restrict__ vig,
+    const maze_band_t *__restrict__ bands, BandParams prm, uint32_t *__restrict__ bits_out,
+    uint16_t *__restrict__ rb_out, maze_run_t *__restrict__ runs, maze_run_stat_t *__restrict__ stats,
+    int32_t *run_counter, int run_cap, maze_band_out_t *__restrict__ band_out)
+{
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    __shared__ int s_warp[34];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const maze_band_t bd = bands[blockIdx.x];
+    const maze_vignette_t v = vig[bd.img];
+    const int H = v.h, W = v.w, wpr = v.wpr;
+    const bool whole = bd.y0 == 0 && bd.y1 == H;  // the band is the vignette: flags are exact, no halo
+    const int halo = whole ? 0 : prm.halo;
+    const int ya = max(0, bd.y0 - halo), yb = min(H, bd.y1 + halo);
+    const int Hb = yb - ya, words = Hb * wpr;      // the host guarantees words <= PW
+    const int oy0 = bd.y0 - ya, oy1 = bd.y1 - ya;  // own rows in plane coordinates
+    uint32_t *A = s_mem, *B = s_mem + words;
+    const int step_y = T / wpr, step_k = T - step_y * wpr;
+    const int y_first = tid / wpr, k_first = tid - y_first * wpr;
+    int zflags = 0;
+
+    // ---- 1. threshold + pack of rows [ya, yb) (loki/pipeline.py:649) ------------------------------------
+    uint32_t *T0 = (prm.n_pass & 1) ? B : A; // an odd number of passes must start in B to end in A
+    bool hz = false;
+    {
+        const uint8_t *base = image + v.pix_off + (size_t)ya * W;
+        const int t = prm.t_int;
+        const uint32_t addc = (uint32_t)((t < 128 ? 127 - t : 255 - t) & 0x7f) * 0x01010101u;
+        const bool lowmode = t < 128;
+        const uint32_t force = t < 0 ? FULL : 0u, kill = t >= 255 ? 0u : FULL;
+        const uint32_t inv0 = (prm.n_pass > 0 && prm.pass[0].invert) ? FULL : 0u;
+        int y = y_first, k = k_first;
+        for (int w = tid; w < words; w += 2 * T) {
+            uint32_t raw[2][9], al[2], vmk[2];
+            int yu[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const bool on = w + u * T < words;
+                const int nvalid = min(32, W - 32 * k);
+                const uint8_t *p = base + (size_t)y * W + 32 * k;
+                al[u] = (uint32_t)((uintptr_t)p & 3u);
+                const uint32_t *q = (const uint32_t *)(p - al[u]);
+                const int last = on ? (int)(al[u] + nvalid - 1) >> 2 : -1; // aligned word holding the last pixel
+                vmk[u] = valid_mask(W, k);
+                yu[u] = y;
+#pragma unroll
+                for (int i = 0; i < 9; i++) raw[u][i] = (i <= last) ? __ldg(q + i) : 0u;
+                y += step_y; k += step_k;
+                if (k >= wpr) { k -= wpr; y++; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (w + u * T < words) {
+                    const uint32_t word = lowmode ? threshold32<true>(raw[u], al[u], addc) : threshold32<false>(raw[u], al[u], addc);
+                    const uint32_t o = ((word | force) & kill) & vmk[u];
+                    T0[w + u * T] = o;
+                    if (yu[u] >= oy0 && yu[u] < oy1) hz |= ((o ^ inv0) | ~vmk[u]) != FULL;
+                }
+            }
+        }
+    }
+    const int hz0 = __syncthreads_or(hz);
+    zflags |= hz0 ? 1 : 0;
+    bool phantom = whole && !hz0 && prm.n_pass > 0 && prm.pass[0].use_phantom;
+
+    // ---- 2. thresholded-EDT passes on the band plane (isotropic.py:35-36, 66-67) ------------------------
+    // rows outside [ya, yb) read as ones: right at the image border, and harmless at a band border because the
+    // halo (sum of the pass radii) absorbs the error before it reaches the band's own rows
+    uint32_t *src = T0, *dst = (T0 == A) ? B : A;
+    for (int ps = 0; ps < prm.n_pass; ps++) {
+        const int R = prm.pass[ps].R;
+        const uint32_t inv = prm.pass[ps].invert ? FULL : 0u;
+        const uint32_t inv_next = (ps + 1 < prm.n_pass && prm.pass[ps + 1].invert) ? FULL : 0u;
+        hz = false;
+        if (R >= 0 && R <= 3) {
+            const int nstrip = max(1, min(Hb, (T + wpr - 1) / wpr));
+            const int S = (Hb + nstrip - 1) / nstrip;
+            const int *wt = prm.pass[ps].w;
+            const int pat = wt[0] != R ? -1 : R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
+            switch (pat) {
+            case 1100: morph_columns<1, T>(src, dst, Hb, W, wpr, WFixed<1, 0, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz, oy0, oy1); break;
+            case 1110: morph_columns<1, T>(src, dst, Hb, W, wpr, WFixed<1, 1, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz, oy0, oy1); break;
+            case 2210: morph_columns<2, T>(src, dst, Hb, W, wpr, WFixed<2, 1, 0, 0>(), inv, phantom, nstrip, S, inv_next, hz, oy0, oy1); break;
+            case 2221: morph_columns<2, T>(src, dst, Hb, W, wpr, WFixed<2, 2, 1, 0>(), inv, phantom, nstrip, S, inv_next, hz, oy0, oy1); break;
+            case 2222: morph_columns<2, T>(src, dst, Hb, W, wpr, WFixed<2, 2, 2, 0>(), inv, phantom, nstrip, S, inv_next, hz, oy0, oy1); break;
+            default:
+                if (R == 0) morph_columns<0, T>(src, dst, Hb, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz, oy0, oy1);
+                else if (R == 1) morph_columns<1, T>(src, dst, Hb, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz, oy0, oy1);
+                else if (R == 2) morph_columns<2, T>(src, dst, Hb, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz, oy0, oy1);
+                else morph_columns<3, T>(src, dst, Hb, W, wpr, WRuntime{wt}, inv, phantom, nstrip, S, inv_next, hz, oy0, oy1);
+            }
+        } else {
+            int y = y_first, k = k_first;
+            for (int w = tid; w < words; w += T) {
+                uint32_t acc = FULL;
+                for (int dy = -R; dy <= R; dy++) {
+                    const int yy = y + dy;
+                    const int hw = prm.pass[ps].w[dy < 0 ? -dy : dy];
+                    const uint32_t C = smem_plane_load(src, Hb, W, wpr, yy, k, inv, phantom);
+                    uint32_t h = C;
+                    if (hw > 0) {
+                        const uint32_t L = smem_plane_load(src, Hb, W, wpr, yy, k - 1, inv, phantom);
+                        const uint32_t Rw = smem_plane_load(src, Hb, W, wpr, yy, k + 1, inv, phantom);
+                        for (int d = 1; d <= hw; d++) {
+                            h &= __funnelshift_rc(C, Rw, d);
+                            h &= __funnelshift_lc(L, C, d);
+                        }
+                    }
+                    acc &= h;
+                }
+                const uint32_t vm = valid_mask(W, k), o = (acc ^ inv) & vm;
+                dst[w] = o;
+                if (y >= oy0 && y < oy1) hz |= ((o ^ inv_next) | ~vm) != FULL;
+                y += step_y; k += step_k;
+                if (k >= wpr) { k -= wpr; y++; }
+            }
+        }
+        const int hzp = __syncthreads_or(hz);
+        zflags |= hzp ? (2 << ps) : 0;
+        phantom = whole && !hzp && ps + 1 < prm.n_pass && prm.pass[ps + 1].use_phantom;
+        uint32_t *tmp = src; src = dst; dst = tmp;
+    }
+    // final plane (== A): own rows -> HBM
+    const uint32_t *Mo = src + oy0 * wpr;
+    const int n_own = (oy1 - oy0) * wpr;
+    {
+        uint32_t *gb = bits_out + v.word_off + (size_t)bd.y0 * wpr;
+        for (int w = tid; w < n_own; w += T) gb[w] = Mo[w];
+    }
+
+    // ---- 3. run list of the own rows -------------------------------------------------------------------
+    const int RC = min((4 * (2 * PW - words)) / 6, 65535); // everything behind the final plane is free
+    u16 *rY = (u16 *)(s_mem + words), *rX0 = rY + RC, *rX1 = rX0 + RC;
+    const int chunk = ((n_own + T - 1) / T) | 1;
+    const int lo = min(tid * chunk, n_own), hi = min(lo + chunk, n_own);
+    int cnt = 0;
+    {
+        int k = lo % wpr;
+        for (int w = lo; w < hi; w++) {
+            const uint32_t m = Mo[w];
+            const uint32_t prevbit = k > 0 ? (Mo[w - 1] >> 31) : 0u;
+            cnt += __popc(m & ~((m << 1) | prevbit));
+            if (++k == wpr) k = 0;
+        }
+    }
+    int n_runs;
+    int run = block_exclusive_scan<T>(cnt, s_warp, &n_runs);
+    if (n_runs > RC) { // more runs than slots (noise): the vignette falls back to the per-operator kernels
+        if (tid == 0) band_out[blockIdx.x] = maze_band_out_t{-1, n_runs, zflags, 0};
+        return;
+    }
+    {
+        u16 *grb = rb_out + v.word_off + (size_t)bd.y0 * wpr;
+        int y = lo / wpr, k = lo - y * wpr;
+        for (int w = lo; w < hi; w++) {
+            grb[w] = (u16)run; // run starts before this word (band raster order)
+            const uint32_t m = Mo[w];
+            const uint32_t prevbit = k > 0 ? (Mo[w - 1] >> 31) : 0u;
+            uint32_t starts = m & ~((m << 1) | prevbit);
+            while (starts) {
+                const int b0 = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const uint32_t rest = ~(m >> b0);
+                const int x0 = 32 * k + b0;
+                int x1;
+                if ((rest & (b0 ? ((1u << (32 - b0)) - 1u) : FULL)) != 0u) {
+                    x1 = x0 + __ffs(rest) - 2; // the run ends inside this word
+                } else {                       // it reaches bit 31: follow it through the next words of the row
+                    x1 = 32 * k + 31;
+                    for (int kk = k + 1; kk < wpr; kk++) {
+                        const uint32_t mm = Mo[w - k + kk];
+                        if (mm == FULL) { x1 += 32; continue; }
+                        x1 += __ffs(~mm) - 1;
+                        break;
+                    }
+                }
+                rY[run] = (u16)(bd.y0 + y); rX0[run] = (u16)x0; rX1[run] = (u16)x1;
+                run++;
+            }
+            if (++k == wpr) { k = 0; y++; }
+        }
+    }
+    if (tid == 0) {
+        int base = n_runs ? atomicAdd(run_counter, n_runs) : 0;
+        if (base + n_runs > run_cap) base = -1; // run buffer full (the counter still tells the host how many were needed)
+        s_base = base;
+        band_out[blockIdx.x] = maze_band_out_t{base, n_runs, zflags, 0};
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (base < 0) return;
+    for (int i = tid; i < n_runs; i += T) {
+        uint2 r;
+        r.x = (uint32_t)rY[i] | ((uint32_t)rX0[i] << 16);
+        r.y = (uint32_t)rX1[i];
+        ((uint2 *)runs)[base + i] = r;
+    }
+    // ---- 4. intensity statistics per run (one warp per run, one aligned word per lane; the bytes were read by
+    // this CTA a moment ago, so the loads hit L2) -----------------------------------------------------------
+    if (intensity) {
+        const uint8_t *gi = intensity + v.pix_off;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int i = warp; i < n_runs; i += T / 32) {
+            const int y = rY[i], a = rX0[i], b = rX1[i];
+            const uint8_t *prow = gi + (size_t)y * W;
+            const int al = (int)((uintptr_t)prow & 3u);
+            const uint32_t *qq = (const uint32_t *)(prow - al);
+            const int ga = (a + al) >> 2, gb = (b + al) >> 2;
+            uint32_t sV = 0, sZ = 0, mn = FULL, mx = 0u;
+            for (int g = ga + lane; g <= gb; g += 32) {
+                const uint32_t px = __ldg(qq + g);
+                const int c0 = 4 * g - al; // column of byte 0 of this word
+                uint32_t nib = 0xfu;
+                if (c0 < a) nib &= 0xfu << (a - c0);
+                if (c0 + 3 > b) nib &= 0xfu >> (c0 + 3 - b);
+                const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                sV = __dp4a(px & bm, 0x01010101u, sV);
+                sZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u);
+                mn = __vminu4(mn, px | ~bm);
+                mx = __vmaxu4(mx, px & bm);
+            }
+            sV = __reduce_add_sync(FULL, sV);
+            sZ = __reduce_add_sync(FULL, sZ);
+            mn = __vminu4(mn, mn >> 16); mn = __vminu4(mn, mn >> 8);
+            mx = __vmaxu4(mx, mx >> 16); mx = __vmaxu4(mx, mx >> 8);
+            mn = __reduce_min_sync(FULL, mn & 0xffu);
+            mx = __reduce_max_sync(FULL, mx & 0xffu);
+            if (lane == 0) {
+                uint2 st;
+                st.x = sV;
+                st.y = (sZ & 0xffffu) | (mn << 16) | (mx << 24);
+                ((uint2 *)stats)[base + i] = st;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: per-vignette labelling + accumulators on the run list
+// ---------------------------------------------------------------------------------------------------------
+struct LabelArgs {
+    const maze_vignette_t *vig;
+    const int32_t *band_off;
+    const maze_band_out_t *band_out;
+    maze_run_t *runs;
+    const maze_run_stat_t *stats;
+    int32_t *n_labels, *fallback, *acc_base, *stage_counter;
+    u64 *acc_stage;
+    double *hi_stage;
+    int32_t *ext_stage;
+    int32_t *big_list, *big_counter;
+    int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
+};
+
+__device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
+{
+    a.fallback[img] = 1;
+    a.n_labels[img] = 0;
+    a.acc_base[img] = -1;
+}
+
+// returns 0 = done (labelled, flagged as fallback, or not a band vignette), 1 = needs a larger run table
+template <int T>
+__device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, uint32_t *s_mem)
+{
+    __shared__ int s_warp[34];
+    __shared__ int s_misc[4];
+    __shared__ int s_base;
+    __shared__ int s_hist[FUSED_LCAP + 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = a.band_off[img], b1 = a.band_off[img + 1], nb = b1 - b0;
+    if (nb <= 0) return 0; // not a band vignette (the per-operator chain owns its counters)
+    const maze_vignette_t v = a.vig[img];
+    const int H = v.h;
+    if (tid < 4) s_misc[tid] = 0;
+    __syncthreads();
+    {
+        int tot = 0, bad = 0, zor = 0;
+        for (int b = b0 + tid; b < b1; b += T) {
+            const maze_band_out_t o = a.band_out[b];
+            tot += o.n_runs; bad |= (o.base < 0) ? 1 : 0; zor |= o.zflags;
+        }
+        tot = __reduce_add_sync(FULL, tot); bad = __reduce_or_sync(FULL, bad); zor = __reduce_or_sync(FULL, zor);
+        if (lane == 0 && (tot | bad | zor)) { atomicAdd(&s_misc[0], tot); atomicOr(&s_misc[1], bad); atomicOr(&s_misc[2], zor); }
+    }
+    __syncthreads();
+    const int n_runs = s_misc[0];
+    int bad = s_misc[1];
+    const int zor = s_misc[2];
+    // scipy's phantom pixel applies to a pass whose (inverted) input plane has no 0 anywhere: a one-band vignette
+    // handled it exactly in K1, a multi-band one is redone by the per-operator kernels
+    if (nb > 1)
+        for (int p = 0; p < a.n_pass; p++)
+            if (((a.phantom_mask >> p) & 1) && !((zor >> p) & 1)) bad = 1;
+    if (bad) {
+        if (tid == 0) mark_fallback(a, img);
+        return 0;
+    }
+    if (n_runs > cap || n_runs >= 0x8000 || H + 2 > hcap) return 1;
+
+    u16 *rY = (u16 *)s_mem, *rX0 = rY + cap, *rX1 = rX0 + cap, *P = rX1 + cap, *rO = P + cap, *rowStart = rO + cap;
+    AccRow *ACC = (AccRow *)(((uintptr_t)(rowStart + hcap) + 15) & ~(uintptr_t)15);
+    {
+        int off = 0;
+        for (int b = b0; b < b1; b++) {
+            const maze_band_out_t o = a.band_out[b];
+            const uint2 *src = (const uint2 *)(a.runs + o.base);
+            for (int i = tid; i < o.n_runs; i += T) {
+                const uint2 r = src[i];
+                rY[off + i] = (u16)(r.x & 0xffffu); rX0[off + i] = (u16)(r.x >> 16); rX1[off + i] = (u16)(r.y & 0xffffu);
+                P[off + i] = (u16)(off + i);
+            }
+            off += o.n_runs;
+        }
+    }
+    __syncthreads();
+    // first run of every row (runs are in raster order)
+    for (int i = tid; i < n_runs; i += T) {
+        const int y = rY[i], yp = i ? (int)rY[i - 1] : -1;
+        for (int yy = yp + 1; yy <= y; yy++) rowStart[yy] = (u16)i;
+    }
+    {
+        const int ylast = n_runs ? (int)rY[n_runs - 1] : -1;
+        for (int yy = ylast + 1 + tid; yy <= H; yy += T) rowStart[yy] = (u16)n_runs;
+    }
+    __syncthreads();
+    // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1): plain store to
+    // the FIRST run it touches, pointer doubling, lock-free unions for the further runs (see maze_fused.cu)
+    for (int i = tid; i < n_runs; i += T) {
+        const int y = rY[i];
+        int first = 0xffff;
+        if (y > 0) {
+            int p = rowStart[y - 1];
+            const int bnd = rowStart[y];
+            const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
+            int e = bnd;
+            while (p < e) {
+                const int mid = (p + e) >> 1;
+                if ((int)rX1[mid] < lo0) p = mid + 1; else e = mid;
+            }
+            if (p < bnd && (int)rX0[p] <= hi0) { first = p; P[i] = (u16)p; }
+        }
+        rO[i] = (u16)first;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) {
+        int p = *(volatile u16 *)(P + i);
+        for (;;) {
+            const int g = *(volatile u16 *)(P + p);
+            if (g == p) break;
+            *(volatile u16 *)(P + i) = (u16)g;
+            p = g;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) {
+        const int first = rO[i];
+        if (first == 0xffff) continue;
+        const int bnd = rowStart[rY[i]];
+        const int hi0 = (int)rX1[i] + 1;
+        for (int j = first + 1; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
+    }
+    __syncthreads();
+    for (int r = tid; r < n_runs; r += T) {
+        const int root = find16(P, r);
+        if (root != r) P[r] = (u16)root;
+    }
+    __syncthreads();
+    // roots in raster order get labels 1..N, stored in their own slot with the top bit set
+    const int rchunk = (n_runs + T - 1) / T;
+    const int rlo = min(tid * rchunk, n_runs), rhi = min(rlo + rchunk, n_runs);
+    int nroot = 0;
+    for (int r = rlo; r < rhi; r++) nroot += (P[r] == r);
+    int n_lab;
+    int rank = block_exclusive_scan<T>(nroot, s_warp, &n_lab);
+    for (int r = rlo; r < rhi; r++)
+        if (P[r] == r) P[r] = (u16)(0x8000 | (++rank));
+    if (tid == 0) {
+        a.n_labels[img] = n_lab;
+        a.fallback[img] = 0;
+        int base = -1;
+        if (a.do_props) {
+            base = n_lab ? atomicAdd(a.stage_counter, n_lab) : 0;
+            if (base + n_lab > a.stage_cap) base = -1; // staging full: maze_regionprops takes this vignette
+        }
+        s_base = base;
+        a.acc_base[img] = base;
+    }
+    {
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int i = tid; i < nsm * (int)(sizeof(AccRow) / 4); i += T) ((uint32_t *)ACC)[i] = 0;
+        if (tid <= FUSED_LCAP + 1) s_hist[tid] = 0;
+    }
+    __syncthreads(); // labels in P are final
+    const int base = s_base;
+    const bool props = a.do_props && base >= 0;
+    if (props) {
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int l = tid; l < nsm; l += T) {
+            ACC[l].e[E_RMIN] = 0x7fffffff; ACC[l].e[E_RMAX] = -1; ACC[l].e[E_CMIN] = 0x7fffffff; ACC[l].e[E_CMAX] = -1;
+            ACC[l].e[E_VMIN] = 0x7fffffff; ACC[l].e[E_VMAX] = -1;
+        }
+        for (int l = FUSED_LCAP + tid; l < n_lab; l += T) { // labels beyond the shared table accumulate in HBM
+            u64 *ga = a.acc_stage + (i64)(base + l) * MAZE_NACC;
+            for (int j = 0; j < MAZE_NACC; j++) ga[j] = 0;
+            double *gh = a.hi_stage + (i64)(base + l) * 8;
+            for (int j = 0; j < 8; j++) gh[j] = 0.0;
+            int32_t *ge = a.ext_stage + (i64)(base + l) * MAZE_NEXT;
+            ge[E_RMIN] = 0x7fffffff; ge[E_RMAX] = -1; ge[E_CMIN] = 0x7fffffff; ge[E_CMAX] = -1;
+            ge[E_VMIN] = 0x7fffffff; ge[E_VMAX] = -1; ge[6] = 0; ge[7] = 0;
+        }
+        for (int i = tid; i < n_runs; i += T) atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1);
+    }
+    __syncthreads();
+    // ---- label of every run -> HBM; per-run intensity statistics -> accumulator rows (warp-aggregated) -----------
+    {
+        const bool with_i = props && a.has_intensity;
+        int off = 0;
+        for (int b = b0; b < b1; b++) {
+            const maze_band_out_t o = a.band_out[b];
+            for (int i0 = warp * 32; i0 < o.n_runs; i0 += T) {
+                const int i = i0 + lane;
+                const bool valid = i < o.n_runs;
+                int lab = 0;
+                uint32_t isum = 0, zeros = 0, vmn = 255, vmx = 0;
+                if (valid) {
+                    lab = label_of(P, off + i);
+                    ((u16 *)(a.runs + o.base + i))[3] = (u16)lab;
+                    if (with_i) {
+                        const uint2 st = ((const uint2 *)a.stats)[o.base + i];
+                        isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
+                    }
+                }
+                if (with_i) {
+                    uint32_t todo = __ballot_sync(FULL, valid);
+                    while (todo) {
+                        const int leader = __ffs(todo) - 1;
+                        const int L = __shfl_sync(FULL, lab, leader);
+                        const bool in = valid && lab == L;
+                        todo &= ~__ballot_sync(FULL, in);
+                        const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
+                        const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
+                        if (lane == leader) {
+                            if (L <= FUSED_LCAP) {
+                                shared_add64(ACC[L - 1].a + A_V, (u64)sV);
+                                if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
+                                atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
+                            } else {
+                                u64 *Aa = a.acc_stage + (i64)(base + L - 1) * MAZE_NACC;
+                                int32_t *Ee = a.ext_stage + (i64)(base + L - 1) * MAZE_NEXT;
+                                atomicAdd(Aa + A_V, (u64)sV); atomicAdd(Aa + A_Z, (u64)sZ);
+                                atomicMin(Ee + E_VMIN, (int)mn); atomicMax(Ee + E_VMAX, (int)mx);
+                            }
+                        }
+                    }
+                }
+            }
+            off += o.n_runs;
+        }
+    }
+    if (!props) return 0;
+
+    // ---- per-label geometry accumulators: counting sort of the runs by label, contiguous pieces per thread ------
+    if (tid == 0) {
+        int acc0 = 0;
+        for (int b = 0; b <= FUSED_LCAP; b++) { const int c = s_hist[b]; s_hist[b] = acc0; acc0 += c; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += T) rO[atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1)] = (u16)i;
+    __syncthreads();
+    const int p_chunk = (n_runs + T - 1) / T;
+    const int p_lo = min(tid * p_chunk, n_runs), p_hi = min(p_lo + p_chunk, n_runs);
+    {
+        int cur = 0;
+        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0;
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1;
+        auto flush = [&](int lab) {
+            const u64 sums[10] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC};
+            int *Ee;
+            if (lab <= FUSED_LCAP) {
+                u64 *Aa = ACC[lab - 1].a; Ee = ACC[lab - 1].e;
+#pragma unroll
+                for (int j = 0; j < 10; j++) shared_add64(Aa + j, sums[j]);
+            } else {
+                u64 *Aa = a.acc_stage + (i64)(base + lab - 1) * MAZE_NACC; Ee = a.ext_stage + (i64)(base + lab - 1) * MAZE_NEXT;
+#pragma unroll
+                for (int j = 0; j < 10; j++) atomicAdd(Aa + j, sums[j]);
+            }
+            atomicMin(Ee + E_RMIN, rmin); atomicMax(Ee + E_RMAX, rmax);
+            atomicMin(Ee + E_CMIN, cmin); atomicMax(Ee + E_CMAX, cmax);
+        };
+        for (int pos = p_lo; pos < p_hi; pos++) {
+            const int i = rO[pos];
+            const int L = label_of(P, i);
+            if (L != cur) {
+                if (cur) flush(cur);
+                aN = aR = aC = aRR = aRC = aCC = aRRR = aRRC = aRCC = aCCC = 0;
+                rmin = 0x7fffffff; rmax = -1; cmin = 0x7fffffff; cmax = -1;
+                cur = L;
+            }
+            const u64 y = rY[i], xa = rX0[i], xb = rX1[i], n = xb - xa + 1;
+            const u64 S1 = n * (xa + xb) / 2;
+            const u64 S2 = pw2(xb) - (xa ? pw2(xa - 1) : 0);
+            const u64 S3 = pw3(xb) - (xa ? pw3(xa - 1) : 0);
+            aN += n; aR += y * n; aC += S1; aRR += y * y * n; aRC += y * S1; aCC += S2;
+            aRRR += y * y * y * n; aRRC += y * y * S1; aRCC += y * S2; aCCC += S3;
+            rmin = min(rmin, (int)y); rmax = max(rmax, (int)y); cmin = min(cmin, (int)xa); cmax = max(cmax, (int)xb);
+        }
+        uint32_t todo = __ballot_sync(FULL, cur != 0);
+        while (todo) { // one flush per label and warp
+            const int leader = __ffs(todo) - 1;
+            const int lab = __shfl_sync(FULL, cur, leader);
+            const bool in = (cur == lab);
+            todo &= ~__ballot_sync(FULL, in);
+            u64 vv[10] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC};
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                u64 x = in ? vv[j] : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                vv[j] = x;
+            }
+            const int r0 = __reduce_min_sync(FULL, in ? rmin : 0x7fffffff), r1 = __reduce_max_sync(FULL, in ? rmax : -1);
+            const int c0 = __reduce_min_sync(FULL, in ? cmin : 0x7fffffff), c1 = __reduce_max_sync(FULL, in ? cmax : -1);
+            if (lane == leader) {
+                aN = vv[0]; aR = vv[1]; aC = vv[2]; aRR = vv[3]; aRC = vv[4]; aCC = vv[5]; aRRR = vv[6]; aRRC = vv[7];
+                aRCC = vv[8]; aCCC = vv[9]; rmin = r0; rmax = r1; cmin = c0; cmax = c1;
+                flush(lab);
+            }
+        }
+    }
+    __syncthreads();
+    if (a.high_order) {
+        // float64 central moments with p + q > 3 about the exact centroid (same walk over the sorted runs)
+        for (int l = tid; l < n_lab; l += T) {
+            const u64 *Aa = l < FUSED_LCAP ? ACC[l].a : a.acc_stage + (i64)(base + l) * MAZE_NACC;
+            double *Hh = l < FUSED_LCAP ? ACC[l].h : a.hi_stage + (i64)(base + l) * 8;
+            const double dn = (double)*(const volatile u64 *)(Aa + A_N);
+            Hh[H_CR] = (double)*(const volatile u64 *)(Aa + A_R) / dn;
+            Hh[H_CC] = (double)*(const volatile u64 *)(Aa + A_C) / dn;
+        }
+        __syncthreads();
+        int cur = 0;
+        double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0, cr = 0, cc = 0;
+        auto hrow = [&](int lab) { return lab <= FUSED_LCAP ? ACC[lab - 1].h : a.hi_stage + (i64)(base + lab - 1) * 8; };
+        for (int pos = p_lo; pos < p_hi; pos++) {
+            const int i = rO[pos];
+            const int L = label_of(P, i);
+            if (L != cur) {
+                if (cur) {
+                    double *Hh = hrow(cur);
+                    atomicAdd(Hh + H_13, h13); atomicAdd(Hh + H_22, h22); atomicAdd(Hh + H_31, h31);
+                    atomicAdd(Hh + H_23, h23); atomicAdd(Hh + H_32, h32); atomicAdd(Hh + H_33, h33);
+                }
+                h13 = h22 = h31 = h23 = h32 = h33 = 0;
+                cur = L;
+                const double *Hc = hrow(L);
+                cr = *(const volatile double *)(Hc + H_CR);
+                cc = *(const volatile double *)(Hc + H_CC);
+            }
+            const int nn = (int)rX1[i] - (int)rX0[i] + 1;
+            const double dn = (double)nn, m1 = (double)(nn - 1);
+            const double S1 = dn * m1 * 0.5;
+            const double S2 = m1 * dn * (2.0 * m1 + 1.0) / 6.0;
+            const double S3 = S1 * S1;
+            const double o = cc - (double)rX0[i];
+            const double T1 = S1 - dn * o;
+            const double T2 = S2 - 2.0 * o * S1 + dn * o * o;
+            const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+            const double dr = (double)rY[i] - cr, dr2 = dr * dr, dr3 = dr2 * dr;
+            h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
+            h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+        }
+        uint32_t todo = __ballot_sync(FULL, cur != 0);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const int lab = __shfl_sync(FULL, cur, leader);
+            const bool in = (cur == lab);
+            todo &= ~__ballot_sync(FULL, in);
+            double vv[6] = {h13, h22, h31, h23, h32, h33};
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double x = in ? vv[j] : 0.0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                vv[j] = x;
+            }
+            if (lane == leader) {
+                double *Hh = hrow(lab);
+                atomicAdd(Hh + H_13, vv[0]); atomicAdd(Hh + H_22, vv[1]); atomicAdd(Hh + H_31, vv[2]);
+                atomicAdd(Hh + H_23, vv[3]); atomicAdd(Hh + H_32, vv[4]); atomicAdd(Hh + H_33, vv[5]);
+            }
+        }
+        __syncthreads();
+    }
+    {   // shared rows -> staging
+        const int nsm = min(n_lab, FUSED_LCAP);
+        for (int i = tid; i < nsm * MAZE_NACC; i += T) {
+            const int l = i / MAZE_NACC, j = i - l * MAZE_NACC;
+            a.acc_stage[(i64)(base + l) * MAZE_NACC + j] = ACC[l].a[j];
+        }
+        for (int i = tid; i < nsm * 8; i += T) {
+            const int l = i >> 3, j = i & 7;
+            a.hi_stage[(i64)(base + l) * 8 + j] = ACC[l].h[j];
+            a.ext_stage[(i64)(base + l) * MAZE_NEXT + j] = ACC[l].e[j];
+        }
+    }
+    return 0;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap)
+{
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    const int img = blockIdx.x;
+    if (label_vignette<T>(a, img, cap, hcap, s_mem) == 1 && threadIdx.x == 0)
+        a.big_list[atomicAdd(a.big_counter, 1)] = img; // more runs than this class holds: the big class takes it
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap)
+{
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    const int n = *(volatile int32_t *)a.big_counter;
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int img = a.big_list[e];
+        if (label_vignette<T>(a, img, cap, hcap, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: dense writer
+// ---------------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T) k_band_write(const maze_vignette_t *__restrict__ vig,
+                                                  const maze_band_t *__restrict__ bands,
+                                                  const maze_band_out_t *__restrict__ band_out,
+                                                  const int32_t *__restrict__ fallback, const uint32_t *__restrict__ bits,
+                                                  const uint16_t *__restrict__ rb, const maze_run_t *__restrict__ runs,
+                                                  uint8_t *__restrict__ mask, int32_t *__restrict__ labels)
+{
+    const maze_band_t bd = bands[blockIdx.x];
+    if (fallback[bd.img]) return; // the per-operator kernels write this vignette
+    const maze_vignette_t v = vig[bd.img];
+    const int H = v.h, W = v.w, wpr = v.wpr;
+    const uint32_t *plane = bits + v.word_off;
+    const uint16_t *RB = rb + v.word_off;
+    const int own_base = band_out[blockIdx.x].base;
+    const int band0 = (int)blockIdx.x - bd.y0 / bd.rpb; // first band of this vignette
+    // groups of 16 pixels of the flat vignette (16-byte mask store, 64-byte label store): the band owns the groups
+    // whose FIRST pixel lies in its rows
+    const int g_lo = (bd.y0 * W + 15) >> 4, g_hi = (bd.y1 * W + 15) >> 4;
+    uint4 *l4 = (uint4 *)(labels + v.pix_off);
+    uint4 *m4 = (uint4 *)(mask + v.pix_off);
+    for (int g = g_lo + threadIdx.x; g < g_hi; g += T) {
+        const int p0 = 16 * g;
+        const int y = p0 / W, x = p0 - y * W;
+        uint32_t bits16 = 0;
+        {
+            int filled = 0, yy = y, xx = x;
+            while (filled < 16 && yy < H) {
+                const int n = min(16 - filled, W - xx);
+                const int k = xx >> 5, sh = xx & 31;
+                const uint32_t lo = plane[yy * wpr + k];
+                const uint32_t hi = (sh + n > 32) ? plane[yy * wpr + k + 1] : 0u; // (pad bits of the last word are 0)
+                bits16 |= (__funnelshift_r(lo, hi, sh) & ((1u << n) - 1u)) << filled;
+                filled += n; xx = 0; yy++;
+            }
+        }
+        uint32_t lab[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) lab[j] = 0;
+        if (bits16) {
+            int filled = 0, yy = y, xx = x;
+            while (filled < 16 && yy < H) {
+                const int n = min(16 - filled, W - xx);
+                uint32_t part = (bits16 >> filled) & ((1u << n) - 1u);
+                while (part) {
+                    const int b0 = __ffs(part) - 1;
+                    const int len = __ffs(~(part >> b0)) - 1;
+                    const int px = xx + b0; // column of the segment's first pixel: its run gives the label
+                    const int k = px >> 5, bb = px & 31, w = yy * wpr + k;
+                    const uint32_t m = plane[w];
+                    const uint32_t prevbit = k > 0 ? (plane[w - 1] >> 31) : 0u;
+                    const uint32_t starts = m & ~((m << 1) | prevbit);
+                    const uint32_t low = bb == 31 ? FULL : ((2u << bb) - 1u);
+                    const int rid = (int)RB[w] + __popc(starts & low) - 1;
+                    const int rbase = yy < bd.y1 ? own_base : band_out[band0 + yy / bd.rpb].base;
+                    const uint32_t L = runs[rbase + rid].label;
+                    const uint32_t seg = ((1u << len) - 1u) << (filled + b0);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if ((seg >> j) & 1u) lab[j] = L;
+                    part &= ~(((1u << len) - 1u) << b0);
+                }
+                filled += n; xx = 0; yy++;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) l4[4 * (size_t)g + j] = make_uint4(lab[4 * j], lab[4 * j + 1], lab[4 * j + 2], lab[4 * j + 3]);
+        uint4 mk;
+        mk.x = ((bits16 & 0xfu) * 0x00204081u) & 0x01010101u;
+        mk.y = (((bits16 >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+        mk.z = (((bits16 >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
+        mk.w = (((bits16 >> 12) & 0xfu) * 0x00204081u) & 0x01010101u;
+        m4[g] = mk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+#define BAND_T 256
+#define LABEL_T 256
+#define LABEL_SMALL_CAP 2048
+#define LABEL_SMALL_HCAP 2050
+#define LABEL_BIG_CAP 16384
+#define LABEL_BIG_HCAP 16386
+
+static size_t label_smem(int cap, int hcap) { return (size_t)cap * 10 + (size_t)hcap * 2 + 16 + FUSED_LCAP * sizeof(AccRow); }
+
+extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig, int n_img,
+                               const maze_band_t *bands, int n_bands, const int32_t *band_off, int t_int, int n_pass,
+                               const int32_t *pass_t_host, const int32_t *pass_invert_host, int halo, int flags,
+                               uint32_t *bits, uint16_t *run_base, maze_run_t *runs, maze_run_stat_t *run_stats,
+                               int run_cap, maze_band_out_t *band_out, uint8_t *mask, int32_t *labels,
+                               int32_t *n_labels, int32_t *fallback, int32_t *acc_base, int32_t *counters,
+                               int32_t *big_list, int stage_cap, unsigned long long *acc_stage, double *hi_stage,
+                               int32_t *ext_stage, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_pass < 0 || n_pass > 4 || halo < 0) return MAZE_ERR_BADARG;
+    if (n_img <= 0 || n_bands <= 0) return MAZE_OK;
+    BandParams prm;
+    prm.t_int = t_int;
+    prm.n_pass = n_pass;
+    prm.halo = halo;
+    prm.high_order = (flags & MAZE_RP_HIGH_ORDER) ? 1 : 0;
+    prm.stage_cap = stage_cap;
+    prm.do_props = (flags & MAZE_FUSED_NO_PROPS) ? 0 : 1;
+    prm.has_intensity = intensity ? 1 : 0;
+    prm.phantom_mask = 0;
+    int sum_r = 0;
+    for (int p = 0; p < 4; p++) {
+        prm.pass[p].R = -1;
+        prm.pass[p].invert = 0;
+        prm.pass[p].use_phantom = 1;
+        for (int i = 0; i <= MAZE_MAX_DISK_RADIUS; i++) prm.pass[p].w[i] = 0;
+    }
+    for (int p = 0; p < n_pass; p++) {
+        prm.pass[p].invert = pass_invert_host[p] ? 1 : 0;
+        if (!maze_pass_table(pass_t_host[p], &prm.pass[p].R, prm.pass[p].w, &prm.pass[p].use_phantom)) return MAZE_ERR_BADARG;
+        if (prm.pass[p].use_phantom) prm.phantom_mask |= 1 << p;
+        sum_r += prm.pass[p].R > 0 ? prm.pass[p].R : 0;
+    }
+    if (halo < sum_r) return MAZE_ERR_BADARG; // the halo must absorb every pass
+    MAZE_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), s), "band counters");
+    int32_t *stage_counter = counters, *run_counter = counters + 1, *big_counter = counters + 2;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    MAZE_CUDA(cudaGetDevice(&dev), "get device");
+    const size_t smem1 = (size_t)PW * 8, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP),
+                 smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP);
+    if (attr_dev != dev) {
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "band smem");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "band carveout");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label<LABEL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s), "label smem");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), "label big smem");
+        attr_dev = dev;
+    }
+    MAZE_KERNEL(KID_BAND_FRONT, s,
+                k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, run_base, runs,
+                                                                   run_stats, run_counter, run_cap, band_out));
+    LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
+                    (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, n_img, n_pass, prm.phantom_mask,
+                    prm.do_props, prm.high_order, prm.has_intensity, stage_cap};
+    MAZE_KERNEL(KID_BAND_LABEL, s, k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP));
+    MAZE_KERNEL(KID_BAND_LABEL_BIG, s, k_band_label_big<LABEL_T><<<74, LABEL_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP));
+    if (mask && labels)
+        MAZE_KERNEL(KID_BAND_WRITE, s,
+                    k_band_write<BAND_T><<<n_bands, BAND_T, 0, s>>>(vig, bands, band_out, fallback, bits, run_base, runs, mask, labels));
+    return MAZE_OK;
+}

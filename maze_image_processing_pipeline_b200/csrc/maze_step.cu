@@ -64,9 +64,18 @@ extern "C" int maze_stage_step(const maze_step_args_t *a, void *lane_stream, voi
                                                                                 a->left_n, n_labels));
         MAZE_CUDA(cudaEventRecord(se->ev[1], side), "step join");
     }
-    rc = maze_vignette_stage(a->image, a->intensity, a->vig, a->img_list, a->class_off, a->t_int, a->n_pass, a->pass_t,
-                             a->pass_invert, a->flags, a->bits, a->mask, a->labels, n_labels, fallback, acc_base,
-                             a->stage_counter, a->stage_cap, a->acc_stage, a->hi_stage, a->ext_stage, lane);
+    if (a->bands) {
+        const bool dense = !(a->step_flags & MAZE_STEP_COMPACT);
+        rc = maze_band_stage(a->image, a->intensity, a->vig, n, a->bands, a->n_bands, a->band_off, a->t_int, a->n_pass,
+                             a->pass_t, a->pass_invert, a->halo, a->flags, a->bits, a->run_base, a->runs, a->run_stats,
+                             a->run_cap, a->band_out, dense ? a->mask : nullptr, dense ? a->labels : nullptr, n_labels,
+                             fallback, acc_base, a->band_counters, a->big_list, a->stage_cap, a->acc_stage, a->hi_stage,
+                             a->ext_stage, lane);
+    } else {
+        rc = maze_vignette_stage(a->image, a->intensity, a->vig, a->img_list, a->class_off, a->t_int, a->n_pass, a->pass_t,
+                                 a->pass_invert, a->flags, a->bits, a->mask, a->labels, n_labels, fallback, acc_base,
+                                 a->stage_counter, a->stage_cap, a->acc_stage, a->hi_stage, a->ext_stage, lane);
+    }
     if (rc != MAZE_OK) return rc;
     if (left) MAZE_CUDA(cudaStreamWaitEvent(lane, se->ev[1], 0), "step join wait");
     rc = maze_count_scan(n_labels, n, a->lab_off, lane);
@@ -87,6 +96,9 @@ extern "C" int maze_stage_step(const maze_step_args_t *a, void *lane_stream, voi
                                   lane), "step readback");
         MAZE_CUDA(cudaMemcpyAsync(a->counts_host + 3 * (size_t)n, a->lab_off + n, sizeof(int32_t),
                                   cudaMemcpyDeviceToHost, lane), "step readback total");
+        if (a->bands)
+            MAZE_CUDA(cudaMemcpyAsync(a->counts_host + 3 * (size_t)n + 1, a->band_counters + 1, sizeof(int32_t),
+                                      cudaMemcpyDeviceToHost, lane), "step readback runs");
     }
     return MAZE_OK;
 }

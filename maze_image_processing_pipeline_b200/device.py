@@ -15,12 +15,16 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FUSED_CAPS, FUSED_NO_PROPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS, TILE_WORDS, check, lib
+from ._lib import (BAND_PLANE_WORDS, FUSED_CAPS, FUSED_NO_PROPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS,
+                   TILE_WORDS, check, lib)
 
 VIG_DTYPE = np.dtype([("pix_off", "<i8"), ("word_off", "<i8"), ("h", "<i4"), ("w", "<i4"),
                       ("wpr", "<i4"), ("tile0", "<i4")])
 TILE_DTYPE = np.dtype([("img", "<i4"), ("word0", "<i4")])
-assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8
+BAND_DTYPE = np.dtype([("img", "<i4"), ("y0", "<i4"), ("y1", "<i4"), ("rpb", "<i4")])        # maze_band_t
+BAND_OUT_DTYPE = np.dtype([("base", "<i4"), ("n_runs", "<i4"), ("zflags", "<i4"), ("reserved", "<i4")])  # maze_band_out_t
+RUN_DTYPE = np.dtype([("y", "<u2"), ("x0", "<u2"), ("x1", "<u2"), ("label", "<u2")])            # maze_run_t
+assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8 and BAND_DTYPE.itemsize == 16 and RUN_DTYPE.itemsize == 8
 
 _DISK_T_LIMIT = (MAX_DISK_RADIUS + 1) ** 2
 _INT_MAX = 2 ** 31 - 1
@@ -105,6 +109,32 @@ class BatchGeometry:
             off.append(off[-1] + len(sel))
         left = np.nonzero(cls == len(FUSED_CAPS))[0]
         return np.concatenate(order).astype(np.int32), np.asarray(off, np.int32), left
+
+    def band_plan(self, halo: int):
+        """(bands, band_off, leftovers) for maze_band_stage: every vignette is cut into row bands that, with `halo`
+        recomputed rows on each side, hold at most BAND_PLANE_WORDS words (a vignette that fits is one band without
+        halo).  Leftovers: a side >= 65536, or so wide that a band would be mostly halo."""
+        wpr = (self.w + 31) // 32
+        small = (self.h < 65536) & (self.w < 65536)
+        single = self.nwords <= BAND_PLANE_WORDS
+        rows_max = BAND_PLANE_WORDS // wpr - 2 * halo
+        ok = small & (single | (rows_max >= max(1, halo)))
+        rows_max = np.maximum(rows_max, 1)
+        nb = np.where(single, 1, (self.h + rows_max - 1) // rows_max)
+        rpb = (self.h + nb - 1) // nb
+        nb = np.where(ok, (self.h + rpb - 1) // rpb, 0)
+        band_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        n_bands = int(band_off[-1])
+        if n_bands >= 2 ** 31:
+            raise ValueError("batch too large")
+        bands = np.zeros(n_bands, BAND_DTYPE)
+        img = np.repeat(np.arange(self.n_img, dtype=np.int64), nb)
+        j = np.arange(n_bands, dtype=np.int64) - band_off[img]
+        bands["img"] = img
+        bands["y0"] = j * rpb[img]
+        bands["y1"] = np.minimum(self.h[img], (j + 1) * rpb[img])
+        bands["rpb"] = rpb[img]
+        return bands, band_off.astype(np.int32), np.nonzero(~ok)[0]
 
     @classmethod
     def from_images(cls, images):
@@ -436,6 +466,16 @@ class DeviceBatch:
             img_list, class_off, left = self.g.fused_classes()
             self._fused = (torch.from_numpy(img_list).to(self.device), class_off, left)
         return self._fused
+
+    def band_lists(self, halo: int):
+        """Device copies of the band plan (cached per halo): (d_bands, d_band_off, n_bands, leftovers, bands_host, band_off_host)."""
+        cache = self.__dict__.setdefault("_bands", {})
+        if halo not in cache:
+            bands, band_off, left = self.g.band_plan(halo)
+            d_bands = torch.from_numpy(bands.view(np.uint8).copy()).to(self.device) if len(bands) else \
+                torch.zeros(16, dtype=torch.uint8, device=self.device)
+            cache[halo] = (d_bands, torch.from_numpy(band_off).to(self.device), len(bands), left, bands, band_off)
+        return cache[halo]
 
     def tiles_of(self, indices):
         """Device tile list (full-batch vignette indices) restricted to the given vignettes (cached)."""

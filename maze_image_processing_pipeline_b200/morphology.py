@@ -120,6 +120,18 @@ def chord_table(footprint: Footprint) -> np.ndarray:
 
 
 _PASS_CODES = {}
+_PASS_RADIUS = {}  # pass code -> vertical radius R of the footprint
+
+
+def pass_radius(t: int) -> int:
+    """Rows a pass reaches up and down: isqrt(t) for a squared-distance threshold, R for a registered footprint."""
+    import math
+    t = int(t)
+    if t >= 0:
+        return math.isqrt(t)
+    if t == -1:
+        return 0
+    return _PASS_RADIUS[t]
 
 
 def footprint_pass_code(footprint: Footprint) -> int:
@@ -131,6 +143,7 @@ def footprint_pass_code(footprint: Footprint) -> int:
         if fid < 0:
             check(fid, "maze_footprint_register")
         _PASS_CODES[key] = -2 - fid
+        _PASS_RADIUS[-2 - fid] = len(w) - 1
     return _PASS_CODES[key]
 
 

@@ -26,7 +26,7 @@ import torch
 import ctypes
 import os
 
-from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, StepArgs, check, lib
+from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, STEP_COMPACT, StepArgs, check, lib
 from ._lib import MAX_DISK_RADIUS
 from .device import (Arena, BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
@@ -71,6 +71,12 @@ class DeviceResult:
         self._sync_main = pending is None
         self.redone = False
         self.ready = None  # event after which mask / labels / bits are complete (None: stream order of the caller)
+        # band pipeline: run list (maze_run_t as int64) + per-band {base, n_runs, ..}, host copies of the band plan,
+        # runs used (after finalize), vignettes whose outputs exist only as dense arrays
+        self.runs = self.band_out = self.bands_host = self.band_off_host = None
+        self.n_runs = 0
+        self.compact = False
+        self.dense_only = []
 
     def finalize(self):
         if self._pending is not None:
@@ -161,8 +167,14 @@ class _PinnedPool:
 
 class LokiSegmentationStage:
     def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True,
-                 merge_errors="raise", shape_features=False, morphology="isotropic"):
-        """morphology: "isotropic" (maze_ipp/isotropic.py, the EDT-based operators of the north-star contract) or
+                 merge_errors="raise", shape_features=False, morphology="isotropic", pipeline=None, compact=False):
+        """pipeline: "bands" (default; maze_band_stage: band front, run-list labelling, dense writer) or "fused" (the
+        vignette-resident kernel maze_vignette_stage); MAZE_PIPELINE overrides the default.
+        compact: the per-pixel outputs stay on the device as the RUN LIST {y, x0, x1, label} (8 bytes per run, a
+        few thousand runs per megapixel) and cross PCIe in that form; StageResult.mask(i) / labels(i) / crops expand
+        them on the host on demand.  Needs the band pipeline without label filters / merge (otherwise the dense
+        arrays are downloaded as before).
+        morphology: "isotropic" (maze_ipp/isotropic.py, the EDT-based operators of the north-star contract) or
         "crosses" (what the live pipeline calls: skimage binary_opening / binary_closing with
         disk(radius, decomposition="crosses"), loki/pipeline.py:408-427).
         shape_features: also produce, per object, the RegionProperties values CalculateZooProcessFeatures reads
@@ -172,6 +184,10 @@ class LokiSegmentationStage:
         swallows a label, merge_labels.py:19-20, and the run aborts) or "ignore" (keep the labels as the loop
         left them for those vignettes and list them in StageResult.merge_failed)."""
         self.fused = fused
+        self.pipeline = pipeline or os.environ.get("MAZE_PIPELINE", "bands")
+        if self.pipeline not in ("bands", "fused"):
+            raise ValueError("pipeline must be 'bands' or 'fused'")
+        self.compact = bool(compact)
         self.merge_errors = merge_errors
         self.shape_features = shape_features
         if morphology not in ("isotropic", "crosses"):
@@ -345,7 +361,21 @@ class LokiSegmentationStage:
         staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
                    ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
         table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
-        d_list, class_off, left = batch.fused_lists()
+        use_bands = self.pipeline == "bands"
+        bands_h = band_off_h = None
+        if use_bands:
+            from .morphology import pass_radius
+            halo = sum(pass_radius(t) for t, _ in passes)
+            d_bands, d_band_off, n_bands, left, bands_h, band_off_h = batch.band_lists(halo)
+            run_cap = max(g.total_words // 3, 1 << 16)
+            runs = ws.get("runs", run_cap, torch.int64, dev)          # maze_run_t, 8 bytes each
+            run_stats = ws.get("run_stats", run_cap, torch.int64, dev)
+            run_base = ws.get("run_base", max(g.total_words, 1), torch.int16, dev)
+            band_out = ws.get("band_out", 4 * max(n_bands, 1), torch.int32, dev)
+            band_counters = ws.get("band_counters", 4, torch.int32, dev)
+            big_list = ws.get("big_list", n, torch.int32, dev)
+        else:
+            d_list, class_off, left = batch.fused_lists()
         # rotating pinned readback slots (one more than lanes): a slot is reused only after its batch was finalised
         nslot = self.n_lanes + 1
         ri = self._readback_i % nslot
@@ -353,21 +383,29 @@ class LokiSegmentationStage:
         while len(self._readback) < nslot:
             self._readback.append(None)
         slot = self._readback[ri]
-        if slot is None or slot.numel() < 3 * n + 1:
-            slot = torch.empty(3 * n + 1 + 256, dtype=torch.int32, pin_memory=True)
+        if slot is None or slot.numel() < 3 * n + 2:
+            slot = torch.empty(3 * n + 2 + 256, dtype=torch.int32, pin_memory=True)
             self._readback[ri] = slot
-        host = slot[:3 * n + 1]
-        # the whole step is ONE call into the library (maze_stage_step): fused kernel on the lane stream, the
-        # oversize vignettes through the per-operator chain on the side stream, offsets, feature rows, readback
+        host = slot[:3 * n + 2]
+        # the whole step is ONE call into the library (maze_stage_step): band pipeline (or fused kernel) on the lane
+        # stream, the oversize vignettes through the per-operator chain on the side stream, offsets, feature rows, readback
         a = StepArgs()
-        a.vig, a.img_list = batch.d_vig.data_ptr(), d_list.data_ptr()
+        a.vig = batch.d_vig.data_ptr()
         a.image, a.intensity = d_src.data_ptr(), d_image.data_ptr()
         a.bits, a.mask, a.labels = bits.data_ptr(), mask.data_ptr(), labels.data_ptr()
         a.counts, a.lab_off, a.stage_counter = counts.data_ptr(), lab_off.data_ptr(), staging[3].data_ptr()
         a.acc_stage, a.hi_stage, a.ext_stage = staging[0].data_ptr(), staging[1].data_ptr(), staging[2].data_ptr()
         a.table, a.counts_host = table.data_ptr(), host.data_ptr()
-        for c in range(len(class_off)):
-            a.class_off[c] = int(class_off[c])
+        if use_bands:
+            a.bands, a.band_off, a.n_bands, a.halo = d_bands.data_ptr(), d_band_off.data_ptr(), n_bands, halo
+            a.run_base, a.runs, a.run_stats = run_base.data_ptr(), runs.data_ptr(), run_stats.data_ptr()
+            a.band_out, a.band_counters, a.big_list = band_out.data_ptr(), band_counters.data_ptr(), big_list.data_ptr()
+            a.run_cap = run_cap
+            a.step_flags = STEP_COMPACT if self.compact else 0
+        else:
+            a.img_list = d_list.data_ptr()
+            for c in range(len(class_off)):
+                a.class_off[c] = int(class_off[c])
         for k, (t, inv) in enumerate(passes):
             a.pass_t[k], a.pass_invert[k] = int(t), int(inv)
         a.n_img, a.t_int, a.n_pass, a.stage_cap = n, int(t_int), len(passes), cap
@@ -402,8 +440,10 @@ class LokiSegmentationStage:
                 side_done.synchronize()
             h = host.numpy()
             total = int(h[3 * n])
+            res.n_runs = int(h[3 * n + 1]) if use_bands else 0
             bad = np.nonzero((h[n:2 * n] != 0) | ((h[2 * n:3 * n] < 0) & (h[:n] > 0)))[0]
             bad = [int(i) for i in bad if int(i) not in left_set]
+            res.dense_only = sorted(left_set | set(bad))  # vignettes without a run list (per-operator kernels)
             if bad or total > cap:
                 # some vignettes overflowed the fused kernel's tables (more runs than slots, or the staging rows
                 # ran out): the per-operator kernels redo just those, then offsets and features are re-derived
@@ -423,6 +463,7 @@ class LokiSegmentationStage:
                         total = total2
                         res._table = table[:total]
                     else:  # the whole batch through the per-operator kernels
+                        res.dense_only = list(range(n))
                         b2, l2, off2, m2 = self._front_generic(batch, d_src, t_int, labels=labels, mask=mask)
                         total = int(off2[-1].item())
                         res.bits, res.lab_off = b2, off2
@@ -437,6 +478,9 @@ class LokiSegmentationStage:
 
         res = DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
         res.ready = done
+        if use_bands:
+            res.runs, res.band_out, res.bands_host, res.band_off_host = runs, band_out, bands_h, band_off_h
+            res.compact = self.compact
         return res
 
     def reserve(self, geometries, device=None):
@@ -452,7 +496,10 @@ class LokiSegmentationStage:
                                   ("counts", 3 * n, torch.int32), ("lab_off", n + 1, torch.int32),
                                   ("acc", cap * NACC, torch.int64), ("hi", cap * 8, torch.float64),
                                   ("ext", cap * NEXT, torch.int32), ("counter", 1, torch.int32),
-                                  ("table", cap * NFEAT, torch.float64)):
+                                  ("table", cap * NFEAT, torch.float64), ("runs", max(words // 3, 1 << 16), torch.int64),
+                                  ("run_stats", max(words // 3, 1 << 16), torch.int64), ("run_base", words, torch.int16),
+                                  ("band_out", 4 * max(2 * n, words // 1024 + n), torch.int32),
+                                  ("band_counters", 4, torch.int32), ("big_list", n, torch.int32)):
                 ws.get(key, size, dt, dev)
             if getattr(ws, "arena", None) is None or ws.arena.device != dev:
                 ws.arena = Arena(dev)
@@ -464,7 +511,11 @@ class LokiSegmentationStage:
         """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
         per-operator path) ahead of run_device; part of making a batch resident."""
         if self.postprocess is not None and self.fused and self._passes() is not None:
-            left = batch.fused_lists()[2]
+            if self.pipeline == "bands":
+                from .morphology import pass_radius
+                left = batch.band_lists(sum(pass_radius(t) for t, _ in self._passes()))[3]
+            else:
+                left = batch.fused_lists()[2]
             if len(left):
                 self._sub(batch, left)
                 batch.tiles_of(left)

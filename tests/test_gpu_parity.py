@@ -372,16 +372,29 @@ def _edge_images(mz):
     faint = np.zeros((64, 64), np.uint8)
     faint[10, 10] = 255                                                   # eroded away -> empty plane feeds the dilation
     imgs.append(faint)
+    # multi-band vignettes of the band pipeline: uniform planes (scipy's phantom pixel -> flagged, per-operator redo),
+    # foreground in a single band, a component crossing every band seam, a tall narrow and a wide flat one
+    imgs += [np.full((300, 800), 255, np.uint8), np.zeros((500, 700), np.uint8)]
+    one = np.zeros((600, 640), np.uint8)
+    one[500:520, 100:300] = 250
+    imgs.append(one)
+    bar = np.zeros((900, 700), np.uint8)
+    bar[5:895, 340:352] = 250
+    bar[100:110, 10:690] = 250
+    bar[700:703, 10:690] = 250
+    imgs.append(bar)
+    imgs += [mz.synth.synth_batch(205, 1, size=(3000, 70))[0], mz.synth.synth_batch(206, 1, size=(70, 3000))[0]]
     return imgs
 
 
+@pytest.mark.parametrize("pipeline", ["bands", "fused"])
 @pytest.mark.parametrize("radii", [(1, 2), (2, 3), (0, 2), (3, 0), (0, 0), (1.5, 2.5)])
-def test_fused_vignette_kernel_equals_reference_chain(mz, radii):
+def test_fused_vignette_kernel_equals_reference_chain(mz, radii, pipeline):
     S = mz.stage
     r_open, r_close = radii
     imgs = _edge_images(mz)
     pp = S.SegmentationPostprocessingConfig(closing_radius=r_close, opening_radius=r_open)
-    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, pipeline=pipeline)
     res = st(imgs)
     for i, im in enumerate(imgs):
         mask, labels, table = scipy_chain.loki_chain(im, 40, r_open, r_close)
