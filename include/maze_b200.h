@@ -270,10 +270,12 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * {y, x0, x1 (inclusive), label}, the runs of a band contiguous and in raster order at runs[band_out[b].base ..
  * + n_runs) -- which is also the compact form of the label image that crosses PCIe; n_labels / fallback /
  * acc_base / staged accumulators exactly as for maze_vignette_stage; and, when mask and labels are given, the
- * dense bool mask and int32 label image (every pixel written once, zeros included).
+ * dense bool mask and int32 label image (both arrays, total_px elements each -- a multiple of 16 --, are zero
+ * filled on a forked stream next to the band kernel, the runs are stored on top; needs run_pix, one uint32 per
+ * run slot, and total_px < 2^32).
  * counters: 4 int32 (cleared by the call): [0] staging rows used, [1] runs used (may exceed run_cap: the bands
- * that did not fit are flagged), [2] vignettes that needed the large run table.  big_list: n_img int32 scratch.
- * run_base: one uint16 per bit-plane word (index of the first run starting in the word, band-relative).
+ * that did not fit are flagged), [2] / [3] vignettes that needed the middle / large run table.  big_list: n_img
+ * int32 scratch.
  * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
  * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
 #define MAZE_BAND_PLANE_WORDS 6144
@@ -284,10 +286,11 @@ typedef struct maze_run_stat { uint32_t isum; uint16_t zeros; uint8_t vmin, vmax
 int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig, int n_img,
                     const maze_band_t *bands, int n_bands, const int32_t *band_off, int t_int, int n_pass,
                     const int32_t *pass_t_host, const int32_t *pass_invert_host, int halo, int flags,
-                    uint32_t *bits, uint16_t *run_base, maze_run_t *runs, maze_run_stat_t *run_stats, int run_cap,
+                    uint32_t *bits, maze_run_t *runs, uint32_t *run_pix, maze_run_stat_t *run_stats, int run_cap,
                     maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
                     int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list, int stage_cap,
-                    unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, void *stream);
+                    unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, long long total_px,
+                    void *stream);
 
 /* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
  * acc_base[i] >= 0 (the others are left to maze_regionprops). */
@@ -341,8 +344,8 @@ typedef struct maze_step_args {
     /* band pipeline (bands != NULL: maze_band_stage runs in place of maze_vignette_stage) */
     const maze_band_t *bands;
     const int32_t *band_off;
-    uint16_t *run_base;
     maze_run_t *runs;
+    uint32_t *run_pix; /* run_cap uint32: element offset of every run's first pixel (dense outputs only) */
     maze_run_stat_t *run_stats;
     maze_band_out_t *band_out;
     int32_t *band_counters; /* 4 int32 */
@@ -351,6 +354,7 @@ typedef struct maze_step_args {
     int32_t pass_t[4], pass_invert[4];
     int32_t n_img, left_n, left_n_tiles, left_n_tiles_full, t_int, n_pass, flags, stage_cap;
     int32_t n_bands, halo, run_cap, step_flags; /* step_flags: MAZE_STEP_COMPACT */
+    int64_t total_px;                           /* elements of mask / labels (band pipeline, dense outputs) */
 } maze_step_args_t;
 #define MAZE_STEP_COMPACT 1 /* band pipeline: no dense mask / label image for the band vignettes (run list only) */
 int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);

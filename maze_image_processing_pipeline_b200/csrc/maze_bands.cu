@@ -24,9 +24,26 @@
 //                                             flagged (fallback) and redone by the per-operator kernels
 //   maze_ipp/loki/pipeline.py:430-433         label(): raster-order labels, 8-connectivity
 //   maze_ipp/loki/pipeline.py:589-625         per-label RegionProperties reads (accumulators)
+#include <stdlib.h>
+
 #include "maze_fused.cuh"
 
 constexpr int PW = MAZE_BAND_PLANE_WORDS;
+
+// run-table classes of the labelling kernel: runs, rows (+2) and bands a vignette may have
+#define BAND_T 256
+#define BAND_ZB 6144 /* bytes of zeros in shared memory behind the planes (source of the TMA zero fill) */
+#define LABEL_T 128
+#define LABEL_BIG_T 256
+#define LABEL_SMALL_CAP 1024
+#define LABEL_SMALL_HCAP 1026
+#define LABEL_SMALL_NB 32
+#define LABEL_MID_CAP 4096
+#define LABEL_MID_HCAP 4098
+#define LABEL_MID_NB 256
+#define LABEL_BIG_CAP 16384
+#define LABEL_BIG_HCAP 16386
+#define LABEL_BIG_NB 2048
 
 struct BandParams {
     int t_int, n_pass, halo, high_order, stage_cap, do_props, phantom_mask, has_intensity;
@@ -40,8 +57,9 @@ template <int T>
 __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     const uint8_t *__restrict__ image, const uint8_t *__restrict__ intensity, const maze_vignette_t *__restrict__ vig,
     const maze_band_t *__restrict__ bands, BandParams prm, uint32_t *__restrict__ bits_out,
-    uint16_t *__restrict__ rb_out, maze_run_t *__restrict__ runs, maze_run_stat_t *__restrict__ stats,
-    int32_t *run_counter, int run_cap, maze_band_out_t *__restrict__ band_out)
+    maze_run_t *__restrict__ runs, uint32_t *__restrict__ run_pix, maze_run_stat_t *__restrict__ stats,
+    int32_t *run_counter, int run_cap, maze_band_out_t *__restrict__ band_out, uint8_t *__restrict__ zmask,
+    int32_t *__restrict__ zlabels)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ int s_warp[34];
@@ -59,6 +77,37 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     const int step_y = T / wpr, step_k = T - step_y * wpr;
     const int y_first = tid / wpr, k_first = tid - y_first * wpr;
     int zflags = 0;
+
+    // ---- 0. dense outputs: zero fill of the band's share of the mask and label image (the 16-pixel groups of the
+    // flat vignette whose first pixel lies in the band's rows) by the TMA engine: ONE thread issues bulk copies
+    // from a zeroed shared-memory buffer (cp.async.bulk shared -> global), in slices between the compute phases.
+    // No store instruction, no LSU queue: the compute warps never see the 5 bytes per pixel that leave the SM.
+    uint8_t *zb = (uint8_t *)(s_mem + 2 * PW);
+    const bool zfill = zlabels != nullptr;
+    constexpr int ZF_PARTS = 4;
+    int zf_next = 0;
+    const int zg_lo = (bd.y0 * W + 15) >> 4, zg_n = ((bd.y1 * W + 15) >> 4) - zg_lo;
+    if (zfill) {
+        for (int i = tid; i < BAND_ZB / 16; i += T) ((uint4 *)zb)[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    auto tma_zero = [&](int upto) { // call after a barrier that follows the zeroing of zb
+        if (!zfill || tid != 0) return;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(zb);
+        for (; zf_next < upto; zf_next++) {
+            const i64 g0 = zg_lo + (i64)zg_n * zf_next / ZF_PARTS, g1 = zg_lo + (i64)zg_n * (zf_next + 1) / ZF_PARTS;
+            uint8_t *pl = (uint8_t *)(zlabels + v.pix_off) + 64 * g0, *pm = zmask + v.pix_off + 16 * g0;
+            for (i64 left = 64 * (g1 - g0); left > 0; left -= BAND_ZB, pl += BAND_ZB) {
+                const uint32_t sz = (uint32_t)(left < BAND_ZB ? left : BAND_ZB);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pl), "r"(src), "r"(sz) : "memory");
+            }
+            for (i64 left = 16 * (g1 - g0); left > 0; left -= BAND_ZB, pm += BAND_ZB) {
+                const uint32_t sz = (uint32_t)(left < BAND_ZB ? left : BAND_ZB);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pm), "r"(src), "r"(sz) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    };
 
     // ---- 1. threshold + pack of rows [ya, yb) (loki/pipeline.py:649) ------------------------------------
     uint32_t *T0 = (prm.n_pass & 1) ? B : A; // an odd number of passes must start in B to end in A
@@ -101,6 +150,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
         }
     }
     const int hz0 = __syncthreads_or(hz);
+    tma_zero(1);
     zflags |= hz0 ? 1 : 0;
     bool phantom = whole && !hz0 && prm.n_pass > 0 && prm.pass[0].use_phantom;
 
@@ -114,7 +164,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
         const uint32_t inv_next = (ps + 1 < prm.n_pass && prm.pass[ps + 1].invert) ? FULL : 0u;
         hz = false;
         if (R >= 0 && R <= 3) {
-            const int nstrip = max(1, min(Hb, (T + wpr - 1) / wpr));
+            const int nstrip = max(1, min(Hb, T / wpr)); // at most T work items: one round
             const int S = (Hb + nstrip - 1) / nstrip;
             const int *wt = prm.pass[ps].w;
             const int pat = wt[0] != R ? -1 : R * 1000 + wt[0] * 100 + (R >= 1 ? wt[1] * 10 : 0) + (R >= 2 ? wt[2] : 0);
@@ -157,10 +207,12 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
             }
         }
         const int hzp = __syncthreads_or(hz);
+        tma_zero(min(2 + ps, ZF_PARTS - 1));
         zflags |= hzp ? (2 << ps) : 0;
         phantom = whole && !hzp && ps + 1 < prm.n_pass && prm.pass[ps + 1].use_phantom;
         uint32_t *tmp = src; src = dst; dst = tmp;
     }
+    tma_zero(ZF_PARTS);
     // final plane (== A): own rows -> HBM
     const uint32_t *Mo = src + oy0 * wpr;
     const int n_own = (oy1 - oy0) * wpr;
@@ -172,52 +224,52 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     // ---- 3. run list of the own rows -------------------------------------------------------------------
     const int RC = min((4 * (2 * PW - words)) / 6, 65535); // everything behind the final plane is free
     u16 *rY = (u16 *)(s_mem + words), *rX0 = rY + RC, *rX1 = rX0 + RC;
+    // every thread walks a contiguous chunk of words; run STARTS and run ENDS are emitted independently (the j-th
+    // start and the j-th end of the band belong to the same run), so no thread ever follows a run across words
     const int chunk = ((n_own + T - 1) / T) | 1;
     const int lo = min(tid * chunk, n_own), hi = min(lo + chunk, n_own);
-    int cnt = 0;
+    int cnt = 0, open = 0;
     {
         int k = lo % wpr;
+        uint32_t prev = (lo < hi && k > 0) ? Mo[lo - 1] : 0u;
+        if (lo < hi && k > 0) open = (int)((prev >> 31) & Mo[lo] & 1u); // a run of the previous chunk continues here
         for (int w = lo; w < hi; w++) {
             const uint32_t m = Mo[w];
-            const uint32_t prevbit = k > 0 ? (Mo[w - 1] >> 31) : 0u;
-            cnt += __popc(m & ~((m << 1) | prevbit));
+            cnt += __popc(m & ~((m << 1) | (k > 0 ? prev >> 31 : 0u)));
+            prev = m;
             if (++k == wpr) k = 0;
         }
     }
     int n_runs;
     int run = block_exclusive_scan<T>(cnt, s_warp, &n_runs);
     if (n_runs > RC) { // more runs than slots (noise): the vignette falls back to the per-operator kernels
-        if (tid == 0) band_out[blockIdx.x] = maze_band_out_t{-1, n_runs, zflags, 0};
+        if (tid == 0) {
+            band_out[blockIdx.x] = maze_band_out_t{-1, n_runs, zflags, 0};
+            if (zfill) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
         return;
     }
-    {
-        u16 *grb = rb_out + v.word_off + (size_t)bd.y0 * wpr;
+    if (lo < hi) {
         int y = lo / wpr, k = lo - y * wpr;
+        int rs = run, re = run - open; // ends before this chunk = starts before it - runs still open
+        uint32_t prev = k > 0 ? Mo[lo - 1] : 0u, m = Mo[lo];
         for (int w = lo; w < hi; w++) {
-            grb[w] = (u16)run; // run starts before this word (band raster order)
-            const uint32_t m = Mo[w];
-            const uint32_t prevbit = k > 0 ? (Mo[w - 1] >> 31) : 0u;
-            uint32_t starts = m & ~((m << 1) | prevbit);
+            const uint32_t nxt = (w + 1 < n_own) ? Mo[w + 1] : 0u;
+            const uint32_t pb = k > 0 ? prev >> 31 : 0u, nbit = (k + 1 < wpr) ? (nxt & 1u) : 0u;
+            uint32_t starts = m & ~((m << 1) | pb), ends = m & ~((m >> 1) | (nbit << 31));
+            const int xw = 32 * k, yy = bd.y0 + y;
             while (starts) {
                 const int b0 = __ffs(starts) - 1;
                 starts &= starts - 1;
-                const uint32_t rest = ~(m >> b0);
-                const int x0 = 32 * k + b0;
-                int x1;
-                if ((rest & (b0 ? ((1u << (32 - b0)) - 1u) : FULL)) != 0u) {
-                    x1 = x0 + __ffs(rest) - 2; // the run ends inside this word
-                } else {                       // it reaches bit 31: follow it through the next words of the row
-                    x1 = 32 * k + 31;
-                    for (int kk = k + 1; kk < wpr; kk++) {
-                        const uint32_t mm = Mo[w - k + kk];
-                        if (mm == FULL) { x1 += 32; continue; }
-                        x1 += __ffs(~mm) - 1;
-                        break;
-                    }
-                }
-                rY[run] = (u16)(bd.y0 + y); rX0[run] = (u16)x0; rX1[run] = (u16)x1;
-                run++;
+                rY[rs] = (u16)yy; rX0[rs] = (u16)(xw + b0);
+                rs++;
             }
+            while (ends) {
+                const int b1 = __ffs(ends) - 1;
+                ends &= ends - 1;
+                rX1[re++] = (u16)(xw + b1);
+            }
+            prev = m; m = nxt;
             if (++k == wpr) { k = 0; y++; }
         }
     }
@@ -229,51 +281,69 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     }
     __syncthreads();
     const int base = s_base;
-    if (base < 0) return;
+    if (base < 0) {
+        if (zfill && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
     for (int i = tid; i < n_runs; i += T) {
         uint2 r;
         r.x = (uint32_t)rY[i] | ((uint32_t)rX0[i] << 16);
         r.y = (uint32_t)rX1[i];
         ((uint2 *)runs)[base + i] = r;
+        if (run_pix) run_pix[base + i] = (uint32_t)(v.pix_off + (i64)rY[i] * W + rX0[i]); // where the dense writer starts
     }
-    // ---- 4. intensity statistics per run (one warp per run, one aligned word per lane; the bytes were read by
-    // this CTA a moment ago, so the loads hit L2) -----------------------------------------------------------
+    // ---- 4. intensity statistics per run: four lanes per run (aligned words round robin, two loads in flight per
+    // lane, byte-SIMD), reduced across the quad; the bytes were read by this CTA a moment ago, so the loads hit L2 --
     if (intensity) {
         const uint8_t *gi = intensity + v.pix_off;
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int i = warp; i < n_runs; i += T / 32) {
-            const int y = rY[i], a = rX0[i], b = rX1[i];
-            const uint8_t *prow = gi + (size_t)y * W;
-            const int al = (int)((uintptr_t)prow & 3u);
-            const uint32_t *qq = (const uint32_t *)(prow - al);
-            const int ga = (a + al) >> 2, gb = (b + al) >> 2;
+        const int q = tid & 3;
+        for (int i0 = 0; i0 < n_runs; i0 += T / 4) {
+            const int i = i0 + (tid >> 2);
             uint32_t sV = 0, sZ = 0, mn = FULL, mx = 0u;
-            for (int g = ga + lane; g <= gb; g += 32) {
-                const uint32_t px = __ldg(qq + g);
-                const int c0 = 4 * g - al; // column of byte 0 of this word
-                uint32_t nib = 0xfu;
-                if (c0 < a) nib &= 0xfu << (a - c0);
-                if (c0 + 3 > b) nib &= 0xfu >> (c0 + 3 - b);
-                const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
-                sV = __dp4a(px & bm, 0x01010101u, sV);
-                sZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u);
-                mn = __vminu4(mn, px | ~bm);
-                mx = __vmaxu4(mx, px & bm);
+            if (i < n_runs) {
+                const int y = rY[i], a = rX0[i], b = rX1[i];
+                const uint8_t *prow = gi + (size_t)y * W;
+                const int al = (int)((uintptr_t)prow & 3u);
+                const uint32_t *qq = (const uint32_t *)(prow - al);
+                const int ga = (a + al) >> 2, gb = (b + al) >> 2;
+                for (int g0 = ga + q; g0 <= gb; g0 += 8) {
+                    uint32_t pxs[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) pxs[u] = __ldg(qq + min(g0 + 4 * u, gb));
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int g = g0 + 4 * u;
+                        const uint32_t px = pxs[u];
+                        const int c0 = 4 * g - al; // column of byte 0 of this word
+                        uint32_t nib = g <= gb ? 0xfu : 0u;
+                        if (c0 < a) nib &= 0xfu << (a - c0);
+                        if (c0 + 3 > b) nib &= 0xfu >> min(c0 + 3 - b, 31);
+                        const uint32_t bm = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+                        sV = __dp4a(px & bm, 0x01010101u, sV);
+                        sZ += __popc(~(((px & 0x7f7f7f7fu) + 0x7f7f7f7fu) | px) & bm & 0x80808080u);
+                        mn = __vminu4(mn, px | ~bm);
+                        mx = __vmaxu4(mx, px & bm);
+                    }
+                }
             }
-            sV = __reduce_add_sync(FULL, sV);
-            sZ = __reduce_add_sync(FULL, sZ);
-            mn = __vminu4(mn, mn >> 16); mn = __vminu4(mn, mn >> 8);
-            mx = __vmaxu4(mx, mx >> 16); mx = __vmaxu4(mx, mx >> 8);
-            mn = __reduce_min_sync(FULL, mn & 0xffu);
-            mx = __reduce_max_sync(FULL, mx & 0xffu);
-            if (lane == 0) {
+#pragma unroll
+            for (int d = 1; d < 4; d <<= 1) {
+                sV += __shfl_xor_sync(FULL, sV, d);
+                sZ += __shfl_xor_sync(FULL, sZ, d);
+                mn = __vminu4(mn, __shfl_xor_sync(FULL, mn, d));
+                mx = __vmaxu4(mx, __shfl_xor_sync(FULL, mx, d));
+            }
+            if (q == 0 && i < n_runs) {
+                mn = __vminu4(mn, mn >> 16); mn = __vminu4(mn, mn >> 8);
+                mx = __vmaxu4(mx, mx >> 16); mx = __vmaxu4(mx, mx >> 8);
                 uint2 st;
                 st.x = sV;
-                st.y = (sZ & 0xffffu) | (mn << 16) | (mx << 24);
+                st.y = (sZ & 0xffffu) | ((mn & 0xffu) << 16) | ((mx & 0xffu) << 24);
                 ((uint2 *)stats)[base + i] = st;
             }
         }
     }
+    if (zfill && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the fill has left the SM
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -302,7 +372,7 @@ __device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
 
 // returns 0 = done (labelled, flagged as fallback, or not a band vignette), 1 = needs a larger run table
 template <int T>
-__device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, uint32_t *s_mem)
+__device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, int nbcap, uint32_t *s_mem)
 {
     __shared__ int s_warp[34];
     __shared__ int s_misc[4];
@@ -313,21 +383,50 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, ui
     if (nb <= 0) return 0; // not a band vignette (the per-operator chain owns its counters)
     const maze_vignette_t v = a.vig[img];
     const int H = v.h;
+    if (nb > nbcap) return 1;
+    // band table -> shared memory: s_bbase[j] = first run of band j in the run buffer, s_bpre[j] = runs before band j
+    int *s_bbase = (int *)s_mem, *s_bpre = s_bbase + nbcap;
     if (tid < 4) s_misc[tid] = 0;
     __syncthreads();
     {
-        int tot = 0, bad = 0, zor = 0;
-        for (int b = b0 + tid; b < b1; b += T) {
-            const maze_band_out_t o = a.band_out[b];
-            tot += o.n_runs; bad |= (o.base < 0) ? 1 : 0; zor |= o.zflags;
+        int bad = 0, zor = 0;
+        for (int j = tid; j < nb; j += T) {
+            const maze_band_out_t o = a.band_out[b0 + j];
+            s_bbase[j] = o.base; s_bpre[j + 1] = o.n_runs;
+            bad |= (o.base < 0) ? 1 : 0; zor |= o.zflags;
         }
-        tot = __reduce_add_sync(FULL, tot); bad = __reduce_or_sync(FULL, bad); zor = __reduce_or_sync(FULL, zor);
-        if (lane == 0 && (tot | bad | zor)) { atomicAdd(&s_misc[0], tot); atomicOr(&s_misc[1], bad); atomicOr(&s_misc[2], zor); }
+        bad = __reduce_or_sync(FULL, bad); zor = __reduce_or_sync(FULL, zor);
+        if (lane == 0 && (bad | zor)) { atomicOr(&s_misc[1], bad); atomicOr(&s_misc[2], zor); }
+    }
+    __syncthreads();
+    if (warp == 0) { // prefix sum of the run counts (a handful of bands)
+        int carry = 0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            const int j = j0 + lane;
+            int x = j < nb ? s_bpre[j + 1] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x += t;
+            }
+            if (j < nb) s_bpre[j + 1] = carry + x;
+            carry += __shfl_sync(FULL, x, 31);
+        }
+        if (lane == 0) { s_bpre[0] = 0; s_misc[0] = carry; }
     }
     __syncthreads();
     const int n_runs = s_misc[0];
     int bad = s_misc[1];
     const int zor = s_misc[2];
+    // position of run i (vignette raster order) in the run buffer
+    auto gidx = [&](int i) {
+        int lo = 0, hi = nb - 1; // last band j with s_bpre[j] <= i
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_bpre[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        return s_bbase[lo] + (i - s_bpre[lo]);
+    };
     // scipy's phantom pixel applies to a pass whose (inverted) input plane has no 0 anywhere: a one-band vignette
     // handled it exactly in K1, a multi-band one is redone by the per-operator kernels
     if (nb > 1)
@@ -339,20 +438,12 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, ui
     }
     if (n_runs > cap || n_runs >= 0x8000 || H + 2 > hcap) return 1;
 
-    u16 *rY = (u16 *)s_mem, *rX0 = rY + cap, *rX1 = rX0 + cap, *P = rX1 + cap, *rO = P + cap, *rowStart = rO + cap;
+    u16 *rY = (u16 *)(s_bpre + nbcap + 1), *rX0 = rY + cap, *rX1 = rX0 + cap, *P = rX1 + cap, *rO = P + cap, *rowStart = rO + cap;
     AccRow *ACC = (AccRow *)(((uintptr_t)(rowStart + hcap) + 15) & ~(uintptr_t)15);
-    {
-        int off = 0;
-        for (int b = b0; b < b1; b++) {
-            const maze_band_out_t o = a.band_out[b];
-            const uint2 *src = (const uint2 *)(a.runs + o.base);
-            for (int i = tid; i < o.n_runs; i += T) {
-                const uint2 r = src[i];
-                rY[off + i] = (u16)(r.x & 0xffffu); rX0[off + i] = (u16)(r.x >> 16); rX1[off + i] = (u16)(r.y & 0xffffu);
-                P[off + i] = (u16)(off + i);
-            }
-            off += o.n_runs;
-        }
+    for (int i = tid; i < n_runs; i += T) {
+        const uint2 r = ((const uint2 *)a.runs)[gidx(i)];
+        rY[i] = (u16)(r.x & 0xffffu); rX0[i] = (u16)(r.x >> 16); rX1[i] = (u16)(r.y & 0xffffu);
+        P[i] = (u16)i;
     }
     __syncthreads();
     // first run of every row (runs are in raster order)
@@ -456,47 +547,43 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, ui
     // ---- label of every run -> HBM; per-run intensity statistics -> accumulator rows (warp-aggregated) -----------
     {
         const bool with_i = props && a.has_intensity;
-        int off = 0;
-        for (int b = b0; b < b1; b++) {
-            const maze_band_out_t o = a.band_out[b];
-            for (int i0 = warp * 32; i0 < o.n_runs; i0 += T) {
-                const int i = i0 + lane;
-                const bool valid = i < o.n_runs;
-                int lab = 0;
-                uint32_t isum = 0, zeros = 0, vmn = 255, vmx = 0;
-                if (valid) {
-                    lab = label_of(P, off + i);
-                    ((u16 *)(a.runs + o.base + i))[3] = (u16)lab;
-                    if (with_i) {
-                        const uint2 st = ((const uint2 *)a.stats)[o.base + i];
-                        isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
-                    }
-                }
+        for (int i0 = warp * 32; i0 < n_runs; i0 += T) {
+            const int i = i0 + lane;
+            const bool valid = i < n_runs;
+            int lab = 0;
+            uint32_t isum = 0, zeros = 0, vmn = 255, vmx = 0;
+            if (valid) {
+                const int g = gidx(i);
+                lab = label_of(P, i);
+                ((u16 *)(a.runs + g))[3] = (u16)lab;
                 if (with_i) {
-                    uint32_t todo = __ballot_sync(FULL, valid);
-                    while (todo) {
-                        const int leader = __ffs(todo) - 1;
-                        const int L = __shfl_sync(FULL, lab, leader);
-                        const bool in = valid && lab == L;
-                        todo &= ~__ballot_sync(FULL, in);
-                        const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
-                        const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
-                        if (lane == leader) {
-                            if (L <= FUSED_LCAP) {
-                                shared_add64(ACC[L - 1].a + A_V, (u64)sV);
-                                if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
-                                atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
-                            } else {
-                                u64 *Aa = a.acc_stage + (i64)(base + L - 1) * MAZE_NACC;
-                                int32_t *Ee = a.ext_stage + (i64)(base + L - 1) * MAZE_NEXT;
-                                atomicAdd(Aa + A_V, (u64)sV); atomicAdd(Aa + A_Z, (u64)sZ);
-                                atomicMin(Ee + E_VMIN, (int)mn); atomicMax(Ee + E_VMAX, (int)mx);
-                            }
+                    const uint2 st = ((const uint2 *)a.stats)[g];
+                    isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
+                }
+            }
+            if (with_i) {
+                uint32_t todo = __ballot_sync(FULL, valid);
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    const int L = __shfl_sync(FULL, lab, leader);
+                    const bool in = valid && lab == L;
+                    todo &= ~__ballot_sync(FULL, in);
+                    const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
+                    const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
+                    if (lane == leader) {
+                        if (L <= FUSED_LCAP) {
+                            shared_add64(ACC[L - 1].a + A_V, (u64)sV);
+                            if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
+                            atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
+                        } else {
+                            u64 *Aa = a.acc_stage + (i64)(base + L - 1) * MAZE_NACC;
+                            int32_t *Ee = a.ext_stage + (i64)(base + L - 1) * MAZE_NEXT;
+                            atomicAdd(Aa + A_V, (u64)sV); atomicAdd(Aa + A_Z, (u64)sZ);
+                            atomicMin(Ee + E_VMIN, (int)mn); atomicMax(Ee + E_VMAX, (int)mx);
                         }
                     }
                 }
             }
-            off += o.n_runs;
         }
     }
     if (!props) return 0;
@@ -649,126 +736,170 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, ui
     return 0;
 }
 
+// small class: one CTA per vignette; a vignette with more runs (or rows) than the class holds goes on the list of
+// the next class (big_list is filled from the front for the middle class, from the back for the large one)
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap)
+__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap, int mid_cap, int mid_hcap)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const int img = blockIdx.x;
-    if (label_vignette<T>(a, img, cap, hcap, s_mem) == 1 && threadIdx.x == 0)
-        a.big_list[atomicAdd(a.big_counter, 1)] = img; // more runs than this class holds: the big class takes it
+    if (label_vignette<T>(a, img, cap, hcap, LABEL_SMALL_NB, s_mem) == 1 && threadIdx.x == 0) {
+        int tot = 0;
+        for (int b = a.band_off[img]; b < a.band_off[img + 1]; b++) tot += a.band_out[b].n_runs;
+        if (tot <= mid_cap && a.vig[img].h + 2 <= mid_hcap && a.band_off[img + 1] - a.band_off[img] <= LABEL_MID_NB) a.big_list[atomicAdd(a.big_counter, 1)] = img;
+        else a.big_list[a.n_img - 1 - atomicAdd(a.big_counter + 1, 1)] = img;
+    }
 }
 
+// middle (which = 0) and large (which = 1) class: a fixed grid walks its list
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap)
+__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap, int which)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
-    const int n = *(volatile int32_t *)a.big_counter;
+    const int n = *(volatile int32_t *)(a.big_counter + which);
     for (int e = blockIdx.x; e < n; e += gridDim.x) {
-        const int img = a.big_list[e];
-        if (label_vignette<T>(a, img, cap, hcap, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
+        const int img = a.big_list[which ? a.n_img - 1 - e : e];
+        if (label_vignette<T>(a, img, cap, hcap, which ? LABEL_BIG_NB : LABEL_MID_NB, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
         __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K3: dense writer
+// K3: dense writer -- every run of the batch's run buffer is stored on top of the zero fill (a warp fetches 32
+// run records at once, then stores run after run with coalesced 4-byte label / 1-byte mask stores).  Runs of
+// vignettes that were flagged as fallback carry label 0 and are overwritten by the per-operator kernels later.
 // ---------------------------------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(T) k_band_write(const maze_vignette_t *__restrict__ vig,
-                                                  const maze_band_t *__restrict__ bands,
-                                                  const maze_band_out_t *__restrict__ band_out,
-                                                  const int32_t *__restrict__ fallback, const uint32_t *__restrict__ bits,
-                                                  const uint16_t *__restrict__ rb, const maze_run_t *__restrict__ runs,
+__global__ void __launch_bounds__(T) k_band_write(const maze_run_t *__restrict__ runs, const uint32_t *__restrict__ run_pix,
+                                                  const int32_t *__restrict__ run_counter, int run_cap,
                                                   uint8_t *__restrict__ mask, int32_t *__restrict__ labels)
 {
-    const maze_band_t bd = bands[blockIdx.x];
-    if (fallback[bd.img]) return; // the per-operator kernels write this vignette
-    const maze_vignette_t v = vig[bd.img];
-    const int H = v.h, W = v.w, wpr = v.wpr;
-    const uint32_t *plane = bits + v.word_off;
-    const uint16_t *RB = rb + v.word_off;
-    const int own_base = band_out[blockIdx.x].base;
-    const int band0 = (int)blockIdx.x - bd.y0 / bd.rpb; // first band of this vignette
-    // groups of 16 pixels of the flat vignette (16-byte mask store, 64-byte label store): the band owns the groups
-    // whose FIRST pixel lies in its rows
-    const int g_lo = (bd.y0 * W + 15) >> 4, g_hi = (bd.y1 * W + 15) >> 4;
-    uint4 *l4 = (uint4 *)(labels + v.pix_off);
-    uint4 *m4 = (uint4 *)(mask + v.pix_off);
-    for (int g = g_lo + threadIdx.x; g < g_hi; g += T) {
-        const int p0 = 16 * g;
-        const int y = p0 / W, x = p0 - y * W;
-        uint32_t bits16 = 0;
-        {
-            int filled = 0, yy = y, xx = x;
-            while (filled < 16 && yy < H) {
-                const int n = min(16 - filled, W - xx);
-                const int k = xx >> 5, sh = xx & 31;
-                const uint32_t lo = plane[yy * wpr + k];
-                const uint32_t hi = (sh + n > 32) ? plane[yy * wpr + k + 1] : 0u; // (pad bits of the last word are 0)
-                bits16 |= (__funnelshift_r(lo, hi, sh) & ((1u << n) - 1u)) << filled;
-                filled += n; xx = 0; yy++;
-            }
+    const int n = min(*run_counter, run_cap);
+    const int lane = threadIdx.x & 31;
+    const int nwarp = gridDim.x * (T / 32);
+    for (int i0 = (blockIdx.x * (T / 32) + (threadIdx.x >> 5)) * 32; i0 < n; i0 += nwarp * 32) {
+        const int nr = min(32, n - i0);
+        uint32_t pix = 0, rec_x = 0, rec_y = 0;
+        if (lane < nr) {
+            const uint2 r = ((const uint2 *)runs)[i0 + lane];
+            pix = run_pix[i0 + lane]; rec_x = r.x; rec_y = r.y;
         }
-        uint32_t lab[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) lab[j] = 0;
-        if (bits16) {
-            int filled = 0, yy = y, xx = x;
-            while (filled < 16 && yy < H) {
-                const int n = min(16 - filled, W - xx);
-                uint32_t part = (bits16 >> filled) & ((1u << n) - 1u);
-                while (part) {
-                    const int b0 = __ffs(part) - 1;
-                    const int len = __ffs(~(part >> b0)) - 1;
-                    const int px = xx + b0; // column of the segment's first pixel: its run gives the label
-                    const int k = px >> 5, bb = px & 31, w = yy * wpr + k;
-                    const uint32_t m = plane[w];
-                    const uint32_t prevbit = k > 0 ? (plane[w - 1] >> 31) : 0u;
-                    const uint32_t starts = m & ~((m << 1) | prevbit);
-                    const uint32_t low = bb == 31 ? FULL : ((2u << bb) - 1u);
-                    const int rid = (int)RB[w] + __popc(starts & low) - 1;
-                    const int rbase = yy < bd.y1 ? own_base : band_out[band0 + yy / bd.rpb].base;
-                    const uint32_t L = runs[rbase + rid].label;
-                    const uint32_t seg = ((1u << len) - 1u) << (filled + b0);
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if ((seg >> j) & 1u) lab[j] = L;
-                    part &= ~(((1u << len) - 1u) << b0);
+        const uint32_t len_me = (rec_y & 0xffffu) - (rec_x >> 16) + 1u;
+        for (int j = 0; j < nr; j++) {
+            const uint32_t p = __shfl_sync(FULL, pix, j), len = __shfl_sync(FULL, len_me, j);
+            const int lab = (int)(__shfl_sync(FULL, rec_y, j) >> 16);
+            int32_t *gl = labels + p;
+            uint8_t *gm = mask + p;
+            // iterations aligned to 32 elements: every store instruction but the first and the last of a run
+            // covers whole 32-byte sectors (one of the mask, four of the label image)
+            for (int x = lane - (int)(p & 31u); x < (int)len; x += 32)
+                if (x >= 0) {
+                    gl[x] = lab;
+                    gm[x] = 1;
                 }
-                filled += n; xx = 0; yy++;
-            }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) l4[4 * (size_t)g + j] = make_uint4(lab[4 * j], lab[4 * j + 1], lab[4 * j + 2], lab[4 * j + 3]);
-        uint4 mk;
-        mk.x = ((bits16 & 0xfu) * 0x00204081u) & 0x01010101u;
-        mk.y = (((bits16 >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
-        mk.z = (((bits16 >> 8) & 0xfu) * 0x00204081u) & 0x01010101u;
-        mk.w = (((bits16 >> 12) & 0xfu) * 0x00204081u) & 0x01010101u;
-        m4[g] = mk;
     }
+}
+
+// zero fill of the dense outputs (runs on a forked stream next to the band front, which leaves the memory system idle)
+__global__ void __launch_bounds__(256) k_band_zero(uint4 *__restrict__ a, size_t na, uint4 *__restrict__ b, size_t nb)
+{
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) a[i] = z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) b[i] = z;
+}
+
+// the same fill by the TMA engine: every lane streams 16 KB bulk copies from a zeroed shared-memory buffer
+// (cp.async.bulk shared -> global, SASS UBLKCP): no store instructions, no LSU queue, 32 threads per SM
+#define ZCH 16384
+__global__ void __launch_bounds__(32) k_band_zero_tma(uint8_t *__restrict__ a, size_t na, uint8_t *__restrict__ b, size_t nb)
+{
+    extern __shared__ __align__(128) uint8_t zbuf[];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < ZCH / 16; i += 32) ((uint4 *)zbuf)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(zbuf);
+    const size_t ca = (na + ZCH - 1) / ZCH, cb = (nb + ZCH - 1) / ZCH;
+    int pending = 0;
+    for (size_t c = (size_t)blockIdx.x * 32 + lane; c < ca + cb; c += (size_t)gridDim.x * 32) {
+        uint8_t *dst;
+        size_t left;
+        if (c < ca) { dst = a + c * ZCH; left = na - c * ZCH; }
+        else { dst = b + (c - ca) * ZCH; left = nb - (c - ca) * ZCH; }
+        const uint32_t size = (uint32_t)(left < (size_t)ZCH ? left : (size_t)ZCH); // multiples of 16 bytes
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(size) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (++pending == 8) {
+            asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+            pending = 4;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static int zero_mode()
+{
+    static int m = -1;
+    if (m < 0) {
+        const char *e = getenv("MAZE_ZERO_MODE");
+        m = !e ? 2 : e[0] == 't' ? 1 : e[0] == 's' ? 0 : 2; // default: inside the band front (TMA)
+    }
+    return m;
+}
+
+static int zero_ctas()
+{
+    static int n = 0;
+    if (!n) {
+        const char *e = getenv("MAZE_ZERO_CTAS"); // experiments: throttle the fill so that it leaves DRAM headroom
+        n = e ? atoi(e) : 148 * 4;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+struct BandFork {
+    int device;
+    cudaStream_t aux;
+    cudaEvent_t fork, join;
+};
+
+static BandFork *band_fork()
+{
+    static thread_local BandFork pool[16];
+    static thread_local int n_pool = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < n_pool; i++)
+        if (pool[i].device == dev) return &pool[i];
+    if (n_pool >= 16) return nullptr;
+    BandFork *f = &pool[n_pool];
+    f->device = dev;
+    if (cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    n_pool++;
+    return f;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-#define BAND_T 256
-#define LABEL_T 256
-#define LABEL_SMALL_CAP 2048
-#define LABEL_SMALL_HCAP 2050
-#define LABEL_BIG_CAP 16384
-#define LABEL_BIG_HCAP 16386
-
-static size_t label_smem(int cap, int hcap) { return (size_t)cap * 10 + (size_t)hcap * 2 + 16 + FUSED_LCAP * sizeof(AccRow); }
+static size_t label_smem(int cap, int hcap, int nbcap)
+{
+    return (size_t)(2 * nbcap + 1) * 4 + (size_t)cap * 10 + (size_t)hcap * 2 + 16 + FUSED_LCAP * sizeof(AccRow);
+}
 
 extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig, int n_img,
                                const maze_band_t *bands, int n_bands, const int32_t *band_off, int t_int, int n_pass,
                                const int32_t *pass_t_host, const int32_t *pass_invert_host, int halo, int flags,
-                               uint32_t *bits, uint16_t *run_base, maze_run_t *runs, maze_run_stat_t *run_stats,
-                               int run_cap, maze_band_out_t *band_out, uint8_t *mask, int32_t *labels,
-                               int32_t *n_labels, int32_t *fallback, int32_t *acc_base, int32_t *counters,
-                               int32_t *big_list, int stage_cap, unsigned long long *acc_stage, double *hi_stage,
-                               int32_t *ext_stage, void *stream)
+                               uint32_t *bits, maze_run_t *runs, uint32_t *run_pix, maze_run_stat_t *run_stats, int run_cap,
+                               maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
+                               int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list,
+                               int stage_cap, unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage,
+                               long long total_px, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_pass < 0 || n_pass > 4 || halo < 0) return MAZE_ERR_BADARG;
@@ -796,31 +927,75 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
         sum_r += prm.pass[p].R > 0 ? prm.pass[p].R : 0;
     }
     if (halo < sum_r) return MAZE_ERR_BADARG; // the halo must absorb every pass
+    const bool dense = mask && labels;
     MAZE_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), s), "band counters");
     int32_t *stage_counter = counters, *run_counter = counters + 1, *big_counter = counters + 2;
     static thread_local int attr_dev = -1;
     int dev = 0;
     MAZE_CUDA(cudaGetDevice(&dev), "get device");
-    const size_t smem1 = (size_t)PW * 8, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP),
-                 smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP);
+    const size_t smem1 = (size_t)PW * 8 + BAND_ZB, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_SMALL_NB),
+                 smem_m = label_smem(LABEL_MID_CAP, LABEL_MID_HCAP, LABEL_MID_NB),
+                 smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP, LABEL_BIG_NB);
     if (attr_dev != dev) {
         MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "band smem");
         MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared), "band carveout");
         MAZE_CUDA(cudaFuncSetAttribute(k_band_label<LABEL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s), "label smem");
-        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), "label big smem");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label<LABEL_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "label carveout");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), "label big smem");
+        // kernels only share an SM when they ask for the same shared-memory carve-out: everything that should run
+        // next to the band front (zero fill, labelling, writer of another lane) asks for the maximum like it does
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_BIG_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "label big carveout");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_write<BAND_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "write carveout");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_zero, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "zero carveout");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_zero_tma, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "zero tma carveout");
         attr_dev = dev;
     }
+    BandFork *fk = nullptr;
+    if (dense && (total_px <= 0 || (total_px & 15) || total_px >= (1ll << 32) || !run_pix)) return MAZE_ERR_BADARG;
+    const bool zin = dense && zero_mode() == 2; // zero fill inside the band front
+    if (dense && !zin) { // experiments: zero fill by a kernel of its own next to the band front
+        fk = band_fork();
+        if (!fk) return MAZE_ERR_CUDA;
+        MAZE_CUDA(cudaEventRecord(fk->fork, s), "band fork");
+        MAZE_CUDA(cudaStreamWaitEvent(fk->aux, fk->fork, 0), "band fork wait");
+        if (zero_mode() == 1) {
+            const char *e = getenv("MAZE_ZERO_CTAS");
+            MAZE_KERNEL(KID_BAND_ZERO, fk->aux,
+                        k_band_zero_tma<<<e ? zero_ctas() : 148, 32, ZCH, fk->aux>>>((uint8_t *)labels, (size_t)total_px * 4,
+                                                                                   mask, (size_t)total_px));
+        } else {
+            MAZE_KERNEL(KID_BAND_ZERO, fk->aux,
+                        k_band_zero<<<zero_ctas(), 256, 0, fk->aux>>>((uint4 *)labels, (size_t)total_px / 4, (uint4 *)mask,
+                                                                  (size_t)total_px / 16));
+        }
+        MAZE_CUDA(cudaEventRecord(fk->join, fk->aux), "band join");
+    }
     MAZE_KERNEL(KID_BAND_FRONT, s,
-                k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, run_base, runs,
-                                                                   run_stats, run_counter, run_cap, band_out));
+                k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, runs,
+                                                                   dense ? run_pix : nullptr, run_stats, run_counter,
+                                                                   run_cap, band_out, zin ? mask : nullptr,
+                                                                   zin ? labels : nullptr));
     LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
                     (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, n_img, n_pass, prm.phantom_mask,
                     prm.do_props, prm.high_order, prm.has_intensity, stage_cap};
-    MAZE_KERNEL(KID_BAND_LABEL, s, k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP));
-    MAZE_KERNEL(KID_BAND_LABEL_BIG, s, k_band_label_big<LABEL_T><<<74, LABEL_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP));
-    if (mask && labels)
+    MAZE_KERNEL(KID_BAND_LABEL, s,
+                k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
+                                                                    LABEL_MID_HCAP));
+    const int grid_mid = n_img < 296 ? n_img : 296, grid_big = n_img < 74 ? n_img : 74;
+    MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                k_band_label_big<LABEL_BIG_T><<<grid_mid, LABEL_BIG_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
+    MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
+    if (dense) {
+        if (fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
         MAZE_KERNEL(KID_BAND_WRITE, s,
-                    k_band_write<BAND_T><<<n_bands, BAND_T, 0, s>>>(vig, bands, band_out, fallback, bits, run_base, runs, mask, labels));
+                    k_band_write<BAND_T><<<148 * 8, BAND_T, 0, s>>>(runs, run_pix, run_counter, run_cap, mask, labels));
+    }
     return MAZE_OK;
 }

@@ -713,6 +713,14 @@ extern "C" int maze_vignette_stage(const uint8_t *image, const uint8_t *intensit
 extern "C" int maze_count_scan(const int32_t *n_labels, int n_img, int32_t *lab_off, void *stream)
 {
     if (n_img < 0) return MAZE_ERR_BADARG;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    MAZE_CUDA(cudaGetDevice(&dev), "get device");
+    if (attr_dev != dev) { // same carve-out as the stage kernels, so that it can share an SM with them
+        MAZE_CUDA(cudaFuncSetAttribute(k_count_scan, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "scan carveout");
+        attr_dev = dev;
+    }
     MAZE_KERNEL(KID_COUNT_SCAN, (cudaStream_t)stream,
                 k_count_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(n_labels, n_img, lab_off));
     return MAZE_OK;

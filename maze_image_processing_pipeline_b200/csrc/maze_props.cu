@@ -478,6 +478,14 @@ extern "C" int maze_props_finish_staged(const unsigned long long *acc_stage, con
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_img <= 0 || n_obj <= 0) return MAZE_OK;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    MAZE_CUDA(cudaGetDevice(&dev), "get device");
+    if (attr_dev != dev) { // same carve-out as the stage kernels, so that it can share an SM with them
+        MAZE_CUDA(cudaFuncSetAttribute(k_props_finish_staged, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "finish carveout");
+        attr_dev = dev;
+    }
     MAZE_KERNEL(KID_PROPS_FINISH_STAGED, s,
                 k_props_finish_staged<<<(n_obj + 127) / 128, 128, 0, s>>>((const u64 *)acc_stage, hi_stage, ext_stage,
                                                                           acc_base, lab_off, n_img, n_obj, has_intensity,

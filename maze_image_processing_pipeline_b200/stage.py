@@ -370,7 +370,7 @@ class LokiSegmentationStage:
             run_cap = max(g.total_words // 3, 1 << 16)
             runs = ws.get("runs", run_cap, torch.int64, dev)          # maze_run_t, 8 bytes each
             run_stats = ws.get("run_stats", run_cap, torch.int64, dev)
-            run_base = ws.get("run_base", max(g.total_words, 1), torch.int16, dev)
+            run_pix = ws.get("run_pix", run_cap, torch.int32, dev)
             band_out = ws.get("band_out", 4 * max(n_bands, 1), torch.int32, dev)
             band_counters = ws.get("band_counters", 4, torch.int32, dev)
             big_list = ws.get("big_list", n, torch.int32, dev)
@@ -398,9 +398,9 @@ class LokiSegmentationStage:
         a.table, a.counts_host = table.data_ptr(), host.data_ptr()
         if use_bands:
             a.bands, a.band_off, a.n_bands, a.halo = d_bands.data_ptr(), d_band_off.data_ptr(), n_bands, halo
-            a.run_base, a.runs, a.run_stats = run_base.data_ptr(), runs.data_ptr(), run_stats.data_ptr()
+            a.runs, a.run_stats, a.run_pix = runs.data_ptr(), run_stats.data_ptr(), run_pix.data_ptr()
             a.band_out, a.band_counters, a.big_list = band_out.data_ptr(), band_counters.data_ptr(), big_list.data_ptr()
-            a.run_cap = run_cap
+            a.run_cap, a.total_px = run_cap, g.total_px
             a.step_flags = STEP_COMPACT if self.compact else 0
         else:
             a.img_list = d_list.data_ptr()
@@ -497,7 +497,7 @@ class LokiSegmentationStage:
                                   ("acc", cap * NACC, torch.int64), ("hi", cap * 8, torch.float64),
                                   ("ext", cap * NEXT, torch.int32), ("counter", 1, torch.int32),
                                   ("table", cap * NFEAT, torch.float64), ("runs", max(words // 3, 1 << 16), torch.int64),
-                                  ("run_stats", max(words // 3, 1 << 16), torch.int64), ("run_base", words, torch.int16),
+                                  ("run_stats", max(words // 3, 1 << 16), torch.int64), ("run_pix", max(words // 3, 1 << 16), torch.int32),
                                   ("band_out", 4 * max(2 * n, words // 1024 + n), torch.int32),
                                   ("band_counters", 4, torch.int32), ("big_list", n, torch.int32)):
                 ws.get(key, size, dt, dev)
