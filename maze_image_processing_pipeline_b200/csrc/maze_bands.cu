@@ -33,14 +33,16 @@ constexpr int PW = MAZE_BAND_PLANE_WORDS;
 // run-table classes of the labelling kernel: runs, rows (+2) and bands a vignette may have
 #define BAND_T 256
 #define BAND_ZB 6144 /* bytes of zeros in shared memory behind the planes (source of the TMA zero fill) */
-#define LABEL_T 128
+#define LABEL_T 64
+#define LABEL_MID_T 256
 #define LABEL_BIG_T 256
-#define LABEL_SMALL_CAP 1024
+#define LABEL_SMALL_CAP 256
 #define LABEL_SMALL_HCAP 1026
-#define LABEL_SMALL_NB 32
-#define LABEL_MID_CAP 4096
-#define LABEL_MID_HCAP 4098
-#define LABEL_MID_NB 256
+#define LABEL_SMALL_NB 16
+#define LABEL_SMALL_LCAP 8 /* labels with accumulators in shared memory (the others accumulate in HBM) */
+#define LABEL_MID_CAP 2048
+#define LABEL_MID_HCAP 2050
+#define LABEL_MID_NB 128
 #define LABEL_BIG_CAP 16384
 #define LABEL_BIG_HCAP 16386
 #define LABEL_BIG_NB 2048
@@ -360,6 +362,8 @@ struct LabelArgs {
     double *hi_stage;
     int32_t *ext_stage;
     int32_t *big_list, *big_counter;
+    uint8_t *mask; // dense outputs (or NULL): the labelling kernel stores the runs on top of the zero fill
+    int32_t *labels;
     int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
 };
 
@@ -371,13 +375,13 @@ __device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
 }
 
 // returns 0 = done (labelled, flagged as fallback, or not a band vignette), 1 = needs a larger run table
-template <int T>
+template <int T, int LCAP>
 __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, int nbcap, uint32_t *s_mem)
 {
     __shared__ int s_warp[34];
     __shared__ int s_misc[4];
     __shared__ int s_base;
-    __shared__ int s_hist[FUSED_LCAP + 2];
+    __shared__ int s_hist[LCAP + 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = a.band_off[img], b1 = a.band_off[img + 1], nb = b1 - b0;
     if (nb <= 0) return 0; // not a band vignette (the per-operator chain owns its counters)
@@ -519,20 +523,25 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         a.acc_base[img] = base;
     }
     {
-        const int nsm = min(n_lab, FUSED_LCAP);
+        const int nsm = min(n_lab, LCAP);
         for (int i = tid; i < nsm * (int)(sizeof(AccRow) / 4); i += T) ((uint32_t *)ACC)[i] = 0;
-        if (tid <= FUSED_LCAP + 1) s_hist[tid] = 0;
+        if (tid <= LCAP + 1) s_hist[tid] = 0;
     }
     __syncthreads(); // labels in P are final
+    for (int r = tid; r < n_runs; r += T) { // every slot holds its label now (roots already do and never change)
+        const int pr = P[r];
+        if (pr < 0x8000) P[r] = P[pr];
+    }
+    __syncthreads();
     const int base = s_base;
     const bool props = a.do_props && base >= 0;
     if (props) {
-        const int nsm = min(n_lab, FUSED_LCAP);
+        const int nsm = min(n_lab, LCAP);
         for (int l = tid; l < nsm; l += T) {
             ACC[l].e[E_RMIN] = 0x7fffffff; ACC[l].e[E_RMAX] = -1; ACC[l].e[E_CMIN] = 0x7fffffff; ACC[l].e[E_CMAX] = -1;
             ACC[l].e[E_VMIN] = 0x7fffffff; ACC[l].e[E_VMAX] = -1;
         }
-        for (int l = FUSED_LCAP + tid; l < n_lab; l += T) { // labels beyond the shared table accumulate in HBM
+        for (int l = LCAP + tid; l < n_lab; l += T) { // labels beyond the shared table accumulate in HBM
             u64 *ga = a.acc_stage + (i64)(base + l) * MAZE_NACC;
             for (int j = 0; j < MAZE_NACC; j++) ga[j] = 0;
             double *gh = a.hi_stage + (i64)(base + l) * 8;
@@ -541,7 +550,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
             ge[E_RMIN] = 0x7fffffff; ge[E_RMAX] = -1; ge[E_CMIN] = 0x7fffffff; ge[E_CMAX] = -1;
             ge[E_VMIN] = 0x7fffffff; ge[E_VMAX] = -1; ge[6] = 0; ge[7] = 0;
         }
-        for (int i = tid; i < n_runs; i += T) atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1);
+        for (int i = tid; i < n_runs; i += T) atomicAdd(&s_hist[min(label_of(P, i) - 1, LCAP)], 1);
     }
     __syncthreads();
     // ---- label of every run -> HBM; per-run intensity statistics -> accumulator rows (warp-aggregated) -----------
@@ -571,7 +580,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
                     const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
                     const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
                     if (lane == leader) {
-                        if (L <= FUSED_LCAP) {
+                        if (L <= LCAP) {
                             shared_add64(ACC[L - 1].a + A_V, (u64)sV);
                             if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
                             atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
@@ -586,15 +595,43 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
             }
         }
     }
+    // ---- dense outputs: the runs of the vignette on top of the zero fill of K1.  Eight lanes per run, four elements
+    // per lane (16-byte label store, 4-byte mask store), steps aligned to 32 elements so that every step but the
+    // first and the last of a run covers a whole 128-byte line of the label image and a whole sector of the mask ---
+    if (a.labels) {
+        int32_t *gl = a.labels + v.pix_off;
+        uint8_t *gm = a.mask + v.pix_off;
+        const int W = v.w, oct = lane >> 3, ol = lane & 7;
+        for (int i0 = warp * 4; i0 < n_runs; i0 += (T / 32) * 4) {
+            const int i = i0 + oct;
+            if (i < n_runs) {
+                const int len = (int)rX1[i] - (int)rX0[i] + 1;
+                const int p = (int)rY[i] * W + (int)rX0[i];
+                const uint32_t lab = (uint32_t)label_of(P, i);
+                int32_t *pl = gl + p;
+                uint8_t *pm = gm + p;
+                for (int x = 4 * ol - (p & 31); x < len; x += 32) {
+                    if (x >= 0 && x + 4 <= len) {
+                        *(uint4 *)(pl + x) = make_uint4(lab, lab, lab, lab);
+                        *(uint32_t *)(pm + x) = 0x01010101u;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (x + u >= 0 && x + u < len) { pl[x + u] = (int32_t)lab; pm[x + u] = 1; }
+                    }
+                }
+            }
+        }
+    }
     if (!props) return 0;
 
     // ---- per-label geometry accumulators: counting sort of the runs by label, contiguous pieces per thread ------
     if (tid == 0) {
         int acc0 = 0;
-        for (int b = 0; b <= FUSED_LCAP; b++) { const int c = s_hist[b]; s_hist[b] = acc0; acc0 += c; }
+        for (int b = 0; b <= LCAP; b++) { const int c = s_hist[b]; s_hist[b] = acc0; acc0 += c; }
     }
     __syncthreads();
-    for (int i = tid; i < n_runs; i += T) rO[atomicAdd(&s_hist[min(label_of(P, i) - 1, FUSED_LCAP)], 1)] = (u16)i;
+    for (int i = tid; i < n_runs; i += T) rO[atomicAdd(&s_hist[min(label_of(P, i) - 1, LCAP)], 1)] = (u16)i;
     __syncthreads();
     const int p_chunk = (n_runs + T - 1) / T;
     const int p_lo = min(tid * p_chunk, n_runs), p_hi = min(p_lo + p_chunk, n_runs);
@@ -605,7 +642,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         auto flush = [&](int lab) {
             const u64 sums[10] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC};
             int *Ee;
-            if (lab <= FUSED_LCAP) {
+            if (lab <= LCAP) {
                 u64 *Aa = ACC[lab - 1].a; Ee = ACC[lab - 1].e;
 #pragma unroll
                 for (int j = 0; j < 10; j++) shared_add64(Aa + j, sums[j]);
@@ -661,8 +698,8 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
     if (a.high_order) {
         // float64 central moments with p + q > 3 about the exact centroid (same walk over the sorted runs)
         for (int l = tid; l < n_lab; l += T) {
-            const u64 *Aa = l < FUSED_LCAP ? ACC[l].a : a.acc_stage + (i64)(base + l) * MAZE_NACC;
-            double *Hh = l < FUSED_LCAP ? ACC[l].h : a.hi_stage + (i64)(base + l) * 8;
+            const u64 *Aa = l < LCAP ? ACC[l].a : a.acc_stage + (i64)(base + l) * MAZE_NACC;
+            double *Hh = l < LCAP ? ACC[l].h : a.hi_stage + (i64)(base + l) * 8;
             const double dn = (double)*(const volatile u64 *)(Aa + A_N);
             Hh[H_CR] = (double)*(const volatile u64 *)(Aa + A_R) / dn;
             Hh[H_CC] = (double)*(const volatile u64 *)(Aa + A_C) / dn;
@@ -670,7 +707,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         __syncthreads();
         int cur = 0;
         double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0, cr = 0, cc = 0;
-        auto hrow = [&](int lab) { return lab <= FUSED_LCAP ? ACC[lab - 1].h : a.hi_stage + (i64)(base + lab - 1) * 8; };
+        auto hrow = [&](int lab) { return lab <= LCAP ? ACC[lab - 1].h : a.hi_stage + (i64)(base + lab - 1) * 8; };
         for (int pos = p_lo; pos < p_hi; pos++) {
             const int i = rO[pos];
             const int L = label_of(P, i);
@@ -722,7 +759,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         __syncthreads();
     }
     {   // shared rows -> staging
-        const int nsm = min(n_lab, FUSED_LCAP);
+        const int nsm = min(n_lab, LCAP);
         for (int i = tid; i < nsm * MAZE_NACC; i += T) {
             const int l = i / MAZE_NACC, j = i - l * MAZE_NACC;
             a.acc_stage[(i64)(base + l) * MAZE_NACC + j] = ACC[l].a[j];
@@ -743,7 +780,7 @@ __global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const int img = blockIdx.x;
-    if (label_vignette<T>(a, img, cap, hcap, LABEL_SMALL_NB, s_mem) == 1 && threadIdx.x == 0) {
+    if (label_vignette<T, LABEL_SMALL_LCAP>(a, img, cap, hcap, LABEL_SMALL_NB, s_mem) == 1 && threadIdx.x == 0) {
         int tot = 0;
         for (int b = a.band_off[img]; b < a.band_off[img + 1]; b++) tot += a.band_out[b].n_runs;
         if (tot <= mid_cap && a.vig[img].h + 2 <= mid_hcap && a.band_off[img + 1] - a.band_off[img] <= LABEL_MID_NB) a.big_list[atomicAdd(a.big_counter, 1)] = img;
@@ -759,7 +796,7 @@ __global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int 
     const int n = *(volatile int32_t *)(a.big_counter + which);
     for (int e = blockIdx.x; e < n; e += gridDim.x) {
         const int img = a.big_list[which ? a.n_img - 1 - e : e];
-        if (label_vignette<T>(a, img, cap, hcap, which ? LABEL_BIG_NB : LABEL_MID_NB, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
+        if (label_vignette<T, FUSED_LCAP>(a, img, cap, hcap, which ? LABEL_BIG_NB : LABEL_MID_NB, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
         __syncthreads();
     }
 }
@@ -775,7 +812,7 @@ __global__ void __launch_bounds__(T) k_band_write(const maze_run_t *__restrict__
                                                   uint8_t *__restrict__ mask, int32_t *__restrict__ labels)
 {
     const int n = min(*run_counter, run_cap);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, oct = lane >> 3, ol = lane & 7; // four octets per warp, one run each at a time
     const int nwarp = gridDim.x * (T / 32);
     for (int i0 = (blockIdx.x * (T / 32) + (threadIdx.x >> 5)) * 32; i0 < n; i0 += nwarp * 32) {
         const int nr = min(32, n - i0);
@@ -784,19 +821,25 @@ __global__ void __launch_bounds__(T) k_band_write(const maze_run_t *__restrict__
             const uint2 r = ((const uint2 *)runs)[i0 + lane];
             pix = run_pix[i0 + lane]; rec_x = r.x; rec_y = r.y;
         }
-        const uint32_t len_me = (rec_y & 0xffffu) - (rec_x >> 16) + 1u;
-        for (int j = 0; j < nr; j++) {
-            const uint32_t p = __shfl_sync(FULL, pix, j), len = __shfl_sync(FULL, len_me, j);
-            const int lab = (int)(__shfl_sync(FULL, rec_y, j) >> 16);
+        const uint32_t len_me = lane < nr ? (rec_y & 0xffffu) - (rec_x >> 16) + 1u : 0u;
+        // an octet stores 32 elements per step, aligned to 32 elements: a whole 32-byte sector of the mask and a
+        // whole 128-byte line of the label image per step (but for the two ends of the run); a lane owns 4 elements
+        for (int j = oct; j < 32; j += 4) { // (all lanes take part in the shuffles; runs past nr have length 0)
+            const uint32_t p = __shfl_sync(FULL, pix, j);
+            const int len = (int)__shfl_sync(FULL, len_me, j);
+            const uint32_t lab = __shfl_sync(FULL, rec_y, j) >> 16;
             int32_t *gl = labels + p;
             uint8_t *gm = mask + p;
-            // iterations aligned to 32 elements: every store instruction but the first and the last of a run
-            // covers whole 32-byte sectors (one of the mask, four of the label image)
-            for (int x = lane - (int)(p & 31u); x < (int)len; x += 32)
-                if (x >= 0) {
-                    gl[x] = lab;
-                    gm[x] = 1;
+            for (int x = 4 * ol - (int)(p & 31u); x < len; x += 32) {
+                if (x >= 0 && x + 4 <= len) {
+                    *(uint4 *)(gl + x) = make_uint4(lab, lab, lab, lab);
+                    *(uint32_t *)(gm + x) = 0x01010101u;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (x + u >= 0 && x + u < len) { gl[x + u] = (int32_t)lab; gm[x + u] = 1; }
                 }
+            }
         }
     }
 }
@@ -887,9 +930,9 @@ static BandFork *band_fork()
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-static size_t label_smem(int cap, int hcap, int nbcap)
+static size_t label_smem(int cap, int hcap, int nbcap, int lcap)
 {
-    return (size_t)(2 * nbcap + 1) * 4 + (size_t)cap * 10 + (size_t)hcap * 2 + 16 + FUSED_LCAP * sizeof(AccRow);
+    return (size_t)(2 * nbcap + 1) * 4 + (size_t)cap * 10 + (size_t)hcap * 2 + 16 + lcap * sizeof(AccRow);
 }
 
 extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_vignette_t *vig, int n_img,
@@ -933,9 +976,10 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     static thread_local int attr_dev = -1;
     int dev = 0;
     MAZE_CUDA(cudaGetDevice(&dev), "get device");
-    const size_t smem1 = (size_t)PW * 8 + BAND_ZB, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_SMALL_NB),
-                 smem_m = label_smem(LABEL_MID_CAP, LABEL_MID_HCAP, LABEL_MID_NB),
-                 smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP, LABEL_BIG_NB);
+    static const size_t smem_pad = getenv("MAZE_K1_PAD") ? (size_t)atoi(getenv("MAZE_K1_PAD")) : 0; // experiments
+    const size_t smem1 = (size_t)PW * 8 + BAND_ZB + smem_pad, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_SMALL_NB, LABEL_SMALL_LCAP),
+                 smem_m = label_smem(LABEL_MID_CAP, LABEL_MID_HCAP, LABEL_MID_NB, FUSED_LCAP),
+                 smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP, LABEL_BIG_NB, FUSED_LCAP);
     if (attr_dev != dev) {
         MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "band smem");
         MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -944,6 +988,10 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
         MAZE_CUDA(cudaFuncSetAttribute(k_band_label<LABEL_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared), "label carveout");
         MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_BIG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), "label big smem");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_MID_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(LABEL_MID_T == LABEL_BIG_T ? smem_b : smem_m)), "label mid smem");
+        MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_MID_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "label mid carveout");
         // kernels only share an SM when they ask for the same shared-memory carve-out: everything that should run
         // next to the band front (zero fill, labelling, writer of another lane) asks for the maximum like it does
         MAZE_CUDA(cudaFuncSetAttribute(k_band_label_big<LABEL_BIG_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -981,19 +1029,21 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                                                    dense ? run_pix : nullptr, run_stats, run_counter,
                                                                    run_cap, band_out, zin ? mask : nullptr,
                                                                    zin ? labels : nullptr));
+    if (dense && fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
     LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
-                    (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, n_img, n_pass, prm.phantom_mask,
+                    (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter,
+                    dense && !getenv("MAZE_K3") ? mask : nullptr, dense && !getenv("MAZE_K3") ? labels : nullptr, n_img, n_pass, prm.phantom_mask,
                     prm.do_props, prm.high_order, prm.has_intensity, stage_cap};
     MAZE_KERNEL(KID_BAND_LABEL, s,
                 k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
                                                                     LABEL_MID_HCAP));
-    const int grid_mid = n_img < 296 ? n_img : 296, grid_big = n_img < 74 ? n_img : 74;
+    const int grid_mid = n_img < 148 * 7 ? n_img : 148 * 7, grid_big = n_img < 74 ? n_img : 74;
     MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                k_band_label_big<LABEL_BIG_T><<<grid_mid, LABEL_BIG_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
+                k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
     MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
                 k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
-    if (dense) {
-        if (fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
+    static const bool k3 = getenv("MAZE_K3") != nullptr; // experiments: runs stored by a kernel of their own
+    if (dense && k3) {
         MAZE_KERNEL(KID_BAND_WRITE, s,
                     k_band_write<BAND_T><<<148 * 8, BAND_T, 0, s>>>(runs, run_pix, run_counter, run_cap, mask, labels));
     }
