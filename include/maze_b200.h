@@ -364,6 +364,22 @@ int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *
 int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,
                    void *dst_host, int n_threads);
 
+/* HOST helpers of the compact result transport.  In compact mode the label image of a vignette crosses PCIe as the
+ * run list of maze_band_stage (8 bytes per run) instead of 5 bytes per pixel; these functions expand it on the
+ * host into what the reference's stage returns (bool mask + int32 labels, loki/pipeline.py:459) or into the
+ * crop of one object (what FindRegions / ExtractROI consume, loki/pipeline.py:589-602).  runs / band_out are
+ * HOST copies of the device arrays.  maze_host_expand: n vignettes, vignette k = bands band_lo[k] .. band_hi[k],
+ * h[k] x w[k] pixels, written to mask_dst[k] / label_dst[k] (either array of pointers may be NULL), n_threads
+ * threads.  maze_host_expand_crop: rows [r0, r1) x columns [c0, c1) of one vignette (inside the image; rpb = rows
+ * per band of that vignette); only_label > 0 keeps that object alone.  MAZE_ERR_CAPACITY: the vignette has no run
+ * list (it was flagged as fallback). */
+int maze_host_expand(const maze_run_t *runs_host, const maze_band_out_t *band_out_host, const int32_t *band_lo_host,
+                     const int32_t *band_hi_host, const int32_t *h_host, const int32_t *w_host, int n,
+                     uint8_t *const *mask_dst_host, int32_t *const *label_dst_host, int n_threads);
+int maze_host_expand_crop(const maze_run_t *runs_host, const maze_band_out_t *band_out_host, int band_lo, int band_hi,
+                          int rpb, int r0, int r1, int c0, int c1, int only_label, uint8_t *mask_dst_host,
+                          int32_t *label_dst_host);
+
 /* Launch accounting and optional per-kernel timing (CUDA events on the launching stream).
  * maze_launch_count: kernels launched by this library since load.  With maze_prof_enable(1) every
  * launch is bracketed by an event pair; maze_prof_collect waits for them and ADDS elapsed

@@ -100,6 +100,8 @@ SIGNATURES = {
                         _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp],
     "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
+    "maze_host_expand": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i],
+    "maze_host_expand_crop": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "maze_stage_step": [_vp, _vp, _vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }

@@ -79,3 +79,104 @@ extern "C" int maze_host_pack(const void *const *srcs, const int64_t *nbytes, co
     for (auto &x : th) x.join();
     return MAZE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side of the compact result transport: the label image of a vignette crosses PCIe as its RUN LIST
+// (maze_run_t {y, x0, x1, label}, 8 bytes per run, written by maze_band_stage) and is expanded here on demand
+// into what the reference's stage returns (bool mask + int32 label image, loki/pipeline.py:459) or into the
+// padded crop of one object (what FindRegions / ExtractROI consume, loki/pipeline.py:589-602).
+// ---------------------------------------------------------------------------------------------------------
+static void expand_one(const maze_run_t *runs, const maze_band_out_t *band_out, int b_lo, int b_hi, int h, int w,
+                       uint8_t *mask, int32_t *labels)
+{
+    const size_t npx = (size_t)h * (size_t)w;
+    if (mask) memset(mask, 0, npx);
+    if (labels) memset(labels, 0, npx * sizeof(int32_t));
+    for (int b = b_lo; b < b_hi; b++) {
+        const maze_band_out_t o = band_out[b];
+        if (o.base < 0) continue;
+        const maze_run_t *r = runs + o.base;
+        for (int i = 0; i < o.n_runs; i++) {
+            const size_t off = (size_t)r[i].y * (size_t)w + r[i].x0;
+            const int len = (int)r[i].x1 - (int)r[i].x0 + 1;
+            if (mask) memset(mask + off, 1, (size_t)len);
+            if (labels) {
+                const int32_t lab = r[i].label;
+                int32_t *d = labels + off;
+                for (int x = 0; x < len; x++) d[x] = lab;
+            }
+        }
+    }
+}
+
+extern "C" int maze_host_expand(const maze_run_t *runs, const maze_band_out_t *band_out, const int32_t *band_lo,
+                                const int32_t *band_hi, const int32_t *h, const int32_t *w, int n,
+                                uint8_t *const *mask_dst, int32_t *const *label_dst, int n_threads)
+{
+    if (n <= 0) return MAZE_OK;
+    if (!runs || !band_out || !band_lo || !band_hi || !h || !w) return MAZE_ERR_BADARG;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) total += (int64_t)h[i] * w[i];
+    auto work = [=](int lo, int hi) {
+        for (int i = lo; i < hi; i++)
+            expand_one(runs, band_out, band_lo[i], band_hi[i], h[i], w[i], mask_dst ? mask_dst[i] : nullptr,
+                       label_dst ? label_dst[i] : nullptr);
+    };
+    if (n_threads == 1 || n == 1 || total < (1 << 20)) {
+        work(0, n);
+        return MAZE_OK;
+    }
+    std::vector<int> cut(n_threads + 1, n);
+    cut[0] = 0;
+    int64_t acc = 0;
+    int t = 1;
+    for (int i = 0; i < n && t < n_threads; i++) {
+        acc += (int64_t)h[i] * w[i];
+        if (acc >= total * t / n_threads) cut[t++] = i + 1;
+    }
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_threads; k++)
+        if (cut[k] < cut[k + 1]) th.emplace_back(work, cut[k], cut[k + 1]);
+    for (auto &x : th) x.join();
+    return MAZE_OK;
+}
+
+// rows [r0, r1) x columns [c0, c1) of one vignette (inside the image) as a contiguous crop.  only_label > 0: the
+// mask holds that object alone (RegionProperties.image), otherwise every foreground pixel.
+extern "C" int maze_host_expand_crop(const maze_run_t *runs, const maze_band_out_t *band_out, int band_lo, int band_hi,
+                                     int rpb, int r0, int r1, int c0, int c1, int only_label, uint8_t *mask_dst,
+                                     int32_t *label_dst)
+{
+    if (!runs || !band_out || rpb < 1 || r0 < 0 || c0 < 0 || r1 < r0 || c1 < c0) return MAZE_ERR_BADARG;
+    const int cw = c1 - c0;
+    const size_t npx = (size_t)(r1 - r0) * (size_t)cw;
+    if (mask_dst) memset(mask_dst, 0, npx);
+    if (label_dst) memset(label_dst, 0, npx * sizeof(int32_t));
+    if (npx == 0) return MAZE_OK;
+    int b_first = band_lo + r0 / rpb, b_last = band_lo + (r1 - 1) / rpb;
+    if (b_last >= band_hi) b_last = band_hi - 1;
+    for (int b = b_first; b <= b_last; b++) {
+        const maze_band_out_t o = band_out[b];
+        if (o.base < 0) return MAZE_ERR_CAPACITY; // this vignette has no run list
+        const maze_run_t *r = runs + o.base;
+        int lo = 0, hi = o.n_runs; // first run with y >= r0 (runs are in raster order)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)r[mid].y < r0) lo = mid + 1; else hi = mid;
+        }
+        for (int i = lo; i < o.n_runs && (int)r[i].y < r1; i++) {
+            if (only_label > 0 && (int)r[i].label != only_label) continue;
+            const int a = (int)r[i].x0 > c0 ? (int)r[i].x0 : c0, e = (int)r[i].x1 + 1 < c1 ? (int)r[i].x1 + 1 : c1;
+            if (a >= e) continue;
+            const size_t off = (size_t)((int)r[i].y - r0) * (size_t)cw + (size_t)(a - c0);
+            if (mask_dst) memset(mask_dst + off, 1, (size_t)(e - a));
+            if (label_dst) {
+                const int32_t lab = r[i].label;
+                for (int x = 0; x < e - a; x++) label_dst[off + x] = lab;
+            }
+        }
+    }
+    return MAZE_OK;
+}

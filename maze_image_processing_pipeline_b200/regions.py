@@ -32,15 +32,20 @@ class Region:
     """The part of skimage's RegionProperties the LOKI pipeline reads, backed by one row of the table."""
 
     def __init__(self, row: np.ndarray, shape, padding: int = 0, labels: Optional[np.ndarray] = None,
-                 intensity: Optional[np.ndarray] = None, shape_row: Optional[np.ndarray] = None):
+                 intensity: Optional[np.ndarray] = None, shape_row: Optional[np.ndarray] = None, mask_fn=None,
+                 sequence: Optional[int] = None, whole_frame: bool = False):
         self._row = row
         self._shape_row = shape_row
         self._shape = shape
         self._labels = labels
         self._intensity = intensity
+        self._mask_fn = mask_fn  # (slice, label) -> bool crop; compact results expand the object from its runs
+        self.sequence = int(row[F_LABEL]) if sequence is None else int(sequence)
         r0, c0, r1, c1 = (int(v) for v in row[F_BBOX:F_BBOX + 4])
         # _enlarge_slice semantics of morphocut's FindRegions: start clipped at 0, stop NOT clipped
         self.slice = (slice(max(0, r0 - padding), r1 + padding), slice(max(0, c0 - padding), c1 + padding))
+        if whole_frame:  # ImageProperties(mask, image), loki/pipeline.py:653: the region's slice is the whole frame
+            self.slice = (slice(0, int(shape[0])), slice(0, int(shape[1])))
 
     @property
     def label(self) -> int:
@@ -85,11 +90,19 @@ class Region:
         return float(self._row[F_IMAX])
 
     @property
+    def crop_shape(self):
+        """Shape of ``image``: the padded slice clipped to the frame (numpy clips the unclipped stop)."""
+        h, w = self._shape
+        return (min(self.slice[0].stop, h) - self.slice[0].start, min(self.slice[1].stop, w) - self.slice[1].start)
+
+    @property
     def image(self) -> np.ndarray:
         """Boolean mask of the object inside the (padded, image-clipped) slice."""
-        if self._labels is None:
-            raise ValueError("label image not attached")
-        return self._labels[self.slice] == self.label
+        if self._labels is not None:
+            return self._labels[self.slice] == self.label
+        if self._mask_fn is not None:
+            return self._mask_fn(self.slice, self.label)
+        raise ValueError("label image not attached")
 
     @property
     def image_intensity(self) -> np.ndarray:
@@ -102,20 +115,33 @@ class Region:
 
 
 def find_regions(result, i: int, padding: int = 0, min_intensity: Optional[float] = None,
-                 image: Optional[np.ndarray] = None) -> Iterator[Region]:
+                 image: Optional[np.ndarray] = None, renumber: bool = True) -> Iterator[Region]:
     """FindRegions(labels, image, padding, min_intensity) for vignette / frame ``i`` of a StageResult
     (loki/pipeline.py:589-594): one Region per label that still has pixels, in label order; regions whose
     maximum intensity is below ``min_intensity`` are skipped."""
     feats = result.features(i)
     shapes = result.shape_features(i) if hasattr(result, "shape_features") else None
-    labels = result.labels(i)
     shape = (int(result.geometry.h[i]), int(result.geometry.w[i]))
+    labels, mask_fn, whole = None, None, False
+    if getattr(result, "compact", False):  # run-list result: objects are expanded one crop at a time
+        mask_fn = lambda sl, lab, _i=i: result.object_mask(_i, sl, lab)  # noqa: E731
+    else:
+        labels = result.labels(i)
+        if labels is None:  # threshold branch (ImageProperties): the whole mask is label 1
+            mask_fn = lambda sl, lab, _i=i: result.mask(_i)[sl]  # noqa: E731
+            whole = True
+    seq = 0
     for j, row in enumerate(feats):
         if not row[F_AREA] > 0:  # label removed by clear_border / remove_small_objects / merge_labels
             continue
+        # morphocut's FindRegions numbers the regions it finds 1..N (it labels its input again); for label images
+        # straight from label() that is the label itself, after the label filters it closes the gaps [memory of
+        # morphocut/image.py at 03dbc6b, not available offline]
+        seq += 1
         if min_intensity is not None and row[F_IMAX] < min_intensity:
             continue
-        yield Region(row, shape, padding, labels, image, None if shapes is None else shapes[j])
+        yield Region(row, shape, padding, labels, image, None if shapes is None else shapes[j], mask_fn,
+                     seq if renumber else None, whole)
 
 
 def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = None) -> Dict:
@@ -126,7 +152,7 @@ def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = N
     (y0, x0, x1, y1) = region.bbox
     meta["object_posx"] = x0
     meta["object_posy"] = y0
-    meta["object_sequence"] = region.label
+    meta["object_sequence"] = region.sequence
     meta["object_width"] = x1 - x0
     meta["object_height"] = y1 - y0
     if object_id_fmt is not None:
@@ -143,15 +169,19 @@ def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str
     ``convex_area``, ``solidity`` as well; without one ``area`` falls back to the pixel count and the perimeter-based keys are absent."""
     out = dict(meta) if meta is not None else {}
     row = region._row
-    r0, c0, r1, c1 = (int(v) for v in row[F_BBOX:F_BBOX + 4])
+    # the reference hands the SAME padded region to recalc_metadata and to CalculateZooProcessFeatures
+    # (loki/pipeline.py:604-625): bbox is the padded slice (start clipped, stop not), bbox_area / extent /
+    # local_centroid come from region.image, i.e. the slice clipped to the frame
+    r0, c0, r1, c1 = region.bbox
+    crop_h, crop_w = region.crop_shape
     area = float(row[F_AREA])
     major, minor = float(row[F_AXIS_MAJOR]), float(row[F_AXIS_MINOR])
     mean = float(row[F_IMEAN])
     has_shape = region._shape_row is not None
     filled = region.filled_area if has_shape else area
-    bbox_area = float((r1 - r0) * (c1 - c0))
+    bbox_area = float(crop_h * crop_w)
     feats = {
-        "label": region.label,
+        "label": region.sequence,
         "width": c1 - c0,
         "height": r1 - r0,
         "bx": c0,

@@ -94,7 +94,14 @@ class DeviceResult:
 
 
 class StageResult:
-    """Host-side outputs: flat mask / label buffers with per-vignette views and the object table."""
+    """Host-side outputs of one batch: per-vignette mask / label image and the object table.
+
+    Dense form: flat mask / label buffers (numpy views per vignette).  Compact form (LokiSegmentationStage(compact=
+    True)): the label image of every vignette is held as its RUN LIST {y, x0, x1, label} -- the form in which it
+    crossed PCIe, 8 bytes per run instead of 5 bytes per pixel -- and ``mask(i)`` / ``labels(i)`` / ``object_mask``
+    expand it on demand (native, include/maze_b200.h: maze_host_expand / maze_host_expand_crop); ``materialize()``
+    expands the whole batch at once.  The arrays are what the reference's stage returns (bool mask, int32 labels,
+    loki/pipeline.py:459) either way."""
 
     def __init__(self, geometry: BatchGeometry, mask_flat, labels_flat, lab_off, table, keep=None):
         self.geometry = geometry
@@ -105,15 +112,110 @@ class StageResult:
         self.keep = keep  # threshold branch: vignettes that survive the empty-mask filter
         self.shape_table = None  # shape_features=True: (n_obj, NSHAPE) perimeter / filled_area / euler_number rows
         self.merge_failed = None  # merge_errors="ignore": vignettes where merge_labels hit the reference's TypeError
+        # compact form
+        self._runs = self._band_out = self._band_off = self._rpb = None
+        self._dense = {}    # vignettes without a run list (per-operator kernels): i -> (mask, labels)
+        self._cache = {}    # vignettes expanded on demand
+
+    @classmethod
+    def from_runs(cls, geometry, runs, band_out, band_off, rpb, dense, lab_off, table):
+        out = cls(geometry, None, None, lab_off, table)
+        out._runs, out._band_out, out._band_off, out._rpb, out._dense = runs, band_out, band_off, rpb, dense
+        return out
+
+    @property
+    def compact(self) -> bool:
+        return self._runs is not None
 
     def __len__(self):
         return self.geometry.n_img
 
+    def _expand(self, i):
+        if i in self._dense:
+            return self._dense[i]
+        if i not in self._cache:
+            g = self.geometry
+            h, w = int(g.h[i]), int(g.w[i])
+            mask = np.empty((h, w), np.uint8)
+            labels = np.empty((h, w), np.int32)
+            lo, hi = np.asarray([self._band_off[i]], np.int32), np.asarray([self._band_off[i + 1]], np.int32)
+            hh, ww = np.asarray([h], np.int32), np.asarray([w], np.int32)
+            pm = np.asarray([mask.ctypes.data], np.uint64)
+            pl = np.asarray([labels.ctypes.data], np.uint64)
+            check(lib().maze_host_expand(self._runs.ctypes.data, self._band_out.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                                         hh.ctypes.data, ww.ctypes.data, 1, pm.ctypes.data, pl.ctypes.data, 1),
+                  "maze_host_expand")
+            if len(self._cache) >= 64:
+                self._cache.clear()
+            self._cache[i] = (mask, labels)
+        return self._cache[i]
+
     def mask(self, i) -> np.ndarray:
+        if self._runs is not None:
+            return self._expand(i)[0].view(bool)
         return self.geometry.view(self._mask, i).view(bool)
 
     def labels(self, i) -> Optional[np.ndarray]:
+        if self._runs is not None:
+            return self._expand(i)[1]
         return None if self._labels is None else self.geometry.view(self._labels, i)
+
+    def runs(self, i) -> np.ndarray:
+        """Run list of vignette i (compact form): structured array with fields y, x0, x1 (inclusive), label."""
+        if self._runs is None:
+            raise ValueError("dense result: no run list")
+        bo = self._band_out[int(self._band_off[i]):int(self._band_off[i + 1])]
+        parts = [self._runs[int(b["base"]):int(b["base"]) + int(b["n_runs"])] for b in bo if b["base"] >= 0]
+        return np.concatenate(parts) if parts else self._runs[:0]
+
+    def object_mask(self, i, sl, label=None) -> np.ndarray:
+        """Boolean crop ``labels(i)[sl] == label`` (``label=None``: ``mask(i)[sl]``) without expanding the vignette:
+        what RegionProperties.image / ExtractROI read (loki/pipeline.py:589-602)."""
+        g = self.geometry
+        h, w = int(g.h[i]), int(g.w[i])
+        r0, r1, _ = sl[0].indices(h)
+        c0, c1, _ = sl[1].indices(w)
+        if self._runs is None or i in self._dense:
+            lab = self.labels(i)
+            return (lab[r0:r1, c0:c1] == label) if label is not None else self.mask(i)[r0:r1, c0:c1]
+        out = np.empty((max(r1 - r0, 0), max(c1 - c0, 0)), np.uint8)
+        check(lib().maze_host_expand_crop(self._runs.ctypes.data, self._band_out.ctypes.data, int(self._band_off[i]),
+                                          int(self._band_off[i + 1]), int(self._rpb[i]), r0, max(r1, r0), c0, max(c1, c0),
+                                          0 if label is None else int(label), out.ctypes.data, None),
+              "maze_host_expand_crop")
+        return out.view(bool)
+
+    def materialize(self, threads=None) -> "StageResult":
+        """Compact -> dense: every mask and label image of the batch as flat host arrays (multi-threaded)."""
+        if self._runs is None:
+            return self
+        g = self.geometry
+        n = g.n_img
+        mask = np.empty(g.total_px, np.uint8)
+        labels = np.empty(g.total_px, np.int32)
+        if threads is None:
+            try:
+                threads = min(16, max(1, len(os.sched_getaffinity(0)) // 2))
+            except Exception:
+                threads = 4
+        todo = np.asarray([i for i in range(n) if i not in self._dense], np.int64)
+        if len(todo):
+            pm = (mask.ctypes.data + g.pix_off[todo]).astype(np.uint64)
+            pl = (labels.ctypes.data + 4 * g.pix_off[todo]).astype(np.uint64)
+            lo = np.ascontiguousarray(self._band_off[todo], np.int32)
+            hi = np.ascontiguousarray(self._band_off[todo + 1], np.int32)
+            hh = np.ascontiguousarray(g.h[todo], np.int32)
+            ww = np.ascontiguousarray(g.w[todo], np.int32)
+            check(lib().maze_host_expand(self._runs.ctypes.data, self._band_out.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                                         hh.ctypes.data, ww.ctypes.data, len(todo), pm.ctypes.data, pl.ctypes.data,
+                                         int(threads)), "maze_host_expand")
+        for i, (m, l) in self._dense.items():
+            g.view(mask, i)[...] = m
+            g.view(labels, i)[...] = l
+        self._mask, self._labels = mask, labels
+        self._runs = self._band_out = None
+        self._dense, self._cache = {}, {}
+        return self
 
     def features(self, i) -> np.ndarray:
         """Rows of the object table that belong to vignette i (row k = label k + 1)."""
@@ -201,7 +303,13 @@ class LokiSegmentationStage:
         self.high_order = high_order
         self._pool = _PinnedPool()
         self._ws = Workspace()
-        self.n_lanes = int(os.environ.get("MAZE_LANES", "4"))  # workspaces (each with its own lane stream) in rotation
+        # workspaces (each with its own lane stream) in rotation; map() keeps batch i+1 in flight while batch i is
+        # downloaded, so fewer than two would let a batch overwrite the buffers its predecessor is still read from
+        self.n_lanes = int(os.environ.get("MAZE_LANES", "6"))
+        if self.n_lanes < 1:
+            raise ValueError("MAZE_LANES must be >= 1")
+        if shape_features:
+            self.compact = False  # maze_label_shape reads the dense label image on the device
         self._ws_ring, self._ws_i = [Workspace() for _ in range(self.n_lanes)], 0
         self._copy_stream = None
         self._small_copy_stream = None
@@ -580,6 +688,8 @@ class LokiSegmentationStage:
         else:
             cs.wait_stream(main)
         h_mask = h_lab = None
+        if getattr(res, "compact", False):
+            want_mask = want_labels = False  # the run list goes down in _complete, once the number of runs is known
         with torch.cuda.stream(cs):
             if want_mask:
                 h_mask = pool.get("mask", geom.total_px, torch.uint8)
@@ -608,8 +718,30 @@ class LokiSegmentationStage:
                 ss.wait_event(res.ready)
             else:
                 ss.wait_stream(main)
+        compact = getattr(res, "compact", False) and res.runs is not None and len(res.dense_only) <= 64
+        if getattr(res, "compact", False) and not compact:
+            with torch.cuda.stream(ss):  # (rare) most of the batch has no run list: dense download after all
+                h_mask = pool.get("mask", geom.total_px, torch.uint8)
+                h_mask.copy_(res.mask, non_blocking=True)
+                h_lab = pool.get("labels", geom.total_px, torch.int32)
+                h_lab.copy_(res.labels, non_blocking=True)
+        h_runs = h_bo = None
+        dense = {}
+        if compact:
+            from .device import BAND_OUT_DTYPE, RUN_DTYPE
+            n_runs = min(int(res.n_runs), res.runs.numel())
+            n_bands = len(res.bands_host)
+            with torch.cuda.stream(ss):
+                h_runs = pool.get("runs", max(n_runs, 1), torch.int64)[:n_runs]
+                h_runs.copy_(res.runs[:n_runs], non_blocking=True)
+                h_bo = pool.get("band_out", 4 * max(n_bands, 1), torch.int32)[:4 * n_bands]
+                h_bo.copy_(res.band_out[:4 * n_bands], non_blocking=True)
+                for i in res.dense_only:  # vignettes of the per-operator kernels: their dense arrays
+                    o, npx = int(geom.pix_off[i]), int(geom.npx[i])
+                    dense[i] = (res.mask[o:o + npx].cpu().numpy().reshape(int(geom.h[i]), int(geom.w[i])),
+                                res.labels[o:o + npx].cpu().numpy().reshape(int(geom.h[i]), int(geom.w[i])))
         with torch.cuda.stream(ss):
-            if res.redone:  # rare: per-pixel outputs were rewritten by the per-operator path
+            if res.redone and not compact:  # rare: per-pixel outputs were rewritten by the per-operator path
                 ss.wait_event(copied)
                 if h_mask is not None:
                     h_mask.copy_(res.mask, non_blocking=True)
@@ -636,8 +768,15 @@ class LokiSegmentationStage:
                 # the reference aborts the run here (merge_labels.py:19-20 via pipeline_runner.py:40-43)
                 raise TypeError("'NoneType' object is not iterable")
             failed = np.nonzero(status == MAZE_ERR_TYPEERROR)[0]
-        out = StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
-                          h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
+        if compact:
+            from .device import BAND_OUT_DTYPE, RUN_DTYPE
+            out = StageResult.from_runs(geom, h_runs.numpy().view(RUN_DTYPE), h_bo.numpy().view(BAND_OUT_DTYPE),
+                                        res.band_off_host, np.ascontiguousarray(
+                                            _rpb_of(res.bands_host, res.band_off_host, geom.n_img)), dense,
+                                        h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT))
+        else:
+            out = StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
+                              h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
         out.merge_failed = failed
         if self.shape_features:
             out.shape_table = h_shape.numpy().reshape(-1, NSHAPE)
@@ -659,8 +798,17 @@ class LokiSegmentationStage:
         dev = self.device
         with torch.cuda.device(dev if dev is not None else torch.cuda.current_device()):
             pending = None
+            # batch i+1 may only be enqueued before batch i is complete when the two use different device buffers:
+            # the asynchronous band / fused path rotates its workspaces (>= 2 lanes); the paths with label filters,
+            # merge_labels, radii beyond the bit-plane kernels or threshold-only work in ONE shared workspace
+            pp = self.postprocess
+            overlap = (pp is not None and self.fused and self.n_lanes >= 2 and self._passes() is not None
+                       and not (pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0))
             for i, item in enumerate(batches):
                 images, pred = item if isinstance(item, tuple) else (item, None)
+                if not overlap and pending is not None:
+                    yield self._complete(pending)
+                    pending = None
                 inflight = self._enqueue(images, pred, self._map_pools[i % 3], want_mask, want_labels)
                 if pending is not None:
                     yield self._complete(pending)
@@ -669,14 +817,24 @@ class LokiSegmentationStage:
                 yield self._complete(pending)
 
 
+def _rpb_of(bands, band_off, n_img):
+    """Rows per band of every vignette (1 for vignettes without bands)."""
+    rpb = np.ones(n_img, np.int32)
+    has = band_off[1:] > band_off[:-1]
+    rpb[has] = bands["rpb"][band_off[:-1][has]]
+    return rpb
+
+
 def stream_objects(stage: "LokiSegmentationStage", objects, batch_size: int = 2048, image_key: str = "image",
-                   meta_key: str = "meta", padding: int = 75, min_intensity=None, object_id_fmt=None):
+                   meta_key: str = "meta", padding: int = 75, min_intensity=None, object_id_fmt=None,
+                   keep_arrays: bool = True):
     """Adapter for a morphocut-style object stream (the place of the `Call` chain of
     maze_ipp/loki/pipeline.py:396-459 and the FindRegions / recalc_metadata / CalculateZooProcessFeatures tail,
     :589-625): consumes an iterable of dict-like stream objects that carry a uint8 vignette or frame under
     `image_key`, buffers `batch_size` of them, runs the stage once per buffer (pipelined over buffers) and yields,
-    in input order, one dict per input object with the keys of the input plus `mask`, `labels` and `objects` (a
-    list of metadata dicts, one per segmented object, see regions.objects_of)."""
+    in input order, one dict per input object with the keys of the input plus `mask`, `labels` (`keep_arrays`) and
+    `objects` (a list of metadata dicts, one per segmented object, see regions.objects_of).  In the threshold branch
+    (loki/pipeline.py:648-656) every vignette that survives the empty-mask filter yields ONE object, the whole mask."""
     from .regions import objects_of
 
     def buffers():
@@ -694,18 +852,30 @@ def stream_objects(stage: "LokiSegmentationStage", objects, batch_size: int = 20
     def images():
         for buf in buffers():
             pending.append(buf)
-            yield [np.ascontiguousarray(o[image_key], dtype=np.uint8) for o in buf]
+            imgs = []
+            for o in buf:
+                im = np.asarray(o[image_key])
+                if im.dtype != np.uint8 or im.ndim != 2:  # ImageReader(picture_fn, "L") delivers uint8 (pipeline.py:919-921)
+                    raise TypeError(f"stream_objects needs 2-D uint8 images, got {im.dtype} with shape {im.shape}")
+                imgs.append(np.ascontiguousarray(im))
+            yield imgs
 
+    threshold_only = stage.postprocess is None
     for res in stage.map(images()):
         buf = pending.pop(0)
         for i, obj in enumerate(buf):
+            if res.keep is not None and not res.keep[i]:
+                continue  # Filter(obj[mask].any()), loki/pipeline.py:651: vignettes with an empty mask are dropped
             out = dict(obj)
-            out["mask"] = res.mask(i).copy()
-            lab = res.labels(i)
-            out["labels"] = None if lab is None else lab.copy()
-            out["objects"] = objects_of(res, i, meta=obj.get(meta_key, {}) if hasattr(obj, "get") else {},
-                                        padding=padding, min_intensity=min_intensity, image=obj[image_key],
-                                        object_id_fmt=object_id_fmt) if lab is not None else []
+            meta = obj.get(meta_key, {}) if hasattr(obj, "get") else {}
+            if keep_arrays:
+                out["mask"] = res.mask(i).copy()
+                lab = res.labels(i)
+                out["labels"] = None if lab is None else lab.copy()
+            # threshold branch: ImageProperties(mask, image) is ONE region over the whole frame, no padding (:653)
+            out["objects"] = objects_of(res, i, meta=meta, padding=0 if threshold_only else padding,
+                                        min_intensity=None if threshold_only else min_intensity, image=obj[image_key],
+                                        object_id_fmt=object_id_fmt)
             yield out
 
 

@@ -308,3 +308,106 @@ def test_ecotaxa_writer_and_rescale_max_intensity(tmp_path):
     with pytest.raises(ValueError):
         with EcotaxaWriter(str(tmp_path / "bad.zip")) as w:
             w.add([("obj.xyz", img)], {})
+
+
+def test_zooprocess_keys_follow_the_padded_region_like_the_reference():
+    """The reference hands the SAME padded region (FindRegions(padding=75)) to recalc_metadata and to
+    CalculateZooProcessFeatures (loki/pipeline.py:589-625): bbox-derived keys come from the padded slice (start clipped
+    at 0, stop not), bbox_area / extent / local_centroid from region.image, i.e. the slice clipped to the frame."""
+    import oracle
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    from maze_image_processing_pipeline_b200.regions import objects_of
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    lab = np.zeros((200, 260), np.int32)
+    lab[100:120, 90:130] = 1       # padding fits on every side
+    lab[10:30, 240:255] = 2        # padding is cut at the top and at the right edge
+    lab[150:160, 5:25] = 5         # labels 3, 4 absent: sequence numbers close the gap
+    img = np.full(lab.shape, 9, np.uint8)
+    table = oracle.regionprops_table(lab, img)
+    g = BatchGeometry([200], [260])
+    res = StageResult(g, g.pack_host([(lab > 0).view(np.uint8)]), g.pack_host([lab], dtype=np.int32),
+                      np.array([0, 5], np.int32), table)
+    pad = 75
+    objs = objects_of(res, 0, padding=pad, image=img)
+    assert [o["object_sequence"] for o in objs] == [1, 2, 3] and [o["object_label"] for o in objs] == [1, 2, 3]
+    for o, l in zip(objs, (1, 2, 5)):
+        rows, cols = np.nonzero(lab == l)
+        sl = (slice(max(0, rows.min() - pad), rows.max() + 1 + pad), slice(max(0, cols.min() - pad), cols.max() + 1 + pad))
+        image = lab[sl] == l                                   # RegionProperties.image: numpy clips the slice
+        bbox = (sl[0].start, sl[1].start, sl[0].stop, sl[1].stop)  # RegionProperties.bbox: the slice as given
+        assert o["object_bx"] == bbox[1] and o["object_by"] == bbox[0]
+        assert o["object_width"] == bbox[3] - bbox[1] and o["object_height"] == bbox[2] - bbox[0]
+        assert o["object_bounding_box_area"] == image.size
+        assert o["object_extent"] == image.sum() / image.size
+        assert abs(o["object_local_centroid_row"] - (rows.mean() - sl[0].start)) < 1e-9
+        assert abs(o["object_local_centroid_col"] - (cols.mean() - sl[1].start)) < 1e-9
+        assert abs(o["object_y"] - rows.mean()) < 1e-9 and abs(o["object_x"] - cols.mean()) < 1e-9
+        assert o["object_posx"] == bbox[1] and o["object_posy"] == bbox[0]
+
+
+def _runs_of(lab, rpb):
+    """Run list + band table of a label image the way maze_band_stage lays them out (test helper)."""
+    from maze_image_processing_pipeline_b200.device import BAND_OUT_DTYPE, RUN_DTYPE
+    h, w = lab.shape
+    runs, band_out = [], []
+    for y0 in range(0, h, rpb):
+        base = len(runs)
+        for y in range(y0, min(h, y0 + rpb)):
+            x = 0
+            while x < w:
+                if lab[y, x]:
+                    x1 = x
+                    while x1 + 1 < w and lab[y, x1 + 1] == lab[y, x]:
+                        x1 += 1
+                    runs.append((y, x, x1, lab[y, x]))
+                    x = x1 + 1
+                else:
+                    x += 1
+        band_out.append((base, len(runs) - base, 0, 0))
+    return np.array(runs, RUN_DTYPE).reshape(-1), np.array(band_out, BAND_OUT_DTYPE).reshape(-1)
+
+
+def test_host_expand_and_crops_from_run_lists():
+    """maze_host_expand / maze_host_expand_crop (the host half of the compact result transport) and the lazy
+    StageResult built on them, on hand-made run lists -- no GPU involved."""
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    from maze_image_processing_pipeline_b200.regions import find_regions
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    rng = np.random.default_rng(5)
+    labs, rpbs = [], [7, 64, 3, 1]
+    for (h, w) in [(40, 70), (33, 1), (1, 90), (25, 31)]:
+        lab = (rng.random((h, w)) < 0.4) * rng.integers(1, 6, (h, w))
+        labs.append(lab.astype(np.int32))
+    g = BatchGeometry([l.shape[0] for l in labs], [l.shape[1] for l in labs])
+    all_runs, all_bo, band_off = [], [], [0]
+    for lab, rpb in zip(labs, rpbs):
+        r, bo = _runs_of(lab, rpb)
+        bo["base"] += sum(len(x) for x in all_runs)
+        all_runs.append(r)
+        all_bo.append(bo)
+        band_off.append(band_off[-1] + len(bo))
+    runs = np.concatenate(all_runs)
+    res = StageResult.from_runs(g, runs, np.concatenate(all_bo), np.asarray(band_off, np.int32),
+                                np.asarray(rpbs, np.int32), {}, np.zeros(5, np.int32), np.zeros((0, 64)))
+    assert res.compact
+    for i, lab in enumerate(labs):
+        assert np.array_equal(res.labels(i), lab) and np.array_equal(res.mask(i), lab > 0)
+        assert res.labels(i).dtype == np.int32 and res.mask(i).dtype == bool
+        rr = res.runs(i)
+        assert int((rr["x1"].astype(int) - rr["x0"] + 1).sum()) == int((lab > 0).sum())
+        h, w = lab.shape
+        for sl in [(slice(0, h), slice(0, w)), (slice(h // 3, h), slice(w // 4, w // 2 + 1)), (slice(2, 2), slice(0, w)),
+                   (slice(0, h + 75), slice(max(0, w - 5), w + 75))]:  # stops beyond the frame are clipped like numpy
+            assert np.array_equal(res.object_mask(i, sl), (lab > 0)[sl])
+            for l in (1, 3, 9):
+                assert np.array_equal(res.object_mask(i, sl, l), lab[sl] == l)
+    # regions of a compact result expand one object at a time
+    import oracle
+    res.table = oracle.regionprops_table(labs[0], np.full(labs[0].shape, 5, np.uint8))
+    res.lab_off = np.array([0, len(res.table)] + [len(res.table)] * 3, np.int32)
+    for reg in find_regions(res, 0, padding=4):
+        assert np.array_equal(reg.image, labs[0][reg.slice] == reg.label)
+    dense = res.materialize(threads=3)
+    assert not dense.compact
+    for i, lab in enumerate(labs):
+        assert np.array_equal(dense.labels(i), lab) and np.array_equal(dense.mask(i), lab > 0)
