@@ -33,19 +33,29 @@ SIZE_SEED = 1        # C2 uses seed 1
 PIXEL_SEED = 20261018
 THRESHOLD, R_OPEN, R_CLOSE = 40, 1, 2
 
-# algorithmic bytes per pixel of each kernel (inputs it must read + outputs it must write; DESIGN.md)
+# algorithmic bytes per pixel of each kernel (inputs it must read + outputs it must write; DESIGN.md section 3)
 KERNEL_BYTES_PER_PX = {
     "k_threshold_pack": 1.125, "k_morph_pass": 0.25, "k_unpack_mask": 1.125, "k_ccl_init": 0.125,
     "k_ccl_union": 0.125, "k_ccl_flatten": 0.125, "k_ccl_assign": 0.125, "k_ccl_write": 4.125,
     "k_props_accumulate": 5.0, "k_props_high_order": 4.0, "k_label_zero": 8.0, "k_label_count": 4.0,
     "k_vignette_fused": 6.125, "k_props_runs": 5.0, "k_props_runs_high": 4.0,
+    # band front: 1 R image + 1 W mask + 4 W label image (the zero fill; the labelling kernel rewrites only the
+    # foreground runs) + 1/8 W bit plane
+    "k_band_front": 6.125,
 }
 STAGE_BYTES_PER_PX = 6.0  # 1 R image + 1 W mask + 4 W labels
-# dram__bytes_read.sum + dram__bytes_write.sum of the four k_vignette_fused launches of one step divided by their
-# algorithmic bytes, from the ncu --set full capture summarised in profiles/ncu_fused_r1_final_metrics.txt
-# (3.081 GB moved for 3.027 GB algorithmic in a 4096-vignette batch: the intensity re-read hits L2, sparse
-# label stores merge in L2)
-MEASURED_TRAFFIC_RATIO = {"k_vignette_fused": 1.018}
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per pixel of `kernel` from the committed ncu capture
+    (profiles/ncu_traffic.json, written from an ncu launch list of THIS bench command), or None when no capture of
+    that kernel is on file: the bench never invents the number."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p)).get(kernel)
+        return None if rec is None else (float(rec["dram_bytes_per_px"]), rec.get("source", p))
+    except Exception:
+        return None
 
 
 def job_sizes():
@@ -155,21 +165,35 @@ class ClockSampler:
 # reference arm / cpu_baseline: the oracle's scipy restatement of the reference chain on host cores
 # ------------------------------------------------------------------------------------------------
 _CPU_MERGE = 0
+_CPU_REF = False
+_CPU_FULL = False
 
 
 def _cpu_one(img):
     from oracle import scipy_chain
     try:
-        mask, labels, table = scipy_chain.loki_chain(img, THRESHOLD, R_OPEN, R_CLOSE, merge_segments_distance=_CPU_MERGE)
+        mask, labels, table = scipy_chain.loki_chain(img, THRESHOLD, R_OPEN, R_CLOSE, merge_segments_distance=_CPU_MERGE,
+                                                     use_reference=_CPU_REF)
     except TypeError:  # the reference's merge_labels raises when a bridge swallows a label (merge_labels.py:19-20)
-        return 0, 0
-    return int(labels.max()), int(mask.sum())
+        return (0, 0, None) if not _CPU_FULL else (0, 0, None, None, None)
+    if _CPU_FULL:
+        return int(labels.max()), int(mask.sum()), np.packbits(mask), labels.astype(np.int32), table
+    return int(labels.max()), int(mask.sum()), None
 
 
-def _cpu_pool(cores, merge=0):
+def cpu_kind():
+    """"reference": morphology + merge_labels are the reference's own files (oracle/_ref/, see oracle/make_ref.sh);
+    "port": the restatement in oracle/scipy_chain.py."""
+    from oracle import scipy_chain
+    return "reference" if scipy_chain.reference_modules() is not None else "port"
+
+
+def _cpu_pool(cores, merge=0, full=False):
     import multiprocessing as mp
-    global _CPU_MERGE
+    global _CPU_MERGE, _CPU_REF, _CPU_FULL
     _CPU_MERGE = merge  # inherited by the forked workers
+    _CPU_REF = cpu_kind() == "reference"
+    _CPU_FULL = full
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     import oracle
     oracle.build()
@@ -198,7 +222,7 @@ def time_cpu(pool, imgs):
     t0 = time.perf_counter()
     out = pool.map(_cpu_one, imgs, chunksize=1)
     dt = time.perf_counter() - t0
-    return dt, sum(o[0] for o in out)
+    return dt, out
 
 
 def run_reference(args):
@@ -218,14 +242,17 @@ def run_reference(args):
         total += dt
     pool.close()
     v = per_step * args.steps / total
-    sample = f"{per_step} vignettes ({px / 1e6:.1f} MPix) of configs[1] per step, multiprocessing.Pool({cores})"
+    kind = cpu_kind()
+    sample = (f"{per_step} vignettes ({px / 1e6:.1f} MPix) of configs[1] per step, multiprocessing.Pool({cores}); "
+              + ("maze_ipp/isotropic.py + maze_ipp/merge_labels.py of the reference (oracle/_ref) around scipy.ndimage.label "
+                 "and the C regionprops oracle" if kind == "reference" else "oracle/scipy_chain.py"))
     line = {
         "impl": "reference", "metric": "loki_vignettes_per_s", "value": v, "unit": "vignettes/s",
         "mpix_per_s": px * args.steps / total / 1e6, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": dict(workload_config(args, args.batch), reference_sample_per_step=per_step),
-        "cpu_baseline": {"value": v, "unit": "vignettes/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.batch), "reference_sample_per_step": per_step,
+        "cpu_baseline": {"value": v, "unit": "vignettes/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "vignettes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -265,7 +292,8 @@ def workload_config(args, batch):
             "min_area": 0, "clear_border": False, "regionprops": "full table incl. high-order moments",
             "morphology": getattr(args, "morphology", "isotropic"),
             "e2e_batch_vignettes": getattr(args, "e2e_batch", batch),
-            "l2": "each batch is larger than L2 (no flush needed)", "parallelism": f"images sharded over {args.gpus} GPU(s)"}
+            "l2": "each batch is larger than L2 (no flush needed)", "parallelism": f"images sharded over {args.gpus} GPU(s)",
+            "pipeline": os.environ.get("MAZE_PIPELINE", "bands")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -361,18 +389,27 @@ def run_b200(args):
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
-    # instrumented repeat of the same steps: per-kernel CUDA-event durations for the roofline
+    # instrumented repeat of the same steps for the roofline: per-kernel CUDA-event durations, on ONE lane so that
+    # an event pair brackets its own kernel only (with several lanes in flight the intervals of concurrent kernels
+    # overlap and every duration is inflated by its neighbours)
+    stage1 = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore",
+                                     morphology=args.morphology, n_lanes=1)
+    stage1.reserve([b[0].g for b in batches])
+    for i in range(2):
+        stage1.run_device(batches[i][0], batches[i][1]).n_obj
+    torch.cuda.synchronize()
     _lib.prof_enable(True)
     evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evp0.record()
     for i in range(args.warmup, need):
-        step(i)
-    stage.join()
+        stage1.run_device(batches[i][0], batches[i][1])
+    stage1.join()
     evp1.record()
     torch.cuda.synchronize()
     _lib.prof_enable(False)
     prof = _lib.prof_collect()
     ms_instr = evp0.elapsed_time(evp1)
+    del stage1
 
     # end to end through the public stage call: host numpy in, host numpy out, copies timed
     # (host memory: every rank keeps its e2e inputs plus three pinned buffer sets; fewer batches per rank at N = 8)
@@ -386,30 +423,48 @@ def run_b200(args):
         end = int(db.g.pix_off[n_k - 1]) + int(db.g.h[n_k - 1]) * int(db.g.w[n_k - 1])
         flat = img[:end].cpu().numpy()  # only the pixels of the vignettes the leg uses stay on the host
         host_batches.append([db.g.view(flat, k) for k in range(n_k)])
-    for r in stage.map(host_batches[:3]):  # warm the three pinned buffer sets
-        pass
-    barrier()
-    t0 = time.perf_counter()
-    e2e_vig = e2e_px = 0
-    h2d = d2h = 0
-    for r in stage.map(host_batches):  # the streaming call a user makes: numpy in, numpy out, copies inside
-        e2e_vig += len(r)
-        e2e_px += r.geometry.pixels
-        h2d += r.geometry.total_px
-        d2h += r.geometry.total_px * 5 + r.table.nbytes + r.lab_off.nbytes
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    def e2e_leg(st, materialize=False):
+        """The streaming call a user makes -- host numpy in, results on the host, copies inside the timed region."""
+        for r in st.map(host_batches[:3]):  # warm the three pinned buffer sets
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        nv = npx = up = down = 0
+        for r in st.map(host_batches):
+            if r.compact:
+                down += r._runs.nbytes + r._band_out.nbytes + sum(5 * m.size for m, _ in r._dense.values())
+            else:
+                down += r.geometry.total_px * 5
+            if materialize:
+                r.materialize()
+            nv += len(r)
+            npx += r.geometry.pixels
+            up += r.geometry.total_px
+            down += r.table.nbytes + r.lab_off.nbytes
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, nv, npx, up, down
+
+    # (1) the headline: compact transport -- label images cross PCIe as run lists (8 B per run) and are expanded on
+    #     demand (StageResult.labels(i) / object_mask); nothing dense is materialised inside the timed region
+    stage_c = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore",
+                                      morphology=args.morphology, compact=True)
+    e2e_s, e2e_vig, e2e_px, h2d, d2h = e2e_leg(stage_c)
+    # (2) contract-complete: every bool mask and int32 label image of the batch materialised on the host inside the
+    #     timed region, (a) dense download as in round 1, (b) run lists + native multi-threaded expansion
+    dense_s, dense_vig, _, _, dense_d2h = e2e_leg(stage)
+    mat_s, mat_vig, _, _, _ = e2e_leg(stage_c, materialize=True)
+    del stage_c
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s, float(n_vig), float(n_px), float(e2e_vig), float(e2e_px), float(launches)],
-                         dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s, float(n_vig), float(n_px), float(e2e_vig), float(e2e_px), float(launches), dense_s,
+                          mat_s, float(dense_vig), float(mat_vig)], dtype=torch.float64, device="cuda")
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(mx[0]), float(mx[1])
-        n_vig, n_px, e2e_vig, e2e_px, launches = (float(sm[k]) for k in (2, 3, 4, 5, 6))
+        ms, e2e_s, dense_s, mat_s = float(mx[0]), float(mx[1]), float(mx[7]), float(mx[8])
+        n_vig, n_px, e2e_vig, e2e_px, launches, dense_vig, mat_vig = (float(sm[k]) for k in (2, 3, 4, 5, 6, 9, 10))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -424,29 +479,97 @@ def run_b200(args):
     alg_bytes = bpp * px_per_launch / max(launches_per_step, 1)
     avg_s = top_ms / top_cnt / 1e3
     achieved = alg_bytes / avg_s / 1e9
-    ratio = MEASURED_TRAFFIC_RATIO.get(top_name)
+    traffic = measured_traffic(top_name)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None if ratio is None else ratio * alg_bytes,
-                "traffic_source": "ncu --set full capture, profiles/ncu_fused_r1_final_metrics.txt", "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": None if traffic is None else traffic[0] * px_per_launch / max(launches_per_step, 1),
+                "traffic_source": None if traffic is None else traffic[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_px": bpp, "avg_launch_ms": top_ms / top_cnt,
-                "share_of_step": top_ms / ms_instr}
+                "share_of_step": top_ms / ms_instr,
+                "timing": "CUDA events around every launch of an instrumented single-lane repeat of the timed steps"}
     stage_gbs = STAGE_BYTES_PER_PX * n_px / (ms / 1e3) / 1e9
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
 
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    # ---- parity gate + CPU baseline: the oracle chain on the first vignettes of the first timed batch (the SAME pixels
+    # the GPU processed) -- timed on all host cores (N = 1 only), and compared with the GPU's masks / label images /
+    # object tables in both transports.  No value is printed when the comparison fails.
+    cpu_baseline = parity = None
+    if not args.no_cpu_baseline:
         cores = host_cores()
-        n_s = max(cores, min(4 * cores, 256))
-        pool = _cpu_pool(cores, args.merge)
+        n_s = max(cores, min(4 * cores, 256)) if world == 1 else 16
+        pool = _cpu_pool(cores, args.merge, full=True)
         imgs = host_batches[0][:n_s]
-        time_cpu(pool, imgs[: max(1, len(imgs) // 4)])
-        dt, _ = time_cpu(pool, imgs)
+        if world == 1:
+            time_cpu(pool, imgs[: max(1, len(imgs) // 4)])
+        dt, want = time_cpu(pool, imgs)
         pool.close()
-        cpu_baseline = {"value": len(imgs) / dt, "unit": "vignettes/s", "cores": cores, "kind": "port",
-                        "mpix_per_s": sum(int(i.size) for i in imgs) / dt / 1e6,
-                        "sample": f"first {len(imgs)} vignettes of the first timed batch (same pixels as the GPU run), "
-                                  f"oracle/scipy_chain.py (the reference chain on scipy.ndimage), Pool({cores})"}
+        if world == 1:
+            kind = cpu_kind()
+            cpu_baseline = {"value": len(imgs) / dt, "unit": "vignettes/s", "cores": cores, "kind": kind,
+                            "mpix_per_s": sum(int(i.size) for i in imgs) / dt / 1e6,
+                            "sample": f"first {len(imgs)} vignettes of the first timed batch (same pixels as the GPU run), "
+                                      + ("the reference's own isotropic.py / merge_labels.py (oracle/_ref) around "
+                                         "scipy.ndimage.label + the C regionprops oracle" if kind == "reference"
+                                         else "oracle/scipy_chain.py (the reference chain on scipy.ndimage)")
+                                      + f", Pool({cores})"}
+        import oracle as _oracle
+        masks_eq = labels_eq = True
+        max_rel = 0.0
+        n_cmp = 0
+        cols = list(range(1, 8)) + list(range(_oracle.F_HU, _oracle.F_HU + 7)) + [49, 50, 51, 53, 54, 55, 56]
+        for compact in (False, True):
+            st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore",
+                                         morphology=args.morphology, compact=compact)
+            got = st(imgs)
+            failed = set() if got.merge_failed is None else set(int(i) for i in got.merge_failed)
+            for i, (im, w) in enumerate(zip(imgs, want)):
+                if w[2] is None or i in failed:  # merge_labels raised in the reference
+                    continue
+                n_cmp += 1
+                masks_eq &= bool(np.array_equal(np.packbits(got.mask(i)), w[2]))
+                labels_eq &= bool(np.array_equal(got.labels(i), w[3]))
+                f, t = got.features(i), w[4]
+                k = min(len(f), len(t))
+                sel = t[:k, _oracle.F_AREA] > 0
+                a_, b_ = f[:k][sel][:, cols], t[:k][sel][:, cols]
+                if a_.size:
+                    max_rel = max(max_rel, float(np.nanmax(np.abs(a_ - b_) / np.maximum(np.abs(b_), 1e-9))))
+                labels_eq &= bool(np.array_equal(f[:k, _oracle.F_AREA], t[:k, _oracle.F_AREA]))
+            del st
+        parity = {"vignettes": n_cmp // 2, "transports": ["dense", "compact"], "masks_equal": masks_eq,
+                  "labels_equal": labels_eq, "table_max_rel": max_rel, "table_rel_tolerance": 1e-5,
+                  "checked_against": cpu_kind()}
+        if not (masks_eq and labels_eq and max_rel <= 1e-5):
+            print(json.dumps({"error": "parity gate failed: no value is reported", "parity": parity}))
+            if world > 1:
+                dist.destroy_process_group()
+            return 2
+
+    # ---- variants SURVEY.md 8d asks to report next to the headline: resident throughput with merge_labels on
+    # (merge_segments_distance = 10) and with the live pipeline's footprints (morphology = crosses)
+    variants = None
+    if world == 1 and not args.no_variants and args.merge == 0 and args.morphology == "isotropic":
+        variants = {}
+        vb = batches[args.warmup][0], batches[args.warmup][1]
+        for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8)):
+            vpp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN, **kw)
+            st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), vpp, merge_errors="ignore",
+                                         morphology="crosses" if name == "crosses" else "isotropic")
+            st.run_device(*vb).n_obj
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            last = [st.run_device(*vb) for _ in range(vsteps)]
+            for r in last:
+                r.n_obj
+            st.join()
+            e1.record()
+            torch.cuda.synchronize()
+            vms = e0.elapsed_time(e1) / vsteps
+            variants[name] = {"value": vb[0].g.n_img / (vms / 1e3), "unit": "vignettes/s", "ms_per_step": vms,
+                              "steps": vsteps, "note": "resident, one 4096-vignette batch repeated"}
+            del st
 
     line = {
         "metric": "loki_vignettes_per_s", "value": n_vig / (ms / 1e3), "unit": "vignettes/s",
@@ -458,9 +581,17 @@ def run_b200(args):
         "stage_hbm": {"achieved": stage_gbs / world, "unit": "GB/s per GPU", "bytes_per_px": STAGE_BYTES_PER_PX,
                       "frac_of_measured": stage_gbs / world / peak, "frac_of_nominal_8TBps": stage_gbs / world / 8000.0},
         "kernels": kernels, "ms_per_step_instrumented": ms_instr / args.steps,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "parity": parity, "variants": variants,
         "e2e": {"value": e2e_vig / e2e_s, "unit": "vignettes/s", "mpix_per_s": e2e_px / e2e_s / 1e6,
-                "steps": e2e_steps, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps},
+                "steps": e2e_steps, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+                "transport": "compact: label images cross PCIe as run lists {y, x0, x1, label} (8 B per run) + object "
+                             "table; StageResult.mask(i) / labels(i) / object_mask expand them on the host on demand"},
+        "e2e_materialized": {
+            "note": "contract-complete: every bool mask and int32 label image of the batch is a host array inside the "
+                    "timed region",
+            "dense_download": {"value": dense_vig / dense_s, "unit": "vignettes/s",
+                               "d2h_bytes_per_step": dense_d2h // e2e_steps},
+            "run_list_expand": {"value": mat_vig / mat_s, "unit": "vignettes/s", "d2h_bytes_per_step": d2h // e2e_steps}},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
@@ -483,7 +614,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=16,
                     help="batches of the streaming end-to-end leg (a 100k-vignette job is 49 batches of 2048)")
     ap.add_argument("--e2e-batch", type=int, default=2048, help="vignettes per stage.map batch in the e2e leg")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline AND the parity gate")
+    ap.add_argument("--no-variants", action="store_true", help="skip the merge10 / crosses variant block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

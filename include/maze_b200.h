@@ -364,6 +364,13 @@ int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *
 int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,
                    void *dst_host, int n_threads);
 
+/* Asynchronous form of maze_host_pack: the copy threads start at once, the call returns a job handle (NULL: bad
+ * argument) and maze_host_pack_wait joins them (and frees the job).  The descriptor arrays are copied into the job;
+ * the source arrays and dst_host must stay alive until the wait returns. */
+void *maze_host_pack_start(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host,
+                           int n, void *dst_host, int n_threads);
+int maze_host_pack_wait(void *job);
+
 /* HOST helpers of the compact result transport.  In compact mode the label image of a vignette crosses PCIe as the
  * run list of maze_band_stage (8 bytes per run) instead of 5 bytes per pixel; these functions expand it on the
  * host into what the reference's stage returns (bool mask + int32 labels, loki/pipeline.py:459) or into the

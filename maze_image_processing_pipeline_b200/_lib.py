@@ -100,12 +100,13 @@ SIGNATURES = {
                         _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp],
     "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
+    "maze_host_pack_wait": [_vp],
     "maze_host_expand": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i],
     "maze_host_expand_crop": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "maze_stage_step": [_vp, _vp, _vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
-OTHER_SYMBOLS = ["maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",
+OTHER_SYMBOLS = ["maze_host_pack_start", "maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",
                  "maze_prof_kernel_name", "maze_prof_enable", "maze_prof_collect"]
 
 _lib = None
@@ -131,6 +132,8 @@ def lib():
             raise MazeLibraryError(f"{SO_PATH} does not export {name}") from e
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    handle.maze_host_pack_start.restype = ctypes.c_void_p
+    handle.maze_host_pack_start.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
     handle.maze_error_string.restype = ctypes.c_char_p
     handle.maze_version.restype = ctypes.c_int
     handle.maze_launch_count.restype = ctypes.c_longlong

@@ -80,6 +80,58 @@ extern "C" int maze_host_pack(const void *const *srcs, const int64_t *nbytes, co
     return MAZE_OK;
 }
 
+// Asynchronous form of maze_host_pack: the copy threads start at once and the call returns a job handle; the caller
+// goes on with its bookkeeping (geometry, descriptors, launches of the previous batch) and waits for the job right
+// before it uploads the staging buffer.  The descriptor arrays are copied into the job; the SOURCE arrays and the
+// destination must stay alive until maze_host_pack_wait returns.
+struct PackJob {
+    std::vector<const void *> srcs;
+    std::vector<int64_t> nbytes, dst_off;
+    std::vector<std::thread> threads;
+};
+
+extern "C" void *maze_host_pack_start(const void *const *srcs, const int64_t *nbytes, const int64_t *dst_off, int n,
+                                      void *dst, int n_threads)
+{
+    if (n < 0 || (n > 0 && (!srcs || !nbytes || !dst_off || !dst))) return nullptr;
+    PackJob *job = new PackJob;
+    if (n == 0) return job;
+    job->srcs.assign(srcs, srcs + n);
+    job->nbytes.assign(nbytes, nbytes + n);
+    job->dst_off.assign(dst_off, dst_off + n);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) total += nbytes[i];
+    std::vector<int> cut(n_threads + 1, n);
+    cut[0] = 0;
+    int64_t acc = 0;
+    int t = 1;
+    for (int i = 0; i < n && t < n_threads; i++) {
+        acc += nbytes[i];
+        if (acc >= total * t / n_threads) cut[t++] = i + 1;
+    }
+    for (int k = 0; k < n_threads; k++) {
+        const int lo = cut[k], hi = cut[k + 1];
+        if (lo >= hi) continue;
+        job->threads.emplace_back([job, dst, lo, hi]() {
+            for (int i = lo; i < hi; i++)
+                stream_copy((char *)dst + job->dst_off[i], (const char *)job->srcs[i], (size_t)job->nbytes[i]);
+            fence_stores();
+        });
+    }
+    return job;
+}
+
+extern "C" int maze_host_pack_wait(void *handle)
+{
+    if (!handle) return MAZE_ERR_BADARG;
+    PackJob *job = (PackJob *)handle;
+    for (auto &t : job->threads) t.join();
+    delete job;
+    return MAZE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Host side of the compact result transport: the label image of a vignette crosses PCIe as its RUN LIST
 // (maze_run_t {y, x0, x1, label}, 8 bytes per run, written by maze_band_stage) and is expanded here on demand

@@ -74,11 +74,18 @@ class BatchGeometry:
         vig["wpr"] = wpr
         vig["tile0"] = self.tile0[:-1]
         self.vig = vig
-        tiles = np.zeros(self.n_tiles, TILE_DTYPE)
-        img_of_tile = np.repeat(np.arange(self.n_img, dtype=np.int64), ntiles)
-        tiles["img"] = img_of_tile
-        tiles["word0"] = (np.arange(self.n_tiles, dtype=np.int64) - self.tile0[img_of_tile]) * TILE_WORDS
-        self.tiles = tiles
+        self._tiles = None
+
+    @property
+    def tiles(self):
+        """Tile list of the per-operator kernels (built on first use: the band pipeline does not need it)."""
+        if self._tiles is None:
+            tiles = np.zeros(self.n_tiles, TILE_DTYPE)
+            img_of_tile = np.repeat(np.arange(self.n_img, dtype=np.int64), self.ntiles)
+            tiles["img"] = img_of_tile
+            tiles["word0"] = (np.arange(self.n_tiles, dtype=np.int64) - self.tile0[img_of_tile]) * TILE_WORDS
+            self._tiles = tiles
+        return self._tiles
 
     def subset(self, indices):
         """Geometry of some vignettes of this batch that keeps THEIR offsets, so kernels launched on the
@@ -148,6 +155,14 @@ class BatchGeometry:
     def pack_host(self, images, out=None, dtype=np.uint8, threads=None):
         """Copy a list of (h, w) arrays into one flat host array laid out like the device batch
         (multi-threaded memcpy in libmaze_b200.so when the arrays already have the right dtype)."""
+        out, arrs, ptrs, nbytes, offs, threads = self._pack_args(images, out, dtype, threads)
+        if len(arrs) == 0:
+            return out
+        check(lib().maze_host_pack(ptrs.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, len(arrs),
+                                   out.__array_interface__["data"][0], int(threads)), "maze_host_pack")
+        return out
+
+    def _pack_args(self, images, out, dtype, threads):
         dtype = np.dtype(dtype)
         if out is None:
             out = np.zeros(self.total_px, dtype)
@@ -158,8 +173,6 @@ class BatchGeometry:
                 a = np.ascontiguousarray(a, dtype=dtype)
             arrs.append(a)
         n = len(arrs)
-        if n == 0:
-            return out
         ptrs = np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uint64, count=n)
         nbytes = (self.npx * dtype.itemsize).astype(np.int64)
         offs = (self.pix_off[:-1] * dtype.itemsize).astype(np.int64)
@@ -170,9 +183,23 @@ class BatchGeometry:
             except Exception:
                 avail = os.cpu_count() or 2
             threads = int(env) if env else min(16, max(1, avail // 2))
-        check(lib().maze_host_pack(ptrs.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, n,
-                                   out.__array_interface__["data"][0], int(threads)), "maze_host_pack")
-        return out
+        return out, arrs, ptrs, nbytes, offs, threads
+
+    def pack_host_start(self, images, out, dtype=np.uint8, threads=None):
+        """pack_host that returns at once: the copy threads run in the background; call the returned function to
+        wait for them (it keeps the source arrays alive until then)."""
+        out, arrs, ptrs, nbytes, offs, threads = self._pack_args(images, out, dtype, threads)
+        job = lib().maze_host_pack_start(ptrs.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, len(arrs),
+                                         out.__array_interface__["data"][0], int(threads))
+        if not job:
+            raise ValueError("maze_host_pack_start: bad argument")
+        keep = [arrs, out]
+
+        def wait():
+            if keep:
+                check(lib().maze_host_pack_wait(job), "maze_host_pack_wait")
+                keep.clear()
+        return wait
 
 
 def _ptr(t):
@@ -267,9 +294,51 @@ class DeviceBatch:
         lib()
         self.g = geometry
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        with torch.cuda.device(self.device):
-            self.d_vig = torch.from_numpy(geometry.vig.view(np.uint8).copy()).to(self.device, non_blocking=False)
-            self.d_tiles = torch.from_numpy(geometry.tiles.view(np.uint8).copy()).to(self.device, non_blocking=False)
+        self._d_vig = self._d_tiles = None
+
+    @property
+    def d_vig(self):
+        if self._d_vig is None:
+            with torch.cuda.device(self.device):
+                self._d_vig = torch.from_numpy(self.g.vig.view(np.uint8).copy()).to(self.device, non_blocking=False)
+        return self._d_vig
+
+    @property
+    def d_tiles(self):
+        """Tile list on the device (uploaded on first use: only the per-operator kernels need it)."""
+        if self._d_tiles is None:
+            with torch.cuda.device(self.device):
+                self._d_tiles = torch.from_numpy(self.g.tiles.view(np.uint8).copy()).to(self.device, non_blocking=False)
+        return self._d_tiles
+
+    def upload_descriptors(self, pool, halo=None):
+        """Vignette descriptors and (halo given) the band plan through ONE pinned staging buffer and ONE asynchronous
+        copy on the current stream, instead of a blocking upload per array (each of which waits for everything queued
+        on the stream, e.g. the image upload of the previous batch).  pool: a stage._PinnedPool that is not reused
+        before this batch is complete."""
+        if self._d_vig is not None:
+            return
+        parts = [self.g.vig.view(np.uint8)]
+        plan = None
+        if halo is not None:
+            plan = self.g.band_plan(halo)
+            parts += [plan[0].view(np.uint8), plan[1].view(np.uint8)]
+        offs, total = [], 0
+        for p in parts:
+            offs.append(total)
+            total += (p.size + 255) // 256 * 256
+        h = pool.get("desc", max(total, 256), torch.uint8)
+        hn = h.numpy()
+        for p, o in zip(parts, offs):
+            hn[o:o + p.size] = p.reshape(-1)
+        d = pool.dev("desc", max(total, 256), torch.uint8, self.device)
+        d.copy_(h, non_blocking=True)
+        self._d_vig = d[offs[0]:offs[0] + parts[0].size]
+        if plan is not None:
+            bands, band_off, left = plan
+            d_bands = d[offs[1]:offs[1] + max(parts[1].size, 16)]
+            d_off = d[offs[2]:offs[2] + parts[2].size].view(torch.int32)
+            self.__dict__.setdefault("_bands", {})[halo] = (d_bands, d_off, len(bands), left, bands, band_off)
 
     # ---- buffers -------------------------------------------------------------------------------
     def _new(self, n, dtype):

@@ -269,7 +269,8 @@ class _PinnedPool:
 
 class LokiSegmentationStage:
     def __init__(self, threshold=None, postprocess=None, device=None, high_order=True, fused=True,
-                 merge_errors="raise", shape_features=False, morphology="isotropic", pipeline=None, compact=False):
+                 merge_errors="raise", shape_features=False, morphology="isotropic", pipeline=None, compact=False,
+                 n_lanes=None):
         """pipeline: "bands" (default; maze_band_stage: band front, run-list labelling, dense writer) or "fused" (the
         vignette-resident kernel maze_vignette_stage); MAZE_PIPELINE overrides the default.
         compact: the per-pixel outputs stay on the device as the RUN LIST {y, x0, x1, label} (8 bytes per run, a
@@ -305,7 +306,7 @@ class LokiSegmentationStage:
         self._ws = Workspace()
         # workspaces (each with its own lane stream) in rotation; map() keeps batch i+1 in flight while batch i is
         # downloaded, so fewer than two would let a batch overwrite the buffers its predecessor is still read from
-        self.n_lanes = int(os.environ.get("MAZE_LANES", "6"))
+        self.n_lanes = int(n_lanes if n_lanes is not None else os.environ.get("MAZE_LANES", "6"))
         if self.n_lanes < 1:
             raise ValueError("MAZE_LANES must be >= 1")
         if shape_features:
@@ -318,7 +319,16 @@ class LokiSegmentationStage:
 
     # ---- device-resident core ----------------------------------------------------------------------
     def _passes(self):
-        """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path."""
+        """[(d2 threshold, invert)] of the morphology passes, or None when a radius needs the exact-EDT path
+        (cached per configuration: the footprint tables of the crosses mode take milliseconds to build)."""
+        pp = self.postprocess
+        key = (self.morphology, pp.opening_radius, pp.closing_radius)
+        cache = self.__dict__.setdefault("_passes_cache", {})
+        if key not in cache:
+            cache[key] = self._passes_uncached()
+        return cache[key]
+
+    def _passes_uncached(self):
         pp = self.postprocess
         out = []
         if self.morphology == "crosses":  # loki/pipeline.py:408-427: erosion + dilation / dilation + erosion
@@ -653,30 +663,53 @@ class LokiSegmentationStage:
         n_labels[idx.long()] = slab_off[1:] - slab_off[:-1]
 
     # ---- host entry: numpy in, numpy out --------------------------------------------------------------
-    def _enqueue(self, images, foreground_pred, pool, want_mask, want_labels):
-        """Pack + upload one batch, launch its kernels and start the download of the per-pixel outputs on the
-        copy stream; returns what _complete needs.  Nothing here waits for the GPU."""
+    def _halo(self):
+        """Halo of the band plan (sum of the pass radii) when the asynchronous band pipeline will take the batch."""
+        pp = self.postprocess
+        if pp is None or not self.fused or self.pipeline != "bands" or self._passes() is None:
+            return None
+        if pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0:
+            return None
+        from .morphology import pass_radius
+        return sum(pass_radius(t) for t, _ in self._passes())
+
+    def _prepack(self, images, foreground_pred, pool):
+        """Geometry of the batch and the START of its packing into the pinned staging buffer (copy threads run in the
+        background); _enqueue waits for them right before the upload."""
         if self.threshold is None and foreground_pred is None:
             raise ValueError("postprocess-only stage needs foreground_pred")
         geom = BatchGeometry.from_images(images)
         if geom.n_img == 0:
+            return (geom, None, None, None)
+        h_img = pool.get("img", geom.total_px, torch.uint8)
+        wait = geom.pack_host_start(images, out=h_img.numpy())
+        h_pred = None
+        if self.threshold is None:
+            h_pred = pool.get("pred", geom.total_px, torch.uint8)
+            geom.pack_host([np.asarray(p, dtype=bool).view(np.uint8) for p in foreground_pred], out=h_pred.numpy())
+        return (geom, h_img, h_pred, wait)
+
+    def _enqueue(self, images, foreground_pred, pool, want_mask, want_labels, pre=None):
+        """Upload one (pre)packed batch, launch its kernels and start the download of the per-pixel outputs on the
+        copy stream; returns what _complete needs.  Nothing here waits for the GPU."""
+        if pre is None:
+            pre = self._prepack(images, foreground_pred, pool)
+        geom, h_img, h_pred, wait = pre
+        if geom.n_img == 0:
             return (geom, None, None, None, None, None, None)
         dev = self.device
         batch = DeviceBatch(geom, dev)
-        # descriptors and launch plan go up BEFORE the image: their (small, blocking) uploads would otherwise queue
-        # behind the image copy on the same stream and cost the host several milliseconds per batch
+        # descriptors and launch plan go up BEFORE the image, through one pinned buffer and one asynchronous copy
+        batch.upload_descriptors(pool, self._halo())
         self.prepare(batch)
         main = torch.cuda.current_stream()
         if self._copy_stream is None or self._copy_stream.device != batch.device:
             self._copy_stream = torch.cuda.Stream(device=batch.device)
-        h_img = pool.get("img", geom.total_px, torch.uint8)
-        geom.pack_host(images, out=h_img.numpy())
+        wait()  # the staging buffer is complete
         d_image = pool.dev("img", geom.total_px, torch.uint8, batch.device)
         d_image.copy_(h_img, non_blocking=True)
         d_pred = None
-        if self.threshold is None:
-            h_pred = pool.get("pred", geom.total_px, torch.uint8)
-            geom.pack_host([np.asarray(p, dtype=bool).view(np.uint8) for p in foreground_pred], out=h_pred.numpy())
+        if h_pred is not None:
             d_pred = pool.dev("pred", geom.total_px, torch.uint8, batch.device)
             d_pred.copy_(h_pred, non_blocking=True)
         res = self.run_device(batch, d_image, d_pred)
@@ -804,17 +837,32 @@ class LokiSegmentationStage:
             pp = self.postprocess
             overlap = (pp is not None and self.fused and self.n_lanes >= 2 and self._passes() is not None
                        and not (pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0))
-            for i, item in enumerate(batches):
-                images, pred = item if isinstance(item, tuple) else (item, None)
-                if not overlap and pending is not None:
-                    yield self._complete(pending)
-                    pending = None
-                inflight = self._enqueue(images, pred, self._map_pools[i % 3], want_mask, want_labels)
+            def split(item):
+                return item if isinstance(item, tuple) else (item, None)
+
+            it = iter(batches)
+            item = next(it, None)
+            pre = None if item is None else self._prepack(*split(item), self._map_pools[0])
+            i = 0
+            try:
+                while item is not None:
+                    if not overlap and pending is not None:
+                        yield self._complete(pending)
+                        pending = None
+                    inflight = self._enqueue(None, None, self._map_pools[i % 3], want_mask, want_labels, pre=pre)
+                    # the NEXT batch is packed in the background while this one computes, the previous one is
+                    # completed and the consumer works on what is yielded
+                    item = next(it, None)
+                    pre = None if item is None else self._prepack(*split(item), self._map_pools[(i + 1) % 3])
+                    if pending is not None:
+                        yield self._complete(pending)
+                    pending = inflight
+                    i += 1
                 if pending is not None:
                     yield self._complete(pending)
-                pending = inflight
-            if pending is not None:
-                yield self._complete(pending)
+            finally:
+                if pre is not None and pre[3] is not None:
+                    pre[3]()  # never leave copy threads behind
 
 
 def _rpb_of(bands, band_off, n_img):

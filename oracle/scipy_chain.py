@@ -138,21 +138,52 @@ def merge_labels(labels, index=None, max_distance=None, path_tolerance=5, return
     return (labels_out, dists) if return_merge_distances else labels_out
 
 
+_REF = None
+
+
+def reference_modules():
+    """(isotropic, merge_labels) modules of the REAL reference from oracle/_ref/ (put there by oracle/make_ref.sh,
+    see its header), or None when they are not present."""
+    global _REF
+    if _REF is None:
+        import importlib.util
+        import os
+        mods = []
+        for name in ("isotropic", "merge_labels"):
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", name + ".py")
+            if not os.path.exists(path):
+                mods = False
+                break
+            spec = importlib.util.spec_from_file_location("maze_ref_" + name, path)
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            mods.append(m)
+        _REF = tuple(mods) if mods else False
+    return _REF or None
+
+
 def loki_chain(image, threshold_brighter=40, opening_radius=1, closing_radius=2, clear_border_flag=False,
-               min_area=0, merge_segments_distance=0, with_props=True):
+               min_area=0, merge_segments_distance=0, with_props=True, use_reference=False):
     """One vignette through threshold -> opening -> closing -> label -> filters -> merge -> regionprops
-    in the order of loki/pipeline.py:405-457 (opening BEFORE closing)."""
+    in the order of loki/pipeline.py:405-457 (opening BEFORE closing).  use_reference: morphology and merge_labels
+    are the reference's own functions (oracle/_ref/), not the restatements above."""
+    ref = reference_modules() if use_reference else None
+    if use_reference and ref is None:
+        raise RuntimeError("oracle/_ref/ is empty: run oracle/make_ref.sh where /root/reference exists")
+    _opening = ref[0].isotropic_opening if ref else opening
+    _closing = ref[0].isotropic_closing if ref else closing
+    _merge = ref[1].merge_labels if ref else merge_labels
     mask = image > threshold_brighter
     if opening_radius > 0:
-        mask = opening(mask, opening_radius)
+        mask = _opening(mask, opening_radius)
     if closing_radius > 0:
-        mask = closing(mask, closing_radius)
+        mask = _closing(mask, closing_radius)
     labels, _ = label(mask)
     if clear_border_flag:
         clear_border(labels)
     if min_area > 0:
         remove_small_objects(labels, min_area)
     if merge_segments_distance > 0:
-        labels = merge_labels(labels, max_distance=merge_segments_distance, labels_out=labels)
+        labels = _merge(labels, max_distance=merge_segments_distance, labels_out=labels)
     table = _c_regionprops(np.ascontiguousarray(labels), image) if with_props else None
     return mask, labels, table

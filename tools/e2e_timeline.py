@@ -7,7 +7,7 @@ from maze_image_processing_pipeline_b200.device import BatchGeometry, DeviceBatc
 hs, ws = bench.job_sizes()
 B = 2048
 pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
-st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
+st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=bool(int(os.environ.get("COMPACT", "1"))))
 hb = []
 for b in range(8):
     g = BatchGeometry(hs[b * B:(b + 1) * B], ws[b * B:(b + 1) * B])
