@@ -315,6 +315,7 @@ class LokiSegmentationStage:
         self._copy_stream = None
         self._small_copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
+        self._img_ring = None  # pinned staging buffers of map() (four sets, allocated on first use)
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
@@ -840,20 +841,34 @@ class LokiSegmentationStage:
             def split(item):
                 return item if isinstance(item, tuple) else (item, None)
 
+            # Batches are PACKED two ahead: the copy threads of batch i+1 and i+2 fill their pinned staging buffers in the
+            # background while batch i computes, batch i-1 is completed and the consumer works on what was yielded.
+            # Staging buffers rotate over four sets: the set of batch i+2 was last used by batch i-2, which is complete.
+            if self._img_ring is None:
+                self._img_ring = [_PinnedPool() for _ in range(4)]
             it = iter(batches)
-            item = next(it, None)
-            pre = None if item is None else self._prepack(*split(item), self._map_pools[0])
+            ahead = []  # prepacked batches, oldest first
+            n_pre = 0
+
+            def prefetch():
+                nonlocal n_pre
+                while len(ahead) < 2:
+                    item = next(it, None)
+                    if item is None:
+                        return
+                    ahead.append(self._prepack(*split(item), self._img_ring[n_pre % 4]))
+                    n_pre += 1
+
             i = 0
             try:
-                while item is not None:
+                prefetch()
+                while ahead:
                     if not overlap and pending is not None:
                         yield self._complete(pending)
                         pending = None
+                    pre = ahead.pop(0)
                     inflight = self._enqueue(None, None, self._map_pools[i % 3], want_mask, want_labels, pre=pre)
-                    # the NEXT batch is packed in the background while this one computes, the previous one is
-                    # completed and the consumer works on what is yielded
-                    item = next(it, None)
-                    pre = None if item is None else self._prepack(*split(item), self._map_pools[(i + 1) % 3])
+                    prefetch()
                     if pending is not None:
                         yield self._complete(pending)
                     pending = inflight
@@ -861,8 +876,9 @@ class LokiSegmentationStage:
                 if pending is not None:
                     yield self._complete(pending)
             finally:
-                if pre is not None and pre[3] is not None:
-                    pre[3]()  # never leave copy threads behind
+                for pre in ahead:  # never leave copy threads behind
+                    if pre[3] is not None:
+                        pre[3]()
 
 
 def _rpb_of(bands, band_off, n_img):
