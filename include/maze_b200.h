@@ -141,6 +141,16 @@ int maze_morph_pass(const uint32_t *in, uint32_t *out, const maze_vignette_t *vi
 #define MAZE_FOOTPRINT_T(id) (-2 - (id))
 int maze_footprint_register(int R, const int32_t *w);
 
+/* The same pass for LARGE radii (squared-distance thresholds up to 254^2, or a registered footprint): a separable
+ * pair of kernels -- vertical distance to the nearest 0 per pixel (one byte, capped at R + 1), then a row test
+ * against the disk's half heights -- whose cost grows with R instead of R^2; results are identical to
+ * maze_morph_pass.  cta_off_a[i] (n_img + 1 int64, device) = prefix sum of ceil(h / 32) * ceil(wpr / 8) over the
+ * vignettes, n_cta_a its total; cta_off_b / n_cta_b the same for ceil(h / 8) * ceil(w / 256).  g_scratch: one byte per pixel; plane_scratch: one bit plane (!= in, out). */
+int maze_morph_pass_wide(const uint32_t *in, uint32_t *out, const maze_vignette_t *vig, int n_img,
+                         const int64_t *cta_off_a, long long n_cta_a, const int64_t *cta_off_b, long long n_cta_b,
+                         int t, int invert, const uint32_t *flags_in, uint32_t *flags_out, uint8_t *g_scratch,
+                         uint32_t *plane_scratch, void *stream);
+
 /* bit plane -> one byte per pixel (numpy bool). */
 int maze_unpack_mask(const uint32_t *bits, const maze_vignette_t *vig, int n_img,
                      const maze_tile_t *tiles, int n_tiles, uint8_t *mask, void *stream);

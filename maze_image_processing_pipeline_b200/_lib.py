@@ -80,6 +80,7 @@ _d = ctypes.c_double
 SIGNATURES = {
     "maze_threshold_pack": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp],
     "maze_morph_pass": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "maze_morph_pass_wide": [_vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "maze_unpack_mask": [_vp, _vp, _i, _vp, _i, _vp, _vp],
     "maze_footprint_register": [_i, _vp],
     "maze_edt_sq": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],

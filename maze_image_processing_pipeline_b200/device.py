@@ -27,6 +27,10 @@ RUN_DTYPE = np.dtype([("y", "<u2"), ("x0", "<u2"), ("x1", "<u2"), ("label", "<u2
 assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8 and BAND_DTYPE.itemsize == 16 and RUN_DTYPE.itemsize == 8
 
 _DISK_T_LIMIT = (MAX_DISK_RADIUS + 1) ** 2
+WIDE_MAX_R = 254                 # maze_morph_pass_wide: squared-distance thresholds up to 254^2
+WIDE_MIN_R = int(os.environ.get("MAZE_WIDE_MIN_R", "28"))  # from this radius on the separable pass pair is the faster one
+# (2048^2 frame, per pass: bit-plane kernel 0.044 ms at r = 16, 0.10 ms at r = 32; separable pair 0.07-0.09 ms up to r = 32,
+# 0.12 ms at r = 64 -- tools/wide_probe.py)
 _INT_MAX = 2 ** 31 - 1
 
 
@@ -372,7 +376,33 @@ class DeviceBatch:
                                         flags.data_ptr(), _stream()), "maze_threshold_pack")
         return bits, flags
 
+    def _wide_plan(self):
+        """CTA prefix sums of maze_morph_pass_wide (device int64 arrays, cached)."""
+        if not hasattr(self, "_wide"):
+            g = self.g
+            wpr = (g.w + 31) // 32
+            a = np.concatenate([[0], np.cumsum(((g.h + 31) // 32) * ((wpr + 7) // 8))]).astype(np.int64)
+            b = np.concatenate([[0], np.cumsum(((g.h + 7) // 8) * ((g.w + 255) // 256))]).astype(np.int64)
+            self._wide = (torch.from_numpy(a).to(self.device), int(a[-1]), torch.from_numpy(b).to(self.device), int(b[-1]))
+        return self._wide
+
+    def morph_pass_wide(self, bits, flags, t: int, invert: int):
+        """maze_morph_pass for large radii (separable vertical-distance + row-test kernels)."""
+        d_a, n_a, d_b, n_b = self._wide_plan()
+        out, fout = self.empty_plane(), self.empty_flags()
+        gbuf, cbuf = self.empty_px(torch.uint8), self.empty_plane()
+        check(lib().maze_morph_pass_wide(bits.data_ptr(), out.data_ptr(), self.d_vig.data_ptr(), self.g.n_img,
+                                         d_a.data_ptr(), n_a, d_b.data_ptr(), n_b, int(t), int(invert), flags.data_ptr(),
+                                         fout.data_ptr(), gbuf.data_ptr(), cbuf.data_ptr(), _stream()), "maze_morph_pass_wide")
+        return out, fout
+
     def morph_pass(self, bits, flags, t: int, invert: int):
+        if t >= 0 and math.isqrt(int(t)) >= WIDE_MIN_R:
+            return self.morph_pass_wide(bits, flags, t, invert)
+        if t < -1:  # registered footprint
+            from .morphology import pass_radius
+            if pass_radius(t) >= WIDE_MIN_R:
+                return self.morph_pass_wide(bits, flags, t, invert)
         vig, n, tiles, nt = self._geo()
         out, fout = self.empty_plane(), self.empty_flags()
         check(lib().maze_morph_pass(bits.data_ptr(), out.data_ptr(), vig, n, tiles, nt, int(t), int(invert),
@@ -400,6 +430,8 @@ class DeviceBatch:
         t = fold_erosion_radius(radius)
         if t < _DISK_T_LIMIT:
             return self.morph_pass(bits, flags, t, 0)
+        if t <= WIDE_MAX_R ** 2:
+            return self.morph_pass_wide(bits, flags, t, 0)
         return self.compare_pack(self.edt_sq(bits, 0), t, 1)
 
     def dilation(self, bits, flags, radius):
@@ -407,6 +439,8 @@ class DeviceBatch:
         t = fold_dilation_radius(radius)
         if t < _DISK_T_LIMIT:
             return self.morph_pass(bits, flags, t, 1)
+        if t <= WIDE_MAX_R ** 2:
+            return self.morph_pass_wide(bits, flags, t, 1)
         return self.compare_pack(self.edt_sq(bits, 1), t, 0)
 
     def opening(self, bits, flags, radius):

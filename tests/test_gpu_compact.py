@@ -44,7 +44,7 @@ def test_compact_streaming_and_objects(mz):
     """stage.map in compact mode (three batches in flight over rotating lanes), consumed through FindRegions /
     recalc_metadata / ZooProcess features with the default padding of 75."""
     S = mz.stage
-    from maze_image_processing_pipeline_b200.regions import find_regions, objects_of
+    from maze_image_processing_pipeline_b200.regions import extract_roi, find_regions, objects_of
     pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
     st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=True)
     batches = [mz.synth.synth_batch(500 + b, 6 + b, lo=64, hi=300) for b in range(5)]
@@ -58,6 +58,9 @@ def test_compact_streaming_and_objects(mz):
             assert [r.label for r in regs] == [int(v) for v in table[table[:, oracle.F_AREA] > 0][:, oracle.F_LABEL]]
             for r in regs:
                 assert np.array_equal(r.image, labels[r.slice] == r.label)
+                # ExtractROI (loki/pipeline.py:596-602): the padded crop, masked with the object expanded from its runs
+                assert np.array_equal(extract_roi(im, r), im[r.slice])
+                assert np.array_equal(extract_roi(im, r, alpha=1, bg_color=7), np.where(labels[r.slice] == r.label, im[r.slice], 7))
             objs = objects_of(res, i, padding=75, image=im)
             assert [o["object_area_exc"] for o in objs] == [float(r.area) for r in regs]
             n += len(objs)
@@ -155,3 +158,85 @@ def test_two_threads_call_the_stage_concurrently(mz):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def _chain(im):
+    return scipy_chain.loki_chain(im, 40, 1, 2)
+
+
+def test_large_vignettes_of_the_bench_distribution_against_the_oracle(mz):
+    """configs[1] sizes: 40 vignettes drawn from the benchmark's OWN size distribution (seed 1, log-uniform 64-1024)
+    among those with more than 9216 bit-plane words -- the multi-band vignettes of the band pipeline, the three
+    largest size classes of the vignette-resident kernel -- plus the largest ones of the job (1024 x 1024 and
+    neighbours: the oversize path of the vignette-resident kernel), bit for bit against the reference chain, through
+    both pipelines and both transports.  The oracle runs on a process pool (scipy's EDT takes ~1 s per megapixel)."""
+    import multiprocessing as mp
+    import bench
+    S = mz.stage
+    hs, ws = bench.job_sizes()
+    words = hs.astype(np.int64) * ((ws.astype(np.int64) + 31) // 32)
+    big = np.nonzero(words > 9216)[0]
+    rng = np.random.default_rng(11)
+    pick = list(rng.choice(big, 34, replace=False)) + list(np.argsort(-words)[:6])
+    imgs = [mz.synth.synth_vignette(np.random.default_rng(1000 + int(i)), int(hs[i]), int(ws[i])) for i in pick]
+    assert sum(im.size > 906_000 for im in imgs) >= 4  # beyond the 28 320-word class of the vignette-resident kernel
+    with mp.get_context("fork").Pool(min(16, len(imgs))) as pool:
+        want = pool.map(_chain, imgs, chunksize=1)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    for kw in (dict(pipeline="bands"), dict(pipeline="bands", compact=True), dict(pipeline="fused")):
+        res = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, **kw)(imgs)
+        for i, (mask, labels, table) in enumerate(want):
+            assert np.array_equal(res.mask(i), mask), (kw, i, imgs[i].shape)
+            assert np.array_equal(res.labels(i), labels), (kw, i, imgs[i].shape)
+            assert len(res.features(i)) == len(table)
+            assert_tables_close(res.features(i), table)
+
+
+def _iso(args):
+    op, mask, r = args
+    return getattr(scipy_chain, op)(mask, r)
+
+
+def test_full_radius_sweep_1_to_32_and_beyond(mz):
+    """BASELINE.json configs[2]: isotropic opening AND closing for EVERY radius 1..32 (plus half-integer and large
+    radii up to 120) against the reference's EDT compare -- the bit-plane disk kernel for small radii, the separable
+    vertical-distance / row-test pair (maze_morph_pass_wide) from radius 6 on -- on a frame with blobs, specks and
+    holes, on uniform planes (scipy's phantom pixel) and on degenerate shapes."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(9)
+    frame = mz.synth.synth_dense_frame(5, size=700, n_blobs=25)[:600, :]
+    frame = np.maximum(frame, (rng.random(frame.shape) < 0.003).astype(np.uint8) * 255)
+    frame[rng.random(frame.shape) < 0.002] = 0
+    masks = [frame > 40, np.ones((90, 140), bool), np.zeros((70, 65), bool), rng.random((1, 300)) < 0.7,
+             rng.random((260, 1)) < 0.7, rng.random((130, 97)) < 0.98]
+    radii = list(range(1, 33)) + [6.5, 12.5, 40, 64, 120]  # (the separable pair takes over at radius 28)
+    jobs = [(op, m, r) for m in masks for r in radii for op in ("opening", "closing")]
+    with mp.get_context("fork").Pool(16) as pool:
+        want = pool.map(_iso, jobs, chunksize=4)
+    for (op, m, r), w in zip(jobs, want):
+        got = getattr(mz.isotropic, f"isotropic_{op}")(m, r)
+        assert np.array_equal(got, w), (op, m.shape, r)
+
+
+def test_wide_pass_equals_the_bit_plane_pass_on_footprints_and_batches(mz):
+    """maze_morph_pass_wide and maze_morph_pass agree bit for bit (planes and flags) on a packed batch, for disks and
+    for registered footprints (the live pipeline's disk(r, "crosses"))."""
+    from maze_image_processing_pipeline_b200 import morphology as M
+    dev = mz.device
+    rng = np.random.default_rng(4)
+    imgs = [(rng.random((h, w)) < p).astype(np.uint8) * 255 for h, w, p in
+            [(80, 300, 0.97), (257, 33, 0.9), (64, 64, 1.0), (50, 70, 0.0), (1, 1, 1.0), (300, 520, 0.995)]]
+    g = dev.BatchGeometry.from_images(imgs)
+    b = dev.DeviceBatch(g)
+    bits, flags = b.threshold_pack(b.upload(g.pack_host(imgs)), 40)
+    codes = [1, 4, 9, 50, 100, 1024] + [M.footprint_pass_code(M.disk(r, decomposition="crosses")) for r in (2, 7, 13)]
+    for t in codes:
+        for inv in (0, 1):
+            vig, n, tiles, nt = b._geo()
+            o1, f1 = b.empty_plane(), b.empty_flags()
+            dev.check(dev.lib().maze_morph_pass(bits.data_ptr(), o1.data_ptr(), vig, n, tiles, nt, int(t), inv,
+                                                flags.data_ptr(), f1.data_ptr(), 0), "maze_morph_pass")
+            o2, f2 = b.morph_pass_wide(bits, flags, t, inv)
+            mz.torch.cuda.synchronize()
+            assert mz.torch.equal(o1, o2), (t, inv)
+            assert mz.torch.equal(f1, f2), (t, inv)
