@@ -286,6 +286,9 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * counters: 4 int32 (cleared by the call): [0] staging rows used, [1] runs used (may exceed run_cap: the bands
  * that did not fit are flagged), [2] / [3] vignettes that needed the middle / large run table.  big_list: n_img
  * int32 scratch.
+ * FRAMES: vignettes with at least huge_px pixels (huge_host: n_huge pairs {vignette index, number of its bands}) are
+ * labelled by a sequence of global-memory kernels (union-find on run ids with atomics) instead of the per-vignette
+ * CTA; gl_scratch: 2 * run_cap + n_bands + 16 int32.  n_huge = 0 or gl_scratch = NULL switches this off.
  * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
  * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
 #define MAZE_BAND_PLANE_WORDS 6144
@@ -300,7 +303,7 @@ int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_v
                     maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
                     int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list, int stage_cap,
                     unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, long long total_px,
-                    void *stream);
+                    const int32_t *huge_host, int n_huge, long long huge_px, int32_t *gl_scratch, void *stream);
 
 /* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
  * acc_base[i] >= 0 (the others are left to maze_regionprops). */
@@ -360,11 +363,15 @@ typedef struct maze_step_args {
     maze_band_out_t *band_out;
     int32_t *band_counters; /* 4 int32 */
     int32_t *big_list;      /* n_img int32 */
+    const int32_t *huge_host; /* HOST: n_huge pairs {vignette, bands} of the frames (global-memory labelling) */
+    int32_t *gl_scratch;      /* 2 * run_cap + n_bands + 16 int32 (or NULL) */
     int32_t class_off[MAZE_FUSED_CLASSES + 1];
     int32_t pass_t[4], pass_invert[4];
     int32_t n_img, left_n, left_n_tiles, left_n_tiles_full, t_int, n_pass, flags, stage_cap;
     int32_t n_bands, halo, run_cap, step_flags; /* step_flags: MAZE_STEP_COMPACT */
     int64_t total_px;                           /* elements of mask / labels (band pipeline, dense outputs) */
+    int64_t huge_px;                            /* vignettes with >= huge_px pixels are frames */
+    int32_t n_huge, reserved;
 } maze_step_args_t;
 #define MAZE_STEP_COMPACT 1 /* band pipeline: no dense mask / label image for the band vignettes (run list only) */
 int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);

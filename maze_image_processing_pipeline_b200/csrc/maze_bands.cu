@@ -365,6 +365,7 @@ struct LabelArgs {
     uint8_t *mask; // dense outputs (or NULL): the labelling kernel stores the runs on top of the zero fill
     int32_t *labels;
     int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
+    long long huge_px; // vignettes with at least this many pixels are labelled by the global-memory kernels
 };
 
 __device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
@@ -387,6 +388,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
     if (nb <= 0) return 0; // not a band vignette (the per-operator chain owns its counters)
     const maze_vignette_t v = a.vig[img];
     const int H = v.h;
+    if ((i64)v.h * v.w >= a.huge_px) return 0; // a frame: the global-memory labelling kernels take it
     if (nb > nbcap) return 1;
     // band table -> shared memory: s_bbase[j] = first run of band j in the run buffer, s_bpre[j] = runs before band j
     int *s_bbase = (int *)s_mem, *s_bpre = s_bbase + nbcap;
@@ -928,6 +930,268 @@ static BandFork *band_fork()
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K2 for FRAMES (BASELINE.json configs[3]: 4096 x 4096, thousands of labels, 10^5 runs): the same labelling and
+// accumulation on the run list, but with the union-find in global memory and every step spread over the whole GPU.
+// One vignette per call sequence: prefix of the band run counts -> init -> link (atomicMin union-find on run ids)
+// -> flatten -> rank (raster order of the roots = label numbers) -> zero rows -> apply (labels into the run records,
+// integer accumulators by atomics) -> high-order moments -> dense write.
+// scratch (int32): parent[run_cap] | lab[run_cap] | bpre[n_bands_of_vignette + 1] | misc[8]
+// ---------------------------------------------------------------------------------------------------------
+struct GlArgs {
+    LabelArgs a;
+    int img;
+    int32_t *parent, *lab, *bpre, *misc; // misc: [0] runs, [1] ok, [2] labels, [3] staging base
+};
+
+__device__ __forceinline__ int gl_band_of(const int32_t *bpre, int nb, int i)
+{
+    int lo = 0, hi = nb - 1; // last band j with bpre[j] <= i
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (bpre[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(1024) k_gl_prefix(GlArgs g)
+{
+    __shared__ int s_warp[34];
+    const LabelArgs &a = g.a;
+    const int b0 = a.band_off[g.img], nb = a.band_off[g.img + 1] - b0;
+    const int tid = threadIdx.x;
+    const int chunk = (nb + 1023) / 1024, lo = min(tid * chunk, nb), hi = min(lo + chunk, nb);
+    int sum = 0, bad = 0, zor = 0;
+    for (int j = lo; j < hi; j++) {
+        const maze_band_out_t o = a.band_out[b0 + j];
+        sum += o.n_runs; bad |= o.base < 0 ? 1 : 0; zor |= o.zflags;
+    }
+    bad = __syncthreads_or(bad);
+    // OR of the zero flags over the bands
+    __shared__ int s_zor;
+    if (tid == 0) s_zor = 0;
+    __syncthreads();
+    if (zor) atomicOr(&s_zor, zor);
+    int total;
+    int run = block_exclusive_scan<1024>(sum, s_warp, &total);
+    for (int j = lo; j < hi; j++) {
+        g.bpre[j] = run;
+        run += a.band_out[b0 + j].n_runs;
+    }
+    if (tid == 0) {
+        g.bpre[nb] = total;
+        if (nb > 1)
+            for (int p = 0; p < a.n_pass; p++)
+                if (((a.phantom_mask >> p) & 1) && !((s_zor >> p) & 1)) bad = 1; // scipy's phantom pixel: per-operator redo
+        g.misc[0] = bad ? 0 : total;
+        g.misc[1] = bad ? 0 : 1;
+        g.misc[2] = 0;
+        g.misc[3] = -1;
+        if (bad) mark_fallback(a, g.img);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gl_init(GlArgs g)
+{
+    const int n = g.misc[0];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) g.parent[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_gl_link(GlArgs g)
+{
+    const LabelArgs &a = g.a;
+    const int n = g.misc[0];
+    const int b0 = a.band_off[g.img], nb = a.band_off[g.img + 1] - b0;
+    const uint2 *R = (const uint2 *)a.runs;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int jb = gl_band_of(g.bpre, nb, i);
+        const uint2 r = R[a.band_out[b0 + jb].base + (i - g.bpre[jb])];
+        const int y = r.x & 0xffffu, x0 = r.x >> 16, x1 = r.y & 0xffffu;
+        if (y == 0) continue;
+        // runs of row y - 1 live in band pb (the same or the previous one), sorted by x: first one whose end reaches x0 - 1
+        int pb = jb;
+        if (i == g.bpre[jb] || (int)(R[a.band_out[b0 + jb].base].x & 0xffffu) > y - 1) pb = jb - 1; // band starts at row y
+        if (pb < 0) continue;
+        const maze_band_out_t po = a.band_out[b0 + pb];
+        const uint2 *P = R + po.base;
+        int lo = 0, hi = po.n_runs; // first run with (row, x1) >= (y - 1, x0 - 1)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const uint2 q = P[mid];
+            const int qy = q.x & 0xffffu, qx1 = q.y & 0xffffu;
+            if (qy < y - 1 || (qy == y - 1 && qx1 < x0 - 1)) lo = mid + 1; else hi = mid;
+        }
+        for (int j = lo; j < po.n_runs; j++) {
+            const uint2 q = P[j];
+            if ((int)(q.x & 0xffffu) != y - 1 || (int)(q.x >> 16) > x1 + 1) break;
+            uf_union(g.parent, i, g.bpre[pb] + j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gl_flatten(GlArgs g)
+{
+    const int n = g.misc[0];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) g.lab[i] = uf_find(g.parent, i);
+}
+
+// roots in raster order get labels 1..N (one CTA: the scan is over run ids, a few 10^5 at most)
+__global__ void __launch_bounds__(1024) k_gl_rank(GlArgs g)
+{
+    __shared__ int s_warp[34];
+    const LabelArgs &a = g.a;
+    const int n = g.misc[0];
+    if (!g.misc[1]) return;
+    const int tid = threadIdx.x;
+    const int chunk = (n + 1023) / 1024, lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int cnt = 0;
+    for (int i = lo; i < hi; i++) cnt += g.lab[i] == i;
+    int n_lab;
+    int rank = block_exclusive_scan<1024>(cnt, s_warp, &n_lab);
+    for (int i = lo; i < hi; i++)
+        if (g.lab[i] == i) g.parent[i] = ++rank; // parent[root] = label (roots only; the others keep their root in lab)
+    if (tid == 0) {
+        if (n_lab > 65535) { // labels are 16 bits in the run records
+            mark_fallback(a, g.img);
+            g.misc[0] = 0; g.misc[1] = 0;
+            return;
+        }
+        a.n_labels[g.img] = n_lab;
+        a.fallback[g.img] = 0;
+        int base = -1;
+        if (a.do_props) {
+            base = n_lab ? atomicAdd(a.stage_counter, n_lab) : 0;
+            if (base + n_lab > a.stage_cap) base = -1;
+        }
+        a.acc_base[g.img] = base;
+        g.misc[2] = n_lab;
+        g.misc[3] = base;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gl_zero_rows(GlArgs g)
+{
+    const LabelArgs &a = g.a;
+    const int n_lab = g.misc[2], base = g.misc[3];
+    if (base < 0) return;
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < n_lab; l += gridDim.x * 256) {
+        u64 *ga = a.acc_stage + (i64)(base + l) * MAZE_NACC;
+        for (int j = 0; j < MAZE_NACC; j++) ga[j] = 0;
+        double *gh = a.hi_stage + (i64)(base + l) * 8;
+        for (int j = 0; j < 8; j++) gh[j] = 0.0;
+        int32_t *ge = a.ext_stage + (i64)(base + l) * MAZE_NEXT;
+        ge[E_RMIN] = 0x7fffffff; ge[E_RMAX] = -1; ge[E_CMIN] = 0x7fffffff; ge[E_CMAX] = -1;
+        ge[E_VMIN] = 0x7fffffff; ge[E_VMAX] = -1; ge[6] = 0; ge[7] = 0;
+    }
+}
+
+// stage 0: label of every run -> run record, integer accumulators; stage 1: float64 moments about the centroid
+__global__ void __launch_bounds__(256) k_gl_apply(GlArgs g, int stage)
+{
+    const LabelArgs &a = g.a;
+    const int n = g.misc[0], base = g.misc[3];
+    const int b0 = a.band_off[g.img], nb = a.band_off[g.img + 1] - b0;
+    const bool props = a.do_props && base >= 0;
+    if (stage == 1 && !(props && a.high_order)) return;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int jb = gl_band_of(g.bpre, nb, i);
+        const int gi = a.band_out[b0 + jb].base + (i - g.bpre[jb]);
+        const uint2 r = ((const uint2 *)a.runs)[gi];
+        const int lab = g.parent[g.lab[i]];
+        const u64 y = r.x & 0xffffu, xa = r.x >> 16, xb = r.y & 0xffffu, nn = xb - xa + 1;
+        if (stage == 0) {
+            ((u16 *)(a.runs + gi))[3] = (u16)lab;
+            if (!props) continue;
+            u64 *Aa = a.acc_stage + (i64)(base + lab - 1) * MAZE_NACC;
+            int32_t *Ee = a.ext_stage + (i64)(base + lab - 1) * MAZE_NEXT;
+            const u64 S1 = nn * (xa + xb) / 2;
+            const u64 S2 = pw2(xb) - (xa ? pw2(xa - 1) : 0);
+            const u64 S3 = pw3(xb) - (xa ? pw3(xa - 1) : 0);
+            atomicAdd(Aa + A_N, nn); atomicAdd(Aa + A_R, y * nn); atomicAdd(Aa + A_C, S1);
+            atomicAdd(Aa + A_RR, y * y * nn); atomicAdd(Aa + A_RC, y * S1); atomicAdd(Aa + A_CC, S2);
+            atomicAdd(Aa + A_RRR, y * y * y * nn); atomicAdd(Aa + A_RRC, y * y * S1); atomicAdd(Aa + A_RCC, y * S2);
+            atomicAdd(Aa + A_CCC, S3);
+            atomicMin(Ee + E_RMIN, (int)y); atomicMax(Ee + E_RMAX, (int)y);
+            atomicMin(Ee + E_CMIN, (int)xa); atomicMax(Ee + E_CMAX, (int)xb);
+            if (a.has_intensity) {
+                const uint2 st = ((const uint2 *)a.stats)[gi];
+                atomicAdd(Aa + A_V, (u64)st.x);
+                if (st.y & 0xffffu) atomicAdd(Aa + A_Z, (u64)(st.y & 0xffffu));
+                atomicMin(Ee + E_VMIN, (int)((st.y >> 16) & 0xffu)); atomicMax(Ee + E_VMAX, (int)(st.y >> 24));
+            }
+        } else {
+            const u64 *Aa = a.acc_stage + (i64)(base + lab - 1) * MAZE_NACC;
+            double *Hh = a.hi_stage + (i64)(base + lab - 1) * 8;
+            const double area = (double)Aa[A_N], cr = (double)Aa[A_R] / area, cc = (double)Aa[A_C] / area;
+            const double dn = (double)nn, m1 = (double)(nn - 1);
+            const double S1 = dn * m1 * 0.5, S2 = m1 * dn * (2.0 * m1 + 1.0) / 6.0, S3 = S1 * S1;
+            const double o = cc - (double)xa;
+            const double T1 = S1 - dn * o, T2 = S2 - 2.0 * o * S1 + dn * o * o;
+            const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+            const double dr = (double)y - cr, dr2 = dr * dr, dr3 = dr2 * dr;
+            atomicAdd(Hh + H_13, dr * T3); atomicAdd(Hh + H_22, dr2 * T2); atomicAdd(Hh + H_31, dr3 * T1);
+            atomicAdd(Hh + H_23, dr2 * T3); atomicAdd(Hh + H_32, dr3 * T2); atomicAdd(Hh + H_33, dr3 * T3);
+        }
+    }
+}
+
+// dense outputs of the frame: its runs on top of the zero fill (eight lanes per run, as in the labelling kernel)
+__global__ void __launch_bounds__(256) k_gl_write(GlArgs g)
+{
+    const LabelArgs &a = g.a;
+    const int n = g.misc[0];
+    if (!a.labels) return;
+    const int b0 = a.band_off[g.img], nb = a.band_off[g.img + 1] - b0;
+    const maze_vignette_t v = a.vig[g.img];
+    int32_t *gl = a.labels + v.pix_off;
+    uint8_t *gm = a.mask + v.pix_off;
+    const int W = v.w, lane = threadIdx.x & 31, oct = lane >> 3, ol = lane & 7;
+    const int nwarp = gridDim.x * 8;
+    for (int i0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4; i0 < n; i0 += nwarp * 4) {
+        const int i = i0 + oct;
+        if (i >= n) continue;
+        const int jb = gl_band_of(g.bpre, nb, i);
+        const uint2 r = ((const uint2 *)a.runs)[a.band_out[b0 + jb].base + (i - g.bpre[jb])];
+        const int len = (int)(r.y & 0xffffu) - (int)(r.x >> 16) + 1;
+        const i64 p = (i64)(r.x & 0xffffu) * W + (r.x >> 16);
+        const uint32_t lab = r.y >> 16;
+        int32_t *pl = gl + p;
+        uint8_t *pm = gm + p;
+        for (int x = 4 * ol - (int)(p & 31); x < len; x += 32) {
+            if (x >= 0 && x + 4 <= len) {
+                *(uint4 *)(pl + x) = make_uint4(lab, lab, lab, lab);
+                *(uint32_t *)(pm + x) = 0x01010101u;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (x + u >= 0 && x + u < len) { pl[x + u] = (int32_t)lab; pm[x + u] = 1; }
+            }
+        }
+    }
+}
+
+static int gl_label_frame(const LabelArgs &la, int img, int32_t *scratch, int run_cap, int nb, cudaStream_t s)
+{
+    GlArgs g;
+    g.a = la;
+    g.img = img;
+    g.parent = scratch;
+    g.lab = scratch + run_cap;
+    g.bpre = scratch + 2 * (size_t)run_cap;
+    g.misc = g.bpre + nb + 1;
+    const int grid = 148 * 4;
+    MAZE_KERNEL(KID_GL_PREFIX, s, k_gl_prefix<<<1, 1024, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_LINK, s, k_gl_init<<<grid, 256, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_LINK, s, k_gl_link<<<grid, 256, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_LINK, s, k_gl_flatten<<<grid, 256, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_RANK, s, k_gl_rank<<<1, 1024, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_APPLY, s, k_gl_zero_rows<<<grid, 256, 0, s>>>(g));
+    MAZE_KERNEL(KID_GL_APPLY, s, k_gl_apply<<<grid, 256, 0, s>>>(g, 0));
+    MAZE_KERNEL(KID_GL_APPLY, s, k_gl_apply<<<grid, 256, 0, s>>>(g, 1));
+    MAZE_KERNEL(KID_GL_APPLY, s, k_gl_write<<<grid, 256, 0, s>>>(g));
+    return MAZE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 static size_t label_smem(int cap, int hcap, int nbcap, int lcap)
@@ -942,7 +1206,8 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
                                int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list,
                                int stage_cap, unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage,
-                               long long total_px, void *stream)
+                               long long total_px, const int32_t *huge_host, int n_huge, long long huge_px,
+                               int32_t *gl_scratch, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_pass < 0 || n_pass > 4 || halo < 0) return MAZE_ERR_BADARG;
@@ -1033,7 +1298,8 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
                     (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter,
                     dense && !getenv("MAZE_K3") ? mask : nullptr, dense && !getenv("MAZE_K3") ? labels : nullptr, n_img, n_pass, prm.phantom_mask,
-                    prm.do_props, prm.high_order, prm.has_intensity, stage_cap};
+                    prm.do_props, prm.high_order, prm.has_intensity, stage_cap,
+                    (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62)};
     MAZE_KERNEL(KID_BAND_LABEL, s,
                 k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
                                                                     LABEL_MID_HCAP));
@@ -1042,6 +1308,14 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                 k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
     MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
                 k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
+    if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
+        if (!huge_host) return MAZE_ERR_BADARG;
+        for (int e = 0; e < n_huge; e++) {
+            // (the band count of the vignette sizes its prefix array; the host knows the band plan)
+            const int rc = gl_label_frame(la, huge_host[2 * e], gl_scratch, run_cap, huge_host[2 * e + 1], s);
+            if (rc != MAZE_OK) return rc;
+        }
+    }
     static const bool k3 = getenv("MAZE_K3") != nullptr; // experiments: runs stored by a kernel of their own
     if (dense && k3) {
         MAZE_KERNEL(KID_BAND_WRITE, s,

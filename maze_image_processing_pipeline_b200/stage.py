@@ -476,7 +476,7 @@ class LokiSegmentationStage:
         counts = ws.get("counts", 3 * n, torch.int32, dev)
         lab_off = ws.get("lab_off", n + 1, torch.int32, dev)
         n_labels, acc_base = counts[:n], counts[2 * n:]
-        cap = 16 * n + 1024
+        cap = _stage_cap(g)
         staging = (ws.get("acc", cap * NACC, torch.int64, dev), ws.get("hi", cap * 8, torch.float64, dev),
                    ws.get("ext", cap * NEXT, torch.int32, dev), ws.get("counter", 1, torch.int32, dev))
         table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
@@ -493,6 +493,12 @@ class LokiSegmentationStage:
             band_out = ws.get("band_out", 4 * max(n_bands, 1), torch.int32, dev)
             band_counters = ws.get("band_counters", 4, torch.int32, dev)
             big_list = ws.get("big_list", n, torch.int32, dev)
+            # frames (>= HUGE_PX pixels) are labelled by the global-memory kernels: {vignette, its number of bands}
+            from ._lib import HUGE_PX
+            nb_of = np.diff(band_off_h)
+            huge = np.nonzero((g.npx >= HUGE_PX) & (nb_of > 0))[0]
+            huge_pairs = np.ascontiguousarray(np.stack([huge, nb_of[huge]], axis=1).astype(np.int32)) if len(huge) else None
+            gl_scratch = ws.get("gl_scratch", 2 * run_cap + n_bands + 16, torch.int32, dev) if len(huge) else None
         else:
             d_list, class_off, left = batch.fused_lists()
         # rotating pinned readback slots (one more than lanes): a slot is reused only after its batch was finalised
@@ -520,6 +526,9 @@ class LokiSegmentationStage:
             a.runs, a.run_stats, a.run_pix = runs.data_ptr(), run_stats.data_ptr(), run_pix.data_ptr()
             a.band_out, a.band_counters, a.big_list = band_out.data_ptr(), band_counters.data_ptr(), big_list.data_ptr()
             a.run_cap, a.total_px = run_cap, g.total_px
+            if huge_pairs is not None:
+                a.huge_host, a.n_huge, a.huge_px = huge_pairs.ctypes.data, len(huge_pairs), HUGE_PX
+                a.gl_scratch = gl_scratch.data_ptr()
             a.step_flags = STEP_COMPACT if self.compact else 0
         else:
             a.img_list = d_list.data_ptr()
@@ -609,7 +618,7 @@ class LokiSegmentationStage:
         px = max(g.total_px for g in geometries)
         words = max(max(g.total_words, 1) for g in geometries)
         n = max(g.n_img for g in geometries)
-        cap = 16 * n + 1024
+        cap = max(_stage_cap(g) for g in geometries)
         for ws in self._ws_ring + [self._ws]:
             for key, size, dt in (("bits", words, torch.int32), ("mask", px, torch.uint8), ("labels", px, torch.int32),
                                   ("counts", 3 * n, torch.int32), ("lab_off", n + 1, torch.int32),
@@ -879,6 +888,14 @@ class LokiSegmentationStage:
                 for pre in ahead:  # never leave copy threads behind
                     if pre[3] is not None:
                         pre[3]()
+
+
+def _stage_cap(g):
+    """Rows of the staging arrays / object table of one batch: 16 objects per vignette on average plus, for frames
+    (BASELINE.json configs[3]: thousands of labels in one image), one per 1024 pixels."""
+    from ._lib import HUGE_PX
+    big = g.npx[g.npx >= HUGE_PX]
+    return 16 * g.n_img + 1024 + int((big // 1024).sum())
 
 
 def _rpb_of(bands, band_off, n_img):

@@ -472,6 +472,22 @@ def test_config4_dense_4096_frame_label_and_regionprops(mz):
     assert_tables_close(res.table, want_tab)
     lab2, n2 = mz.measure.label(frame > 40, return_num=True)
     assert n2 == n and np.array_equal(lab2, want_lab)
+    # the frame takes the band pipeline with the global-memory labelling kernels (no per-operator redo): in compact
+    # form it comes down as a run list
+    resc = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=True)([frame])
+    assert resc.compact and 0 not in resc._dense
+    assert np.array_equal(resc.labels(0), want_lab) and len(resc.table) == n
+    assert_tables_close(resc.table, want_tab)
+    # and with the default morphology on a smaller frame (still labelled in global memory: >= 2 MPix)
+    f2 = mz.synth.synth_dense_frame(12, size=2300, n_blobs=900)[:2200, :]
+    mask, labels, table = scipy_chain.loki_chain(f2, 40, 1, 2)
+    pp2 = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    for compact in (False, True):
+        r2 = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp2, compact=compact)([f2, frame[:70, :90]])
+        assert np.array_equal(r2.mask(0), mask) and np.array_equal(r2.labels(0), labels)
+        assert_tables_close(r2.features(0), table)
+        if compact:
+            assert 0 not in r2._dense
 
 
 def test_stream_objects_adapter_and_odd_geometries(mz):

@@ -43,3 +43,25 @@ print(json.dumps({"config": "configs[3]", "frame": "4096x4096", "labels": n, "ms
                   "ms_total": round(ms_t + ms_l + ms_p + ms_u, 4),
                   "mpix_per_s": round(px / (ms_t + ms_l + ms_p + ms_u) / 1e3, 1),
                   "label_GBps_5B_per_px": round(5 * px / ms_l / 1e6, 1)}))
+
+# configs[3] through the stage (band pipeline: band front, global-memory labelling of the frame, dense outputs)
+from maze_image_processing_pipeline_b200 import stage as S
+for name, pp in (("threshold+label+regionprops", S.SegmentationPostprocessingConfig()),
+                 ("threshold+opening1+closing2+label+regionprops", S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1))):
+    for compact in (False, True):
+        st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=compact)
+        db = st.prepare(DeviceBatch(g))
+        st.reserve([g])
+        for _ in range(st.n_lanes + 1):
+            st.run_device(db, d).n_obj
+        def run():
+            rs = [st.run_device(db, d) for _ in range(4)]
+            for r in rs:
+                r.n_obj
+            st.join()
+            return rs[-1]
+        ms, r = timed(run)
+        ms /= 4
+        print(json.dumps({"config": "configs[3]", "frame": "4096x4096", "path": "stage, band pipeline" + (" (compact)" if compact else ""),
+                          "chain": name, "labels": int(r.n_obj), "redone": bool(r.redone), "ms_per_frame": round(ms, 4),
+                          "mpix_per_s": round(px / ms / 1e3, 1), "stage_GBps_6B_per_px": round(6 * px / ms / 1e6, 1)}))
