@@ -795,8 +795,15 @@ template <int T>
 __global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap, int which)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
+    // the CTAs take the vignettes of the list one by one from a counter: a CTA that drew small ones simply takes more
+    __shared__ int s_next;
     const int n = *(volatile int32_t *)(a.big_counter + which);
-    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(a.big_counter + 2 + which, 1);
+        __syncthreads();
+        const int e = s_next;
+        __syncthreads();
+        if (e >= n) break;
         const int img = a.big_list[which ? a.n_img - 1 - e : e];
         if (label_vignette<T, FUSED_LCAP>(a, img, cap, hcap, which ? LABEL_BIG_NB : LABEL_MID_NB, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
         __syncthreads();
@@ -1236,7 +1243,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     }
     if (halo < sum_r) return MAZE_ERR_BADARG; // the halo must absorb every pass
     const bool dense = mask && labels;
-    MAZE_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), s), "band counters");
+    MAZE_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int32_t), s), "band counters");
     int32_t *stage_counter = counters, *run_counter = counters + 1, *big_counter = counters + 2;
     static thread_local int attr_dev = -1;
     int dev = 0;
