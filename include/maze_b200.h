@@ -289,6 +289,9 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * FRAMES: vignettes with at least huge_px pixels (huge_host: n_huge pairs {vignette index, number of its bands}) are
  * labelled by a sequence of global-memory kernels (union-find on run ids with atomics) instead of the per-vignette
  * CTA; gl_scratch: 2 * run_cap + n_bands + 16 int32.  n_huge = 0 or gl_scratch = NULL switches this off.
+ * band_done (n_img int32 scratch, cleared by the call; may be NULL): with it, the LAST band CTA of a vignette to finish
+ * labels the vignette in place inside the band kernel (run tables up to 4096 runs / 2048 rows / 64 bands, the rest goes to
+ * the list kernel); without it a labelling kernel of its own runs behind the band kernel.
  * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
  * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
 #define MAZE_BAND_PLANE_WORDS 6144
@@ -303,7 +306,8 @@ int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_v
                     maze_band_out_t *band_out, uint8_t *mask, int32_t *labels, int32_t *n_labels,
                     int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list, int stage_cap,
                     unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, long long total_px,
-                    const int32_t *huge_host, int n_huge, long long huge_px, int32_t *gl_scratch, void *stream);
+                    const int32_t *huge_host, int n_huge, long long huge_px, int32_t *gl_scratch, int32_t *band_done,
+                    void *stream);
 
 /* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
  * acc_base[i] >= 0 (the others are left to maze_regionprops). */
@@ -365,6 +369,7 @@ typedef struct maze_step_args {
     int32_t *big_list;      /* n_img int32 */
     const int32_t *huge_host; /* HOST: n_huge pairs {vignette, bands} of the frames (global-memory labelling) */
     int32_t *gl_scratch;      /* 2 * run_cap + n_bands + 16 int32 (or NULL) */
+    int32_t *band_done;       /* n_img int32 (or NULL) */
     int32_t class_off[MAZE_FUSED_CLASSES + 1];
     int32_t pass_t[4], pass_invert[4];
     int32_t n_img, left_n, left_n_tiles, left_n_tiles_full, t_int, n_pass, flags, stage_cap;

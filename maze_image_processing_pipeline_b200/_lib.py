@@ -41,7 +41,7 @@ class StepArgs(ctypes.Structure):
         "mask", "labels", "counts", "lab_off", "stage_counter", "acc_stage", "hi_stage", "ext_stage", "table",
         "scratch_plane", "scratch_flags", "scratch_parent", "scratch_tile_scan", "scratch_lab_off", "scratch_acc",
         "scratch_ext", "counts_host", "bands", "band_off", "runs", "run_pix", "run_stats", "band_out", "band_counters",
-        "big_list", "huge_host", "gl_scratch")]
+        "big_list", "huge_host", "gl_scratch", "band_done")]
         + [("class_off", ctypes.c_int32 * (len(FUSED_CAPS) + 1)), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
         + [(k, ctypes.c_int32) for k in ("n_img", "left_n", "left_n_tiles", "left_n_tiles_full", "t_int", "n_pass",
                                          "flags", "stage_cap", "n_bands", "halo", "run_cap", "step_flags")]
@@ -99,7 +99,7 @@ SIGNATURES = {
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
     "maze_band_stage": [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp],
     "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
     "maze_host_pack_wait": [_vp],

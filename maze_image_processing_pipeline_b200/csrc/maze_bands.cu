@@ -52,6 +52,38 @@ struct BandParams {
     FusedPass pass[4];
 };
 
+struct LabelArgs {
+    const maze_vignette_t *vig;
+    const int32_t *band_off;
+    const maze_band_out_t *band_out;
+    maze_run_t *runs;
+    const maze_run_stat_t *stats;
+    int32_t *n_labels, *fallback, *acc_base, *stage_counter;
+    u64 *acc_stage;
+    double *hi_stage;
+    int32_t *ext_stage;
+    int32_t *big_list, *big_counter;
+    uint8_t *mask; // dense outputs (or NULL): the labelling kernel stores the runs on top of the zero fill
+    int32_t *labels;
+    int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
+    long long huge_px; // vignettes with at least this many pixels are labelled by the global-memory kernels
+};
+
+__device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
+{
+    a.fallback[img] = 1;
+    a.n_labels[img] = 0;
+    a.acc_base[img] = -1;
+}
+
+template <int T, int LCAP>
+__device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, int nbcap, uint32_t *s_mem);
+
+// run table of the labelling that the LAST band CTA of a vignette runs in place (it reuses the CTA's planes)
+#define LABEL_INBAND_CAP 4096
+#define LABEL_INBAND_HCAP 2050
+#define LABEL_INBAND_NB 64
+
 // ---------------------------------------------------------------------------------------------------------
 // K1: band front
 // ---------------------------------------------------------------------------------------------------------
@@ -61,7 +93,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     const maze_band_t *__restrict__ bands, BandParams prm, uint32_t *__restrict__ bits_out,
     maze_run_t *__restrict__ runs, uint32_t *__restrict__ run_pix, maze_run_stat_t *__restrict__ stats,
     int32_t *run_counter, int run_cap, maze_band_out_t *__restrict__ band_out, uint8_t *__restrict__ zmask,
-    int32_t *__restrict__ zlabels)
+    int32_t *__restrict__ zlabels, LabelArgs la, int32_t *band_done)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ int s_warp[34];
@@ -244,14 +276,8 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     }
     int n_runs;
     int run = block_exclusive_scan<T>(cnt, s_warp, &n_runs);
-    if (n_runs > RC) { // more runs than slots (noise): the vignette falls back to the per-operator kernels
-        if (tid == 0) {
-            band_out[blockIdx.x] = maze_band_out_t{-1, n_runs, zflags, 0};
-            if (zfill) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
-        return;
-    }
-    if (lo < hi) {
+    const bool fits = n_runs <= RC; // else: more runs than slots (noise), the vignette falls back to the per-operator kernels
+    if (fits && lo < hi) {
         int y = lo / wpr, k = lo - y * wpr;
         int rs = run, re = run - open; // ends before this chunk = starts before it - runs still open
         uint32_t prev = k > 0 ? Mo[lo - 1] : 0u, m = Mo[lo];
@@ -276,17 +302,17 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
         }
     }
     if (tid == 0) {
-        int base = n_runs ? atomicAdd(run_counter, n_runs) : 0;
-        if (base + n_runs > run_cap) base = -1; // run buffer full (the counter still tells the host how many were needed)
+        int base = -1;
+        if (fits) {
+            base = n_runs ? atomicAdd(run_counter, n_runs) : 0;
+            if (base + n_runs > run_cap) base = -1; // run buffer full (the counter still tells the host how many were needed)
+        }
         s_base = base;
         band_out[blockIdx.x] = maze_band_out_t{base, n_runs, zflags, 0};
     }
     __syncthreads();
     const int base = s_base;
-    if (base < 0) {
-        if (zfill && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        return;
-    }
+    if (base >= 0)
     for (int i = tid; i < n_runs; i += T) {
         uint2 r;
         r.x = (uint32_t)rY[i] | ((uint32_t)rX0[i] << 16);
@@ -296,7 +322,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
     }
     // ---- 4. intensity statistics per run: four lanes per run (aligned words round robin, two loads in flight per
     // lane, byte-SIMD), reduced across the quad; the bytes were read by this CTA a moment ago, so the loads hit L2 --
-    if (intensity) {
+    if (intensity && base >= 0) {
         const uint8_t *gi = intensity + v.pix_off;
         const int q = tid & 3;
         for (int i0 = 0; i0 < n_runs; i0 += T / 4) {
@@ -345,36 +371,33 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
             }
         }
     }
-    if (zfill && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the fill has left the SM
+    if (zfill && tid == 0) { // the fill is complete; order it (async proxy) before the generic stores that follow it
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    // ---- 5. the LAST band of a vignette to get here labels it in place (run-list labelling, accumulators, dense runs;
+    // see label_vignette): the latency-bound work on the run list runs inside this memory-bound kernel instead of
+    // behind it.  Runs, statistics and the zero fill of every band are complete and visible before its ticket.
+    if (band_done) {
+        __shared__ int s_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const int nb_v = la.band_off[bd.img + 1] - la.band_off[bd.img];
+            s_last = atomicAdd(band_done + bd.img, 1) == nb_v - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (label_vignette<T, FUSED_LCAP>(la, bd.img, LABEL_INBAND_CAP, LABEL_INBAND_HCAP, LABEL_INBAND_NB, s_mem) == 1 && tid == 0)
+                la.big_list[atomicAdd(la.big_counter, 1)] = bd.img; // larger than the in-place table: the list kernel takes it
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // K2: per-vignette labelling + accumulators on the run list
 // ---------------------------------------------------------------------------------------------------------
-struct LabelArgs {
-    const maze_vignette_t *vig;
-    const int32_t *band_off;
-    const maze_band_out_t *band_out;
-    maze_run_t *runs;
-    const maze_run_stat_t *stats;
-    int32_t *n_labels, *fallback, *acc_base, *stage_counter;
-    u64 *acc_stage;
-    double *hi_stage;
-    int32_t *ext_stage;
-    int32_t *big_list, *big_counter;
-    uint8_t *mask; // dense outputs (or NULL): the labelling kernel stores the runs on top of the zero fill
-    int32_t *labels;
-    int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
-    long long huge_px; // vignettes with at least this many pixels are labelled by the global-memory kernels
-};
-
-__device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
-{
-    a.fallback[img] = 1;
-    a.n_labels[img] = 0;
-    a.acc_base[img] = -1;
-}
-
 // returns 0 = done (labelled, flagged as fallback, or not a band vignette), 1 = needs a larger run table
 template <int T, int LCAP>
 __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, int nbcap, uint32_t *s_mem)
@@ -397,7 +420,8 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
     {
         int bad = 0, zor = 0;
         for (int j = tid; j < nb; j += T) {
-            const maze_band_out_t o = a.band_out[b0 + j];
+            const int4 oq = __ldcg((const int4 *)(a.band_out + b0 + j)); // (written by other CTAs of this launch: not through L1)
+            const maze_band_out_t o = {oq.x, oq.y, oq.z, oq.w};
             s_bbase[j] = o.base; s_bpre[j + 1] = o.n_runs;
             bad |= (o.base < 0) ? 1 : 0; zor |= o.zflags;
         }
@@ -447,7 +471,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
     u16 *rY = (u16 *)(s_bpre + nbcap + 1), *rX0 = rY + cap, *rX1 = rX0 + cap, *P = rX1 + cap, *rO = P + cap, *rowStart = rO + cap;
     AccRow *ACC = (AccRow *)(((uintptr_t)(rowStart + hcap) + 15) & ~(uintptr_t)15);
     for (int i = tid; i < n_runs; i += T) {
-        const uint2 r = ((const uint2 *)a.runs)[gidx(i)];
+        const uint2 r = __ldcg((const uint2 *)a.runs + gidx(i));
         rY[i] = (u16)(r.x & 0xffffu); rX0[i] = (u16)(r.x >> 16); rX1[i] = (u16)(r.y & 0xffffu);
         P[i] = (u16)i;
     }
@@ -568,7 +592,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
                 lab = label_of(P, i);
                 ((u16 *)(a.runs + g))[3] = (u16)lab;
                 if (with_i) {
-                    const uint2 st = ((const uint2 *)a.stats)[g];
+                    const uint2 st = __ldcg((const uint2 *)a.stats + g);
                     isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
                 }
             }
@@ -1214,7 +1238,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list,
                                int stage_cap, unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage,
                                long long total_px, const int32_t *huge_host, int n_huge, long long huge_px,
-                               int32_t *gl_scratch, void *stream)
+                               int32_t *gl_scratch, int32_t *band_done, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_pass < 0 || n_pass > 4 || halo < 0) return MAZE_ERR_BADARG;
@@ -1279,6 +1303,11 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     BandFork *fk = nullptr;
     if (dense && (total_px <= 0 || (total_px & 15) || total_px >= (1ll << 32) || !run_pix)) return MAZE_ERR_BADARG;
     const bool zin = dense && zero_mode() == 2; // zero fill inside the band front
+    // experiment (MAZE_K2_FUSED=1): labelling inside the band front, by the last band CTA of every vignette.  Correct
+    // (all parity tests), but the band kernel then takes 0.86 ms instead of 0.57 + 0.30 ms for the two kernels: the
+    // labelling holds a CTA slot and the issue slots the band front needs, nothing is hidden.  Off by default.
+    static const bool inband_env = getenv("MAZE_K2_FUSED") && getenv("MAZE_K2_FUSED")[0] == '1';
+    const bool inband = inband_env && band_done && (!dense || zin);
     if (dense && !zin) { // experiments: zero fill by a kernel of its own next to the band front
         fk = band_fork();
         if (!fk) return MAZE_ERR_CUDA;
@@ -1296,25 +1325,32 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
         }
         MAZE_CUDA(cudaEventRecord(fk->join, fk->aux), "band join");
     }
+    static const bool k3 = getenv("MAZE_K3") != nullptr; // experiments: runs stored by a kernel of their own
+    LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
+                    (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, dense && !k3 ? mask : nullptr,
+                    dense && !k3 ? labels : nullptr, n_img, n_pass, prm.phantom_mask, prm.do_props, prm.high_order,
+                    prm.has_intensity, stage_cap, (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62)};
+    if (inband) MAZE_CUDA(cudaMemsetAsync(band_done, 0, sizeof(int32_t) * (size_t)n_img, s), "band done");
     MAZE_KERNEL(KID_BAND_FRONT, s,
                 k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, runs,
                                                                    dense ? run_pix : nullptr, run_stats, run_counter,
                                                                    run_cap, band_out, zin ? mask : nullptr,
-                                                                   zin ? labels : nullptr));
+                                                                   zin ? labels : nullptr, la, inband ? band_done : nullptr));
     if (dense && fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
-    LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
-                    (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter,
-                    dense && !getenv("MAZE_K3") ? mask : nullptr, dense && !getenv("MAZE_K3") ? labels : nullptr, n_img, n_pass, prm.phantom_mask,
-                    prm.do_props, prm.high_order, prm.has_intensity, stage_cap,
-                    (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62)};
-    MAZE_KERNEL(KID_BAND_LABEL, s,
-                k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
-                                                                    LABEL_MID_HCAP));
-    const int grid_mid = n_img < 148 * 7 ? n_img : 148 * 7, grid_big = n_img < 74 ? n_img : 74;
-    MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
-    MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
+    if (inband) { // what the in-place labelling passed on (more than 4096 runs, 2048 rows or 64 bands)
+        const int grid_big = n_img < 148 ? n_img : 148;
+        MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                    k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 0));
+    } else {
+        MAZE_KERNEL(KID_BAND_LABEL, s,
+                    k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
+                                                                        LABEL_MID_HCAP));
+        const int grid_mid = n_img < 148 * 7 ? n_img : 148 * 7, grid_big = n_img < 74 ? n_img : 74;
+        MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                    k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
+        MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                    k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
+    }
     if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
         if (!huge_host) return MAZE_ERR_BADARG;
         for (int e = 0; e < n_huge; e++) {
@@ -1323,7 +1359,6 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
             if (rc != MAZE_OK) return rc;
         }
     }
-    static const bool k3 = getenv("MAZE_K3") != nullptr; // experiments: runs stored by a kernel of their own
     if (dense && k3) {
         MAZE_KERNEL(KID_BAND_WRITE, s,
                     k_band_write<BAND_T><<<148 * 8, BAND_T, 0, s>>>(runs, run_pix, run_counter, run_cap, mask, labels));

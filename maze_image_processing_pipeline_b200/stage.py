@@ -493,6 +493,7 @@ class LokiSegmentationStage:
             band_out = ws.get("band_out", 4 * max(n_bands, 1), torch.int32, dev)
             band_counters = ws.get("band_counters", 8, torch.int32, dev)
             big_list = ws.get("big_list", n, torch.int32, dev)
+            band_done = ws.get("band_done", n, torch.int32, dev)
             # frames (>= HUGE_PX pixels) are labelled by the global-memory kernels: {vignette, its number of bands}
             from ._lib import HUGE_PX
             nb_of = np.diff(band_off_h)
@@ -526,6 +527,7 @@ class LokiSegmentationStage:
             a.runs, a.run_stats, a.run_pix = runs.data_ptr(), run_stats.data_ptr(), run_pix.data_ptr()
             a.band_out, a.band_counters, a.big_list = band_out.data_ptr(), band_counters.data_ptr(), big_list.data_ptr()
             a.run_cap, a.total_px = run_cap, g.total_px
+            a.band_done = band_done.data_ptr()
             if huge_pairs is not None:
                 a.huge_host, a.n_huge, a.huge_px = huge_pairs.ctypes.data, len(huge_pairs), HUGE_PX
                 a.gl_scratch = gl_scratch.data_ptr()
@@ -627,7 +629,7 @@ class LokiSegmentationStage:
                                   ("table", cap * NFEAT, torch.float64), ("runs", max(words // 3, 1 << 16), torch.int64),
                                   ("run_stats", max(words // 3, 1 << 16), torch.int64), ("run_pix", max(words // 3, 1 << 16), torch.int32),
                                   ("band_out", 4 * max(2 * n, words // 1024 + n), torch.int32),
-                                  ("band_counters", 8, torch.int32), ("big_list", n, torch.int32)):
+                                  ("band_counters", 8, torch.int32), ("big_list", n, torch.int32), ("band_done", n, torch.int32)):
                 ws.get(key, size, dt, dev)
             if getattr(ws, "arena", None) is None or ws.arena.device != dev:
                 ws.arena = Arena(dev)
