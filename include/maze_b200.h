@@ -238,6 +238,18 @@ int maze_merge_labels(const int32_t *labels, int32_t *labels_out, const maze_vig
                       double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status,
                       const int32_t *order, void *stream);
 
+/* The same for a SUBSET of the vignettes and with a choice of how many CTAs work on one vignette: the call handles
+ * the n_order vignettes order[0 .. n_order) (order = NULL: all n_img) with cluster_size CTAs each -- 1, or 8: a
+ * thread-block cluster (cluster barrier between the steps, reductions through distributed shared memory) that gives a
+ * large vignette eight times the memory parallelism of one CTA.  Vignettes that are not listed are not touched
+ * (n_merge / status / index_state keep what the caller put there). */
+int maze_merge_labels_ex(const int32_t *labels, int32_t *labels_out, const maze_vignette_t *vig, int n_img,
+                         const int32_t *lab_off, int n_obj_cap, const int32_t *index, const int32_t *index_off,
+                         int have_max, double max_distance, double path_tolerance,
+                         int32_t *d2a, int32_t *d2b, int32_t *d2c, int32_t *obj_scratch,
+                         double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status,
+                         const int32_t *order, int n_order, int cluster_size, void *stream);
+
 /* Synthetic LOKI-shaped vignettes for the benchmark: dark noisy background plus
  * 1-6 anisotropic Gaussian blobs per vignette, counter-based RNG keyed by (seed, vignette, pixel). */
 int maze_synth_vignettes(uint8_t *image, const maze_vignette_t *vig, int n_img,

@@ -93,6 +93,8 @@ SIGNATURES = {
     "maze_regionprops": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "maze_merge_labels": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                           _vp],
+    "maze_merge_labels_ex": [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _i, _i, _vp],
     "maze_synth_vignettes": [_vp, _vp, _i, _vp, _i, _u64, _i64, _vp],
     "maze_vignette_stage": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
                             _vp, _vp, _vp, _vp],

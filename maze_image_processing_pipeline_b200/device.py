@@ -523,9 +523,12 @@ class DeviceBatch:
         return table
 
     def merge_labels(self, labels, labels_out, lab_off, n_obj: int, max_distance, path_tolerance=5.0,
-                     index=None, index_off=None):
+                     index=None, index_off=None, live=None):
         """merge_labels.py:29-113 for every vignette.  Returns (merge_dist, n_merge, index_state, status,
-        obj_scratch) device tensors."""
+        obj_scratch) device tensors.  live: optional host array with (an upper bound of) the number of labels of
+        every vignette -- vignettes with fewer than two are not touched (the reference returns at :59-60).  When only
+        a few vignettes are large (MAZE_MERGE_CLUSTER_PX pixels and up) each of them gets a thread-block cluster of
+        eight CTAs."""
         g = self.g
         n_obj = max(int(n_obj), 1)
         d2a, d2b, d2c = (self.empty_px(torch.int32) for _ in range(3))
@@ -535,14 +538,28 @@ class DeviceBatch:
         index_state = torch.zeros(2 * g.n_img, dtype=torch.int32, device=self.device)
         status = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
         have_max = max_distance is not None
-        if not hasattr(self, "_merge_order"):  # largest vignettes first
-            self._merge_order = torch.from_numpy(np.argsort(-g.npx, kind="stable").astype(np.int32)).to(self.device)
-        check(lib().maze_merge_labels(labels.data_ptr(), labels_out.data_ptr(), self.d_vig.data_ptr(), g.n_img,
-                                      lab_off.data_ptr(), n_obj, _ptr(index), _ptr(index_off), int(have_max),
-                                      float(max_distance) if have_max else 0.0, float(path_tolerance),
-                                      d2a.data_ptr(), d2b.data_ptr(), d2c.data_ptr(), obj_scratch.data_ptr(),
-                                      merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
-                                      status.data_ptr(), self._merge_order.data_ptr(), _stream()), "maze_merge_labels")
+        todo = np.arange(g.n_img)
+        if live is not None and index is None:
+            todo = todo[np.asarray(live)[:g.n_img] >= 2]
+        # a cluster of eight CTAs finishes ONE large vignette several times sooner, but a full batch keeps every SM busy
+        # with one CTA per vignette anyway (measured: 33.6 ms per 4096-vignette batch either way): clusters only when
+        # the large vignettes are few (frames, small batches)
+        cluster_px = int(os.environ.get("MAZE_MERGE_CLUSTER_PX", str(1 << 16)))
+        big = g.npx[todo] >= cluster_px
+        if big.sum() > int(os.environ.get("MAZE_MERGE_CLUSTER_MAX", "64")):
+            big[:] = False
+        for sel, cs in ((todo[~big], 1), (todo[big], 8)):
+            if len(sel) == 0:
+                continue
+            sel = sel[np.argsort(-g.npx[sel], kind="stable")]  # largest vignettes first: they decide the makespan
+            order = torch.from_numpy(sel.astype(np.int32)).to(self.device)
+            check(lib().maze_merge_labels_ex(labels.data_ptr(), labels_out.data_ptr(), self.d_vig.data_ptr(), g.n_img,
+                                             lab_off.data_ptr(), n_obj, _ptr(index), _ptr(index_off), int(have_max),
+                                             float(max_distance) if have_max else 0.0, float(path_tolerance),
+                                             d2a.data_ptr(), d2b.data_ptr(), d2c.data_ptr(), obj_scratch.data_ptr(),
+                                             merge_dist.data_ptr(), n_merge.data_ptr(), index_state.data_ptr(),
+                                             status.data_ptr(), order.data_ptr(), len(sel), cs, _stream()),
+                  "maze_merge_labels_ex")
         return merge_dist, n_merge, index_state, status, obj_scratch
 
     def front_chain(self, d_src, t_int, passes, labels, mask):

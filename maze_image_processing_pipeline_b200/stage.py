@@ -389,6 +389,7 @@ class LokiSegmentationStage:
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
         if passes is not None and not filters:
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
+        live_counts = None
         if passes is None:
             bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
             n_obj = int(lab_off[-1].item())  # one 4-byte readback sizes the object table
@@ -415,6 +416,7 @@ class LokiSegmentationStage:
                 self._redo_generic(batch, redo, d_src, t_int, bits, mask, labels, n_labels)
                 h_counts = counts.cpu().numpy()
             lab_off, n_obj = batch.lab_off_from_bounds(h_counts[:n])
+            live_counts = h_counts[:n]
         merge_status = None
         if n_obj > 0 and filters:
             if pp.clear_border:
@@ -422,7 +424,8 @@ class LokiSegmentationStage:
             if pp.min_area > 0:
                 batch.remove_small_objects(labels, lab_off, n_obj, pp.min_area)
             if pp.merge_segments_distance > 0:
-                merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance)[3]
+                merge_status = batch.merge_labels(labels, labels, lab_off, n_obj, pp.merge_segments_distance,
+                                                  live=live_counts)[3]
         # merge_labels paints bridges over background, so only then do labels leave the runs of `bits`
         runs = merge_status is None
         table = batch.regionprops(lab_off, n_obj, labels=labels, bits=bits if runs else None, image=d_image,
