@@ -296,7 +296,7 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * filled on a forked stream next to the band kernel, the runs are stored on top; needs run_pix, one uint32 per
  * run slot, and total_px < 2^32).
  * counters: 8 int32 (cleared by the call): [0] staging rows used, [1] runs used (may exceed run_cap: the bands
- * that did not fit are flagged), [2] / [3] vignettes that needed the middle / large run table.  big_list: n_img
+ * that did not fit are flagged), [2..4] vignettes that needed the larger run tables.  big_list: 3 * n_img
  * int32 scratch.
  * FRAMES: vignettes with at least huge_px pixels (huge_host: n_huge pairs {vignette index, number of its bands}) are
  * labelled by a sequence of global-memory kernels (union-find on run ids with atomics) instead of the per-vignette
@@ -378,7 +378,7 @@ typedef struct maze_step_args {
     maze_run_stat_t *run_stats;
     maze_band_out_t *band_out;
     int32_t *band_counters; /* 8 int32 */
-    int32_t *big_list;      /* n_img int32 */
+    int32_t *big_list;      /* 3 * n_img int32 */
     const int32_t *huge_host; /* HOST: n_huge pairs {vignette, bands} of the frames (global-memory labelling) */
     int32_t *gl_scratch;      /* 2 * run_cap + n_bands + 16 int32 (or NULL) */
     int32_t *band_done;       /* n_img int32 (or NULL) */

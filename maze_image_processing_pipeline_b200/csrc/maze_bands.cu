@@ -34,7 +34,7 @@ constexpr int PW = MAZE_BAND_PLANE_WORDS;
 #define BAND_T 256
 #define BAND_ZB 6144 /* bytes of zeros in shared memory behind the planes (source of the TMA zero fill) */
 #define LABEL_T 64
-#define LABEL_MID_T 256
+#define LABEL_MID_T 256 /* (128 threads / 1024 runs / 13 CTAs per SM was measured: 0.35 ms instead of 0.21 ms) */
 #define LABEL_BIG_T 256
 #define LABEL_SMALL_CAP 256
 #define LABEL_SMALL_HCAP 1026
@@ -43,6 +43,9 @@ constexpr int PW = MAZE_BAND_PLANE_WORDS;
 #define LABEL_MID_CAP 2048
 #define LABEL_MID_HCAP 2050
 #define LABEL_MID_NB 128
+#define LABEL_LARGE_CAP 4096
+#define LABEL_LARGE_HCAP 4098
+#define LABEL_LARGE_NB 256
 #define LABEL_BIG_CAP 16384
 #define LABEL_BIG_HCAP 16386
 #define LABEL_BIG_NB 2048
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(T, 1024 / T) k_band_front(
         if (s_last) {
             __threadfence();
             if (label_vignette<T, FUSED_LCAP>(la, bd.img, LABEL_INBAND_CAP, LABEL_INBAND_HCAP, LABEL_INBAND_NB, s_mem) == 1 && tid == 0)
-                la.big_list[atomicAdd(la.big_counter, 1)] = bd.img; // larger than the in-place table: the list kernel takes it
+                la.big_list[2 * la.n_img + atomicAdd(la.big_counter + 2, 1)] = bd.img; // larger than the in-place table: the list kernel takes it
         }
     }
 }
@@ -621,9 +624,9 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
             }
         }
     }
-    // ---- dense outputs: the runs of the vignette on top of the zero fill of K1.  Eight lanes per run, four elements
-    // per lane (16-byte label store, 4-byte mask store), steps aligned to 32 elements so that every step but the
-    // first and the last of a run covers a whole 128-byte line of the label image and a whole sector of the mask ---
+    // ---- dense outputs: the runs of the vignette on top of the zero fill of K1.  Eight lanes per run: the up to three
+    // elements in front of the first 16-byte boundary of the label row (lanes 0-2) and behind the last one (lanes
+    // 4-6) are stored one by one, the body with one 16-byte label store and one 4-byte mask store per lane and step ---
     if (a.labels) {
         int32_t *gl = a.labels + v.pix_off;
         uint8_t *gm = a.mask + v.pix_off;
@@ -636,15 +639,13 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
                 const uint32_t lab = (uint32_t)label_of(P, i);
                 int32_t *pl = gl + p;
                 uint8_t *pm = gm + p;
-                for (int x = 4 * ol - (p & 31); x < len; x += 32) {
-                    if (x >= 0 && x + 4 <= len) {
-                        *(uint4 *)(pl + x) = make_uint4(lab, lab, lab, lab);
-                        *(uint32_t *)(pm + x) = 0x01010101u;
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (x + u >= 0 && x + u < len) { pl[x + u] = (int32_t)lab; pm[x + u] = 1; }
-                    }
+                const int head = min((-p) & 3, len), body = (len - head) & ~3, tail = len - head - body;
+                if (ol < head) { pl[ol] = (int32_t)lab; pm[ol] = 1; }
+                if (ol >= 4 && ol - 4 < tail) { pl[head + body + ol - 4] = (int32_t)lab; pm[head + body + ol - 4] = 1; }
+                const uint4 l4 = make_uint4(lab, lab, lab, lab);
+                for (int x = head + 4 * ol; x < head + body; x += 32) {
+                    *(uint4 *)(pl + x) = l4;
+                    *(uint32_t *)(pm + x) = 0x01010101u;
                 }
             }
         }
@@ -799,37 +800,39 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
     return 0;
 }
 
-// small class: one CTA per vignette; a vignette with more runs (or rows) than the class holds goes on the list of
-// the next class (big_list is filled from the front for the middle class, from the back for the large one)
+// small class: one CTA per vignette; a vignette with more runs (rows, bands) than the class holds goes on the list of
+// the smallest class that holds it (list k = big_list[k * n_img ..], its length in big_counter[k], the counter its
+// CTAs draw from in big_counter[3 + k])
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap, int mid_cap, int mid_hcap)
+__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const int img = blockIdx.x;
     if (label_vignette<T, LABEL_SMALL_LCAP>(a, img, cap, hcap, LABEL_SMALL_NB, s_mem) == 1 && threadIdx.x == 0) {
         int tot = 0;
+        const int nb = a.band_off[img + 1] - a.band_off[img], h2 = a.vig[img].h + 2;
         for (int b = a.band_off[img]; b < a.band_off[img + 1]; b++) tot += a.band_out[b].n_runs;
-        if (tot <= mid_cap && a.vig[img].h + 2 <= mid_hcap && a.band_off[img + 1] - a.band_off[img] <= LABEL_MID_NB) a.big_list[atomicAdd(a.big_counter, 1)] = img;
-        else a.big_list[a.n_img - 1 - atomicAdd(a.big_counter + 1, 1)] = img;
+        const int k = (tot <= LABEL_MID_CAP && h2 <= LABEL_MID_HCAP && nb <= LABEL_MID_NB) ? 0
+                      : (tot <= LABEL_LARGE_CAP && h2 <= LABEL_LARGE_HCAP && nb <= LABEL_LARGE_NB) ? 1 : 2;
+        a.big_list[k * a.n_img + atomicAdd(a.big_counter + k, 1)] = img;
     }
 }
 
-// middle (which = 0) and large (which = 1) class: a fixed grid walks its list
+// the list classes: a fixed grid, the CTAs take the vignettes of their list one by one from a counter
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap, int which)
+__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap, int nbcap, int which)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
-    // the CTAs take the vignettes of the list one by one from a counter: a CTA that drew small ones simply takes more
     __shared__ int s_next;
     const int n = *(volatile int32_t *)(a.big_counter + which);
     for (;;) {
-        if (threadIdx.x == 0) s_next = atomicAdd(a.big_counter + 2 + which, 1);
+        if (threadIdx.x == 0) s_next = atomicAdd(a.big_counter + 3 + which, 1);
         __syncthreads();
         const int e = s_next;
         __syncthreads();
         if (e >= n) break;
-        const int img = a.big_list[which ? a.n_img - 1 - e : e];
-        if (label_vignette<T, FUSED_LCAP>(a, img, cap, hcap, which ? LABEL_BIG_NB : LABEL_MID_NB, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
+        const int img = a.big_list[which * a.n_img + e];
+        if (label_vignette<T, FUSED_LCAP>(a, img, cap, hcap, nbcap, s_mem) == 1 && threadIdx.x == 0) mark_fallback(a, img);
         __syncthreads();
     }
 }
@@ -1275,6 +1278,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     static const size_t smem_pad = getenv("MAZE_K1_PAD") ? (size_t)atoi(getenv("MAZE_K1_PAD")) : 0; // experiments
     const size_t smem1 = (size_t)PW * 8 + BAND_ZB + smem_pad, smem_s = label_smem(LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_SMALL_NB, LABEL_SMALL_LCAP),
                  smem_m = label_smem(LABEL_MID_CAP, LABEL_MID_HCAP, LABEL_MID_NB, FUSED_LCAP),
+                 smem_l = label_smem(LABEL_LARGE_CAP, LABEL_LARGE_HCAP, LABEL_LARGE_NB, FUSED_LCAP),
                  smem_b = label_smem(LABEL_BIG_CAP, LABEL_BIG_HCAP, LABEL_BIG_NB, FUSED_LCAP);
     if (attr_dev != dev) {
         MAZE_CUDA(cudaFuncSetAttribute(k_band_front<BAND_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "band smem");
@@ -1337,19 +1341,24 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                                                    run_cap, band_out, zin ? mask : nullptr,
                                                                    zin ? labels : nullptr, la, inband ? band_done : nullptr));
     if (dense && fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
+    const int grid_xl = n_img < 74 ? n_img : 74;
     if (inband) { // what the in-place labelling passed on (more than 4096 runs, 2048 rows or 64 bands)
-        const int grid_big = n_img < 148 ? n_img : 148;
         MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                    k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 0));
+                    k_band_label_big<LABEL_BIG_T><<<grid_xl, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP,
+                                                                                     LABEL_BIG_NB, 2));
     } else {
         MAZE_KERNEL(KID_BAND_LABEL, s,
-                    k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP, LABEL_MID_CAP,
-                                                                        LABEL_MID_HCAP));
-        const int grid_mid = n_img < 148 * 7 ? n_img : 148 * 7, grid_big = n_img < 74 ? n_img : 74;
+                    k_band_label<LABEL_T><<<n_img, LABEL_T, smem_s, s>>>(la, LABEL_SMALL_CAP, LABEL_SMALL_HCAP));
+        const int grid_mid = n_img < 148 * 7 ? n_img : 148 * 7, grid_large = n_img < 148 * 4 ? n_img : 148 * 4;
         MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                    k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP, 0));
+                    k_band_label_big<LABEL_MID_T><<<grid_mid, LABEL_MID_T, smem_m, s>>>(la, LABEL_MID_CAP, LABEL_MID_HCAP,
+                                                                                      LABEL_MID_NB, 0));
         MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
-                    k_band_label_big<LABEL_BIG_T><<<grid_big, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP, 1));
+                    k_band_label_big<LABEL_BIG_T><<<grid_large, LABEL_BIG_T, smem_l, s>>>(la, LABEL_LARGE_CAP, LABEL_LARGE_HCAP,
+                                                                                        LABEL_LARGE_NB, 1));
+        MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
+                    k_band_label_big<LABEL_BIG_T><<<grid_xl, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP,
+                                                                                     LABEL_BIG_NB, 2));
     }
     if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
         if (!huge_host) return MAZE_ERR_BADARG;

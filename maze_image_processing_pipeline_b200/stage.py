@@ -495,7 +495,7 @@ class LokiSegmentationStage:
             run_pix = ws.get("run_pix", run_cap, torch.int32, dev)
             band_out = ws.get("band_out", 4 * max(n_bands, 1), torch.int32, dev)
             band_counters = ws.get("band_counters", 8, torch.int32, dev)
-            big_list = ws.get("big_list", n, torch.int32, dev)
+            big_list = ws.get("big_list", 3 * n, torch.int32, dev)
             band_done = ws.get("band_done", n, torch.int32, dev)
             # frames (>= HUGE_PX pixels) are labelled by the global-memory kernels: {vignette, its number of bands}
             from ._lib import HUGE_PX
@@ -632,7 +632,7 @@ class LokiSegmentationStage:
                                   ("table", cap * NFEAT, torch.float64), ("runs", max(words // 3, 1 << 16), torch.int64),
                                   ("run_stats", max(words // 3, 1 << 16), torch.int64), ("run_pix", max(words // 3, 1 << 16), torch.int32),
                                   ("band_out", 4 * max(2 * n, words // 1024 + n), torch.int32),
-                                  ("band_counters", 8, torch.int32), ("big_list", n, torch.int32), ("band_done", n, torch.int32)):
+                                  ("band_counters", 8, torch.int32), ("big_list", 3 * n, torch.int32), ("band_done", n, torch.int32)):
                 ws.get(key, size, dt, dev)
             if getattr(ws, "arena", None) is None or ws.arena.device != dev:
                 ws.arena = Arena(dev)

@@ -1,35 +1,26 @@
-import sys, os, time
+"""How many vignettes of the WHOLE configs[1] job (100k vignettes, 25 batches of 4096) leave the band pipeline for
+the per-operator kernels (oversize for a band, run tables full, phantom pixel, staging rows exhausted), and how many
+runs / objects a batch holds against the capacities of its buffers."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from maze_image_processing_pipeline_b200 import stage as S
 from maze_image_processing_pipeline_b200.device import BatchGeometry, DeviceBatch
 hs, ws = bench.job_sizes()
-B = 2048
+B = 4096
 pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
-st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
-batches = []
-for b in range(8):
-    g = BatchGeometry(hs[b * B:(b + 1) * B], ws[b * B:(b + 1) * B])
+st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=bool(int(os.environ.get("COMPACT", "0"))))
+tot_dense = tot_redo = 0
+for b in range((bench.JOB_VIGNETTES + B - 1) // B):
+    lo, hi = b * B, min((b + 1) * B, bench.JOB_VIGNETTES)
+    g = BatchGeometry(hs[lo:hi], ws[lo:hi])
     db = st.prepare(DeviceBatch(g))
-    batches.append((db, db.synth(bench.PIXEL_SEED, b * B)))
-st.reserve([b[0].g for b in batches])
-for db, img in batches:
+    img = db.synth(bench.PIXEL_SEED, lo)
     r = st.run_device(db, img)
-    n = db.g.n_img
+    n_obj = r.n_obj
     torch.cuda.synchronize()
-    ws_ = st._ws_ring[(st._ws_i - 1) % 2]
-    c = ws_._t["counts"][:3 * n].cpu().numpy()
-    left = db.fused_lists()[2]
-    print("fallback flags", int((c[n:2 * n] != 0).sum()), "acc_base<0 & nlab>0", int(((c[2 * n:] < 0) & (c[:n] > 0)).sum()), "left", len(left), "n_obj", r.n_obj)
-for mode in ("nofinalize", "finalize_prev"):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    prev = None
-    for rep in range(5):
-        for db, img in batches:
-            r = st.run_device(db, img)
-            if mode == "finalize_prev" and prev is not None:
-                prev.n_obj
-            prev = r
-    torch.cuda.synchronize()
-    print(mode, (time.perf_counter() - t0) / 40 * 1e3, "ms/step")
+    tot_dense += len(r.dense_only); tot_redo += int(r.redone)
+    print(f"batch {b:2d}: vignettes {g.n_img} MPix {g.pixels / 1e6:.0f} runs {r.n_runs} (cap {max(g.total_words // 3, 1 << 16)}) "
+          f"objects {n_obj} (cap {S._stage_cap(g)}) per-operator vignettes {len(r.dense_only)} redone {r.redone}")
+print("job: vignettes without a run list", tot_dense, "batches redone", tot_redo)
