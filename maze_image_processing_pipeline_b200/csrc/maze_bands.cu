@@ -34,7 +34,7 @@ constexpr int PW = MAZE_BAND_PLANE_WORDS;
 #define BAND_T 256
 #define BAND_ZB 6144 /* bytes of zeros in shared memory behind the planes (source of the TMA zero fill) */
 #define LABEL_T 64
-#define LABEL_MID_T 256 /* (128 threads / 1024 runs / 13 CTAs per SM was measured: 0.35 ms instead of 0.21 ms) */
+#define LABEL_MID_T 256 /* (128 threads with 1024 runs: 0.35 ms instead of 0.21 ms for the list; 512 threads: no change) */
 #define LABEL_BIG_T 256
 #define LABEL_SMALL_CAP 256
 #define LABEL_SMALL_HCAP 1026

@@ -485,6 +485,8 @@ class LokiSegmentationStage:
         table = ws.get("table", cap * NFEAT, torch.float64, dev).view(cap, NFEAT)
         use_bands = self.pipeline == "bands"
         bands_h = band_off_h = None
+        if use_bands and not self.compact and g.total_px >= 2 ** 32:
+            raise ValueError("a batch with dense outputs must hold fewer than 2**32 pixels (split it, or use compact=True)")
         if use_bands:
             from .morphology import pass_radius
             halo = sum(pass_radius(t) for t, _ in passes)
