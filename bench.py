@@ -29,6 +29,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 JOB_VIGNETTES = 100_000
+MAX_RESIDENT = 24    # distinct resident batches per rank (the job has 25 batches of 4096)
 SIZE_SEED = 1        # C2 uses seed 1
 PIXEL_SEED = 20261018
 THRESHOLD, R_OPEN, R_CLOSE = 40, 1, 2
@@ -56,6 +57,29 @@ def measured_traffic(kernel):
         return None if rec is None else (float(rec["dram_bytes_per_px"]), rec.get("source", p))
     except Exception:
         return None
+
+
+def release(*objs):
+    """Drop device workspaces of stage objects that are no longer needed (each holds several GB per lane)."""
+    import gc
+    import torch
+    del objs
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def windowed_steps(stage, items):
+    """Run the stage over resident (batch, image) pairs with the read-back of a step checked n_lanes - 1 steps later
+    (a result is valid until its lane's workspace is reused); returns the number of objects."""
+    inflight, n_obj = [], 0
+    for db, img in items:
+        inflight.append(stage.run_device(db, img))
+        if len(inflight) > stage.n_lanes - 1:
+            n_obj += inflight.pop(0).n_obj
+    for r in inflight:
+        n_obj += r.n_obj
+    stage.join()
+    return n_obj
 
 
 def job_sizes():
@@ -341,9 +365,12 @@ def run_b200(args):
     stage = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), pp, merge_errors="ignore",
                                     morphology=args.morphology)
 
-    # resident inputs: the batches this rank will touch, generated on the device
+    # resident inputs: the batches this rank will touch, generated on the device.  At most MAX_RESIDENT distinct
+    # batches stay in HBM (~0.5 GB of pixels each); longer runs cycle through them -- consecutive steps still work on
+    # different batches, each larger than L2, and a batch comes round again only after ~12 GB of other pixels
+    n_res = min(need, MAX_RESIDENT)
     batches = []
-    for s in range(need):
+    for s in range(n_res):
         b = (rank + s * world) % n_batches_job
         lo = b * B
         hi = min(lo + B, JOB_VIGNETTES)
@@ -358,10 +385,13 @@ def run_b200(args):
         sampler.start()
 
     def step(i):
-        db, img = batches[i]
+        db, img = batches[i % n_res]
         res = stage.run_device(db, img)
         return res, res.mask
 
+    for i in range(stage.n_lanes):  # every lane runs once (streams, workspaces, kernel attributes) before the warm-up
+        step(i)[0].n_obj
+    stage.join()
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -377,8 +407,8 @@ def run_b200(args):
         inflight.append(res)
         if len(inflight) > stage.n_lanes - 1:
             n_obj += inflight.pop(0).n_obj  # readback check n_lanes - 1 steps behind (rotating workspaces)
-        n_vig += batches[i][0].g.n_img
-        n_px += batches[i][0].g.pixels
+        n_vig += batches[i % n_res][0].g.n_img
+        n_px += batches[i % n_res][0].g.pixels
     for r in inflight:
         n_obj += r.n_obj
     stage.join()
@@ -396,13 +426,13 @@ def run_b200(args):
                                      morphology=args.morphology, n_lanes=1)
     stage1.reserve([b[0].g for b in batches])
     for i in range(2):
-        stage1.run_device(batches[i][0], batches[i][1]).n_obj
+        stage1.run_device(batches[i % n_res][0], batches[i % n_res][1]).n_obj
     torch.cuda.synchronize()
     _lib.prof_enable(True)
     evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evp0.record()
     for i in range(args.warmup, need):
-        stage1.run_device(batches[i][0], batches[i][1])
+        stage1.run_device(batches[i % n_res][0], batches[i % n_res][1])
     stage1.join()
     evp1.record()
     torch.cuda.synchronize()
@@ -410,13 +440,14 @@ def run_b200(args):
     prof = _lib.prof_collect()
     ms_instr = evp0.elapsed_time(evp1)
     del stage1
+    release()
 
     # end to end through the public stage call: host numpy in, host numpy out, copies timed
     # (host memory: every rank keeps its e2e inputs plus three pinned buffer sets; fewer batches per rank at N = 8)
     e2e_steps = max(1, min(args.steps, args.e2e_steps, max(6, 48 // world)))
     host_batches = []
     for i in range(args.warmup, args.warmup + e2e_steps):
-        db, img = batches[i]
+        db, img = batches[i % n_res]
         # the end-to-end call uses batches of --e2e-batch vignettes (three pinned buffer sets per rank: smaller
         # batches keep the pinned working set of 8 ranks on one host in check; measured 2.4x faster at N = 8)
         n_k = min(db.g.n_img, args.e2e_batch)
@@ -463,14 +494,12 @@ def run_b200(args):
     torch.cuda.synchronize()
     ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ec0.record()
-    rs = [stage_c.run_device(batches[i][0], batches[i][1]) for i in range(args.warmup, need)]
-    for r in rs:
-        r.n_obj
-    stage_c.join()
+    windowed_steps(stage_c, [batches[i % n_res] for i in range(args.warmup, need)])
     ec1.record()
     torch.cuda.synchronize()
     ms_compact = ec0.elapsed_time(ec1) / args.steps
-    del stage_c, rs
+    del stage_c
+    release()
 
     # max over ranks
     if world > 1:
@@ -553,7 +582,8 @@ def run_b200(args):
                 if a_.size:
                     max_rel = max(max_rel, float(np.nanmax(np.abs(a_ - b_) / np.maximum(np.abs(b_), 1e-9))))
                 labels_eq &= bool(np.array_equal(f[:k, _oracle.F_AREA], t[:k, _oracle.F_AREA]))
-            del st
+            del st, got
+            release()
         parity = {"vignettes": n_cmp // 2, "transports": ["dense", "compact"], "masks_equal": masks_eq,
                   "labels_equal": labels_eq, "table_max_rel": max_rel, "table_rel_tolerance": 1e-5,
                   "checked_against": cpu_kind()}
@@ -568,7 +598,7 @@ def run_b200(args):
     variants = None
     if world == 1 and not args.no_variants and args.merge == 0 and args.morphology == "isotropic":
         variants = {}
-        vb = batches[args.warmup][0], batches[args.warmup][1]
+        vb = batches[args.warmup % n_res][0], batches[args.warmup % n_res][1]
         for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8)):
             vpp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN, **kw)
             st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), vpp, merge_errors="ignore",
@@ -579,16 +609,14 @@ def run_b200(args):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            last = [st.run_device(*vb) for _ in range(vsteps)]
-            for r in last:
-                r.n_obj
-            st.join()
+            windowed_steps(st, [vb] * vsteps)
             e1.record()
             torch.cuda.synchronize()
             vms = e0.elapsed_time(e1) / vsteps
             variants[name] = {"value": vb[0].g.n_img / (vms / 1e3), "unit": "vignettes/s", "ms_per_step": vms,
                               "steps": vsteps, "note": "resident, one 4096-vignette batch repeated"}
             del st
+            release()
 
     line = {
         "metric": "loki_vignettes_per_s", "value": n_vig / (ms / 1e3), "unit": "vignettes/s",
@@ -615,6 +643,7 @@ def run_b200(args):
                                "d2h_bytes_per_step": dense_d2h // e2e_steps},
             "run_list_expand": {"value": mat_vig / mat_s, "unit": "vignettes/s", "d2h_bytes_per_step": d2h // e2e_steps}},
         "gpu_launches": int(launches), "clocks": clocks,
+        "device_memory_peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
     }
     print(json.dumps(line))
     if world > 1:
@@ -625,7 +654,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)

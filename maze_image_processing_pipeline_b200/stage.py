@@ -638,9 +638,13 @@ class LokiSegmentationStage:
                 ws.get(key, size, dt, dev)
             if getattr(ws, "arena", None) is None or ws.arena.device != dev:
                 ws.arena = Arena(dev)
-            # scratch of the per-operator path for the oversize vignettes: ~8 planes, parent + misc per pixel
-            # (twice: a redo of overflowed vignettes in finalize() takes a second set)
-            ws.arena.reserve(int(2.2 * (8 * 4 * words + 5 * px + cap * (NACC * 8 + NEXT * 4))) + (8 << 20))
+            # (the scratch arena of the per-operator path -- oversize vignettes, redo of flagged ones -- gets a token
+            # reservation only: with the band pipeline that path is the exception, and batch-sized scratch for every
+            # lane costs several GB per lane; the arena grows on first use)
+            ws.arena.reserve(8 << 20)
+            if getattr(ws, "lane", None) is None or ws.lane.device != dev:
+                ws.lane = torch.cuda.Stream(device=dev)
+                ws.side = torch.cuda.Stream(device=dev)
 
     def prepare(self, batch: DeviceBatch):
         """Build the per-batch launch plan (size classes, descriptors of the vignettes that need the
