@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(WIDE_CHUNK) k_wide_rows(const uint8_t *__restr
                                                            const int64_t *__restrict__ cta_off, WideTab tab, int invert,
                                                            uint32_t *__restrict__ out, uint32_t *flags_out)
 {
-    __shared__ uint8_t s_g[2][WIDE_CHUNK + 2 * WIDE_MAX_R + 8];
-    __shared__ uint32_t s_c[2][WIDE_CW];
+    __shared__ uint8_t s_g[WIDE_ROWS][WIDE_CHUNK + 2 * WIDE_MAX_R + 8];
+    __shared__ uint32_t s_c[WIDE_ROWS][WIDE_CW];
     __shared__ uint8_t s_h[WIDE_MAX_R + 1];
     __shared__ uint32_t s_fl;
     const int img = wide_find(cta_off, n_img, (int64_t)blockIdx.x);
@@ -124,26 +124,23 @@ __global__ void __launch_bounds__(WIDE_CHUNK) k_wide_rows(const uint8_t *__restr
     const int k0 = (x0 >> 5) - gw;               // plane word held by s_c[.][0]
     for (int i = threadIdx.x; i <= Rw; i += WIDE_CHUNK) s_h[i] = tab.h[i];
     if (threadIdx.x == 0) s_fl = 0;
-    auto stage = [&](int y, int buf) { // columns outside the image hold no 0: "far" (255 > every h) / clear
-        const uint8_t *row = g + v.pix_off + (size_t)y * W;
-        for (int i = threadIdx.x; i < WIDE_CHUNK + 2 * Rw; i += WIDE_CHUNK) {
-            const int xx = x0 - Rw + i;
-            s_g[buf][i] = (xx >= 0 && xx < W) ? row[xx] : 255;
-        }
-        const uint32_t *crow = clear + v.word_off + (size_t)y * wpr;
-        for (int i = threadIdx.x; i < WIDE_CHUNK / 32 + 2 * gw; i += WIDE_CHUNK) {
-            const int kk = k0 + i;
-            s_c[buf][i] = (kk >= 0 && kk < wpr) ? crow[kk] : FULL;
-        }
-    };
-    stage(y0, 0);
+    // all rows of the strip are staged at once (every thread has a dozen independent loads in flight); columns
+    // outside the image hold no 0: "far" (255 > every h) / clear
+    const int span = WIDE_CHUNK + 2 * Rw, cspan = WIDE_CHUNK / 32 + 2 * gw;
+    for (int i = threadIdx.x; i < (y1 - y0) * span; i += WIDE_CHUNK) {
+        const int r = i / span, c = i - r * span, xx = x0 - Rw + c;
+        s_g[r][c] = (xx >= 0 && xx < W) ? g[v.pix_off + (size_t)(y0 + r) * W + xx] : 255;
+    }
+    for (int i = threadIdx.x; i < (y1 - y0) * cspan; i += WIDE_CHUNK) {
+        const int r = i / cspan, c = i - r * cspan, kk = k0 + c;
+        s_c[r][c] = (kk >= 0 && kk < wpr) ? clear[v.word_off + (size_t)(y0 + r) * wpr + kk] : FULL;
+    }
     __syncthreads();
     const int x = x0 + threadIdx.x;
     const int k = (x0 >> 5) + (threadIdx.x >> 5);
     uint32_t fl = 0;
     for (int y = y0; y < y1; y++) {
-        const int buf = (y - y0) & 1;
-        if (y + 1 < y1) stage(y + 1, buf ^ 1); // the next row is fetched while this one is tested
+        const int buf = y - y0;
         bool keep = false;
         if (x < W) {
             const uint32_t *cw = s_c[buf];
@@ -172,7 +169,6 @@ __global__ void __launch_bounds__(WIDE_CHUNK) k_wide_rows(const uint8_t *__restr
             out[v.word_off + (size_t)y * wpr + k] = res;
             fl |= (res ? 1u : 0u) | ((res ^ vm) ? 2u : 0u);
         }
-        __syncthreads();
     }
     if (fl) atomicOr(&s_fl, fl);
     __syncthreads();

@@ -28,9 +28,9 @@ assert VIG_DTYPE.itemsize == 32 and TILE_DTYPE.itemsize == 8 and BAND_DTYPE.item
 
 _DISK_T_LIMIT = (MAX_DISK_RADIUS + 1) ** 2
 WIDE_MAX_R = 254                 # maze_morph_pass_wide: squared-distance thresholds up to 254^2
-WIDE_MIN_R = int(os.environ.get("MAZE_WIDE_MIN_R", "28"))  # from this radius on the separable pass pair is the faster one
-# (2048^2 frame, per pass: bit-plane kernel 0.044 ms at r = 16, 0.10 ms at r = 32; separable pair 0.07-0.09 ms up to r = 32,
-# 0.12 ms at r = 64 -- tools/wide_probe.py)
+WIDE_MIN_R = int(os.environ.get("MAZE_WIDE_MIN_R", "22"))  # from this radius on the separable pass pair is the faster one
+# (2048^2 frame, per pass: bit-plane kernel 0.027 / 0.045 / 0.10 ms at r = 8 / 16 / 32; separable pair 0.06 / 0.065 / 0.077 /
+# 0.11 ms at r = 8 / 16 / 32 / 64 -- tools/wide_probe.py)
 _INT_MAX = 2 ** 31 - 1
 
 

@@ -209,7 +209,7 @@ def test_full_radius_sweep_1_to_32_and_beyond(mz):
     frame[rng.random(frame.shape) < 0.002] = 0
     masks = [frame > 40, np.ones((90, 140), bool), np.zeros((70, 65), bool), rng.random((1, 300)) < 0.7,
              rng.random((260, 1)) < 0.7, rng.random((130, 97)) < 0.98]
-    radii = list(range(1, 33)) + [6.5, 12.5, 40, 64, 120]  # (the separable pair takes over at radius 28)
+    radii = list(range(1, 33)) + [6.5, 12.5, 40, 64, 120]  # (the separable pair takes over at radius 22)
     jobs = [(op, m, r) for m in masks for r in radii for op in ("opening", "closing")]
     with mp.get_context("fork").Pool(16) as pool:
         want = pool.map(_iso, jobs, chunksize=4)

@@ -3,7 +3,7 @@ on the device, CUDA events, best of 5.  Prints one JSON line per measurement (ke
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from maze_image_processing_pipeline_b200.device import BatchGeometry, DeviceBatch
+from maze_image_processing_pipeline_b200.device import WIDE_MIN_R, BatchGeometry, DeviceBatch
 from maze_image_processing_pipeline_b200.synth import synth_dense_frame
 
 
@@ -27,7 +27,7 @@ for r in (1, 2, 4, 8, 16, 32, 40, 64):
         ms, _ = timed(lambda: getattr(b, op)(bits, flags, r))
         print(json.dumps({"config": "configs[2]", "op": f"isotropic_{op}", "radius": r, "frame": "2048x2048",
                           "ms": round(ms, 4), "mpix_per_s": round(2048 * 2048 / ms / 1e3, 1),
-                          "path": "bit-plane disk" if r < 6 else "separable vertical distance + row test"}))
+                          "path": "bit-plane disk" if r < WIDE_MIN_R else "separable vertical distance + row test"}))
 # configs[3]: 4096 x 4096 dense frame: threshold -> label -> regionprops (thousands of labels)
 frame = synth_dense_frame(11, size=4096, n_blobs=3000)
 g = BatchGeometry([4096], [4096]); b = DeviceBatch(g)
