@@ -594,12 +594,14 @@ def run_b200(args):
             return 2
 
     # ---- variants SURVEY.md 8d asks to report next to the headline: resident throughput with merge_labels on
-    # (merge_segments_distance = 10) and with the live pipeline's footprints (morphology = crosses)
+    # (merge_segments_distance = 10), with the live pipeline's footprints (morphology = crosses) and with the label
+    # filters on (clear_border + min_area = 12: applied on the run list inside the band pipeline)
     variants = None
     if world == 1 and not args.no_variants and args.merge == 0 and args.morphology == "isotropic":
         variants = {}
         vb = batches[args.warmup % n_res][0], batches[args.warmup % n_res][1]
-        for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8)):
+        for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8),
+                                 ("label_filters", dict(clear_border=True, min_area=12), 8)):
             vpp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN, **kw)
             st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), vpp, merge_errors="ignore",
                                          morphology="crosses" if name == "crosses" else "isotropic")

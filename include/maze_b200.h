@@ -304,6 +304,9 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * band_done (n_img int32 scratch, cleared by the call; may be NULL): with it, the LAST band CTA of a vignette to finish
  * labels the vignette in place inside the band kernel (run tables up to 4096 runs / 2048 rows / 64 bands, the rest goes to
  * the list kernel); without it a labelling kernel of its own runs behind the band kernel.
+ * clear_border / min_area: the label filters of loki/pipeline.py:435-448 applied ON THE RUN LIST by the labelling kernel
+ * (labels touching the outermost rows / columns, labels with fewer than min_area pixels: their runs get label 0, their
+ * rows are emptied; no renumbering); not available together with frames (n_huge > 0).
  * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
  * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
 #define MAZE_BAND_PLANE_WORDS 6144
@@ -319,7 +322,7 @@ int maze_band_stage(const uint8_t *image, const uint8_t *intensity, const maze_v
                     int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list, int stage_cap,
                     unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage, long long total_px,
                     const int32_t *huge_host, int n_huge, long long huge_px, int32_t *gl_scratch, int32_t *band_done,
-                    void *stream);
+                    int clear_border, long long min_area, void *stream);
 
 /* Feature rows from the staged accumulators: row lab_off[i] + l - 1 of table for every vignette with
  * acc_base[i] >= 0 (the others are left to maze_regionprops). */
@@ -388,7 +391,8 @@ typedef struct maze_step_args {
     int32_t n_bands, halo, run_cap, step_flags; /* step_flags: MAZE_STEP_COMPACT */
     int64_t total_px;                           /* elements of mask / labels (band pipeline, dense outputs) */
     int64_t huge_px;                            /* vignettes with >= huge_px pixels are frames */
-    int32_t n_huge, reserved;
+    int64_t min_area;                           /* label filters on the run list (band pipeline) */
+    int32_t n_huge, clear_border;
 } maze_step_args_t;
 #define MAZE_STEP_COMPACT 1 /* band pipeline: no dense mask / label image for the band vignettes (run list only) */
 int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);

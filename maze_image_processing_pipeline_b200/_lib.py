@@ -45,7 +45,8 @@ class StepArgs(ctypes.Structure):
         + [("class_off", ctypes.c_int32 * (len(FUSED_CAPS) + 1)), ("pass_t", ctypes.c_int32 * 4), ("pass_invert", ctypes.c_int32 * 4)]
         + [(k, ctypes.c_int32) for k in ("n_img", "left_n", "left_n_tiles", "left_n_tiles_full", "t_int", "n_pass",
                                          "flags", "stage_cap", "n_bands", "halo", "run_cap", "step_flags")]
-        + [("total_px", ctypes.c_int64), ("huge_px", ctypes.c_int64), ("n_huge", ctypes.c_int32), ("reserved", ctypes.c_int32)])
+        + [("total_px", ctypes.c_int64), ("huge_px", ctypes.c_int64), ("min_area", ctypes.c_int64), ("n_huge", ctypes.c_int32),
+           ("clear_border", ctypes.c_int32)])
 
 
 class MazeLibraryError(RuntimeError):
@@ -101,7 +102,7 @@ SIGNATURES = {
     "maze_props_finish_staged": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "maze_count_scan": [_vp, _i, _vp, _vp],
     "maze_band_stage": [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, ctypes.c_longlong, _vp, _i, ctypes.c_longlong, _vp, _vp, _i, ctypes.c_longlong, _vp],
     "maze_label_shape": [_vp, _vp, _vp, _vp, _i, _vp, ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp],
     "maze_host_pack": [_vp, _vp, _vp, _i, _vp, _i],
     "maze_host_pack_wait": [_vp],

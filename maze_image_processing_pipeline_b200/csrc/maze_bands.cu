@@ -70,6 +70,8 @@ struct LabelArgs {
     int32_t *labels;
     int n_img, n_pass, phantom_mask, do_props, high_order, has_intensity, stage_cap;
     long long huge_px; // vignettes with at least this many pixels are labelled by the global-memory kernels
+    long long min_area; // label filters (0 / 0: none)
+    int clear_border;
 };
 
 __device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
@@ -582,75 +584,85 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         for (int i = tid; i < n_runs; i += T) atomicAdd(&s_hist[min(label_of(P, i) - 1, LCAP)], 1);
     }
     __syncthreads();
-    // ---- label of every run -> HBM; per-run intensity statistics -> accumulator rows (warp-aggregated) -----------
-    {
-        const bool with_i = props && a.has_intensity;
-        for (int i0 = warp * 32; i0 < n_runs; i0 += T) {
-            const int i = i0 + lane;
-            const bool valid = i < n_runs;
-            int lab = 0;
-            uint32_t isum = 0, zeros = 0, vmn = 255, vmx = 0;
-            if (valid) {
-                const int g = gidx(i);
-                lab = label_of(P, i);
-                ((u16 *)(a.runs + g))[3] = (u16)lab;
-                if (with_i) {
-                    const uint2 st = __ldcg((const uint2 *)a.stats + g);
-                    isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
+    // label of every run -> HBM, per-run statistics -> accumulator rows, dense outputs (after the label filters)
+    auto write_out = [&]() {
+        // ---- label of every run -> HBM; per-run intensity statistics -> accumulator rows (warp-aggregated) -----------
+        {
+            const bool with_i = props && a.has_intensity;
+            for (int i0 = warp * 32; i0 < n_runs; i0 += T) {
+                const int i = i0 + lane;
+                const bool valid = i < n_runs;
+                int lab = 0;
+                uint32_t isum = 0, zeros = 0, vmn = 255, vmx = 0;
+                if (valid) {
+                    const int g = gidx(i);
+                    lab = label_of(P, i);
+                    ((u16 *)(a.runs + g))[3] = (u16)lab;
+                    if (with_i) {
+                        const uint2 st = __ldcg((const uint2 *)a.stats + g);
+                        isum = st.x; zeros = st.y & 0xffffu; vmn = (st.y >> 16) & 0xffu; vmx = st.y >> 24;
+                    }
                 }
-            }
-            if (with_i) {
-                uint32_t todo = __ballot_sync(FULL, valid);
-                while (todo) {
-                    const int leader = __ffs(todo) - 1;
-                    const int L = __shfl_sync(FULL, lab, leader);
-                    const bool in = valid && lab == L;
-                    todo &= ~__ballot_sync(FULL, in);
-                    const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
-                    const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
-                    if (lane == leader) {
-                        if (L <= LCAP) {
-                            shared_add64(ACC[L - 1].a + A_V, (u64)sV);
-                            if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
-                            atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
-                        } else {
-                            u64 *Aa = a.acc_stage + (i64)(base + L - 1) * MAZE_NACC;
-                            int32_t *Ee = a.ext_stage + (i64)(base + L - 1) * MAZE_NEXT;
-                            atomicAdd(Aa + A_V, (u64)sV); atomicAdd(Aa + A_Z, (u64)sZ);
-                            atomicMin(Ee + E_VMIN, (int)mn); atomicMax(Ee + E_VMAX, (int)mx);
+                if (with_i) {
+                    uint32_t todo = __ballot_sync(FULL, valid);
+                    while (todo) {
+                        const int leader = __ffs(todo) - 1;
+                        const int L = __shfl_sync(FULL, lab, leader);
+                        const bool in = valid && lab == L;
+                        todo &= ~__ballot_sync(FULL, in);
+                        const uint32_t sV = __reduce_add_sync(FULL, in ? isum : 0u), sZ = __reduce_add_sync(FULL, in ? zeros : 0u);
+                        const uint32_t mn = __reduce_min_sync(FULL, in ? vmn : 255u), mx = __reduce_max_sync(FULL, in ? vmx : 0u);
+                        if (lane == leader) {
+                            if (L <= LCAP) {
+                                shared_add64(ACC[L - 1].a + A_V, (u64)sV);
+                                if (sZ) shared_add64(ACC[L - 1].a + A_Z, (u64)sZ);
+                                atomicMin(&ACC[L - 1].e[E_VMIN], (int)mn); atomicMax(&ACC[L - 1].e[E_VMAX], (int)mx);
+                            } else {
+                                u64 *Aa = a.acc_stage + (i64)(base + L - 1) * MAZE_NACC;
+                                int32_t *Ee = a.ext_stage + (i64)(base + L - 1) * MAZE_NEXT;
+                                atomicAdd(Aa + A_V, (u64)sV); atomicAdd(Aa + A_Z, (u64)sZ);
+                                atomicMin(Ee + E_VMIN, (int)mn); atomicMax(Ee + E_VMAX, (int)mx);
+                            }
                         }
                     }
                 }
             }
         }
-    }
-    // ---- dense outputs: the runs of the vignette on top of the zero fill of K1.  Eight lanes per run: the up to three
-    // elements in front of the first 16-byte boundary of the label row (lanes 0-2) and behind the last one (lanes
-    // 4-6) are stored one by one, the body with one 16-byte label store and one 4-byte mask store per lane and step ---
-    if (a.labels) {
-        int32_t *gl = a.labels + v.pix_off;
-        uint8_t *gm = a.mask + v.pix_off;
-        const int W = v.w, oct = lane >> 3, ol = lane & 7;
-        for (int i0 = warp * 4; i0 < n_runs; i0 += (T / 32) * 4) {
-            const int i = i0 + oct;
-            if (i < n_runs) {
-                const int len = (int)rX1[i] - (int)rX0[i] + 1;
-                const int p = (int)rY[i] * W + (int)rX0[i];
-                const uint32_t lab = (uint32_t)label_of(P, i);
-                int32_t *pl = gl + p;
-                uint8_t *pm = gm + p;
-                const int head = min((-p) & 3, len), body = (len - head) & ~3, tail = len - head - body;
-                if (ol < head) { pl[ol] = (int32_t)lab; pm[ol] = 1; }
-                if (ol >= 4 && ol - 4 < tail) { pl[head + body + ol - 4] = (int32_t)lab; pm[head + body + ol - 4] = 1; }
-                const uint4 l4 = make_uint4(lab, lab, lab, lab);
-                for (int x = head + 4 * ol; x < head + body; x += 32) {
-                    *(uint4 *)(pl + x) = l4;
-                    *(uint32_t *)(pm + x) = 0x01010101u;
+        // ---- dense outputs: the runs of the vignette on top of the zero fill of K1.  Eight lanes per run: the up to three
+        // elements in front of the first 16-byte boundary of the label row (lanes 0-2) and behind the last one (lanes
+        // 4-6) are stored one by one, the body with one 16-byte label store and one 4-byte mask store per lane and step ---
+        if (a.labels) {
+            int32_t *gl = a.labels + v.pix_off;
+            uint8_t *gm = a.mask + v.pix_off;
+            const int W = v.w, oct = lane >> 3, ol = lane & 7;
+            for (int i0 = warp * 4; i0 < n_runs; i0 += (T / 32) * 4) {
+                const int i = i0 + oct;
+                if (i < n_runs) {
+                    const int len = (int)rX1[i] - (int)rX0[i] + 1;
+                    const int p = (int)rY[i] * W + (int)rX0[i];
+                    const uint32_t lab = (uint32_t)label_of(P, i);
+                    int32_t *pl = gl + p;
+                    uint8_t *pm = gm + p;
+                    const int head = min((-p) & 3, len), body = (len - head) & ~3, tail = len - head - body;
+                    if (ol < head) { pl[ol] = (int32_t)lab; pm[ol] = 1; }
+                    if (ol >= 4 && ol - 4 < tail) { pl[head + body + ol - 4] = (int32_t)lab; pm[head + body + ol - 4] = 1; }
+                    const uint4 l4 = make_uint4(lab, lab, lab, lab);
+                    for (int x = head + 4 * ol; x < head + body; x += 32) {
+                        *(uint4 *)(pl + x) = l4;
+                        *(uint32_t *)(pm + x) = 0x01010101u;
+                    }
                 }
             }
         }
+    };
+    if (!props) {
+        if (a.clear_border || a.min_area > 0) { // the filters need the accumulators: per-operator redo
+            if (tid == 0) mark_fallback(a, img);
+            return 0;
+        }
+        write_out();
+        return 0;
     }
-    if (!props) return 0;
 
     // ---- per-label geometry accumulators: counting sort of the runs by label, contiguous pieces per thread ------
     if (tid == 0) {
@@ -722,6 +734,36 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         }
     }
     __syncthreads();
+    // ---- label filters on the run list (loki/pipeline.py:435-448): clear_border removes every label that touches the
+    // outermost rows / columns, remove_small_objects every label with fewer than min_area pixels.  Both follow from
+    // the accumulators just taken (bbox, area): the runs of a removed label get label 0 (no renumbering, as in the
+    // reference; their mask bytes stay 1) and its row is emptied.
+    if (a.clear_border || a.min_area > 0) {
+        const int W = v.w;
+        __threadfence();
+        auto removed = [&](int lab) {
+            const u64 *Aa = lab <= LCAP ? ACC[lab - 1].a : a.acc_stage + (i64)(base + lab - 1) * MAZE_NACC;
+            const int *Ee = lab <= LCAP ? ACC[lab - 1].e : a.ext_stage + (i64)(base + lab - 1) * MAZE_NEXT;
+            if (a.min_area > 0 && (i64) * (const volatile u64 *)(Aa + A_N) < a.min_area) return true;
+            if (a.clear_border)
+                return *(const volatile int *)(Ee + E_RMIN) == 0 || *(const volatile int *)(Ee + E_RMAX) == H - 1 ||
+                       *(const volatile int *)(Ee + E_CMIN) == 0 || *(const volatile int *)(Ee + E_CMAX) == W - 1;
+            return false;
+        };
+        for (int i = tid; i < n_runs; i += T)
+            if (removed(label_of(P, i))) P[i] = (u16)0x8000; // label 0
+        __syncthreads();
+        for (int l = tid; l < n_lab; l += T)
+            if (removed(l + 1)) {
+                u64 *Aa = l < LCAP ? ACC[l].a : a.acc_stage + (i64)(base + l) * MAZE_NACC;
+                int *Ee = l < LCAP ? ACC[l].e : a.ext_stage + (i64)(base + l) * MAZE_NEXT;
+                for (int j = 0; j < MAZE_NACC; j++) Aa[j] = 0;
+                Ee[E_RMIN] = 0x7fffffff; Ee[E_RMAX] = -1; Ee[E_CMIN] = 0x7fffffff; Ee[E_CMAX] = -1;
+            }
+        __syncthreads();
+    }
+    write_out();
+    __syncthreads();
     if (a.high_order) {
         // float64 central moments with p + q > 3 about the exact centroid (same walk over the sorted runs)
         for (int l = tid; l < n_lab; l += T) {
@@ -738,6 +780,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         for (int pos = p_lo; pos < p_hi; pos++) {
             const int i = rO[pos];
             const int L = label_of(P, i);
+            if (L == 0) continue; // removed by a label filter
             if (L != cur) {
                 if (cur) {
                     double *Hh = hrow(cur);
@@ -1241,7 +1284,8 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                int32_t *fallback, int32_t *acc_base, int32_t *counters, int32_t *big_list,
                                int stage_cap, unsigned long long *acc_stage, double *hi_stage, int32_t *ext_stage,
                                long long total_px, const int32_t *huge_host, int n_huge, long long huge_px,
-                               int32_t *gl_scratch, int32_t *band_done, void *stream)
+                               int32_t *gl_scratch, int32_t *band_done, int clear_border, long long min_area,
+                               void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_pass < 0 || n_pass > 4 || halo < 0) return MAZE_ERR_BADARG;
@@ -1333,7 +1377,8 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
     LabelArgs la = {vig, band_off, band_out, runs, run_stats, n_labels, fallback, acc_base, stage_counter,
                     (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, dense && !k3 ? mask : nullptr,
                     dense && !k3 ? labels : nullptr, n_img, n_pass, prm.phantom_mask, prm.do_props, prm.high_order,
-                    prm.has_intensity, stage_cap, (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62)};
+                    prm.has_intensity, stage_cap, (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62), min_area,
+                    clear_border ? 1 : 0};
     if (inband) MAZE_CUDA(cudaMemsetAsync(band_done, 0, sizeof(int32_t) * (size_t)n_img, s), "band done");
     MAZE_KERNEL(KID_BAND_FRONT, s,
                 k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, runs,
@@ -1361,7 +1406,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                                                                      LABEL_BIG_NB, 2));
     }
     if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
-        if (!huge_host) return MAZE_ERR_BADARG;
+        if (!huge_host || clear_border || min_area > 0) return MAZE_ERR_BADARG; // (no label filters on this path)
         for (int e = 0; e < n_huge; e++) {
             // (the band count of the vignette sizes its prefix array; the host knows the band plan)
             const int rc = gl_label_frame(la, huge_host[2 * e], gl_scratch, run_cap, huge_host[2 * e + 1], s);

@@ -70,7 +70,7 @@ extern "C" int maze_stage_step(const maze_step_args_t *a, void *lane_stream, voi
                              a->pass_t, a->pass_invert, a->halo, a->flags, a->bits, a->runs, a->run_pix, a->run_stats,
                              a->run_cap, a->band_out, dense ? a->mask : nullptr, dense ? a->labels : nullptr, n_labels,
                              fallback, acc_base, a->band_counters, a->big_list, a->stage_cap, a->acc_stage, a->hi_stage,
-                             a->ext_stage, a->total_px, a->huge_host, a->n_huge, a->huge_px, a->gl_scratch, a->band_done, lane);
+                             a->ext_stage, a->total_px, a->huge_host, a->n_huge, a->huge_px, a->gl_scratch, a->band_done, a->clear_border, a->min_area, lane);
     } else {
         rc = maze_vignette_stage(a->image, a->intensity, a->vig, a->img_list, a->class_off, a->t_int, a->n_pass, a->pass_t,
                                  a->pass_invert, a->flags, a->bits, a->mask, a->labels, n_labels, fallback, acc_base,

@@ -316,6 +316,7 @@ class LokiSegmentationStage:
         self._small_copy_stream = None
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._img_ring = None  # pinned staging buffers of map() (four sets, allocated on first use)
+        self._shared_busy = None  # download event of the last batch that used the shared (non-rotating) workspace
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
@@ -387,8 +388,32 @@ class LokiSegmentationStage:
             return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
         passes = self._passes() if self.fused else None
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
-        if passes is not None and not filters:
+        if passes is not None and (not filters or self._band_filters(batch)):
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
+        return self._run_filter_path(batch, d_src, d_image, t_int, passes)
+
+    def _band_filters(self, batch) -> bool:
+        """clear_border / remove_small_objects run on the run list inside the band pipeline (no merge_labels, no frames,
+        no vignette that needs the per-operator kernels)."""
+        pp = self.postprocess
+        if self.pipeline != "bands" or pp.merge_segments_distance > 0:
+            return False
+        from ._lib import HUGE_PX
+        from .morphology import pass_radius
+        if (batch.g.npx >= HUGE_PX).any():
+            return False
+        return len(batch.band_lists(sum(pass_radius(t) for t, _ in self._passes()))[3]) == 0
+
+    def _run_filter_path(self, batch, d_src, d_image, t_int, passes) -> DeviceResult:
+        """Label filters / merge_labels with the per-operator kernels on the dense label image (synchronous, ONE shared
+        workspace): the vignette-resident kernel for the labels, then clear_border / remove_small_objects /
+        merge_labels, then regionprops."""
+        pp = self.postprocess
+        g = batch.g
+        filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
+        if self._shared_busy is not None:  # a download of the previous batch may still read the shared workspace
+            self._shared_busy.synchronize()
+            self._shared_busy = None
         live_counts = None
         if passes is None:
             bits, labels, lab_off, mask = self._front_generic(batch, d_src, t_int)
@@ -533,6 +558,8 @@ class LokiSegmentationStage:
             a.band_out, a.band_counters, a.big_list = band_out.data_ptr(), band_counters.data_ptr(), big_list.data_ptr()
             a.run_cap, a.total_px = run_cap, g.total_px
             a.band_done = band_done.data_ptr()
+            pp = self.postprocess
+            a.clear_border, a.min_area = int(bool(pp.clear_border)), int(pp.min_area)
             if huge_pairs is not None:
                 a.huge_host, a.n_huge, a.huge_px = huge_pairs.ctypes.data, len(huge_pairs), HUGE_PX
                 a.gl_scratch = gl_scratch.data_ptr()
@@ -579,7 +606,19 @@ class LokiSegmentationStage:
             bad = np.nonzero((h[n:2 * n] != 0) | ((h[2 * n:3 * n] < 0) & (h[:n] > 0)))[0]
             bad = [int(i) for i in bad if int(i) not in left_set]
             res.dense_only = sorted(left_set | set(bad))  # vignettes without a run list (per-operator kernels)
-            if bad or total > cap:
+            ppf = self.postprocess
+            if (bad or total > cap) and (ppf.clear_border or ppf.min_area > 0):
+                # the per-operator redo below knows no label filters: the whole batch takes the filter path instead
+                with torch.cuda.stream(main):
+                    r2 = self._run_filter_path(batch, d_src, d_image, t_int, passes)
+                    res.redone = True
+                    res.dense_only = list(range(n))
+                    res.bits, res.labels, res.mask, res.lab_off = r2.bits, r2.labels, r2.mask, r2.lab_off
+                    res._table, total = r2._table, r2._n_obj
+                    res._sync_main = True
+                    res.ready = torch.cuda.Event()
+                    res.ready.record(main)
+            elif bad or total > cap:
                 # some vignettes overflowed the fused kernel's tables (more runs than slots, or the staging rows
                 # ran out): the per-operator kernels redo just those, then offsets and features are re-derived
                 with torch.cuda.stream(main):
@@ -689,7 +728,7 @@ class LokiSegmentationStage:
         pp = self.postprocess
         if pp is None or not self.fused or self.pipeline != "bands" or self._passes() is None:
             return None
-        if pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0:
+        if pp.merge_segments_distance > 0:
             return None
         from .morphology import pass_radius
         return sum(pass_radius(t) for t, _ in self._passes())
@@ -753,6 +792,8 @@ class LokiSegmentationStage:
                 h_lab.copy_(res.labels, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(cs)
+        if res._sync_main:  # produced in the shared workspace: the next batch on that path must wait for this download
+            self._shared_busy = copied
         return (geom, batch, res, h_mask, h_lab, pool, (d_image, d_pred, copied))
 
     def _complete(self, inflight) -> StageResult:
@@ -857,7 +898,8 @@ class LokiSegmentationStage:
             # merge_labels, radii beyond the bit-plane kernels or threshold-only work in ONE shared workspace
             pp = self.postprocess
             overlap = (pp is not None and self.fused and self.n_lanes >= 2 and self._passes() is not None
-                       and not (pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0))
+                       and pp.merge_segments_distance <= 0
+                       and (self.pipeline == "bands" or not (pp.clear_border or pp.min_area > 0)))
             def split(item):
                 return item if isinstance(item, tuple) else (item, None)
 

@@ -240,3 +240,29 @@ def test_wide_pass_equals_the_bit_plane_pass_on_footprints_and_batches(mz):
             mz.torch.cuda.synchronize()
             assert mz.torch.equal(o1, o2), (t, inv)
             assert mz.torch.equal(f1, f2), (t, inv)
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_label_filters_on_the_run_list(mz, compact):
+    """clear_border / remove_small_objects (loki/pipeline.py:435-448) applied by the labelling kernel on the run list:
+    removed labels keep their mask pixels, lose their label (no renumbering) and leave an empty table row -- dense and
+    compact transport, on the edge images too (border-touching blobs, specks below min_area, uniform planes)."""
+    S = mz.stage
+    imgs = _edge_images(mz)[:16] + mz.synth.synth_batch(321, 24, lo=64, hi=500)
+    for kw in (dict(clear_border=True), dict(min_area=40), dict(clear_border=True, min_area=12)):
+        pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1, **kw)
+        st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=compact)
+        res = st(imgs)
+        assert res.compact == compact
+        removed = 0
+        for i, im in enumerate(imgs):
+            mask, labels, table = scipy_chain.loki_chain(im, 40, 1, 2, clear_border_flag=kw.get("clear_border", False),
+                                                         min_area=kw.get("min_area", 0))
+            assert np.array_equal(res.mask(i), mask), (kw, i, im.shape)
+            assert np.array_equal(res.labels(i), labels), (kw, i, im.shape)
+            f = res.features(i)
+            k = min(len(f), len(table))
+            assert_tables_close(f[:k], table[:k])
+            assert (f[k:, oracle.F_AREA] == 0).all()
+            removed += int((f[:, oracle.F_AREA] == 0).sum())
+        assert removed > 0, kw
