@@ -411,3 +411,50 @@ def test_host_expand_and_crops_from_run_lists():
     assert not dense.compact
     for i, lab in enumerate(labs):
         assert np.array_equal(dense.labels(i), lab) and np.array_equal(dense.mask(i), lab > 0)
+
+
+def test_band_plan_covers_every_row_once_and_fits_the_planes():
+    """Band plan of maze_band_stage: the bands of a vignette are consecutive, cover its rows exactly once with a uniform
+    height, and a band plus its halo never exceeds MAZE_BAND_PLANE_WORDS; vignettes that cannot be cut are listed."""
+    from maze_image_processing_pipeline_b200._lib import BAND_PLANE_WORDS
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    rng = np.random.default_rng(0)
+    hs = np.concatenate([rng.integers(1, 1500, 200), [1, 70000, 4096, 300, 2, 5000]])
+    ws = np.concatenate([rng.integers(1, 1500, 200), [70000, 1, 4096, 20000, 65535, 40]])
+    g = BatchGeometry(hs, ws)
+    for halo in (0, 4, 6, 40):
+        bands, off, left = g.band_plan(halo)
+        assert off[0] == 0 and off[-1] == len(bands)
+        for i in range(g.n_img):
+            b = bands[off[i]:off[i + 1]]
+            wpr = (int(ws[i]) + 31) // 32
+            if len(b) == 0:
+                assert i in left
+                assert hs[i] >= 65536 or ws[i] >= 65536 or BAND_PLANE_WORDS // wpr - 2 * halo < max(1, halo)
+                continue
+            assert i not in left and (b["img"] == i).all()
+            assert b["y0"][0] == 0 and b["y1"][-1] == hs[i] and (b["y0"][1:] == b["y1"][:-1]).all()
+            assert (b["rpb"] == b["rpb"][0]).all() and (b["y0"] == np.arange(len(b)) * b["rpb"][0]).all()
+            if len(b) == 1:
+                assert hs[i] * wpr <= BAND_PLANE_WORDS                      # the whole vignette, no halo
+            else:
+                lo = np.maximum(0, b["y0"] - halo)
+                hi = np.minimum(int(hs[i]), b["y1"] + halo)
+                assert ((hi - lo) * wpr <= BAND_PLANE_WORDS).all()
+
+
+def test_host_pack_async_equals_sync():
+    """maze_host_pack_start / maze_host_pack_wait (background packing of the next batch) against maze_host_pack."""
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    rng = np.random.default_rng(1)
+    imgs = [rng.integers(0, 256, (int(h), int(w)), dtype=np.uint8) for h, w in rng.integers(1, 700, (300, 2))]
+    imgs.append(np.asfortranarray(rng.integers(0, 256, (50, 60), dtype=np.uint8)))  # not C-contiguous: copied first
+    g = BatchGeometry.from_images(imgs)
+    want = g.pack_host(imgs, out=np.zeros(g.total_px, np.uint8), threads=3)
+    got = np.zeros(g.total_px, np.uint8)
+    wait = g.pack_host_start(imgs, out=got, threads=5)
+    wait()
+    wait()  # idempotent
+    assert np.array_equal(got, want)
+    for i, im in enumerate(imgs):
+        assert np.array_equal(g.view(got, i), im)
