@@ -601,8 +601,11 @@ def run_b200(args):
         variants = {}
         vb = batches[args.warmup % n_res][0], batches[args.warmup % n_res][1]
         for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8),
-                                 ("label_filters", dict(clear_border=True, min_area=12), 8)):
-            vpp = S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN, **kw)
+                                 ("label_filters", dict(clear_border=True, min_area=12), 8),
+                                 ("threshold_branch", None, 8)):
+            # (threshold_branch: the reference's shipped `threshold` segmentation, loki/pipeline.py:648-656 -- mask +
+            # one region per vignette, no morphology / labelling)
+            vpp = None if kw is None else S.SegmentationPostprocessingConfig(closing_radius=R_CLOSE, opening_radius=R_OPEN, **kw)
             st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), vpp, merge_errors="ignore",
                                          morphology="crosses" if name == "crosses" else "isotropic")
             st.reserve([vb[0].g])

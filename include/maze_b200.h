@@ -306,10 +306,13 @@ int maze_vignette_stage(const uint8_t *image, const uint8_t *intensity, const ma
  * the list kernel); without it a labelling kernel of its own runs behind the band kernel.
  * clear_border / min_area: the label filters of loki/pipeline.py:435-448 applied ON THE RUN LIST by the labelling kernel
  * (labels touching the outermost rows / columns, labels with fewer than min_area pixels: their runs get label 0, their
- * rows are emptied; no renumbering); not available together with frames (n_huge > 0).
+ * rows are emptied; no renumbering); not available together with frames (n_huge > 0), nor is MAZE_BAND_SINGLE_REGION.
+ * flags: MAZE_RP_HIGH_ORDER, MAZE_FUSED_NO_PROPS, MAZE_BAND_SINGLE_REGION.
  * fallback[i] = 1: nothing valid was produced for vignette i (more runs than slots, run buffer full, or scipy's
  * phantom pixel applies to a multi-band vignette): use the per-operator entry points for it. */
 #define MAZE_BAND_PLANE_WORDS 6144
+#define MAZE_BAND_SINGLE_REGION 8 /* flag: no labelling, the whole mask of a vignette is label 1 (ImageProperties,
+                                     loki/pipeline.py:653); n_labels is 1 for every vignette, also for an empty mask */
 typedef struct maze_band { int32_t img, y0, y1, rpb; } maze_band_t;
 typedef struct maze_band_out { int32_t base, n_runs, zflags, reserved; } maze_band_out_t;
 typedef struct maze_run { uint16_t y, x0, x1, label; } maze_run_t;

@@ -29,6 +29,7 @@ RP_HIGH_ORDER = 1
 RP_RUNS = 2
 FUSED_CAPS = (1024, 2560, 4096, 6144, 9216, 13312, 19456, 28320)  # MAZE_FUSED_CAPS of include/maze_b200.h
 FUSED_NO_PROPS = 4
+BAND_SINGLE_REGION = 8   # MAZE_BAND_SINGLE_REGION
 BAND_PLANE_WORDS = 6144  # MAZE_BAND_PLANE_WORDS
 HUGE_PX = 1 << 21        # vignettes from 2 MPix on are frames: labelled by the global-memory kernels
 STEP_COMPACT = 1         # MAZE_STEP_COMPACT

@@ -72,6 +72,7 @@ struct LabelArgs {
     long long huge_px; // vignettes with at least this many pixels are labelled by the global-memory kernels
     long long min_area; // label filters (0 / 0: none)
     int clear_border;
+    int single_region; // ImageProperties semantics: no labelling, every run belongs to label 1
 };
 
 __device__ __forceinline__ void mark_fallback(const LabelArgs &a, int img)
@@ -471,6 +472,137 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         if (tid == 0) mark_fallback(a, img);
         return 0;
     }
+    if (a.single_region && n_runs > cap && cap < LABEL_BIG_CAP) return 1; // (the tiers only spread the work here)
+    if (a.single_region) {
+        // ---- ImageProperties(mask, image), loki/pipeline.py:653: the whole mask of the vignette is ONE region with
+        // label 1 (also when it is empty: the row then has area 0 and the caller drops the vignette, :651).  No
+        // labelling, hence no run table and no limit on the number of runs: the runs are streamed from the run buffer,
+        // sums per thread, one reduction per warp into the single accumulator row.
+        AccRow *ACC1 = (AccRow *)(((uintptr_t)(s_bpre + nbcap + 1) + 15) & ~(uintptr_t)15);
+        if (tid == 0) {
+            a.n_labels[img] = 1;
+            a.fallback[img] = 0;
+            int base = -1;
+            if (a.do_props) {
+                base = atomicAdd(a.stage_counter, 1);
+                if (base + 1 > a.stage_cap) base = -1;
+            }
+            s_base = base;
+            a.acc_base[img] = base;
+        }
+        for (int i = tid; i < (int)(sizeof(AccRow) / 4); i += T) ((uint32_t *)ACC1)[i] = 0;
+        __syncthreads();
+        const int base = s_base;
+        const bool props = a.do_props && base >= 0;
+        const int W = v.w;
+        if (tid == 0) {
+            ACC1->e[E_RMIN] = 0x7fffffff; ACC1->e[E_RMAX] = -1; ACC1->e[E_CMIN] = 0x7fffffff; ACC1->e[E_CMAX] = -1;
+            ACC1->e[E_VMIN] = 0x7fffffff; ACC1->e[E_VMAX] = -1;
+        }
+        __syncthreads();
+        u64 aN = 0, aR = 0, aC = 0, aRR = 0, aRC = 0, aCC = 0, aRRR = 0, aRRC = 0, aRCC = 0, aCCC = 0, aV = 0, aZ = 0;
+        int rmin = 0x7fffffff, rmax = -1, cmin = 0x7fffffff, cmax = -1, vmin = 255, vmax = 0;
+#pragma unroll 4
+        for (int i = tid; i < (props ? n_runs : 0); i += T) { // (independent iterations: several loads in flight)
+            const int g = gidx(i);
+            const uint2 r = __ldcg((const uint2 *)a.runs + g);
+            const u64 y = r.x & 0xffffu, xa = r.x >> 16, xb = r.y & 0xffffu, n = xb - xa + 1;
+            const u64 S1 = n * (xa + xb) / 2;
+            const u64 S2 = pw2(xb) - (xa ? pw2(xa - 1) : 0);
+            const u64 S3 = pw3(xb) - (xa ? pw3(xa - 1) : 0);
+            aN += n; aR += y * n; aC += S1; aRR += y * y * n; aRC += y * S1; aCC += S2;
+            aRRR += y * y * y * n; aRRC += y * y * S1; aRCC += y * S2; aCCC += S3;
+            rmin = min(rmin, (int)y); rmax = max(rmax, (int)y); cmin = min(cmin, (int)xa); cmax = max(cmax, (int)xb);
+            if (a.has_intensity) {
+                const uint2 st = __ldcg((const uint2 *)a.stats + g);
+                aV += st.x; aZ += st.y & 0xffffu;
+                vmin = min(vmin, (int)((st.y >> 16) & 0xffu)); vmax = max(vmax, (int)(st.y >> 24));
+            }
+        }
+        if (props) {
+            u64 vv[12] = {aN, aR, aC, aRR, aRC, aCC, aRRR, aRRC, aRCC, aCCC, aV, aZ};
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                u64 x = vv[j];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                vv[j] = x;
+            }
+            rmin = __reduce_min_sync(FULL, rmin); rmax = __reduce_max_sync(FULL, rmax);
+            cmin = __reduce_min_sync(FULL, cmin); cmax = __reduce_max_sync(FULL, cmax);
+            vmin = __reduce_min_sync(FULL, vmin); vmax = __reduce_max_sync(FULL, vmax);
+            if (lane == 0 && vv[0]) { // (the label field of the run records stays 0: there is no label image here)
+#pragma unroll
+                for (int j = 0; j < 10; j++) shared_add64(ACC1->a + j, vv[j]);
+                if (a.has_intensity) { shared_add64(ACC1->a + A_V, vv[10]); shared_add64(ACC1->a + A_Z, vv[11]); }
+                atomicMin(&ACC1->e[E_RMIN], rmin); atomicMax(&ACC1->e[E_RMAX], rmax);
+                atomicMin(&ACC1->e[E_CMIN], cmin); atomicMax(&ACC1->e[E_CMAX], cmax);
+                if (a.has_intensity) { atomicMin(&ACC1->e[E_VMIN], vmin); atomicMax(&ACC1->e[E_VMAX], vmax); }
+            }
+        }
+        // dense outputs: mask bytes (and label 1) of every run, eight lanes per run as below
+        if (a.labels) {
+            int32_t *gl = a.labels + v.pix_off;
+            uint8_t *gm = a.mask + v.pix_off;
+            const int oct = lane >> 3, ol = lane & 7;
+            for (int i0 = warp * 4; i0 < n_runs; i0 += (T / 32) * 4) {
+                const int i = i0 + oct;
+                if (i < n_runs) {
+                    const uint2 r = __ldcg((const uint2 *)a.runs + gidx(i));
+                    const int len = (int)(r.y & 0xffffu) - (int)(r.x >> 16) + 1;
+                    const int p = (int)(r.x & 0xffffu) * W + (int)(r.x >> 16);
+                    int32_t *pl = gl + p;
+                    uint8_t *pm = gm + p;
+                    const int head = min((-p) & 3, len), body = (len - head) & ~3, tail = len - head - body;
+                    if (ol < head) { pl[ol] = 1; pm[ol] = 1; }
+                    if (ol >= 4 && ol - 4 < tail) { pl[head + body + ol - 4] = 1; pm[head + body + ol - 4] = 1; }
+                    for (int x = head + 4 * ol; x < head + body; x += 32) {
+                        *(uint4 *)(pl + x) = make_uint4(1, 1, 1, 1);
+                        *(uint32_t *)(pm + x) = 0x01010101u;
+                    }
+                }
+            }
+        }
+        if (!props) return 0;
+        __syncthreads();
+        if (a.high_order) { // float64 moments with p + q > 3 about the exact centroid: a second pass over the runs
+            const double dnA = (double)*(const volatile u64 *)(ACC1->a + A_N);
+            const double cr = (double)*(const volatile u64 *)(ACC1->a + A_R) / dnA, cc = (double)*(const volatile u64 *)(ACC1->a + A_C) / dnA;
+            double h13 = 0, h22 = 0, h31 = 0, h23 = 0, h32 = 0, h33 = 0;
+#pragma unroll 4
+            for (int i = tid; i < n_runs; i += T) {
+                const uint2 r = __ldcg((const uint2 *)a.runs + gidx(i));
+                const int x0 = r.x >> 16, nn = (int)(r.y & 0xffffu) - x0 + 1;
+                const double dn = (double)nn, m1 = (double)(nn - 1);
+                const double S1 = dn * m1 * 0.5, S2 = m1 * dn * (2.0 * m1 + 1.0) / 6.0, S3 = S1 * S1;
+                const double o = cc - (double)x0;
+                const double T1 = S1 - dn * o, T2 = S2 - 2.0 * o * S1 + dn * o * o;
+                const double T3 = S3 - 3.0 * o * S2 + 3.0 * o * o * S1 - dn * o * o * o;
+                const double dr = (double)(r.x & 0xffffu) - cr, dr2 = dr * dr, dr3 = dr2 * dr;
+                h13 += dr * T3; h22 += dr2 * T2; h31 += dr3 * T1;
+                h23 += dr2 * T3; h32 += dr3 * T2; h33 += dr3 * T3;
+            }
+            double hv[6] = {h13, h22, h31, h23, h32, h33};
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                double x = hv[j];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(FULL, x, d);
+                hv[j] = x;
+            }
+            if (lane == 0 && n_runs > 0) {
+                atomicAdd(ACC1->h + H_13, hv[0]); atomicAdd(ACC1->h + H_22, hv[1]); atomicAdd(ACC1->h + H_31, hv[2]);
+                atomicAdd(ACC1->h + H_23, hv[3]); atomicAdd(ACC1->h + H_32, hv[4]); atomicAdd(ACC1->h + H_33, hv[5]);
+            }
+            __syncthreads();
+        }
+        for (int j = tid; j < MAZE_NACC; j += T) a.acc_stage[(i64)base * MAZE_NACC + j] = ACC1->a[j];
+        for (int j = tid; j < 8; j += T) {
+            a.hi_stage[(i64)base * 8 + j] = ACC1->h[j];
+            a.ext_stage[(i64)base * MAZE_NEXT + j] = ACC1->e[j];
+        }
+        return 0;
+    }
     if (n_runs > cap || n_runs >= 0x8000 || H + 2 > hcap) return 1;
 
     u16 *rY = (u16 *)(s_bpre + nbcap + 1), *rX0 = rY + cap, *rX1 = rX0 + cap, *P = rX1 + cap, *rO = P + cap, *rowStart = rO + cap;
@@ -481,67 +613,69 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
         P[i] = (u16)i;
     }
     __syncthreads();
-    // first run of every row (runs are in raster order)
-    for (int i = tid; i < n_runs; i += T) {
-        const int y = rY[i], yp = i ? (int)rY[i - 1] : -1;
-        for (int yy = yp + 1; yy <= y; yy++) rowStart[yy] = (u16)i;
-    }
-    {
-        const int ylast = n_runs ? (int)rY[n_runs - 1] : -1;
-        for (int yy = ylast + 1 + tid; yy <= H; yy += T) rowStart[yy] = (u16)n_runs;
-    }
-    __syncthreads();
-    // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1): plain store to
-    // the FIRST run it touches, pointer doubling, lock-free unions for the further runs (see maze_fused.cu)
-    for (int i = tid; i < n_runs; i += T) {
-        const int y = rY[i];
-        int first = 0xffff;
-        if (y > 0) {
-            int p = rowStart[y - 1];
-            const int bnd = rowStart[y];
-            const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
-            int e = bnd;
-            while (p < e) {
-                const int mid = (p + e) >> 1;
-                if ((int)rX1[mid] < lo0) p = mid + 1; else e = mid;
-            }
-            if (p < bnd && (int)rX0[p] <= hi0) { first = p; P[i] = (u16)p; }
-        }
-        rO[i] = (u16)first;
-    }
-    __syncthreads();
-    for (int i = tid; i < n_runs; i += T) {
-        int p = *(volatile u16 *)(P + i);
-        for (;;) {
-            const int g = *(volatile u16 *)(P + p);
-            if (g == p) break;
-            *(volatile u16 *)(P + i) = (u16)g;
-            p = g;
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < n_runs; i += T) {
-        const int first = rO[i];
-        if (first == 0xffff) continue;
-        const int bnd = rowStart[rY[i]];
-        const int hi0 = (int)rX1[i] + 1;
-        for (int j = first + 1; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
-    }
-    __syncthreads();
-    for (int r = tid; r < n_runs; r += T) {
-        const int root = find16(P, r);
-        if (root != r) P[r] = (u16)root;
-    }
-    __syncthreads();
-    // roots in raster order get labels 1..N, stored in their own slot with the top bit set
-    const int rchunk = (n_runs + T - 1) / T;
-    const int rlo = min(tid * rchunk, n_runs), rhi = min(rlo + rchunk, n_runs);
-    int nroot = 0;
-    for (int r = rlo; r < rhi; r++) nroot += (P[r] == r);
     int n_lab;
-    int rank = block_exclusive_scan<T>(nroot, s_warp, &n_lab);
-    for (int r = rlo; r < rhi; r++)
-        if (P[r] == r) P[r] = (u16)(0x8000 | (++rank));
+    {
+        // first run of every row (runs are in raster order)
+        for (int i = tid; i < n_runs; i += T) {
+            const int y = rY[i], yp = i ? (int)rY[i - 1] : -1;
+            for (int yy = yp + 1; yy <= y; yy++) rowStart[yy] = (u16)i;
+        }
+        {
+            const int ylast = n_runs ? (int)rY[n_runs - 1] : -1;
+            for (int yy = ylast + 1 + tid; yy <= H; yy += T) rowStart[yy] = (u16)n_runs;
+        }
+        __syncthreads();
+        // link every run to the runs of the previous row it touches (8-connectivity: x ranges within 1): plain store to
+        // the FIRST run it touches, pointer doubling, lock-free unions for the further runs (see maze_fused.cu)
+        for (int i = tid; i < n_runs; i += T) {
+            const int y = rY[i];
+            int first = 0xffff;
+            if (y > 0) {
+                int p = rowStart[y - 1];
+                const int bnd = rowStart[y];
+                const int lo0 = (int)rX0[i] - 1, hi0 = (int)rX1[i] + 1;
+                int e = bnd;
+                while (p < e) {
+                    const int mid = (p + e) >> 1;
+                    if ((int)rX1[mid] < lo0) p = mid + 1; else e = mid;
+                }
+                if (p < bnd && (int)rX0[p] <= hi0) { first = p; P[i] = (u16)p; }
+            }
+            rO[i] = (u16)first;
+        }
+        __syncthreads();
+        for (int i = tid; i < n_runs; i += T) {
+            int p = *(volatile u16 *)(P + i);
+            for (;;) {
+                const int g = *(volatile u16 *)(P + p);
+                if (g == p) break;
+                *(volatile u16 *)(P + i) = (u16)g;
+                p = g;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < n_runs; i += T) {
+            const int first = rO[i];
+            if (first == 0xffff) continue;
+            const int bnd = rowStart[rY[i]];
+            const int hi0 = (int)rX1[i] + 1;
+            for (int j = first + 1; j < bnd && (int)rX0[j] <= hi0; j++) union16(P, i, j);
+        }
+        __syncthreads();
+        for (int r = tid; r < n_runs; r += T) {
+            const int root = find16(P, r);
+            if (root != r) P[r] = (u16)root;
+        }
+        __syncthreads();
+        // roots in raster order get labels 1..N, stored in their own slot with the top bit set
+        const int rchunk = (n_runs + T - 1) / T;
+        const int rlo = min(tid * rchunk, n_runs), rhi = min(rlo + rchunk, n_runs);
+        int nroot = 0;
+        for (int r = rlo; r < rhi; r++) nroot += (P[r] == r);
+        int rank = block_exclusive_scan<T>(nroot, s_warp, &n_lab);
+        for (int r = rlo; r < rhi; r++)
+            if (P[r] == r) P[r] = (u16)(0x8000 | (++rank));
+    }
     if (tid == 0) {
         a.n_labels[img] = n_lab;
         a.fallback[img] = 0;
@@ -847,7 +981,7 @@ __device__ int label_vignette(const LabelArgs &a, int img, int cap, int hcap, in
 // the smallest class that holds it (list k = big_list[k * n_img ..], its length in big_counter[k], the counter its
 // CTAs draw from in big_counter[3 + k])
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap)
+__global__ void __launch_bounds__(T, 1024 / T) k_band_label(LabelArgs a, int cap, int hcap)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const int img = blockIdx.x;
@@ -863,7 +997,7 @@ __global__ void __launch_bounds__(T) k_band_label(LabelArgs a, int cap, int hcap
 
 // the list classes: a fixed grid, the CTAs take the vignettes of their list one by one from a counter
 template <int T>
-__global__ void __launch_bounds__(T) k_band_label_big(LabelArgs a, int cap, int hcap, int nbcap, int which)
+__global__ void __launch_bounds__(T, 1024 / T) k_band_label_big(LabelArgs a, int cap, int hcap, int nbcap, int which)
 {
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ int s_next;
@@ -1378,7 +1512,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                     (u64 *)acc_stage, hi_stage, ext_stage, big_list, big_counter, dense && !k3 ? mask : nullptr,
                     dense && !k3 ? labels : nullptr, n_img, n_pass, prm.phantom_mask, prm.do_props, prm.high_order,
                     prm.has_intensity, stage_cap, (n_huge > 0 && gl_scratch) ? huge_px : (1ll << 62), min_area,
-                    clear_border ? 1 : 0};
+                    clear_border ? 1 : 0, (flags & MAZE_BAND_SINGLE_REGION) ? 1 : 0};
     if (inband) MAZE_CUDA(cudaMemsetAsync(band_done, 0, sizeof(int32_t) * (size_t)n_img, s), "band done");
     MAZE_KERNEL(KID_BAND_FRONT, s,
                 k_band_front<BAND_T><<<n_bands, BAND_T, smem1, s>>>(image, intensity, vig, bands, prm, bits, runs,
@@ -1406,7 +1540,7 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                                                                      LABEL_BIG_NB, 2));
     }
     if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
-        if (!huge_host || clear_border || min_area > 0) return MAZE_ERR_BADARG; // (no label filters on this path)
+        if (!huge_host || clear_border || min_area > 0 || (flags & MAZE_BAND_SINGLE_REGION)) return MAZE_ERR_BADARG; // (not on this path)
         for (int e = 0; e < n_huge; e++) {
             // (the band count of the vignette sizes its prefix array; the host knows the band plan)
             const int rc = gl_label_frame(la, huge_host[2 * e], gl_scratch, run_cap, huge_host[2 * e + 1], s);

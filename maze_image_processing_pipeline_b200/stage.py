@@ -26,7 +26,8 @@ import torch
 import ctypes
 import os
 
-from ._lib import MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, STEP_COMPACT, StepArgs, check, lib
+from ._lib import (BAND_SINGLE_REGION, MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, STEP_COMPACT, StepArgs,
+                   check, lib)
 from ._lib import MAX_DISK_RADIUS
 from .device import (Arena, BatchGeometry, DeviceBatch, fold_dilation_radius, fold_erosion_radius, fold_threshold)
 
@@ -77,6 +78,7 @@ class DeviceResult:
         self.n_runs = 0
         self.compact = False
         self.dense_only = []
+        self.single_region = False  # threshold branch on the band pipeline: one region per vignette, no label image
 
     def finalize(self):
         if self._pending is not None:
@@ -112,6 +114,7 @@ class StageResult:
         self.keep = keep  # threshold branch: vignettes that survive the empty-mask filter
         self.shape_table = None  # shape_features=True: (n_obj, NSHAPE) perimeter / filled_area / euler_number rows
         self.merge_failed = None  # merge_errors="ignore": vignettes where merge_labels hit the reference's TypeError
+        self._no_labels = False  # threshold branch: there is no label image (labels(i) is None)
         # compact form
         self._runs = self._band_out = self._band_off = self._rpb = None
         self._dense = {}    # vignettes without a run list (per-operator kernels): i -> (mask, labels)
@@ -156,6 +159,8 @@ class StageResult:
         return self.geometry.view(self._mask, i).view(bool)
 
     def labels(self, i) -> Optional[np.ndarray]:
+        if self._no_labels:
+            return None
         if self._runs is not None:
             return self._expand(i)[1]
         return None if self._labels is None else self.geometry.view(self._labels, i)
@@ -211,7 +216,8 @@ class StageResult:
                                          int(threads)), "maze_host_expand")
         for i, (m, l) in self._dense.items():
             g.view(mask, i)[...] = m
-            g.view(labels, i)[...] = l
+            if l is not None:
+                g.view(labels, i)[...] = l
         self._mask, self._labels = mask, labels
         self._runs = self._band_out = None
         self._dense, self._cache = {}, {}
@@ -379,18 +385,39 @@ class LokiSegmentationStage:
             d_src, t_int = d_image, fold_threshold(self.threshold.threshold_brighter)
         else:
             d_src, t_int = d_pred, 0  # np.asarray(pred, dtype=bool), loki/pipeline.py:405
+        if pp is None and self._threshold_bands(batch):
+            # ImageProperties(mask, image) through the band pipeline: threshold, run list, ONE region per vignette
+            return self._run_fused_async(batch, d_src, d_image, t_int, [])
         if pp is None:
-            # ImageProperties(mask, image): one region per vignette; empty masks are dropped (:651)
-            bits, flags = batch.threshold_pack(d_src, t_int)
-            lab_off, n_obj = batch.lab_off_from_bounds(np.ones(g.n_img, np.int64))
-            table = batch.regionprops(lab_off, n_obj, bits=bits, image=d_image, high_order=self.high_order)
-            keep = (flags & 1).bool()
-            return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
+            return self.run_device_threshold_generic(batch, d_src, d_image, t_int)
         passes = self._passes() if self.fused else None
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
         if passes is not None and (not filters or self._band_filters(batch)):
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
         return self._run_filter_path(batch, d_src, d_image, t_int, passes)
+
+    def run_device_threshold_generic(self, batch, d_src, d_image, t_int) -> DeviceResult:
+        """Threshold branch with the per-operator kernels: ImageProperties(mask, image), one region per vignette; empty
+        masks are dropped (loki/pipeline.py:651-653)."""
+        g = batch.g
+        if self._shared_busy is not None:
+            self._shared_busy.synchronize()
+            self._shared_busy = None
+        bits, flags = batch.threshold_pack(d_src, t_int)
+        lab_off, n_obj = batch.lab_off_from_bounds(np.ones(g.n_img, np.int64))
+        table = batch.regionprops(lab_off, n_obj, bits=bits, image=d_image, high_order=self.high_order)
+        keep = (flags & 1).bool()
+        return DeviceResult(batch, bits, None, lab_off, table, n_obj, keep=keep, mask=batch.unpack_mask(bits))
+
+    def _threshold_bands(self, batch) -> bool:
+        """The threshold branch (loki/pipeline.py:648-656) runs on the band pipeline unless the batch holds frames or
+        vignettes a band cannot take."""
+        if self.pipeline != "bands" or not self.fused:
+            return False
+        from ._lib import HUGE_PX
+        if (batch.g.npx >= HUGE_PX).any():
+            return False
+        return len(batch.band_lists(0)[3]) == 0
 
     def _band_filters(self, batch) -> bool:
         """clear_border / remove_small_objects run on the run list inside the band pipeline (no merge_labels, no frames,
@@ -559,7 +586,8 @@ class LokiSegmentationStage:
             a.run_cap, a.total_px = run_cap, g.total_px
             a.band_done = band_done.data_ptr()
             pp = self.postprocess
-            a.clear_border, a.min_area = int(bool(pp.clear_border)), int(pp.min_area)
+            if pp is not None:
+                a.clear_border, a.min_area = int(bool(pp.clear_border)), int(pp.min_area)
             if huge_pairs is not None:
                 a.huge_host, a.n_huge, a.huge_px = huge_pairs.ctypes.data, len(huge_pairs), HUGE_PX
                 a.gl_scratch = gl_scratch.data_ptr()
@@ -572,6 +600,9 @@ class LokiSegmentationStage:
             a.pass_t[k], a.pass_invert[k] = int(t), int(inv)
         a.n_img, a.t_int, a.n_pass, a.stage_cap = n, int(t_int), len(passes), cap
         a.flags = RP_HIGH_ORDER if self.high_order else 0
+        single = self.postprocess is None  # threshold branch: the whole mask is one region (ImageProperties)
+        if single:
+            a.flags |= BAND_SINGLE_REGION
         a.left_n = len(left)
         keep = None
         if len(left):
@@ -607,7 +638,38 @@ class LokiSegmentationStage:
             bad = [int(i) for i in bad if int(i) not in left_set]
             res.dense_only = sorted(left_set | set(bad))  # vignettes without a run list (per-operator kernels)
             ppf = self.postprocess
-            if (bad or total > cap) and (ppf.clear_border or ppf.min_area > 0):
+            if bad and ppf is None and total <= cap and len(bad) <= 256:
+                # threshold branch: the few vignettes whose run tables overflowed (speckle) are thresholded again with
+                # the per-operator kernels, in place; every vignette keeps exactly one row
+                with torch.cuda.stream(main):
+                    res.redone = True
+                    sub, word_idx, idx = self._sub(batch, bad)
+                    sub.arena = batch.arena
+                    sbits, _ = sub.threshold_pack(d_src, t_int)
+                    bits[word_idx] = sbits[word_idx]
+                    sub.unpack_mask(sbits, out=mask)
+                    n_labels[idx.long()] = 1
+                    batch.count_scan(n_labels, out=lab_off)
+                    batch.props_finish_staged(staging, acc_base, lab_off, cap, True, self.high_order, table)
+                    batch.regionprops(lab_off, cap, labels=None, bits=bits, image=d_image, high_order=self.high_order,
+                                      table=table, acc_base=acc_base, tiles=batch.tiles_of(sorted(bad)))
+                    total = n
+                    res._table = table[:total]
+                    res._sync_main = True
+                    res.ready = torch.cuda.Event()
+                    res.ready.record(main)
+            elif (bad or total > cap) and ppf is None:
+                # threshold branch: the whole batch through the per-operator kernels
+                with torch.cuda.stream(main):
+                    r2 = self.run_device_threshold_generic(batch, d_src, d_image, t_int)
+                    res.redone = True
+                    res.dense_only = list(range(n))
+                    res.bits, res.mask, res.lab_off, res.keep = r2.bits, r2.mask, r2.lab_off, r2.keep
+                    res._table, total = r2._table, r2._n_obj
+                    res._sync_main = True
+                    res.ready = torch.cuda.Event()
+                    res.ready.record(main)
+            elif (bad or total > cap) and (ppf.clear_border or ppf.min_area > 0):
                 # the per-operator redo below knows no label filters: the whole batch takes the filter path instead
                 with torch.cuda.stream(main):
                     r2 = self._run_filter_path(batch, d_src, d_image, t_int, passes)
@@ -650,7 +712,8 @@ class LokiSegmentationStage:
                 res._table = table[:total]
             res._n_obj = total
 
-        res = DeviceResult(batch, bits, labels, lab_off, None, None, mask=mask, pending=pending)
+        res = DeviceResult(batch, bits, None if single else labels, lab_off, None, None, mask=mask, pending=pending)
+        res.single_region = single
         res.ready = done
         if use_bands:
             res.runs, res.band_out, res.bands_host, res.band_off_host = runs, band_out, bands_h, band_off_h
@@ -726,7 +789,9 @@ class LokiSegmentationStage:
     def _halo(self):
         """Halo of the band plan (sum of the pass radii) when the asynchronous band pipeline will take the batch."""
         pp = self.postprocess
-        if pp is None or not self.fused or self.pipeline != "bands" or self._passes() is None:
+        if pp is None:
+            return 0 if (self.fused and self.pipeline == "bands") else None
+        if not self.fused or self.pipeline != "bands" or self._passes() is None:
             return None
         if pp.merge_segments_distance > 0:
             return None
@@ -833,8 +898,9 @@ class LokiSegmentationStage:
                 h_bo.copy_(res.band_out[:4 * n_bands], non_blocking=True)
                 for i in res.dense_only:  # vignettes of the per-operator kernels: their dense arrays
                     o, npx = int(geom.pix_off[i]), int(geom.npx[i])
-                    dense[i] = (res.mask[o:o + npx].cpu().numpy().reshape(int(geom.h[i]), int(geom.w[i])),
-                                res.labels[o:o + npx].cpu().numpy().reshape(int(geom.h[i]), int(geom.w[i])))
+                    shp = (int(geom.h[i]), int(geom.w[i]))
+                    dense[i] = (res.mask[o:o + npx].cpu().numpy().reshape(shp),
+                                None if res.labels is None else res.labels[o:o + npx].cpu().numpy().reshape(shp))
         with torch.cuda.stream(ss):
             if res.redone and not compact:  # rare: per-pixel outputs were rewritten by the per-operator path
                 ss.wait_event(copied)
@@ -853,7 +919,7 @@ class LokiSegmentationStage:
                 d_shape = batch.label_shape(table, labels=res.labels, bits=res.bits, runs=res.merge_status is None)
                 h_shape = pool.get("shape", max(d_shape.numel(), 1), torch.float64)[:d_shape.numel()]
                 h_shape.copy_(d_shape.reshape(-1), non_blocking=True)
-            keep = None if res.keep is None else res.keep.cpu().numpy()
+            keep = None if res.keep is None or not torch.is_tensor(res.keep) else res.keep.cpu().numpy()
             status = None if res.merge_status is None else res.merge_status.cpu().numpy()
         ss.synchronize()
         copied.synchronize()
@@ -872,6 +938,12 @@ class LokiSegmentationStage:
         else:
             out = StageResult(geom, None if h_mask is None else h_mask.numpy(), None if h_lab is None else h_lab.numpy(),
                               h_off.numpy(), h_tab.numpy().reshape(-1, NFEAT), keep=keep)
+        if res.single_region and keep is None:
+            # Filter(obj[mask].any()), loki/pipeline.py:651: a vignette is kept when its (single) region has pixels
+            t_np, o_np = h_tab.numpy().reshape(-1, NFEAT), h_off.numpy()
+            keep = t_np[o_np[:-1], 1] > 0 if len(t_np) else np.zeros(geom.n_img, bool)
+            out.keep = keep
+            out._no_labels = True
         out.merge_failed = failed
         if self.shape_features:
             out.shape_table = h_shape.numpy().reshape(-1, NSHAPE)
@@ -897,9 +969,12 @@ class LokiSegmentationStage:
             # the asynchronous band / fused path rotates its workspaces (>= 2 lanes); the paths with label filters,
             # merge_labels, radii beyond the bit-plane kernels or threshold-only work in ONE shared workspace
             pp = self.postprocess
-            overlap = (pp is not None and self.fused and self.n_lanes >= 2 and self._passes() is not None
-                       and pp.merge_segments_distance <= 0
-                       and (self.pipeline == "bands" or not (pp.clear_border or pp.min_area > 0)))
+            if pp is None:
+                overlap = self.fused and self.n_lanes >= 2 and self.pipeline == "bands"
+            else:
+                overlap = (self.fused and self.n_lanes >= 2 and self._passes() is not None
+                           and pp.merge_segments_distance <= 0
+                           and (self.pipeline == "bands" or not (pp.clear_border or pp.min_area > 0)))
             def split(item):
                 return item if isinstance(item, tuple) else (item, None)
 

@@ -266,3 +266,27 @@ def test_label_filters_on_the_run_list(mz, compact):
             assert (f[k:, oracle.F_AREA] == 0).all()
             removed += int((f[:, oracle.F_AREA] == 0).sum())
         assert removed > 0, kw
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_threshold_branch_on_the_band_pipeline(mz, compact):
+    """The branch the reference ships (loki/pipeline.py:648-656): mask = image > t, the whole mask ONE region
+    (ImageProperties), empty masks dropped.  Runs on the band pipeline (threshold, run list, single-region
+    accumulators), dense or compact; multi-band vignettes, uniform planes and float thresholds included."""
+    S = mz.stage
+    imgs = _edge_images(mz)
+    for thr in (40, 35.5, 254.5, -1):
+        st = S.LokiSegmentationStage(threshold=S.ThresholdSegmentationConfig(thr), compact=compact)
+        res = st(imgs)
+        assert res.compact == compact
+        for i, im in enumerate(imgs):
+            mask = im > thr
+            assert np.array_equal(res.mask(i), mask), (thr, i, im.shape)
+            assert res.labels(i) is None
+            assert bool(res.keep[i]) == bool(mask.any())
+            f = res.features(i)
+            assert len(f) == 1
+            if mask.any():
+                assert_tables_close(f, oracle.regionprops_table(mask.astype(np.int32), im))
+            else:
+                assert f[0, oracle.F_AREA] == 0
