@@ -609,7 +609,7 @@ def run_b200(args):
             st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(THRESHOLD), vpp, merge_errors="ignore",
                                          morphology="crosses" if name == "crosses" else "isotropic")
             st.reserve([vb[0].g])
-            for _ in range(st.n_lanes):  # every lane allocates its workspace on first use
+            for _ in range(2 * st.n_lanes):  # every lane allocates (and then grows) its workspace on its first uses
                 st.run_device(*vb).n_obj
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

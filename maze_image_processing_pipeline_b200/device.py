@@ -523,23 +523,25 @@ class DeviceBatch:
         return table
 
     def merge_labels(self, labels, labels_out, lab_off, n_obj: int, max_distance, path_tolerance=5.0,
-                     index=None, index_off=None, live=None):
+                     index=None, index_off=None, live=None, only=None, scratch=None):
         """merge_labels.py:29-113 for every vignette.  Returns (merge_dist, n_merge, index_state, status,
         obj_scratch) device tensors.  live: optional host array with (an upper bound of) the number of labels of
-        every vignette -- vignettes with fewer than two are not touched (the reference returns at :59-60).  When only
+        every vignette -- vignettes with fewer than two are not touched (the reference returns at :59-60); only: the
+        vignettes to work on (the others are not touched).  When only
         a few vignettes are large (MAZE_MERGE_CLUSTER_PX pixels and up) each of them gets a thread-block cluster of
         eight CTAs."""
         g = self.g
         n_obj = max(int(n_obj), 1)
-        d2a, d2b, d2c = (self.empty_px(torch.int32) for _ in range(3))
+        # scratch: three per-pixel int32 maps (a caller that merges batch after batch passes its own, see stage.py)
+        d2a, d2b, d2c = scratch if scratch is not None else (self.empty_px(torch.int32) for _ in range(3))
         obj_scratch = torch.zeros(2 * n_obj, dtype=torch.int32, device=self.device)
         merge_dist = torch.zeros(n_obj, dtype=torch.float64, device=self.device)
         n_merge = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
         index_state = torch.zeros(2 * g.n_img, dtype=torch.int32, device=self.device)
         status = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
         have_max = max_distance is not None
-        todo = np.arange(g.n_img)
-        if live is not None and index is None:
+        todo = np.arange(g.n_img) if only is None else np.asarray(only, np.int64)
+        if live is not None and index is None and only is None:
             todo = todo[np.asarray(live)[:g.n_img] >= 2]
         # a cluster of eight CTAs finishes ONE large vignette several times sooner, but a full batch keeps every SM busy
         # with one CTA per vignette anyway (measured: 33.6 ms per 4096-vignette batch either way): clusters only when

@@ -394,7 +394,59 @@ class LokiSegmentationStage:
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
         if passes is not None and (not filters or self._band_filters(batch)):
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
+        if passes is not None and pp.merge_segments_distance > 0 and self._band_filters(batch, merge_ok=True):
+            res = self._run_merge_on_bands(batch, d_src, d_image, t_int, passes)
+            if res is not None:
+                return res
         return self._run_filter_path(batch, d_src, d_image, t_int, passes)
+
+    def _run_merge_on_bands(self, batch, d_src, d_image, t_int, passes):
+        """merge_labels behind the band pipeline: the band step (labels, label filters, table) runs first; the object
+        table then tells, EXACTLY, which vignettes merge_labels can change at all, and only those go through the
+        merge kernel and get their rows recomputed.
+
+        The reference's loop (merge_labels.py:81-96) grows ONE cluster from the smallest label l0 and stops at the first
+        candidate whose merge distance exceeds max_distance.  If every other label l lies farther than max_distance from
+        l0 -- certain when the bounding boxes are more than max_distance apart in rows or in columns -- then whichever
+        candidate the first iteration picks, min(distmap + cur_distmap) > max_distance: inside both windows the sum is
+        at least dist(l0, l) (triangle inequality, the windowed EDTs are exact there), and outside a window the map
+        holds its window maximum, which is at least pad = ceil(max_distance) + 1 as soon as the window reaches one
+        unclipped margin.  The loop then breaks at once and the aliased call returns the labels unchanged."""
+        pp = self.postprocess
+        g = batch.g
+        n = g.n_img
+        saved_compact, self.compact = self.compact, False  # merge_labels needs the dense label image on the device
+        try:
+            res = self._run_fused_async(batch, d_src, d_image, t_int, passes)
+        finally:
+            self.compact = saved_compact
+        res.finalize()
+        if res.redone or len(res.dense_only):
+            return None  # flagged vignettes: the plain filter path takes the whole batch
+        main = torch.cuda.current_stream()
+        main.wait_event(res.ready)
+        tab = res._table[:, :6].cpu().numpy()          # label, area, bbox
+        off = res.lab_off.cpu().numpy().astype(np.int64)
+        need = _merge_candidates(tab, off, g.h, g.w, float(pp.merge_segments_distance))
+        merge_status = torch.zeros(n, dtype=torch.int32, device=batch.device)
+        if len(need):
+            n_obj = int(off[-1])
+            scratch = tuple(self._ws.get(k, g.total_px, torch.int32, batch.device) for k in ("d2a", "d2b", "d2c"))
+            saved_arena, batch.arena = batch.arena, None  # (scratch of this synchronous tail does not belong to a lane)
+            merge_status = batch.merge_labels(res.labels, res.labels, res.lab_off, n_obj, pp.merge_segments_distance,
+                                              only=need, scratch=scratch)[3]
+            # rows of the merged vignettes from the dense label image (bridges leave the runs of the bit plane)
+            acc_base = torch.zeros(n, dtype=torch.int32, device=batch.device)
+            acc_base[torch.as_tensor(need, device=batch.device)] = -1
+            cap = res._table.shape[0]
+            batch.regionprops(res.lab_off, cap, labels=res.labels, bits=None, image=d_image, high_order=self.high_order,
+                              runs=False, table=res._table, acc_base=acc_base, tiles=batch.tiles_of(need))
+            batch.arena = saved_arena
+        res.merge_status = merge_status
+        res._sync_main = True
+        res.ready = torch.cuda.Event()
+        res.ready.record(main)
+        return res
 
     def run_device_threshold_generic(self, batch, d_src, d_image, t_int) -> DeviceResult:
         """Threshold branch with the per-operator kernels: ImageProperties(mask, image), one region per vignette; empty
@@ -419,11 +471,11 @@ class LokiSegmentationStage:
             return False
         return len(batch.band_lists(0)[3]) == 0
 
-    def _band_filters(self, batch) -> bool:
+    def _band_filters(self, batch, merge_ok=False) -> bool:
         """clear_border / remove_small_objects run on the run list inside the band pipeline (no merge_labels, no frames,
         no vignette that needs the per-operator kernels)."""
         pp = self.postprocess
-        if self.pipeline != "bands" or pp.merge_segments_distance > 0:
+        if self.pipeline != "bands" or (pp.merge_segments_distance > 0 and not merge_ok):
             return False
         from ._lib import HUGE_PX
         from .morphology import pass_radius
@@ -1016,6 +1068,38 @@ class LokiSegmentationStage:
                 for pre in ahead:  # never leave copy threads behind
                     if pre[3] is not None:
                         pre[3]()
+
+
+def _merge_candidates(tab, off, hs, ws, max_distance):
+    """Vignettes merge_labels may change (see LokiSegmentationStage._run_merge_on_bands): those with two or more live
+    labels in which some label's bounding box comes within max_distance of the smallest label's in both directions, or
+    in which a label's distance window is clipped by the frame on all four sides.  tab: columns label, area, bbox of the
+    object table; off: first row of every vignette."""
+    import math
+    n = len(off) - 1
+    if len(tab) == 0:
+        return np.zeros(0, np.int64)
+    img = np.repeat(np.arange(n), np.diff(off))
+    live = tab[:, 1] > 0
+    rows = np.nonzero(live)[0]
+    if len(rows) == 0:
+        return np.zeros(0, np.int64)
+    iv = img[rows]
+    cnt = np.bincount(iv, minlength=n)
+    first = np.full(n, -1, np.int64)
+    first[iv[::-1]] = rows[::-1]                      # first live row of every vignette = its smallest label l0
+    r0, c0, r1, c1 = (tab[rows, 2 + k] for k in range(4))           # r1 / c1 exclusive
+    f = first[iv]
+    R0, C0, R1, C1 = tab[f, 2], tab[f, 3], tab[f, 4], tab[f, 5]
+    dy = np.maximum(np.maximum(r0 - (R1 - 1), R0 - (r1 - 1)), 0)    # rows between the nearest pixel rows
+    dx = np.maximum(np.maximum(c0 - (C1 - 1), C0 - (c1 - 1)), 0)
+    near = (np.maximum(dy, dx) <= max_distance) & (rows != f)
+    pad = math.ceil(max_distance) + 1
+    H, W = np.asarray(hs)[iv], np.asarray(ws)[iv]
+    clipped = (r0 - pad < 0) & (r1 - 1 + pad > H - 1) & (c0 - pad < 0) & (c1 - 1 + pad > W - 1)
+    flag = np.zeros(n, bool)
+    np.logical_or.at(flag, iv, near | clipped)
+    return np.nonzero(flag & (cnt >= 2))[0].astype(np.int64)
 
 
 def _stage_cap(g):
