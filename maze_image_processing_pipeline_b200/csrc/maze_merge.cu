@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 #define MG_CTA 1024
 #define MG_INF (1 << 24)
 #define MG_MAXCS 8
+#define MG_SMIN 2048 /* labels per vignette whose per-iteration minima are taken in shared memory */
 
 struct MgShared {
     int red_i[MG_CTA / 32][4];
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
 {
     __shared__ MgShared S;
     __shared__ int s_scan[MG_CTA / 32 + 2];
+    __shared__ uint32_t s_min[MG_SMIN];
     const MgTeam<CS> tm;
     constexpr int GT = MgTeam<CS>::GT;
     const int gt = tm.gt;
@@ -344,7 +346,12 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
 
     int nm = 0;
     while (head < n_idx) { // :81
-        // :83 per-label minimum of distmap, initial = max_dist
+        // :83 per-label minimum of distmap, initial = max_dist.  The minima are taken in SHARED memory first (every
+        // labelled pixel of the vignette is one atomicMin on one of a handful of addresses: in global memory they
+        // serialise at the L2) and reach the global table with one atomic per label and CTA
+        const bool smin = bound <= MG_SMIN;
+        if (smin)
+            for (int j = threadIdx.x; j < bound; j += MG_CTA) s_min[j] = 0xffffffffu;
         for (int j = gt; j < bound; j += GT) mintab[j] = 0xffffffffu;
         tm.sync();
         for (int p0 = gt; p0 < npx; p0 += 4 * GT) { // four independent pixels per thread in flight
@@ -357,7 +364,12 @@ __global__ void __launch_bounds__(MG_CTA) k_merge_labels(const int32_t *labels, 
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (l[u] > 0 && l[u] <= bound) atomicMin(mintab + (l[u] - 1), (uint32_t)a[u]);
+                if (l[u] > 0 && l[u] <= bound) atomicMin((smin ? s_min : mintab) + (l[u] - 1), (uint32_t)a[u]);
+        }
+        if (smin) {
+            __syncthreads();
+            for (int j = threadIdx.x; j < bound; j += MG_CTA)
+                if (s_min[j] != 0xffffffffu) atomicMin(mintab + j, s_min[j]);
         }
         tm.sync();
         u64 best = ~0ull;
