@@ -225,7 +225,8 @@ int maze_label_shape(const int32_t *labels, const uint32_t *bits, const maze_vig
  * call, loki/pipeline.py:452-457).  index/index_off: optional explicit label lists (index_off has
  * n_img + 1 entries) or NULL for "sorted positive labels".  lab_off bounds the label values as in
  * maze_clear_border.  have_max = 0 restates max_distance=None.  d2a, d2b, d2c: per-pixel int32 scratch;
- * obj_scratch: 2 * n_obj_cap int32.  merge_dist (n_obj_cap doubles, optional) / n_merge (n_img):
+ * obj_scratch: 7 * n_obj_cap int32 (label list and per-label minima in the first 2 * n_obj_cap; label boxes and flags
+ * of the windowed kernel behind).  merge_dist (n_obj_cap doubles, optional) / n_merge (n_img):
  * the distances at which labels were merged.  index_state (2 * n_img int32): the length of the
  * label list the loop started from and how many entries it popped (the list itself, popped entries
  * first, is left in obj_scratch + 2 * lab_off[i]).  status (n_img int32): MAZE_OK or

@@ -29,7 +29,7 @@ enum MazeKernelId {
     KID_THRESHOLD_PACK = 0, KID_COMPARE_PACK, KID_UNPACK_MASK, KID_MORPH_PASS, KID_PLANE_HAS_ZERO, KID_EDT_COLS,
     KID_EDT_ROWS, KID_CCL_INIT, KID_CCL_UNION, KID_CCL_FLATTEN, KID_TILE_SCAN, KID_CCL_ASSIGN, KID_CCL_WRITE,
     KID_BORDER_MARK, KID_LABEL_ZERO, KID_LABEL_COUNT, KID_MAX_LABEL, KID_PROPS_INIT, KID_PROPS_ACCUMULATE,
-    KID_PROPS_FINISH, KID_PROPS_HIGH_ORDER, KID_MERGE_LABELS, KID_SYNTH, KID_PROPS_RUNS, KID_PROPS_RUNS_HIGH, KID_VIGNETTE_FUSED, KID_COUNT_SCAN, KID_PROPS_FINISH_STAGED, KID_SCATTER_COUNTS, KID_LABEL_SHAPE, KID_BAND_FRONT, KID_BAND_LABEL, KID_BAND_LABEL_BIG, KID_BAND_WRITE, KID_BAND_ZERO, KID_WIDE_VDIST, KID_WIDE_ROWS, KID_GL_PREFIX, KID_GL_LINK, KID_GL_RANK, KID_GL_APPLY, KID_COUNT
+    KID_PROPS_FINISH, KID_PROPS_HIGH_ORDER, KID_MERGE_LABELS, KID_SYNTH, KID_PROPS_RUNS, KID_PROPS_RUNS_HIGH, KID_VIGNETTE_FUSED, KID_COUNT_SCAN, KID_PROPS_FINISH_STAGED, KID_SCATTER_COUNTS, KID_LABEL_SHAPE, KID_BAND_FRONT, KID_BAND_LABEL, KID_BAND_LABEL_BIG, KID_BAND_WRITE, KID_BAND_ZERO, KID_WIDE_VDIST, KID_WIDE_ROWS, KID_GL_PREFIX, KID_GL_LINK, KID_GL_RANK, KID_GL_APPLY, KID_MERGE_WINDOWED, KID_MERGE_PREPARE, KID_COUNT
 };
 void maze_prof_begin(int kid, cudaStream_t s);
 void maze_prof_end(int kid, cudaStream_t s);

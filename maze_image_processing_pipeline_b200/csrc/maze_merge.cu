@@ -11,6 +11,7 @@
 // float64 numbers, and `cur_distmap < distmap` / the per-label minima are decided on the integers
 // (sqrt is strictly monotone on them).
 #include <math.h>
+#include <stdlib.h>
 
 #include <cooperative_groups.h>
 
@@ -503,6 +504,12 @@ static int launch_merge(int n_teams, cudaStream_t s, const int32_t *labels, int3
     return MAZE_OK;
 }
 
+int maze_merge_windowed_launch(int n_teams, cudaStream_t s, const int32_t *labels, int32_t *labels_out,
+                               const maze_vignette_t *vig, const int32_t *lab_off, int n_obj_cap, double max_distance,
+                               double path_tolerance, int32_t *d2a, int32_t *d2b, int32_t *gbuf, int32_t *obj_scratch,
+                               double *merge_dist, int32_t *n_merge, int32_t *index_state, int32_t *status,
+                               const int32_t *order); // maze_merge_win.cu
+
 // n_order vignettes (order[0 .. n_order), or all n_img in index order when order is NULL), each worked on by
 // cluster_size CTAs (1, or 8: a thread-block cluster with DSMEM reductions -- for large vignettes)
 extern "C" int maze_merge_labels_ex(const int32_t *labels, int32_t *labels_out, const maze_vignette_t *vig, int n_img,
@@ -517,6 +524,14 @@ extern "C" int maze_merge_labels_ex(const int32_t *labels, int32_t *labels_out, 
     if (cluster_size != 1 && cluster_size != MG_MAXCS) return MAZE_ERR_BADARG;
     const int n_teams = order ? n_order : n_img;
     if (n_teams <= 0) return MAZE_OK;
+    // "sorted positive labels" with a maximum distance (the pipeline's call): the windowed kernel
+    if (!index && have_max) {
+        const char *e = getenv("MAZE_MERGE_WINDOWED");
+        if (!e || e[0] != '0')
+            return maze_merge_windowed_launch(n_teams, (cudaStream_t)stream, labels, labels_out, vig, lab_off, n_obj_cap,
+                                              max_distance, path_tolerance, d2a, d2b, gbuf, obj_scratch, merge_dist, n_merge,
+                                              index_state, status, order);
+    }
     if (cluster_size == 1)
         return launch_merge<1>(n_teams, (cudaStream_t)stream, labels, labels_out, vig, lab_off, n_obj_cap, index, index_off,
                                have_max, max_distance, path_tolerance, d2a, d2b, gbuf, obj_scratch, merge_dist, n_merge,

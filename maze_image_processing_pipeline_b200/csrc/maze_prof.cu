@@ -13,7 +13,7 @@ static const char *const k_names[KID_COUNT] = {
     "k_threshold_pack", "k_compare_pack", "k_unpack_mask", "k_morph_pass", "k_plane_has_zero", "k_edt_cols",
     "k_edt_rows", "k_ccl_init", "k_ccl_union", "k_ccl_flatten", "k_tile_scan", "k_ccl_assign", "k_ccl_write",
     "k_border_mark", "k_label_zero", "k_label_count", "k_max_label", "k_props_init", "k_props_accumulate",
-    "k_props_finish", "k_props_high_order", "k_merge_labels", "k_synth", "k_props_runs", "k_props_runs_high", "k_vignette_fused", "k_count_scan", "k_props_finish_staged", "k_scatter_counts", "k_label_shape", "k_band_front", "k_band_label", "k_band_label_big", "k_band_write", "k_band_zero", "k_wide_vdist", "k_wide_rows", "k_gl_prefix", "k_gl_link", "k_gl_rank", "k_gl_apply"};
+    "k_props_finish", "k_props_high_order", "k_merge_labels", "k_synth", "k_props_runs", "k_props_runs_high", "k_vignette_fused", "k_count_scan", "k_props_finish_staged", "k_scatter_counts", "k_label_shape", "k_band_front", "k_band_label", "k_band_label_big", "k_band_write", "k_band_zero", "k_wide_vdist", "k_wide_rows", "k_gl_prefix", "k_gl_link", "k_gl_rank", "k_gl_apply", "k_merge_windowed", "k_mw_prepare"};
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_enabled{0};

@@ -534,7 +534,7 @@ class DeviceBatch:
         n_obj = max(int(n_obj), 1)
         # scratch: three per-pixel int32 maps (a caller that merges batch after batch passes its own, see stage.py)
         d2a, d2b, d2c = scratch if scratch is not None else (self.empty_px(torch.int32) for _ in range(3))
-        obj_scratch = torch.zeros(2 * n_obj, dtype=torch.int32, device=self.device)
+        obj_scratch = torch.zeros(7 * n_obj, dtype=torch.int32, device=self.device)
         merge_dist = torch.zeros(n_obj, dtype=torch.float64, device=self.device)
         n_merge = torch.zeros(g.n_img, dtype=torch.int32, device=self.device)
         index_state = torch.zeros(2 * g.n_img, dtype=torch.int32, device=self.device)

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C-ABI) with the reference-pinned oracle.  Bit-exact for
 masks, labels, distances (float64 merge distances included) and all integer features; float
 features within rel 1e-5 (north_star) with an absolute floor scaled by area^((p+q)/2+1)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -217,6 +219,79 @@ def test_merge_labels_batched_vs_oracle(mz):
         assert np.array_equal(geom.view(got, i), want), i
         assert list(md[off[i]:off[i] + nm[i]]) == list(dists)
     assert (status.cpu().numpy() == 0).all()
+
+
+def _merge_stress_images(rng):
+    """Label images that stress the windowed merge kernel: sparse specks, touching mosaics (bridges overwrite other
+    labels: boxes and minima must be recomputed), more labels than the shared-memory tables hold, a label that fills
+    the frame."""
+    out = []
+    for k in range(6):  # specks around a blob
+        h, w = int(rng.integers(40, 160)), int(rng.integers(40, 160))
+        m = rng.random((h, w)) < 0.012
+        yy, xx = np.mgrid[:h, :w]
+        m |= (yy - h / 2) ** 2 / (h / 5) ** 2 + (xx - w / 2) ** 2 / (w / 4) ** 2 < 1
+        out.append(oracle.label(m)[0])
+    for k in range(6):  # mosaics: labels touch, every label has several pieces
+        h, w = int(rng.integers(24, 90)), int(rng.integers(24, 90))
+        cells = rng.integers(0, 9, (h // 4 + 1, w // 4 + 1))
+        lab = np.kron(cells, np.ones((4, 4), np.int64))[:h, :w]
+        lab[rng.random((h, w)) < 0.5] = 0
+        out.append(lab.astype(np.int32))
+    lab = np.zeros((200, 250), np.int32)  # 1100 single pixels on a grid: tables in global memory
+    ys, xs = np.mgrid[2:200:6, 2:250:7]
+    ys, xs = ys.ravel()[:1100], xs.ravel()[:1100]
+    lab[ys, xs] = rng.permutation(len(ys)) + 1
+    out.append(lab)
+    lab = np.ones((50, 70), np.int32)  # one label fills the frame, others inside it
+    lab[10:14, 10:14] = 2
+    lab[10:14, 20:24] = 0
+    lab[11:13, 21:23] = 3
+    out.append(lab)
+    lab = np.zeros((180, 40), np.int32)  # tall windows (several 32-row segments), gaps inside columns
+    lab[5:60:9, 5:30] = 1
+    lab[66:170:13, 8:12] = 2
+    lab[100:175, 18:21] = 3
+    out.append(lab)
+    h, w = 260, 300  # large windows: the lower-envelope row pass; an irregular blob with holes, satellites around it
+    yy, xx = np.mgrid[:h, :w]
+    m = np.zeros((h, w), bool)
+    for cy, cx, ry, rx in ((130, 150, 80, 60), (90, 90, 30, 70), (190, 200, 40, 50), (60, 230, 25, 25)):
+        m |= (yy - cy) ** 2 / ry ** 2 + (xx - cx) ** 2 / rx ** 2 < 1
+    m &= ~((yy - 140) ** 2 + (xx - 150) ** 2 < 400)
+    m |= rng.random((h, w)) < 0.004
+    out.append(oracle.label(m)[0])
+    # a one-pixel label swallowed by a bridge while later labels remain: its minimum is `initial`, it is never popped
+    # (a crop of a synthetic bench vignette on which the first version of the kernel raised)
+    out.append(np.load(os.path.join(os.path.dirname(__file__), "golden", "merge_swallowed_label.npy")).astype(np.int32))
+    return out
+
+
+@pytest.mark.parametrize("md,tol", [(10.0, 5.0), (3.0, 5.0), (12.5, 0.0), (6.0, 1.5)])
+@pytest.mark.parametrize("alias", [True, False])
+def test_merge_labels_windowed_stress(mz, md, tol, alias):
+    """The windowed kernel (index = None, max_distance given) against the oracle on images built to hit its corner
+    cases; `tol >= md + 2` makes the bridge condition hold OUTSIDE the distance window."""
+    labs = _merge_stress_images(np.random.default_rng(int(md * 10 + tol)))
+    geom = mz.device.BatchGeometry.from_images(labs)
+    batch = mz.device.DeviceBatch(geom)
+    d_lab = batch.upload(geom.pack_host(labs, dtype=np.int32))
+    lab_off, n_obj = batch.lab_off_from_bounds([int(l.max()) for l in labs])
+    d_out = d_lab if alias else d_lab.clone()
+    dist, nm, _, status, _ = batch.merge_labels(d_lab, d_out, lab_off, n_obj, md, tol)
+    got = d_out.cpu().numpy()
+    dist, nm, off, status = dist.cpu().numpy(), nm.cpu().numpy(), lab_off.cpu().numpy(), status.cpu().numpy()
+    for i, l in enumerate(labs):
+        work = l.copy()
+        try:
+            want, dists = oracle.merge_labels(work, max_distance=md, path_tolerance=tol, return_merge_distances=True,
+                                              labels_out=work if alias else None)
+        except TypeError:
+            assert status[i] != 0, i
+            continue
+        assert status[i] == 0, i
+        assert np.array_equal(geom.view(got, i), want), (i, md, tol, alias)
+        assert list(dist[off[i]:off[i] + nm[i]]) == list(dists), i
 
 
 # ------------------------------------------------------------------------------------------------

@@ -24,7 +24,21 @@ def run(sel):
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) * 1e3
     return dt, out[1].cpu().numpy(), out[3].cpu().numpy()
 allsel = np.arange(B)
-dt, nm, stt = run(allsel); print("all: ms", dt, "merges", nm.sum(), "errors", (stt != 0).sum())
+def run_labels(windowed):
+    os.environ["MAZE_MERGE_WINDOWED"] = "1" if windowed else "0"
+    lab = labels.clone()
+    out = db.merge_labels(lab, lab, res.lab_off, int(res.lab_off[-1]), 10.0)
+    torch.cuda.synchronize()
+    return lab, out
+la, oa = run_labels(False)
+lb, ob = run_labels(True)
+print("windowed == whole-image kernel: labels", bool(torch.equal(la, lb)), "dists", bool(torch.equal(oa[0], ob[0])),
+      "n_merge", bool(torch.equal(oa[1], ob[1])), "status", bool(torch.equal(oa[3], ob[3])))
+for wflag in ("0", "1"):
+    os.environ["MAZE_MERGE_WINDOWED"] = wflag
+    run(allsel)
+    dt, nm, stt = run(allsel); print("windowed", wflag, "all: ms", dt, "merges", nm.sum(), "errors", (stt != 0).sum(),
+                                     "merge hist", np.bincount(np.minimum(nm, 12)))
 px = g.npx
 for lo, hi in [(0, 2e4), (2e4, 1e5), (1e5, 3e5), (3e5, 2e6)]:
     sel = np.nonzero((px >= lo) & (px < hi))[0]
