@@ -22,7 +22,10 @@
 
 #include "maze_common.cuh"
 
-#define MW_CTA 512
+#ifndef MW_CTA
+#define MW_CTA 1024 /* one CTA per SM: the long vignettes decide the makespan, they get the whole SM */
+#endif
+#define MW_MINB (1024 / MW_CTA)
 #define MW_NW (MW_CTA / 32)
 #define MW_INF (1 << 24)
 #define MW_WCAP 6144 /* window pixels whose column distances and squared distances stay in shared memory */
@@ -33,6 +36,39 @@
 #define MW_BIG 0x7f7f7f7f     /* "not computed yet": every stored distance is below it */
 #define MW_FLIP 0x3fffffff    /* the preparation kernel keeps box minima as MW_FLIP - v: every update is an atomicMax on -1 */
 #define MW_SMEM_BYTES ((2 * MW_WCAP + 6 * MW_TCAP) * 4)
+
+#ifdef MW_TIMING
+// per-vignette phase times (ns, thread 0): total, tables, edt0, mins0, dirty, pop, edt, summin, fill, outside | iterations
+__device__ long long mw_dbg[8192 * 16];
+__shared__ int mw_img; // (vignette of this CTA, for the laps inside mw_edt)
+__device__ __forceinline__ long long mw_now()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MW_T0() long long t__ = mw_now(), tstart__ = t__; if (threadIdx.x == 0) mw_img = img; __syncthreads()
+#define MW_ELAP(k) do { __syncthreads(); long long n__ = mw_now(); if (threadIdx.x == 0) mw_dbg[(i64)mw_img * 16 + (k)] += n__ - te__; te__ = n__; } while (0)
+#define MW_ET0() long long te__ = mw_now()
+#define MW_LAP(k) do { long long n__ = mw_now(); if (threadIdx.x == 0) mw_dbg[(i64)img * 16 + (k)] += n__ - t__; t__ = n__; } while (0)
+#define MW_END(it) do { if (threadIdx.x == 0) { mw_dbg[(i64)img * 16] = mw_now() - tstart__; mw_dbg[(i64)img * 16 + 10] = (it); \
+                                               mw_dbg[(i64)img * 16 + 11] = blockIdx.x; } } while (0)
+extern "C" int maze_merge_debug_read(long long *host, int n_img)
+{
+    return cudaMemcpyFromSymbol(host, mw_dbg, sizeof(long long) * 16 * (size_t)n_img) == cudaSuccess ? 0 : -1;
+}
+extern "C" int maze_merge_debug_clear(void)
+{
+    static long long z[8192 * 16];
+    return cudaMemcpyToSymbol(mw_dbg, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define MW_T0()
+#define MW_LAP(k)
+#define MW_END(it)
+#define MW_ELAP(k)
+#define MW_ET0()
+#endif
 
 struct MwShared {
     u64 red_u[MW_NW];
@@ -157,6 +193,124 @@ __device__ int mw_edt(MwShared &S, const int32_t *L, int W, int l, const int *wi
 {
     const int r0 = win[0], c0 = win[2];
     const int wh = win[1] - r0, ww = win[3] - c0, npw = wh * ww;
+    if (npw > MW_WCAP && wh <= 32767 && ww <= 32767) {
+        // LARGE window.  Horizontal distances first (a warp per row, coalesced), then the lower envelope of the
+        // parabolas (y - v)^2 + g[v]^2 down every COLUMN, one thread per column: the lanes of a warp walk neighbouring
+        // columns in step, so the loads of g, the stack of the envelope and the distances written at the end are all
+        // row-major accesses of neighbouring words.  Exact in integers.
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        MW_ET0();
+        for (int yy = warp; yy < wh; yy += MW_NW) {
+            const int32_t *src = L + (i64)(r0 + yy) * W + c0;
+            int32_t *g = Gp + (i64)yy * gs;
+            int last = -MW_INF; // column of the last pixel of the label seen so far
+            for (int xb = 0; xb < ww; xb += 256) {
+                bool is[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int x = xb + 32 * u + lane;
+                    is[u] = x < ww && src[x] == l;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int x0 = xb + 32 * u, x = x0 + lane;
+                    if (x0 >= ww) break;
+                    const unsigned bits = __ballot_sync(FULL, is[u]);
+                    const unsigned lo = bits & (0xffffffffu >> (31 - lane)); // the label's pixels at or left of this lane
+                    const int d = lo ? lane - (31 - __clz(lo)) : min(x - last, MW_INF);
+                    if (x < ww) g[x] = d;
+                    if (bits) last = x0 + 31 - __clz(bits);
+                }
+            }
+            int nxt = 2 * MW_INF; // column of the nearest pixel of the label to the right of the group
+            for (int xb = ((ww - 1) >> 8) << 8; xb >= 0; xb -= 256) {
+                int dl[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int x = xb + 32 * u + lane;
+                    dl[u] = x < ww ? g[x] : MW_INF;
+                }
+#pragma unroll
+                for (int u = 7; u >= 0; u--) {
+                    const int x0 = xb + 32 * u, x = x0 + lane;
+                    if (x0 >= ww) continue;
+                    const unsigned bits = __ballot_sync(FULL, dl[u] == 0);
+                    const unsigned hi = bits & (0xffffffffu << lane);
+                    const int d = hi ? __ffs(hi) - 1 - lane : min(nxt - x, MW_INF);
+                    if (x < ww && d < dl[u]) g[x] = d;
+                    if (bits) nxt = x0 + __ffs(bits) - 1;
+                }
+            }
+        }
+        __syncthreads();
+        MW_ELAP(12);
+        // The stack of the envelope lives in the column itself: entry k = v | start << 16 in dst[k][x] (start = first
+        // row where the parabola at v is strictly below its predecessor, clamped to the window) and g[v] in Gp[k][x]
+        // (k <= the row being read).  The second sweep runs bottom up, so that the distances it writes over dst[q][x]
+        // only hit stack entries that are no longer needed (k <= start[k] <= q).
+        // (sides <= 32767: every intermediate below fits 32 bits -- g^2 + q^2 < 2^31, st * den < 32767 * 65534 < 2^31)
+        int mx = 0;
+        for (int xx = threadIdx.x; xx < ww; xx += MW_CTA) {
+            int32_t *gc = Gp + xx;
+            int32_t *col = dst + xx;
+            int k = -1, vt = 0, st = 0, gt = 0;
+            int ft = 0; // g[vt]^2 + vt^2
+            int gn8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) gn8[u] = u < wh ? gc[u * gs] : MW_INF;
+            for (int q0 = 0; q0 < wh; q0 += 8) {
+                int g8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    g8[u] = gn8[u];
+                    gn8[u] = q0 + 8 + u < wh ? gc[(q0 + 8 + u) * gs] : MW_INF; // (the stack writes stay at rows <= q0 + 7)
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int q = q0 + u, gq = g8[u];
+                    if (gq >= MW_INF) continue;
+                    const int fq = gq * gq + q * q;
+                    int s = 0;
+                    while (k >= 0) {
+                        // the parabola at q is strictly below the one at vt from floor(num / den) + 1 on; it leaves the
+                        // top of the stack in place iff that is beyond the top's start: floor(num / den) >= st
+                        const int num = fq - ft, den = 2 * (q - vt);
+                        if (num >= st * den) {
+                            s = min((int)((unsigned)num / (unsigned)den) + 1, wh); // (num >= 0 here)
+                            break;
+                        }
+                        if (--k >= 0) {
+                            const uint32_t e = (uint32_t)col[k * ds];
+                            vt = (int)(e & 0xffffu); st = (int)(e >> 16); gt = gc[k * gs];
+                            ft = gt * gt + vt * vt;
+                        }
+                    }
+                    if (k < 0) s = 0;
+                    else if (s >= wh) continue; // never the minimum inside the window
+                    k++;
+                    col[k * ds] = (int32_t)((uint32_t)q | ((uint32_t)s << 16));
+                    gc[k * gs] = gq;
+                    vt = q; st = s; gt = gq; ft = fq;
+                }
+            }
+            // (the entry below the current one is loaded ahead of its use)
+            int nk = k - 1;
+            uint32_t en = nk >= 0 ? (uint32_t)col[nk * ds] : 0u;
+            int gn = nk >= 0 ? gc[nk * gs] : 0;
+            for (int q = wh - 1; q >= 0; q--) {
+                while (st > q) {
+                    k = nk; vt = (int)(en & 0xffffu); st = (int)(en >> 16); gt = gn;
+                    nk = k - 1;
+                    if (nk >= 0) { en = (uint32_t)col[nk * ds]; gn = gc[nk * gs]; }
+                }
+                const int d = (q - vt) * (q - vt) + gt * gt;
+                col[q * ds] = d;
+                mx = max(mx, d);
+            }
+        }
+        MW_ELAP(13);
+        return mw_max_int(S, mx);
+    }
     const int nseg = (wh + 31) >> 5;
     const int items = nseg * ww;
     // columns in segments of 32 rows: the label's rows of a (segment, column) as one word -> row s of dst (free until
@@ -202,53 +356,6 @@ __device__ int mw_edt(MwShared &S, const int32_t *L, int W, int l, const int *wi
     }
     __syncthreads();
     int mx = 0;
-    if (npw > MW_WCAP && ww < 65536) {
-        // large window: lower envelope of the parabolas (x - v)^2 + g[v]^2 per row, one thread per row, exact in
-        // integers.  The stack of the envelope lives in the row itself: entry k = v | start << 16 in dst (start = first
-        // column where the parabola at v is strictly below its predecessor, clamped to the window) and g[v] in Gp[k]
-        // (k <= the column being read).  The second sweep runs right to left, so that the distances it writes over
-        // dst[q] only hit stack entries that are no longer needed (k <= start[k] <= q).
-        for (int yy = threadIdx.x; yy < wh; yy += MW_CTA) {
-            int32_t *g = Gp + (i64)yy * gs;
-            int32_t *row = dst + (i64)yy * ds;
-            int k = -1, vt = 0, st = 0, gt = 0;
-            i64 ft = 0; // g[vt]^2 + vt^2
-            for (int q = 0; q < ww; q++) {
-                const int gq = g[q];
-                if (gq >= MW_INF) continue;
-                const i64 fq = (i64)gq * gq + (i64)q * q;
-                int s = 0;
-                while (k >= 0) {
-                    const i64 num = fq - ft, den = 2 * (i64)(q - vt);
-                    const i64 fl = num >= 0 ? num / den : -((-num + den - 1) / den); // floor
-                    s = (int)max((i64)0, min(fl + 1, (i64)ww));
-                    if (s > st) break;
-                    if (--k >= 0) {
-                        const uint32_t e = (uint32_t)row[k];
-                        vt = (int)(e & 0xffffu); st = (int)(e >> 16); gt = g[k];
-                        ft = (i64)gt * gt + (i64)vt * vt;
-                    }
-                }
-                if (k < 0) s = 0;
-                else if (s >= ww) continue; // never the minimum inside the window
-                k++;
-                row[k] = (int32_t)((uint32_t)q | ((uint32_t)s << 16));
-                g[k] = gq;
-                vt = q; st = s; gt = gq; ft = fq;
-            }
-            for (int q = ww - 1; q >= 0; q--) {
-                while (st > q) {
-                    k--;
-                    const uint32_t e = (uint32_t)row[k];
-                    vt = (int)(e & 0xffffu); st = (int)(e >> 16); gt = g[k];
-                }
-                const i64 d = (i64)(q - vt) * (q - vt) + (i64)gt * gt;
-                row[q] = (int)d;
-                mx = max(mx, (int)d);
-            }
-        }
-        return mw_max_int(S, mx);
-    }
     // row pass: min over the row of k^2 + g^2 (integers); four pixels per thread with their first loads in flight
     for (int q0 = threadIdx.x; q0 < npw; q0 += 4 * MW_CTA) {
         int g0[4], yy[4], xx[4];
@@ -371,7 +478,7 @@ __global__ void __launch_bounds__(MW_PREP_CTA) k_mw_prepare(const int32_t *__res
     flush();
 }
 
-__global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *labels, int32_t *labels_out,
+__global__ void __launch_bounds__(MW_CTA, MW_MINB) k_merge_windowed(const int32_t *labels, int32_t *labels_out,
                                                               const maze_vignette_t *__restrict__ vig,
                                                               const int32_t *__restrict__ lab_off, int n_obj_cap,
                                                               double max_distance, double path_tolerance, int32_t *d2a,
@@ -399,6 +506,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
     uint32_t *mintab = stab ? (uint32_t *)(sT + 4 * MW_TCAP) : (uint32_t *)(idx + bound);
     int *dflag = stab ? sT + 5 * MW_TCAP : obj_scratch + 6 * (i64)n_obj_cap + obj0;
     if (tid == 0) { n_merge[img] = 0; status[img] = MAZE_OK; S.n_dirty = 0; }
+    MW_T0();
 
     {
         // label boxes of k_mw_prepare (atomicMax form) -> r0, r1, c0, c1
@@ -434,7 +542,8 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
         __syncthreads();
     }
     if (tid == 0) { index_state[2 * img] = n_idx; index_state[2 * img + 1] = 0; }
-    if (n_idx < 2) return; // :59-60, nothing is written
+    MW_LAP(1);
+    if (n_idx < 2) { MW_END(0); return; } // :59-60, nothing is written
 
     const int pad = (int)ceil(max_distance) + 1; // :70 and :20
     const int l0 = idx[0];                        // :66
@@ -461,19 +570,30 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
         maxd2 = (uint32_t)mw_edt(S, L, W, l0, win, sm ? sG : G + (i64)win[0] * W + win[2], sm ? win[3] - win[2] : W,
                                  A + (i64)win[0] * W + win[2], W);
     }
+    MW_LAP(2);
     // :24 result = full(dist_sliced.max()); result[slices] = dist_sliced: outside the window A still holds MW_BIG
     // (k_mw_prepare), read as min(A, cap) with cap = max_dist from the start
     // per-label minimum of distmap (:83): outside the window every pixel holds max_dist, the `initial`
     {
         const int ww = win[3] - win[2], npw = (win[1] - win[0]) * ww;
-        for (int q = tid; q < npw; q += MW_CTA) {
-            const int yy = q / ww, p = (win[0] + yy) * W + win[2] + (q - yy * ww);
-            const int l = L[p];
-            if (l > 0 && l <= bound && l != l0) atomicMin(mintab + (l - 1), (uint32_t)A[p]);
+        for (int q0 = tid; q0 < npw; q0 += 8 * MW_CTA) {
+            int lv[8];
+            i64 pp[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * MW_CTA;
+                const int yy = q / ww;
+                pp[u] = (i64)(win[0] + yy) * W + win[2] + (q - yy * ww);
+                lv[u] = q < npw ? L[pp[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (lv[u] > 0 && lv[u] <= bound && lv[u] != l0) atomicMin(mintab + (lv[u] - 1), (uint32_t)A[pp[u]]);
         }
     }
     uint32_t cap = maxd2; // distmap = min(A, cap)
     __syncthreads();
+    MW_LAP(3);
 
     int nm = 0;
     while (head < n_idx) { // :81
@@ -527,6 +647,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
             if (tid == 0) S.n_dirty = 0;
             __syncthreads();
         }
+        MW_LAP(4);
         // :83-84 first minimum of min(distmap over the label, max_dist)
         u64 best = ~0ull;
         for (int j = head + tid; j < n_idx; j += MW_CTA) {
@@ -550,6 +671,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
         if (tid == 0) { idx[head] = cur_l; index_state[2 * img + 1] = head + 1; } // popped entries stay in front, in pop order
         head++;
 
+        MW_LAP(5);
         int cb[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) cb[k] = box[4 * (cur_l - 1) + k];
@@ -557,6 +679,14 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
             if (tid == 0) { status[img] = MAZE_ERR_TYPEERROR; n_merge[img] = nm; }
             return;
         }
+        // The popped label's minimum of distmap already tells when the loop ends here: if it exceeds max_distance^2
+        // (so do the cap and max_dist, which are part of it), then merge_dist > max_distance.  Proof: a pixel p with
+        // sqrt(A) + sqrt(B) <= max_distance has A below every fill value, i.e. A(p) = d(p, m)^2 for a merged label m
+        // with p in m's window, and lies inside this label's window (outside, B is the window maximum >= pad^2); with
+        // x in m and q in this label nearest to p, |x - q| <= max_distance, so q is inside m's window and
+        // A(q) <= |x - q|^2 <= max_distance^2 -- but A(q) >= the label's minimum.  (1e-9: |x - q|^2 is an integer, the
+        // float64 sum cannot round across max_distance unless max_distance^2 sits that close below an integer.)
+        if ((double)(uint32_t)(best >> 32) > max_distance * max_distance * (1.0 + 1e-9)) break; // :94-96 without :87-92
         win[0] = max(0, cb[0] - pad); win[1] = (int)min((i64)H, (i64)cb[1] + 1 + pad);
         win[2] = max(0, cb[2] - pad); win[3] = (int)min((i64)W, (i64)cb[3] + 1 + pad);
         const int wh = win[1] - win[0], ww = win[3] - win[2], npw = wh * ww;
@@ -565,6 +695,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
         const int bs = sm ? ww : W;
         const int fillB = mw_edt(S, L, W, cur_l, win, sm ? sG : G + (i64)win[0] * W + win[2], bs, Bp, bs); // :87
         __syncthreads();
+        MW_LAP(6);
         const bool has_out = !(win[0] == 0 && win[1] == H && win[2] == 0 && win[3] == W);
         const bool m_out = Mb[0] < win[0] || Mb[1] >= win[1] || Mb[2] < win[2] || Mb[3] >= win[3];
 
@@ -590,6 +721,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
             }
         }
         md = mw_min_double(S, md);
+        MW_LAP(7);
         if (md > max_distance) break; // :94-96
         const double lim = md + path_tolerance;
         if (tid == 0 && merge_dist) merge_dist[obj0 + nm] = md; // :100
@@ -636,6 +768,7 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
                 }
             }
         }
+        MW_LAP(8);
         if (has_out && sqrt((double)fillB) <= lim) {
             // the bridge condition can hold outside the window too: exact pass over the rest of the vignette
             const double sfb = sqrt((double)fillB);
@@ -657,7 +790,9 @@ __global__ void __launch_bounds__(MW_CTA, 2) k_merge_windowed(const int32_t *lab
         if (has_out) cap = min(cap, (uint32_t)fillB); // :109-111 outside the window
         Mb[0] = min(Mb[0], cb[0]); Mb[1] = max(Mb[1], cb[1]); Mb[2] = min(Mb[2], cb[2]); Mb[3] = max(Mb[3], cb[3]);
         __syncthreads();
+        MW_LAP(9);
     }
+    MW_END(head);
     if (tid == 0) n_merge[img] = nm;
 }
 

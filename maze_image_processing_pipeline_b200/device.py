@@ -548,8 +548,9 @@ class DeviceBatch:
         # the large vignettes are few (frames, small batches)
         cluster_px = int(os.environ.get("MAZE_MERGE_CLUSTER_PX", str(1 << 16)))
         big = g.npx[todo] >= cluster_px
-        if big.sum() > int(os.environ.get("MAZE_MERGE_CLUSTER_MAX", "64")):
-            big[:] = False
+        windowed = index is None and have_max and os.environ.get("MAZE_MERGE_WINDOWED", "1") != "0"
+        if windowed or big.sum() > int(os.environ.get("MAZE_MERGE_CLUSTER_MAX", "64")):
+            big[:] = False  # (the windowed kernel, maze_merge_win.cu, takes one CTA per vignette)
         for sel, cs in ((todo[~big], 1), (todo[big], 8)):
             if len(sel) == 0:
                 continue

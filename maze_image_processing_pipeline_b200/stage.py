@@ -323,6 +323,7 @@ class LokiSegmentationStage:
         self._map_pools = [_PinnedPool(), _PinnedPool(), _PinnedPool()]
         self._img_ring = None  # pinned staging buffers of map() (four sets, allocated on first use)
         self._shared_busy = None  # download event of the last batch that used the shared (non-rotating) workspace
+        self._merge_busy = None   # last merge_labels launch that uses the shared distance maps (deferred merge tails)
         self._readback, self._readback_i = [], 0
 
     # ---- device-resident core ----------------------------------------------------------------------
@@ -395,15 +396,14 @@ class LokiSegmentationStage:
         if passes is not None and (not filters or self._band_filters(batch)):
             return self._run_fused_async(batch, d_src, d_image, t_int, passes)
         if passes is not None and pp.merge_segments_distance > 0 and self._band_filters(batch, merge_ok=True):
-            res = self._run_merge_on_bands(batch, d_src, d_image, t_int, passes)
-            if res is not None:
-                return res
+            return self._run_merge_on_bands(batch, d_src, d_image, t_int, passes)
         return self._run_filter_path(batch, d_src, d_image, t_int, passes)
 
     def _run_merge_on_bands(self, batch, d_src, d_image, t_int, passes):
         """merge_labels behind the band pipeline: the band step (labels, label filters, table) runs first; the object
         table then tells, EXACTLY, which vignettes merge_labels can change at all, and only those go through the
-        merge kernel and get their rows recomputed.
+        merge kernel; the rows of the vignettes in which labels did merge are recomputed.  The tail (candidates, merge,
+        rows) runs in DeviceResult.finalize().
 
         The reference's loop (merge_labels.py:81-96) grows ONE cluster from the smallest label l0 and stops at the first
         candidate whose merge distance exceeds max_distance.  If every other label l lies farther than max_distance from
@@ -420,32 +420,58 @@ class LokiSegmentationStage:
             res = self._run_fused_async(batch, d_src, d_image, t_int, passes)
         finally:
             self.compact = saved_compact
-        res.finalize()
-        if res.redone or len(res.dense_only):
-            return None  # flagged vignettes: the plain filter path takes the whole batch
-        main = torch.cuda.current_stream()
-        main.wait_event(res.ready)
-        tab = res._table[:, :6].cpu().numpy()          # label, area, bbox
-        off = res.lab_off.cpu().numpy().astype(np.int64)
-        need = _merge_candidates(tab, off, g.h, g.w, float(pp.merge_segments_distance))
-        merge_status = torch.zeros(n, dtype=torch.int32, device=batch.device)
-        if len(need):
-            n_obj = int(off[-1])
-            scratch = tuple(self._ws.get(k, g.total_px, torch.int32, batch.device) for k in ("d2a", "d2b", "d2c"))
-            saved_arena, batch.arena = batch.arena, None  # (scratch of this synchronous tail does not belong to a lane)
-            merge_status = batch.merge_labels(res.labels, res.labels, res.lab_off, n_obj, pp.merge_segments_distance,
-                                              only=need, scratch=scratch)[3]
-            # rows of the merged vignettes from the dense label image (bridges leave the runs of the bit plane)
-            acc_base = torch.zeros(n, dtype=torch.int32, device=batch.device)
-            acc_base[torch.as_tensor(need, device=batch.device)] = -1
-            cap = res._table.shape[0]
-            batch.regionprops(res.lab_off, cap, labels=res.labels, bits=None, image=d_image, high_order=self.high_order,
-                              runs=False, table=res._table, acc_base=acc_base, tiles=batch.tiles_of(need))
-            batch.arena = saved_arena
-        res.merge_status = merge_status
-        res._sync_main = True
-        res.ready = torch.cuda.Event()
-        res.ready.record(main)
+        lane = self._ws_ring[(self._ws_i - 1) % self.n_lanes].lane
+        band_pending, res._pending = res._pending, None
+
+        def pending(r):
+            # the merge tail runs when the result is finalised, on the batch's own lane stream: the band steps of the
+            # batches behind it (other lanes) fill the SMs that the long vignettes of the merge kernel leave idle
+            band_pending(r)
+            if r.redone or len(r.dense_only):
+                # flagged vignettes: the plain filter path takes the whole batch
+                r2 = self._run_filter_path(batch, d_src, d_image, t_int, passes)
+                r.redone = True
+                r.dense_only = list(range(n))
+                r.bits, r.labels, r.mask, r.lab_off = r2.bits, r2.labels, r2.mask, r2.lab_off
+                r._table, r._n_obj, r.merge_status = r2._table, r2._n_obj, r2.merge_status
+                r.runs = None
+                r._sync_main = True
+                r.ready = torch.cuda.Event()
+                r.ready.record(torch.cuda.current_stream())
+                return
+            with torch.cuda.stream(lane):
+                tab = r._table[:, :6].cpu().numpy()          # label, area, bbox
+                off = r.lab_off.cpu().numpy().astype(np.int64)
+                need = _merge_candidates(tab, off, g.h, g.w, float(pp.merge_segments_distance))
+                merge_status = torch.zeros(n, dtype=torch.int32, device=batch.device)
+                if len(need):
+                    n_obj = int(off[-1])
+                    if self._merge_busy is not None:
+                        lane.wait_event(self._merge_busy)  # ONE set of distance maps for all lanes
+                    scratch = tuple(self._ws.get(k, g.total_px, torch.int32, batch.device) for k in ("d2a", "d2b", "d2c"))
+                    saved_arena, batch.arena = batch.arena, None  # (scratch of this tail does not belong to a lane)
+                    _, n_merge, _, merge_status, _ = batch.merge_labels(r.labels, r.labels, r.lab_off, n_obj,
+                                                                        pp.merge_segments_distance, only=need, scratch=scratch)
+                    self._merge_busy = torch.cuda.Event()
+                    self._merge_busy.record(lane)
+                    # rows of the vignettes in which something merged, from the dense label image (bridges leave the
+                    # runs of the bit plane)
+                    merged = need[n_merge.cpu().numpy()[need] > 0]
+                    if len(merged):
+                        acc_base = torch.zeros(n, dtype=torch.int32, device=batch.device)
+                        acc_base[torch.from_numpy(merged).to(batch.device)] = -1
+                        cap = r._table.shape[0]
+                        batch.regionprops(r.lab_off, cap, labels=r.labels, bits=None, image=d_image,
+                                          high_order=self.high_order, runs=False, table=r._table, acc_base=acc_base,
+                                          tiles=batch.tiles_of(merged))
+                    batch.arena = saved_arena
+                r.merge_status = merge_status
+                r._sync_main = True
+                r.ready = torch.cuda.Event()
+                r.ready.record(lane)
+
+        res._pending = pending
+        res.deferred_pixels = True  # the label image is final only after finalize()
         return res
 
     def run_device_threshold_generic(self, batch, d_src, d_image, t_int) -> DeviceResult:
@@ -487,6 +513,9 @@ class LokiSegmentationStage:
         """Label filters / merge_labels with the per-operator kernels on the dense label image (synchronous, ONE shared
         workspace): the vignette-resident kernel for the labels, then clear_border / remove_small_objects /
         merge_labels, then regionprops."""
+        if self._merge_busy is not None:
+            self._merge_busy.synchronize()
+            self._merge_busy = None
         pp = self.postprocess
         g = batch.g
         filters = pp.clear_border or pp.min_area > 0 or pp.merge_segments_distance > 0
@@ -890,6 +919,8 @@ class LokiSegmentationStage:
             d_pred = pool.dev("pred", geom.total_px, torch.uint8, batch.device)
             d_pred.copy_(h_pred, non_blocking=True)
         res = self.run_device(batch, d_image, d_pred)
+        if getattr(res, "deferred_pixels", False):
+            res.finalize()  # (merge_labels rewrites the label image in finalize)
         # the per-pixel outputs do not depend on the object counts: download them on the copy stream while
         # the next batch is packed, uploaded and computed
         cs = self._copy_stream
