@@ -600,7 +600,7 @@ def run_b200(args):
     if world == 1 and not args.no_variants and args.merge == 0 and args.morphology == "isotropic":
         variants = {}
         vb = batches[args.warmup % n_res][0], batches[args.warmup % n_res][1]
-        for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 3), ("crosses", dict(), 8),
+        for name, kw, vsteps in (("merge10", dict(merge_segments_distance=10), 8), ("crosses", dict(), 8),
                                  ("label_filters", dict(clear_border=True, min_area=12), 8),
                                  ("threshold_branch", None, 8)):
             # (threshold_branch: the reference's shipped `threshold` segmentation, loki/pipeline.py:648-656 -- mask +

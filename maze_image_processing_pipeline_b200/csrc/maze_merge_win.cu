@@ -31,6 +31,7 @@
 #define MW_WCAP 6144 /* window pixels whose column distances and squared distances stay in shared memory */
 #define MW_TCAP 1024 /* labels per vignette whose tables (box, minimum, flag) stay in shared memory */
 #define MW_DIRTY 32
+#define MW_NEAR_BUDGET 2048 /* pixels of other labels whose neighbourhood is searched for l0 before its distance map is built */
 #define MW_PARTS 8            /* CTAs of the preparation kernel per vignette */
 #define MW_PREP_CTA 256
 #define MW_BIG 0x7f7f7f7f     /* "not computed yet": every stored distance is below it */
@@ -80,6 +81,7 @@ struct MwShared {
     int tmp[5];
     int n_dirty;
     int dirty[MW_DIRTY];
+    int near, tested;
     int scan[MW_NW + 1];
 };
 
@@ -563,6 +565,57 @@ __global__ void __launch_bounds__(MW_CTA, MW_MINB) k_merge_windowed(const int32_
     int win[4];
     win[0] = max(0, Mb[0] - pad); win[1] = (int)min((i64)H, (i64)Mb[1] + 1 + pad);
     win[2] = max(0, Mb[2] - pad); win[3] = (int)min((i64)W, (i64)Mb[3] + 1 + pad);
+    // Can anything merge at all?  Search the neighbourhood (radius ceil(max_distance)) of every pixel of another label
+    // inside the window for a pixel of l0 -- these pixels are few, the distance map of l0 is the expensive part of a
+    // vignette.  If no pair comes within max_distance, every label's minimum of distmap exceeds max_distance^2 (inside
+    // the window the distances are exact, outside the map holds its maximum >= pad^2), so whichever label the first
+    // iteration pops, merge_dist > max_distance (see the loop) and :94-96 ends the loop before anything is written.
+    {
+        const double t2d = max_distance * max_distance * (1.0 + 1e-9);
+        const int T = t2d >= 2.0e9 ? 0x7fffffff : (int)floor(t2d);
+        const int r = pad - 1;
+        // (at most ~4 M pixel tests: the budget shrinks with the search radius)
+        const i64 side = 2 * (i64)r + 1;
+        const int budget = (int)max((i64)1, min((i64)MW_NEAR_BUDGET, ((i64)1 << 22) / (side * side)));
+        if (tid == 0) { S.near = 0; S.tested = 0; }
+        __syncthreads();
+        const int ww = win[3] - win[2], npw = (win[1] - win[0]) * ww;
+        for (int q0 = tid; q0 < npw; q0 += 8 * MW_CTA) {
+            int lv[8], ys[8], xs[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int q = q0 + u * MW_CTA;
+                const int yy = q / ww;
+                ys[u] = win[0] + yy; xs[u] = win[2] + (q - yy * ww);
+                lv[u] = q < npw ? L[(i64)ys[u] * W + xs[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (!(lv[u] > 0 && lv[u] <= bound && lv[u] != l0)) continue;
+                if (*(volatile int *)&S.near) continue;
+                const int ya = max(Mb[0], ys[u] - r), yb = min(Mb[1], ys[u] + r);
+                const int xa = max(Mb[2], xs[u] - r), xb = min(Mb[3], xs[u] + r);
+                if (ya > yb || xa > xb) continue; // farther than r from the box of l0
+                if (atomicAdd(&S.tested, 1) >= budget) { S.near = 1; continue; } // too many: build the map
+                bool hit = false;
+                for (int y = ya; y <= yb && !hit; y++) {
+                    const int dy = y - ys[u];
+                    for (int x = xa; x <= xb; x++) {
+                        const int dx = x - xs[u];
+                        if (dy * dy + dx * dx <= T && L[(i64)y * W + x] == l0) { hit = true; break; }
+                    }
+                }
+                if (hit) S.near = 1;
+            }
+        }
+        __syncthreads();
+        if (!S.near) {
+            if (tid == 0) index_state[2 * img + 1] = 2; // l0 and the label the first iteration pops
+            MW_END(2);
+            return;
+        }
+    }
+    MW_LAP(4);
     uint32_t maxd2; // :74 distmap.max()
     {
         const int npw = (win[1] - win[0]) * (win[3] - win[2]);
@@ -702,22 +755,38 @@ __global__ void __launch_bounds__(MW_CTA, MW_MINB) k_merge_windowed(const int32_
         // :90-92 min of sqrt(A) + sqrt(B).  sqrt(a) + sqrt(b) >= sqrt(a + b): a pixel whose a + b is clearly above the
         // running minimum squared cannot lower it
         double md = (has_out && m_out) ? sqrt((double)fillB) : INFINITY;
-        for (int q0 = tid; q0 < npw; q0 += 4 * MW_CTA) {
-            uint32_t a[4];
-            int b[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int q = q0 + u * MW_CTA;
-                const int yy = q / ww, xx = q - yy * ww;
-                const bool in = q < npw;
-                a[u] = in ? min((uint32_t)A[(i64)(win[0] + yy) * W + win[2] + xx], cap) : 0x3fffffffu;
-                b[u] = in ? Bp[(i64)yy * bs + xx] : 0x3fffffff;
+        // Where can the minimum sit?  A pixel of this label that holds the label's minimum m of distmap gives the sum
+        // sqrt(m); a pixel with a sum that small has distmap <= m, and if m is below the cap that is an exact distance to
+        // a merged label: the pixel lies within sqrt(m) of the box of the merged labels.  (Outside that box distmap >=
+        // m + 1, and sqrt(m + 1) > sqrt(m) in float64 too.)
+        int sy0 = 0, sy1 = wh, sx0 = 0, sx1 = ww;
+        {
+            const uint32_t mb = (uint32_t)(best >> 32);
+            if (mb < min(cap, maxd2)) {
+                const int rr = (int)sqrt((double)mb) + 1;
+                sy0 = max(0, Mb[0] - rr - win[0]); sy1 = min(wh, Mb[1] + rr + 1 - win[0]);
+                sx0 = max(0, Mb[2] - rr - win[2]); sx1 = min(ww, Mb[3] + rr + 1 - win[2]);
             }
+        }
+        for (int yy = sy0 + warp; yy < sy1; yy += MW_NW) { // a warp per row, four groups of 32 pixels in flight
+            const int32_t *Ar = A + (i64)(win[0] + yy) * W + win[2];
+            const int32_t *Br = Bp + (i64)yy * bs;
+            for (int xb = sx0; xb < sx1; xb += 128) {
+                uint32_t a[4];
+                int b[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if ((double)a[u] + (double)b[u] > md * md * (1.0 + 1e-12)) continue;
-                const double s = sqrt((double)a[u]) + sqrt((double)b[u]);
-                md = s < md ? s : md;
+                for (int u = 0; u < 4; u++) {
+                    const int xx = xb + 32 * u + lane;
+                    const bool in = xx < sx1;
+                    a[u] = in ? min((uint32_t)Ar[xx], cap) : 0x3fffffffu;
+                    b[u] = in ? Br[xx] : 0x3fffffff;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if ((double)a[u] + (double)b[u] > md * md * (1.0 + 1e-12)) continue;
+                    const double s = sqrt((double)a[u]) + sqrt((double)b[u]);
+                    md = s < md ? s : md;
+                }
             }
         }
         md = mw_min_double(S, md);
@@ -729,42 +798,46 @@ __global__ void __launch_bounds__(MW_CTA, MW_MINB) k_merge_windowed(const int32_
         {
             // :98, :103-106 (labelmap only ever holds l0) and :109-111 inside the window
             const double lim2 = lim * lim;
-            for (int q0 = tid; q0 < npw; q0 += 4 * MW_CTA) {
-                uint32_t ar[4];
-                int bv[4], lv[4], ys[4], xs[4];
+            for (int yy = warp; yy < wh; yy += MW_NW) { // a warp per row, four groups of 32 pixels in flight
+                const int y = win[0] + yy;
+                int32_t *Ar = A + (i64)y * W + win[2];
+                const int32_t *Br = Bp + (i64)yy * bs;
+                const int32_t *Lr = L + (i64)y * W + win[2];
+                int32_t *Or = O + (i64)y * W + win[2];
+                for (int xb = 0; xb < ww; xb += 128) {
+                    uint32_t ar[4];
+                    int bv[4], lv[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int q = q0 + u * MW_CTA;
-                    const int yy = q / ww, xx = q - yy * ww;
-                    ys[u] = win[0] + yy; xs[u] = win[2] + xx;
-                    const bool in = q < npw;
-                    ar[u] = in ? (uint32_t)A[(i64)ys[u] * W + xs[u]] : 0u;
-                    bv[u] = in ? Bp[(i64)yy * bs + xx] : 0;
-                    lv[u] = in ? L[(i64)ys[u] * W + xs[u]] : 0;
-                }
+                    for (int u = 0; u < 4; u++) {
+                        const int xx = xb + 32 * u + lane;
+                        const bool in = xx < ww;
+                        ar[u] = in ? (uint32_t)Ar[xx] : 0u;
+                        bv[u] = in ? Br[xx] : 0;
+                        lv[u] = in ? Lr[xx] : 0;
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (q0 + u * MW_CTA >= npw) break;
-                    const int y = ys[u], x = xs[u];
-                    const i64 p = (i64)y * W + x;
-                    const uint32_t araw = ar[u];
-                    const uint32_t a = min(araw, cap);
-                    const int b = bv[u];
-                    const int l = lv[u];
-                    const double ab = (double)a + (double)b;
-                    bool fill = l == cur_l;
-                    if (!fill && !(ab > lim2 * (1.0 + 1e-12))) {
-                        if (2.0 * ab < lim2 * (1.0 - 1e-12)) fill = true;
-                        else fill = sqrt((double)a) + sqrt((double)b) <= lim;
+                    for (int u = 0; u < 4; u++) {
+                        const int xx = xb + 32 * u + lane;
+                        if (xx >= ww) continue;
+                        const uint32_t araw = ar[u];
+                        const uint32_t a = min(araw, cap);
+                        const int b = bv[u];
+                        const int l = lv[u];
+                        const double ab = (double)a + (double)b;
+                        bool fill = l == cur_l;
+                        if (!fill && !(ab > lim2 * (1.0 + 1e-12))) {
+                            if (2.0 * ab < lim2 * (1.0 - 1e-12)) fill = true;
+                            else fill = sqrt((double)a) + sqrt((double)b) <= lim;
+                        }
+                        const uint32_t an = min(a, (uint32_t)b);
+                        const bool other = l > 0 && l <= bound && l != l0 && l != cur_l;
+                        if (fill) {
+                            if (aliased && other) mw_lose_pixel(S, box, mintab, dflag, l, y, win[2] + xx, araw);
+                            Or[xx] = l0;
+                        }
+                        if (an != araw) Ar[xx] = (int32_t)an;
+                        if (other && !(fill && aliased)) atomicMin(mintab + (l - 1), an);
                     }
-                    const uint32_t an = min(a, (uint32_t)b);
-                    const bool other = l > 0 && l <= bound && l != l0 && l != cur_l;
-                    if (fill) {
-                        if (aliased && other) mw_lose_pixel(S, box, mintab, dflag, l, y, x, araw);
-                        O[p] = l0;
-                    }
-                    if (an != araw) A[p] = (int32_t)an;
-                    if (other && !(fill && aliased)) atomicMin(mintab + (l - 1), an);
                 }
             }
         }

@@ -49,17 +49,29 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_accumulate(const int32_t *__
     int nlab = lab_off[c.img + 1] - obj0;
     int wbase = c.word0 + warp * 32;
     int y = wbase / c.v.wpr, k = wbase - y * c.v.wpr;
+    int lq[4] = {0, 0, 0, 0}; // labels of four words at a time: their loads are in flight together
     for (int i = 0; i < 32; i++, k++) {
         if (k == c.v.wpr) { k = 0; y++; }
         int widx = wbase + i;
         if (widx >= c.nwords) break;
         int x = 32 * k + lane;
-        int l = 0;
-        if (labels) {
-            if (x < W) l = labels[c.v.pix_off + (i64)y * W + x];
-        } else {
-            l = (__ldg(bits + c.v.word_off + widx) >> lane) & 1u;
+        if ((i & 3) == 0) {
+            int yy = y, kk = k;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                lq[u] = 0;
+                if (widx + u < c.nwords) {
+                    const int xx = 32 * kk + lane;
+                    if (labels) {
+                        if (xx < W) lq[u] = labels[c.v.pix_off + (i64)yy * W + xx];
+                    } else {
+                        lq[u] = (__ldg(bits + c.v.word_off + widx + u) >> lane) & 1u;
+                    }
+                }
+                if (++kk == c.v.wpr) { kk = 0; yy++; }
+            }
         }
+        int l = (i & 3) == 0 ? lq[0] : (i & 3) == 1 ? lq[1] : (i & 3) == 2 ? lq[2] : lq[3];
         if (l < 0 || l > nlab) l = 0;
         if (!__ballot_sync(FULL, l > 0)) continue;
         int v = (image && l > 0) ? (int)__ldg(image + c.v.pix_off + (i64)y * W + x) : 0;
@@ -377,17 +389,29 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_high_order(const int32_t *__
     int nlab = lab_off[c.img + 1] - obj0;
     int wbase = c.word0 + warp * 32;
     int y = wbase / c.v.wpr, k = wbase - y * c.v.wpr;
+    int lq[4] = {0, 0, 0, 0}; // labels of four words at a time: their loads are in flight together
     for (int i = 0; i < 32; i++, k++) {
         if (k == c.v.wpr) { k = 0; y++; }
         int widx = wbase + i;
         if (widx >= c.nwords) break;
         int x = 32 * k + lane;
-        int l = 0;
-        if (labels) {
-            if (x < W) l = labels[c.v.pix_off + (i64)y * W + x];
-        } else {
-            l = (__ldg(bits + c.v.word_off + widx) >> lane) & 1u;
+        if ((i & 3) == 0) {
+            int yy = y, kk = k;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                lq[u] = 0;
+                if (widx + u < c.nwords) {
+                    const int xx = 32 * kk + lane;
+                    if (labels) {
+                        if (xx < W) lq[u] = labels[c.v.pix_off + (i64)yy * W + xx];
+                    } else {
+                        lq[u] = (__ldg(bits + c.v.word_off + widx + u) >> lane) & 1u;
+                    }
+                }
+                if (++kk == c.v.wpr) { kk = 0; yy++; }
+            }
         }
+        int l = (i & 3) == 0 ? lq[0] : (i & 3) == 1 ? lq[1] : (i & 3) == 2 ? lq[2] : lq[3];
         if (l < 0 || l > nlab) l = 0;
         if (!__ballot_sync(FULL, l > 0)) continue;
         int lp = __shfl_up_sync(FULL, l, 1);
