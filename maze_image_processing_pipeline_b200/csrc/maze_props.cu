@@ -40,9 +40,10 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_accumulate(const int32_t *__
                                                                const maze_vignette_t *__restrict__ vig,
                                                                const maze_tile_t *__restrict__ tiles,
                                                                const int32_t *__restrict__ lab_off, int n_obj_cap,
-                                                               u64 *acc, int32_t *ext)
+                                                               u64 *acc, int32_t *ext, const int32_t *__restrict__ skip_base)
 {
     TileCtx c = load_tile(vig, tiles);
+    if (skip_base && skip_base[c.img] >= 0) return; // rows of this vignette come from the staging arrays
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = c.v.w;
     int obj0 = lab_off[c.img];
@@ -139,9 +140,10 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_runs(const int32_t *__restri
                                                          const maze_vignette_t *__restrict__ vig,
                                                          const maze_tile_t *__restrict__ tiles,
                                                          const int32_t *__restrict__ lab_off, int n_obj_cap,
-                                                         u64 *acc, int32_t *ext)
+                                                         u64 *acc, int32_t *ext, const int32_t *__restrict__ skip_base)
 {
     TileCtx c = load_tile(vig, tiles);
+    if (skip_base && skip_base[c.img] >= 0) return; // rows of this vignette come from the staging arrays
     int widx = c.word0 + threadIdx.x;
     if (widx >= c.nwords) return;
     uint32_t m = __ldg(bits + c.v.word_off + widx);
@@ -201,9 +203,10 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_runs_high(const int32_t *__r
                                                               const maze_vignette_t *__restrict__ vig,
                                                               const maze_tile_t *__restrict__ tiles,
                                                               const int32_t *__restrict__ lab_off, int n_obj_cap,
-                                                              double *table)
+                                                              double *table, const int32_t *__restrict__ skip_base)
 {
     TileCtx c = load_tile(vig, tiles);
+    if (skip_base && skip_base[c.img] >= 0) return;
     int widx = c.word0 + threadIdx.x;
     if (widx >= c.nwords) return;
     uint32_t m = __ldg(bits + c.v.word_off + widx);
@@ -380,9 +383,10 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_high_order(const int32_t *__
                                                                const maze_vignette_t *__restrict__ vig,
                                                                const maze_tile_t *__restrict__ tiles,
                                                                const int32_t *__restrict__ lab_off, int n_obj_cap,
-                                                               double *table)
+                                                               double *table, const int32_t *__restrict__ skip_base)
 {
     TileCtx c = load_tile(vig, tiles);
+    if (skip_base && skip_base[c.img] >= 0) return;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = c.v.w;
     int obj0 = lab_off[c.img];
@@ -394,7 +398,6 @@ __global__ void __launch_bounds__(MAZE_CTA) k_props_high_order(const int32_t *__
         if (k == c.v.wpr) { k = 0; y++; }
         int widx = wbase + i;
         if (widx >= c.nwords) break;
-        int x = 32 * k + lane;
         if ((i & 3) == 0) {
             int yy = y, kk = k;
 #pragma unroll
@@ -455,15 +458,15 @@ extern "C" int maze_regionprops(const int32_t *labels, const uint32_t *bits, con
     MAZE_KERNEL(KID_PROPS_INIT, s, k_props_init<<<nb, 256, 0, s>>>(acc, ext, n_obj_cap));
     const bool runs = (flags & MAZE_RP_RUNS) && labels && bits;
     if (runs)
-        MAZE_KERNEL(KID_PROPS_RUNS, s, k_props_runs<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
+        MAZE_KERNEL(KID_PROPS_RUNS, s, k_props_runs<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext, acc_base));
     else
-        MAZE_KERNEL(KID_PROPS_ACCUMULATE, s, k_props_accumulate<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext));
+        MAZE_KERNEL(KID_PROPS_ACCUMULATE, s, k_props_accumulate<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, image, vig, tiles, lab_off, n_obj_cap, acc, ext, acc_base));
     MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 0, acc_base, table));
     if (high) {
         if (runs)
-            MAZE_KERNEL(KID_PROPS_RUNS_HIGH, s, k_props_runs_high<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
+            MAZE_KERNEL(KID_PROPS_RUNS_HIGH, s, k_props_runs_high<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table, acc_base));
         else
-            MAZE_KERNEL(KID_PROPS_HIGH_ORDER, s, k_props_high_order<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table));
+            MAZE_KERNEL(KID_PROPS_HIGH_ORDER, s, k_props_high_order<<<n_tiles, MAZE_CTA, 0, s>>>(labels, bits, vig, tiles, lab_off, n_obj_cap, table, acc_base));
         MAZE_KERNEL(KID_PROPS_FINISH, s, k_props_finish<<<nb, 256, 0, s>>>(acc, ext, lab_off, n_img, n_obj_cap, image ? 1 : 0, high, 1, acc_base, table));
     }
     return MAZE_OK;

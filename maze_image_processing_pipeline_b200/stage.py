@@ -455,15 +455,13 @@ class LokiSegmentationStage:
                     self._merge_busy = torch.cuda.Event()
                     self._merge_busy.record(lane)
                     # rows of the vignettes in which something merged, from the dense label image (bridges leave the
-                    # runs of the bit plane)
-                    merged = need[n_merge.cpu().numpy()[need] > 0]
-                    if len(merged):
-                        acc_base = torch.zeros(n, dtype=torch.int32, device=batch.device)
-                        acc_base[torch.from_numpy(merged).to(batch.device)] = -1
-                        cap = r._table.shape[0]
-                        batch.regionprops(r.lab_off, cap, labels=r.labels, bits=None, image=d_image,
-                                          high_order=self.high_order, runs=False, table=r._table, acc_base=acc_base,
-                                          tiles=batch.tiles_of(merged))
+                    # runs of the bit plane).  Which ones is decided on the device -- no round trip: the tiles of every
+                    # candidate are launched, those of a vignette without a merge return at once
+                    acc_base = torch.where(n_merge > 0, -1, 0).to(torch.int32)
+                    cap = r._table.shape[0]
+                    batch.regionprops(r.lab_off, cap, labels=r.labels, bits=None, image=d_image,
+                                      high_order=self.high_order, runs=False, table=r._table, acc_base=acc_base,
+                                      tiles=batch.tiles_of(need))
                     batch.arena = saved_arena
                 r.merge_status = merge_status
                 r._sync_main = True
