@@ -243,7 +243,13 @@ int maze_merge_labels(const int32_t *labels, int32_t *labels_out, const maze_vig
  * the n_order vignettes order[0 .. n_order) (order = NULL: all n_img) with cluster_size CTAs each -- 1, or 8: a
  * thread-block cluster (cluster barrier between the steps, reductions through distributed shared memory) that gives a
  * large vignette eight times the memory parallelism of one CTA.  Vignettes that are not listed are not touched
- * (n_merge / status / index_state keep what the caller put there). */
+ * (n_merge / status / index_state keep what the caller put there).
+ *
+ * index = NULL with have_max = 1 -- the pipeline's call -- runs the WINDOWED kernel (maze_merge_win.cu; cluster_size is
+ * ignored, MAZE_MERGE_WINDOWED=0 in the environment selects the whole-image kernel): a preparation kernel finds the
+ * bounding box of every label with the whole GPU, then one 1024-thread CTA per vignette runs the loop and every
+ * iteration only touches the distance window of the label it pops; the loop ends without a distance map when the
+ * popped label's minimum of distmap already exceeds max_distance^2.  Same results, bit for bit. */
 int maze_merge_labels_ex(const int32_t *labels, int32_t *labels_out, const maze_vignette_t *vig, int n_img,
                          const int32_t *lab_off, int n_obj_cap, const int32_t *index, const int32_t *index_off,
                          int have_max, double max_distance, double path_tolerance,
