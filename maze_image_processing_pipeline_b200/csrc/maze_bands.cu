@@ -1140,6 +1140,28 @@ static BandFork *band_fork()
     return f;
 }
 
+// experiment (MAZE_K2_PRIO=1): the labelling kernels on a HIGH-PRIORITY stream, so that their CTAs take the slots the
+// band front of the next lane frees, instead of queueing behind it
+static BandFork *band_fork_prio()
+{
+    static thread_local BandFork pool[16];
+    static thread_local int n_pool = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int i = 0; i < n_pool; i++)
+        if (pool[i].device == dev) return &pool[i];
+    if (n_pool >= 16) return nullptr;
+    BandFork *f = &pool[n_pool];
+    f->device = dev;
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&f->aux, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f->join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    n_pool++;
+    return f;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K2 for FRAMES (BASELINE.json configs[3]: 4096 x 4096, thousands of labels, 10^5 runs): the same labelling and
 // accumulation on the run list, but with the union-find in global memory and every step spread over the whole GPU.
@@ -1521,6 +1543,16 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
                                                                    zin ? labels : nullptr, la, inband ? band_done : nullptr));
     if (dense && fk) MAZE_CUDA(cudaStreamWaitEvent(s, fk->join, 0), "band join wait");
     const int grid_xl = n_img < 74 ? n_img : 74;
+    static const bool k2prio = getenv("MAZE_K2_PRIO") && getenv("MAZE_K2_PRIO")[0] == '1';
+    BandFork *pk = nullptr;
+    const cudaStream_t s_main = s;
+    if (k2prio && !inband) {
+        pk = band_fork_prio();
+        if (!pk) return MAZE_ERR_CUDA;
+        MAZE_CUDA(cudaEventRecord(pk->fork, s), "k2 fork");
+        MAZE_CUDA(cudaStreamWaitEvent(pk->aux, pk->fork, 0), "k2 fork wait");
+        s = pk->aux;
+    }
     if (inband) { // what the in-place labelling passed on (more than 4096 runs, 2048 rows or 64 bands)
         MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
                     k_band_label_big<LABEL_BIG_T><<<grid_xl, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP,
@@ -1538,6 +1570,11 @@ extern "C" int maze_band_stage(const uint8_t *image, const uint8_t *intensity, c
         MAZE_KERNEL(KID_BAND_LABEL_BIG, s,
                     k_band_label_big<LABEL_BIG_T><<<grid_xl, LABEL_BIG_T, smem_b, s>>>(la, LABEL_BIG_CAP, LABEL_BIG_HCAP,
                                                                                      LABEL_BIG_NB, 2));
+    }
+    if (pk) {
+        MAZE_CUDA(cudaEventRecord(pk->join, s), "k2 join");
+        s = s_main;
+        MAZE_CUDA(cudaStreamWaitEvent(s, pk->join, 0), "k2 join wait");
     }
     if (n_huge > 0 && gl_scratch) { // frames: labelling in global memory, one after the other
         if (!huge_host || clear_border || min_area > 0 || (flags & MAZE_BAND_SINGLE_REGION)) return MAZE_ERR_BADARG; // (not on this path)
