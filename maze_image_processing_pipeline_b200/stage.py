@@ -25,6 +25,7 @@ import torch
 
 import ctypes
 import os
+import threading
 
 from ._lib import (BAND_SINGLE_REGION, MAZE_ERR_TYPEERROR, NACC, NEXT, NFEAT, NSHAPE, RP_HIGH_ORDER, STEP_COMPACT, StepArgs,
                    check, lib)
@@ -93,6 +94,36 @@ class DeviceResult:
     @property
     def table(self):
         return self.finalize()._table
+
+
+class _HostArrayPool:
+    """Flat host arrays for StageResult.materialize().  A fresh ``np.empty`` of a gigabyte is mapped in page by page
+    (and zeroed by the kernel) while the expansion writes it, every batch; an array that nothing refers to any more --
+    no StageResult, no per-vignette view: checked by its reference count -- is handed out again instead."""
+
+    def __init__(self, keep=6):
+        self._bufs = []
+        self._keep = keep
+        self._lock = threading.Lock()
+
+    def take(self, n, dtype):
+        import sys
+        dtype = np.dtype(dtype)
+        with self._lock:
+            for b in self._bufs:
+                # list entry + loop variable + getrefcount's argument: nobody else holds it (views keep their base alive)
+                if b.dtype == dtype and n <= b.size <= 2 * n + 4096 and sys.getrefcount(b) == 3:
+                    return b[:n]
+            b = np.empty(max(int(n), 1), dtype)
+            idle = [k for k, o in enumerate(self._bufs) if sys.getrefcount(o) == 3]
+            if len(self._bufs) >= self._keep and idle:
+                del self._bufs[idle[0]]
+            if len(self._bufs) < self._keep:
+                self._bufs.append(b)
+            return b[:n]
+
+
+_HOST_POOL = _HostArrayPool()
 
 
 class StageResult:
@@ -196,8 +227,10 @@ class StageResult:
             return self
         g = self.geometry
         n = g.n_img
-        mask = np.empty(g.total_px, np.uint8)
-        labels = np.empty(g.total_px, np.int32)
+        mask = _HOST_POOL.take(g.total_px, np.uint8)
+        labels = _HOST_POOL.take(g.total_px, np.int32)
+        if threads is None and os.environ.get("MAZE_EXPAND_THREADS"):
+            threads = int(os.environ["MAZE_EXPAND_THREADS"])
         if threads is None:
             try:
                 threads = min(16, max(1, len(os.sched_getaffinity(0)) // 2))

@@ -458,3 +458,27 @@ def test_host_pack_async_equals_sync():
     assert np.array_equal(got, want)
     for i, im in enumerate(imgs):
         assert np.array_equal(g.view(got, i), im)
+
+
+def test_host_array_pool_never_hands_out_an_array_that_is_still_referenced():
+    """materialize() recycles its flat host arrays: only arrays nobody refers to any more (no view, no result)."""
+    from maze_image_processing_pipeline_b200.stage import _HostArrayPool
+    pool = _HostArrayPool(keep=2)
+    a = pool.take(1000, np.uint8)
+    base_a = a.base
+    view = a[100:200]          # what StageResult.mask(i) hands to the caller
+    del a
+    b = pool.take(1000, np.uint8)
+    assert b.base is not base_a            # the view keeps the first array busy
+    view[:] = 7
+    b[:] = 1
+    assert (view == 7).all()
+    del view, b
+    c = pool.take(900, np.uint8)           # both are idle now: one of them comes back
+    assert c.base is base_a or c.size == 900
+    assert len(pool._bufs) <= 2
+    d = pool.take(10, np.int32)            # another dtype never aliases
+    assert d.dtype == np.int32 and d.base is not c.base
+    for _ in range(5):                     # busy arrays beyond `keep` are simply not pooled
+        pool.take(50, np.uint8)
+    assert len(pool._bufs) <= 2
