@@ -407,6 +407,14 @@ typedef struct maze_step_args {
 #define MAZE_STEP_COMPACT 1 /* band pipeline: no dense mask / label image for the band vignettes (run list only) */
 int maze_stage_step(const maze_step_args_t *args_host, void *lane_stream, void *side_stream);
 
+/* The same step as a CUDA graph (a batch that is one frame is some twenty small launches: issuing them takes the host
+ * longer than the GPU needs for the frame).  *exec == NULL: the step is captured on the lane stream, instantiated and
+ * launched; the handle and the number of kernel launches inside are returned.  Otherwise the graph is launched.  A graph
+ * replays the arguments it was captured with -- key the handles by the argument block (and the band plan behind
+ * huge_host).  Steps with leftover vignettes (left_n > 0) or under maze_prof_enable run plainly: *n_launches = -1. */
+int maze_stage_step_graph(const maze_step_args_t *a, void *lane_stream, void *side_stream, void **exec, int *n_launches);
+int maze_graph_destroy(void *exec);
+
 /* HOST helper: copies n host arrays (srcs[i], nbytes[i] bytes) to dst + dst_off[i] with n_threads threads.
  * Used to pack the vignettes of a batch into one pinned staging buffer (one upload per batch). */
 int maze_host_pack(const void *const *srcs_host, const int64_t *nbytes_host, const int64_t *dst_off_host, int n,

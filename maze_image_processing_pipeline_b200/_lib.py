@@ -110,6 +110,8 @@ SIGNATURES = {
     "maze_host_expand": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i],
     "maze_host_expand_crop": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "maze_stage_step": [_vp, _vp, _vp],
+    "maze_stage_step_graph": [_vp, _vp, _vp, _vp, _vp],
+    "maze_graph_destroy": [_vp],
     "maze_front_chain": [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 OTHER_SYMBOLS = ["maze_host_pack_start", "maze_error_string", "maze_version", "maze_launch_count", "maze_prof_kernel_count",

@@ -55,6 +55,8 @@ void maze_prof_end(int kid, cudaStream_t s)
 }
 
 extern "C" long long maze_launch_count(void) { return g_launches.load(); }
+void maze_prof_add_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int maze_prof_is_enabled(void) { return g_enabled.load(std::memory_order_relaxed) ? 1 : 0; }
 extern "C" int maze_prof_kernel_count(void) { return KID_COUNT; }
 extern "C" const char *maze_prof_kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : ""; }
 extern "C" int maze_prof_enable(int on)

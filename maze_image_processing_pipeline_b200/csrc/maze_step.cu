@@ -102,3 +102,60 @@ extern "C" int maze_stage_step(const maze_step_args_t *a, void *lane_stream, voi
     }
     return MAZE_OK;
 }
+
+void maze_prof_add_launches(long long n); // maze_prof.cu
+int maze_prof_is_enabled(void);
+
+// The same step as a CUDA GRAPH: a batch that is one frame (BASELINE.json configs[3]) is some twenty small launches, and
+// the host time of issuing them (~0.1 ms) exceeds the GPU time of the frame; replaying the captured step costs one launch.
+// *exec == NULL: the step is captured on the lane stream (relaxed mode), instantiated, launched, and the handle and the
+// number of kernel launches it holds are returned; otherwise the graph is launched.  A graph replays the ARGUMENTS it was
+// captured with: the caller keys its handles by the argument block (pointers, sizes, flags -- and the band plan behind
+// huge_host, which is read on the host at capture time).  Steps with leftover vignettes (side-stream work that joins
+// later) and steps under the per-kernel profiler are not captured: *n_launches = -1 tells the caller to stop asking.
+extern "C" int maze_stage_step_graph(const maze_step_args_t *a, void *lane_stream, void *side_stream, void **exec,
+                                     int *n_launches)
+{
+    cudaStream_t lane = (cudaStream_t)lane_stream;
+    if (!exec || !n_launches) return MAZE_ERR_BADARG;
+    if (*exec) {
+        MAZE_CUDA(cudaGraphLaunch((cudaGraphExec_t)*exec, lane), "step graph launch");
+        maze_prof_add_launches(*n_launches);
+        return MAZE_OK;
+    }
+    if (a->left_n > 0 || maze_prof_is_enabled()) {
+        *n_launches = -1;
+        return maze_stage_step(a, lane_stream, side_stream);
+    }
+    const long long before = maze_launch_count();
+    if (cudaStreamBeginCapture(lane, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        *n_launches = -1;
+        return maze_stage_step(a, lane_stream, side_stream);
+    }
+    const int rc = maze_stage_step(a, lane_stream, side_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(lane, &graph);
+    const long long captured = maze_launch_count() - before;
+    maze_prof_add_launches(-captured); // (nothing ran yet)
+    cudaGraphExec_t ge = nullptr;
+    if (rc != MAZE_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&ge, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        *n_launches = -1;
+        if (rc != MAZE_OK) return rc;
+        return maze_stage_step(a, lane_stream, side_stream);
+    }
+    cudaGraphDestroy(graph);
+    *exec = (void *)ge;
+    *n_launches = (int)captured;
+    MAZE_CUDA(cudaGraphLaunch(ge, lane), "step graph launch");
+    maze_prof_add_launches(captured);
+    return MAZE_OK;
+}
+
+extern "C" int maze_graph_destroy(void *exec)
+{
+    if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec);
+    return MAZE_OK;
+}

@@ -15,12 +15,13 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (BAND_PLANE_WORDS, FUSED_CAPS, FUSED_NO_PROPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS,
+from ._lib import (BAND_PLANE_WORDS, HUGE_PX, FUSED_CAPS, FUSED_NO_PROPS, MAX_DISK_RADIUS, NACC, NEXT, NFEAT, RP_HIGH_ORDER, RP_RUNS,
                    TILE_WORDS, check, lib)
 
 VIG_DTYPE = np.dtype([("pix_off", "<i8"), ("word_off", "<i8"), ("h", "<i4"), ("w", "<i4"),
                       ("wpr", "<i4"), ("tile0", "<i4")])
 TILE_DTYPE = np.dtype([("img", "<i4"), ("word0", "<i4")])
+BAND_TARGET_CTAS = 444  # 148 SMs x 3
 BAND_DTYPE = np.dtype([("img", "<i4"), ("y0", "<i4"), ("y1", "<i4"), ("rpb", "<i4")])        # maze_band_t
 BAND_OUT_DTYPE = np.dtype([("base", "<i4"), ("n_runs", "<i4"), ("zflags", "<i4"), ("reserved", "<i4")])  # maze_band_out_t
 RUN_DTYPE = np.dtype([("y", "<u2"), ("x0", "<u2"), ("x1", "<u2"), ("label", "<u2")])            # maze_run_t
@@ -134,6 +135,15 @@ class BatchGeometry:
         nb = np.where(single, 1, (self.h + rows_max - 1) // rows_max)
         rpb = (self.h + nb - 1) // nb
         nb = np.where(ok, (self.h + rpb - 1) // rpb, 0)
+        # a batch that is one frame (or a few): full-height bands would leave most SMs without a CTA (a 4096 x 4096
+        # frame is ~100 bands for 148 SMs x 4 slots).  Frames -- which are labelled in global memory, whatever their
+        # number of bands -- are cut into thinner bands, down to twice the halo, until the batch has ~3 CTAs per SM.
+        frames = ok & (self.npx >= HUGE_PX) & (nb > 1)
+        total = int(nb.sum())
+        if frames.any() and total < BAND_TARGET_CTAS:
+            thin = np.maximum(np.ceil(rpb * (total / BAND_TARGET_CTAS)).astype(np.int64), max(2 * halo, 4))
+            rpb = np.where(frames, np.minimum(rpb, thin), rpb)
+            nb = np.where(ok, (self.h + rpb - 1) // rpb, 0)
         band_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         n_bands = int(band_off[-1])
         if n_bands >= 2 ** 31:

@@ -443,6 +443,23 @@ def test_band_plan_covers_every_row_once_and_fits_the_planes():
                 assert ((hi - lo) * wpr <= BAND_PLANE_WORDS).all()
 
 
+def test_band_plan_cuts_a_lone_frame_into_enough_bands_for_every_sm():
+    """A batch that is one frame gets thinner bands (down to twice the halo) so that ~3 CTAs per SM exist; the
+    invariants of the plan stay; a batch with plenty of bands is left alone."""
+    from maze_image_processing_pipeline_b200._lib import BAND_PLANE_WORDS
+    from maze_image_processing_pipeline_b200.device import BAND_TARGET_CTAS, BatchGeometry
+    for halo in (0, 6):
+        g = BatchGeometry([4096], [4096])
+        bands, off, left = g.band_plan(halo)
+        assert len(left) == 0 and 300 <= len(bands) <= BAND_TARGET_CTAS + 64
+        assert bands["y0"][0] == 0 and bands["y1"][-1] == 4096 and (bands["y0"][1:] == bands["y1"][:-1]).all()
+        assert (bands["rpb"] == bands["rpb"][0]).all() and bands["rpb"][0] >= max(2 * halo, 4)
+        assert ((np.minimum(4096, bands["y1"] + halo) - np.maximum(0, bands["y0"] - halo)) * 128 <= BAND_PLANE_WORDS).all()
+    many = BatchGeometry([4096] * 8, [4096] * 8)       # enough bands already: full-height bands
+    bands, off, _ = many.band_plan(6)
+    assert bands["rpb"][0] == BatchGeometry([4096] * 8, [4096] * 8).band_plan(6)[0]["rpb"][0] > 24
+
+
 def test_host_pack_async_equals_sync():
     """maze_host_pack_start / maze_host_pack_wait (background packing of the next batch) against maze_host_pack."""
     from maze_image_processing_pipeline_b200.device import BatchGeometry
