@@ -758,7 +758,11 @@ class LokiSegmentationStage:
                 a.huge_host = saved_hh
                 graphs = ws.__dict__.setdefault("graphs", {})
                 entry = graphs.get(key)
-                if entry is None and len(graphs) < 16:
+                if entry is None:
+                    if len(graphs) >= 16:  # (a stream of ever new batches: the oldest argument block goes)
+                        old = graphs.pop(next(iter(graphs)))
+                        if old[1].value:
+                            lib().maze_graph_destroy(old[1])
                     entry = graphs[key] = [0, ctypes.c_void_p(0), ctypes.c_int(0)]  # times seen, exec handle, launches inside
             ws.plan = None
             if use_graph and entry is not None:

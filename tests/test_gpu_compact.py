@@ -290,3 +290,45 @@ def test_threshold_branch_on_the_band_pipeline(mz, compact):
                 assert_tables_close(f, oracle.regionprops_table(mask.astype(np.int32), im))
             else:
                 assert f[0, oracle.F_AREA] == 0
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_small_steps_replayed_as_cuda_graphs_follow_their_inputs(mz, compact):
+    """Steps of a few vignettes are captured once per lane and argument block and replayed as a CUDA graph
+    (maze_stage_step_graph); the plan of the step is cached per lane.  A replay must see the CURRENT contents of the
+    input buffer, and another batch must not reuse the cached plan."""
+    import torch
+    S, device = mz.stage, mz.device
+    a = mz.synth.synth_batch(77, 3, lo=90, hi=180)
+    b = [np.ascontiguousarray(im[::-1, ::-1]) for im in a]            # same shapes, other contents
+    c = mz.synth.synth_batch(78, 4, lo=60, hi=120)                    # another batch on the same lanes
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=compact, n_lanes=2)
+    want = {id(x): [scipy_chain.loki_chain(im, 40, 1, 2) for im in x] for x in (a, b, c)}
+    geom = device.BatchGeometry.from_images(a)
+    batch = st.prepare(device.DeviceBatch(geom))
+    d = batch.upload(geom.pack_host(a))
+    geom_c = device.BatchGeometry.from_images(c)
+    batch_c = st.prepare(device.DeviceBatch(geom_c))
+    d_c = batch_c.upload(geom_c.pack_host(c))
+
+    def check(res, g, imgs):
+        res.finalize()
+        torch.cuda.synchronize()
+        labels = None if res.labels is None else res.labels.cpu().numpy()
+        table = res.table.cpu().numpy()
+        off = res.lab_off.cpu().numpy()
+        for i, (mask, lab, tab) in enumerate(want[id(imgs)]):
+            if labels is not None and not compact:
+                assert np.array_equal(g.view(labels, i), lab), i
+            assert off[i + 1] - off[i] == len(tab)
+            assert_tables_close(table[off[i]:off[i + 1]], tab)
+
+    for rep in range(8):      # two lanes: calls 0-1 run plainly, 2-3 are captured, 4-7 replay
+        imgs = a if rep % 3 != 1 else b
+        d.copy_(torch.from_numpy(geom.pack_host(imgs)).to(d.device))
+        check(st.run_device(batch, d), geom, imgs)
+        if rep == 5:          # another batch in between: its own plan, its own graph
+            check(st.run_device(batch_c, d_c), geom_c, c)
+    handles = [e for ws in st._ws_ring for e in getattr(ws, "graphs", {}).values()]
+    assert st.graphs and any(e[1].value for e in handles), "no step was captured"
