@@ -33,7 +33,9 @@ constexpr int PW = MAZE_BAND_PLANE_WORDS;
 // run-table classes of the labelling kernel: runs, rows (+2) and bands a vignette may have
 #define BAND_T 256
 #define BAND_ZB 6144 /* bytes of zeros in shared memory behind the planes (source of the TMA zero fill) */
+#ifndef LABEL_T
 #define LABEL_T 64
+#endif
 #define LABEL_MID_T 256 /* (128 threads with 1024 runs: 0.35 ms instead of 0.21 ms for the list; 512 threads: no change) */
 #define LABEL_BIG_T 256
 #define LABEL_SMALL_CAP 256
