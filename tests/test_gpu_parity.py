@@ -261,6 +261,12 @@ def _merge_stress_images(rng):
     m &= ~((yy - 140) ** 2 + (xx - 150) ** 2 < 400)
     m |= rng.random((h, w)) < 0.004
     out.append(oracle.label(m)[0])
+    lab = np.zeros((215, 20), np.int32)  # ONE bridge (bar 1 - line 2) takes a pixel from each of 35 labels at once:
+    lab[:, 0:3] = 1                      # more than the kernel lists -> boxes and minima of all labels are rebuilt
+    lab[:, 9] = 2
+    for k, r in enumerate(range(3, 213, 6)):
+        lab[r, 11:14] = 3 + k
+    out.append(lab)
     # a one-pixel label swallowed by a bridge while later labels remain: its minimum is `initial`, it is never popped
     # (a crop of a synthetic bench vignette on which the first version of the kernel raised)
     out.append(np.load(os.path.join(os.path.dirname(__file__), "golden", "merge_swallowed_label.npy")).astype(np.int32))
