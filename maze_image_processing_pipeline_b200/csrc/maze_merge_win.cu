@@ -596,6 +596,15 @@ __global__ void __launch_bounds__(MW_CTA, MW_MINB) k_merge_windowed(const int32_
                 const int ya = max(Mb[0], ys[u] - r), yb = min(Mb[1], ys[u] + r);
                 const int xa = max(Mb[2], xs[u] - r), xb = min(Mb[3], xs[u] + r);
                 if (ya > yb || xa > xb) continue; // farther than r from the box of l0
+                {
+                    // the closest pair of two pixel sets joins BOUNDARY pixels: a pixel whose four neighbours carry the
+                    // same label cannot be nearer to l0 than all of them (a large second object costs its outline only)
+                    const int y = ys[u], x = xs[u];
+                    const int32_t *c = L + (i64)y * W + x;
+                    if (y > 0 && y < H - 1 && x > 0 && x < W - 1 && c[-W] == lv[u] && c[W] == lv[u] && c[-1] == lv[u] &&
+                        c[1] == lv[u])
+                        continue;
+                }
                 if (atomicAdd(&S.tested, 1) >= budget) { S.near = 1; continue; } // too many: build the map
                 bool hit = false;
                 for (int y = ya; y <= yb && !hit; y++) {
