@@ -33,13 +33,14 @@ class Region:
 
     def __init__(self, row: np.ndarray, shape, padding: int = 0, labels: Optional[np.ndarray] = None,
                  intensity: Optional[np.ndarray] = None, shape_row: Optional[np.ndarray] = None, mask_fn=None,
-                 sequence: Optional[int] = None, whole_frame: bool = False):
+                 sequence: Optional[int] = None, whole_frame: bool = False, label_fn=None):
         self._row = row
         self._shape_row = shape_row
         self._shape = shape
         self._labels = labels
         self._intensity = intensity
         self._mask_fn = mask_fn  # (slice, label) -> bool crop; compact results expand the object from its runs
+        self._label_fn = label_fn  # slice -> int32 crop of the label image (compact results: from the run list)
         self.sequence = int(row[F_LABEL]) if sequence is None else int(sequence)
         r0, c0, r1, c1 = (int(v) for v in row[F_BBOX:F_BBOX + 4])
         # _enlarge_slice semantics of morphocut's FindRegions: start clipped at 0, stop NOT clipped
@@ -105,6 +106,15 @@ class Region:
         raise ValueError("label image not attached")
 
     @property
+    def label_image(self) -> np.ndarray:
+        """The label image inside the (padded, image-clipped) slice: what tells this object from the others."""
+        if self._labels is not None:
+            return self._labels[self.slice]
+        if self._label_fn is not None:
+            return self._label_fn(self.slice)
+        raise ValueError("label image not attached")
+
+    @property
     def image_intensity(self) -> np.ndarray:
         if self._intensity is None:
             raise ValueError("intensity image not attached")
@@ -122,9 +132,10 @@ def find_regions(result, i: int, padding: int = 0, min_intensity: Optional[float
     feats = result.features(i)
     shapes = result.shape_features(i) if hasattr(result, "shape_features") else None
     shape = (int(result.geometry.h[i]), int(result.geometry.w[i]))
-    labels, mask_fn, whole = None, None, False
+    labels, mask_fn, label_fn, whole = None, None, None, False
     if getattr(result, "compact", False):  # run-list result: objects are expanded one crop at a time
         mask_fn = lambda sl, lab, _i=i: result.object_mask(_i, sl, lab)  # noqa: E731
+        label_fn = lambda sl, _i=i: result.label_crop(_i, sl)  # noqa: E731
     else:
         labels = result.labels(i)
         if labels is None:  # threshold branch (ImageProperties): the whole mask is label 1
@@ -141,7 +152,7 @@ def find_regions(result, i: int, padding: int = 0, min_intensity: Optional[float
         if min_intensity is not None and row[F_IMAX] < min_intensity:
             continue
         yield Region(row, shape, padding, labels, image, None if shapes is None else shapes[j], mask_fn,
-                     seq if renumber else None, whole)
+                     seq if renumber else None, whole, label_fn)
 
 
 def recalc_metadata(region: Region, meta: Dict, object_id_fmt: Optional[str] = None) -> Dict:
@@ -228,18 +239,26 @@ def zooprocess_features(region: Region, meta: Optional[Dict] = None, prefix: str
     return out
 
 
-def extract_roi(image: np.ndarray, region: Region, alpha: float = 0, bg_color=0) -> np.ndarray:
-    """``ExtractROI(image, region, alpha=1 if config.apply_mask else 0, bg_color=...)`` (loki/pipeline.py:596-602):
-    the padded crop ``image[region.slice]``; with ``alpha`` = 1 everything outside the object is painted with the
-    scalar ``bg_color``.  ``apply_mask`` defaults to False (config_schema.py:97-100), i.e. the plain crop; the
-    ``keep_background`` variant and colour names / quantiles of ``background_color`` are morphocut internals that
-    cannot be restated offline and raise NotImplementedError."""
+def extract_roi(image: np.ndarray, region: Region, alpha: float = 0, bg_color=0, keep_background: bool = False) -> np.ndarray:
+    """``ExtractROI(image, region, alpha=1 if config.apply_mask else 0, bg_color=config.background_color,
+    keep_background=config.keep_background)`` (loki/pipeline.py:596-602): the padded crop ``image[region.slice]``.
+    ``apply_mask`` defaults to False (config_schema.py:97-100), i.e. the plain crop.  With ``alpha`` = 1 the pixels
+    that are "not part of the current object" (config_schema.py:97-100) are painted with the scalar ``bg_color``:
+    everything outside the object -- or, with ``keep_background`` ("when hiding non-object image regions, keep
+    background", config_schema.py:105-107), only the pixels of OTHER objects, the unlabelled background stays.
+    Restated from the schema's descriptions: morphocut's ExtractROI is not available offline (parity unpinned); colour
+    names / quantiles of ``background_color`` and fractional ``alpha`` raise NotImplementedError."""
     crop = np.asarray(image)[region.slice]
     if alpha == 0:
         return crop
     if alpha != 1 or not np.isscalar(bg_color):
         raise NotImplementedError("only alpha in {0, 1} with a scalar background colour")
-    return np.where(region.image, crop, np.asarray(bg_color, dtype=crop.dtype))
+    if keep_background:
+        lab = region.label_image
+        keep = (lab == 0) | (lab == region.label)
+    else:
+        keep = region.image
+    return np.where(keep, crop, np.asarray(bg_color, dtype=crop.dtype))
 
 
 def objects_of(result, i: int, meta: Optional[Dict] = None, padding: int = 75, min_intensity: Optional[float] = None,

@@ -221,6 +221,24 @@ class StageResult:
               "maze_host_expand_crop")
         return out.view(bool)
 
+    def label_crop(self, i, sl) -> np.ndarray:
+        """``labels(i)[sl]`` (int32) without expanding the vignette: the crop in which ExtractROI tells the object from
+        the others (loki/pipeline.py:596-602)."""
+        g = self.geometry
+        h, w = int(g.h[i]), int(g.w[i])
+        r0, r1, _ = sl[0].indices(h)
+        c0, c1, _ = sl[1].indices(w)
+        if self._runs is None or i in self._dense:
+            lab = self.labels(i)
+            if lab is None:
+                raise ValueError("this result has no label image (threshold branch)")
+            return lab[r0:r1, c0:c1]
+        out = np.empty((max(r1 - r0, 0), max(c1 - c0, 0)), np.int32)
+        check(lib().maze_host_expand_crop(self._runs.ctypes.data, self._band_out.ctypes.data, int(self._band_off[i]),
+                                          int(self._band_off[i + 1]), int(self._rpb[i]), r0, max(r1, r0), c0, max(c1, c0),
+                                          0, None, out.ctypes.data), "maze_host_expand_crop")
+        return out
+
     def materialize(self, threads=None) -> "StageResult":
         """Compact -> dense: every mask and label image of the batch as flat host arrays (multi-threaded)."""
         if self._runs is None:

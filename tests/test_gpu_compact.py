@@ -61,6 +61,11 @@ def test_compact_streaming_and_objects(mz):
                 # ExtractROI (loki/pipeline.py:596-602): the padded crop, masked with the object expanded from its runs
                 assert np.array_equal(extract_roi(im, r), im[r.slice])
                 assert np.array_equal(extract_roi(im, r, alpha=1, bg_color=7), np.where(labels[r.slice] == r.label, im[r.slice], 7))
+                # keep_background: only other objects are painted; the label crop comes from the run list
+                assert np.array_equal(r.label_image, labels[r.slice])
+                lab = labels[r.slice]
+                assert np.array_equal(extract_roi(im, r, alpha=1, bg_color=7, keep_background=True),
+                                      np.where((lab == 0) | (lab == r.label), im[r.slice], 7))
             objs = objects_of(res, i, padding=75, image=im)
             assert [o["object_area_exc"] for o in objs] == [float(r.area) for r in regs]
             n += len(objs)

@@ -237,6 +237,12 @@ def test_regions_zooprocess_keys_with_shape_table():
     assert crop.shape == (5 + 6, 3 + 6) and crop.base is not None
     masked = extract_roi(img, reg, alpha=1, bg_color=7)
     assert (masked[reg.image] == 50).all() and (masked[~reg.image] == 7).all()
+    # keep_background (the schema's default when apply_mask is on): only the pixels of OTHER objects are painted
+    reg0 = list(find_regions(res, 0, padding=40, image=img))[1]      # a crop that reaches the first object too
+    kept = extract_roi(img, reg0, alpha=1, bg_color=7, keep_background=True)
+    lab = reg0.label_image
+    assert ((lab != 0) & (lab != reg0.label)).any()
+    assert np.array_equal(kept, np.where((lab == 0) | (lab == reg0.label), img[reg0.slice], 7))
 
 
 def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
