@@ -1248,15 +1248,18 @@ def _rpb_of(bands, band_off, n_img):
 
 def stream_objects(stage: "LokiSegmentationStage", objects, batch_size: int = 2048, image_key: str = "image",
                    meta_key: str = "meta", padding: int = 75, min_intensity=None, object_id_fmt=None,
-                   keep_arrays: bool = True):
+                   keep_arrays: bool = True, rois: bool = False, apply_mask: bool = False, background_color=0,
+                   keep_background: bool = True):
     """Adapter for a morphocut-style object stream (the place of the `Call` chain of
     maze_ipp/loki/pipeline.py:396-459 and the FindRegions / recalc_metadata / CalculateZooProcessFeatures tail,
     :589-625): consumes an iterable of dict-like stream objects that carry a uint8 vignette or frame under
     `image_key`, buffers `batch_size` of them, runs the stage once per buffer (pipelined over buffers) and yields,
     in input order, one dict per input object with the keys of the input plus `mask`, `labels` (`keep_arrays`) and
     `objects` (a list of metadata dicts, one per segmented object, see regions.objects_of).  In the threshold branch
-    (loki/pipeline.py:648-656) every vignette that survives the empty-mask filter yields ONE object, the whole mask."""
-    from .regions import objects_of
+    (loki/pipeline.py:648-656) every vignette that survives the empty-mask filter yields ONE object, the whole mask.
+    ``rois=True`` adds ``rois``: per object the ExtractROI crop (``apply_mask`` / ``background_color`` /
+    ``keep_background`` as in the schema) and the object's mask inside it."""
+    from .regions import extract_roi, find_regions, recalc_metadata, zooprocess_features
 
     def buffers():
         buf = []
@@ -1294,9 +1297,14 @@ def stream_objects(stage: "LokiSegmentationStage", objects, batch_size: int = 20
                 lab = res.labels(i)
                 out["labels"] = None if lab is None else lab.copy()
             # threshold branch: ImageProperties(mask, image) is ONE region over the whole frame, no padding (:653)
-            out["objects"] = objects_of(res, i, meta=meta, padding=0 if threshold_only else padding,
-                                        min_intensity=None if threshold_only else min_intensity, image=obj[image_key],
-                                        object_id_fmt=object_id_fmt)
+            regs = list(find_regions(res, i, 0 if threshold_only else padding, None if threshold_only else min_intensity,
+                                     obj[image_key]))
+            out["objects"] = [zooprocess_features(r, recalc_metadata(r, meta, object_id_fmt)) for r in regs]
+            if rois:
+                # ExtractROI (loki/pipeline.py:596-602, options of config_schema.py:90-107): the vignette and the mask
+                # of every object, what the EcoTaxa writer stores (`image`, and `mask` with store_mask)
+                out["rois"] = [(extract_roi(obj[image_key], r, 1 if apply_mask else 0, background_color, keep_background),
+                                r.image) for r in regs]
             yield out
 
 

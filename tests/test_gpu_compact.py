@@ -337,3 +337,30 @@ def test_small_steps_replayed_as_cuda_graphs_follow_their_inputs(mz, compact):
             check(st.run_device(batch_c, d_c), geom_c, c)
     handles = [e for ws in st._ws_ring for e in getattr(ws, "graphs", {}).values()]
     assert st.graphs and any(e[1].value for e in handles), "no step was captured"
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_stream_objects_emits_the_extract_roi_crops(mz, compact):
+    """stream_objects(rois=True): per object the padded crop and its mask (loki/pipeline.py:596-602), with the
+    schema's masking options, from dense and from run-list results."""
+    S = mz.stage
+    imgs = mz.synth.synth_batch(91, 6, lo=70, hi=160)
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=compact)
+    stream = [{"image": im, "meta": {"k": k}, "k": k} for k, im in enumerate(imgs)]
+    n = 0
+    for o in S.stream_objects(st, stream, batch_size=4, padding=10, rois=True, apply_mask=True, background_color=9,
+                              keep_background=True, keep_arrays=False):
+        im = imgs[o["k"]]
+        _, labels, table = scipy_chain.loki_chain(im, 40, 1, 2)
+        live = [int(r[oracle.F_LABEL]) for r in table if r[oracle.F_AREA] > 0]
+        assert len(o["rois"]) == len(o["objects"]) == len(live)
+        for (crop, mask), meta, l in zip(o["rois"], o["objects"], live):
+            ys, xs = np.nonzero(labels == l)
+            sl = (slice(max(0, ys.min() - 10), ys.max() + 1 + 10), slice(max(0, xs.min() - 10), xs.max() + 1 + 10))
+            lab = labels[sl]
+            assert np.array_equal(mask, lab == l)
+            assert np.array_equal(crop, np.where((lab == 0) | (lab == l), im[sl], 9))
+            assert meta["object_posx"] == sl[1].start and meta["object_posy"] == sl[0].start
+            n += 1
+    assert n > 6
