@@ -505,3 +505,45 @@ def test_host_array_pool_never_hands_out_an_array_that_is_still_referenced():
     for _ in range(5):                     # busy arrays beyond `keep` are simply not pooled
         pool.take(50, np.uint8)
     assert len(pool._bufs) <= 2
+
+
+def test_zooprocess_table_equals_the_per_object_dicts():
+    """The batch-wide, vectorised metadata table against objects_of (FindRegions -> recalc_metadata ->
+    CalculateZooProcessFeatures per object), with and without the shape table, padding and min_intensity."""
+    import oracle
+    from oracle import shape as oshape
+    from maze_image_processing_pipeline_b200.device import BatchGeometry
+    from maze_image_processing_pipeline_b200.regions import objects_of, zooprocess_table
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    rng = np.random.default_rng(5)
+    labs, imgs = [], []
+    for k in range(5):
+        h, w = int(rng.integers(30, 90)), int(rng.integers(30, 90))
+        m = rng.random((h, w)) < 0.08
+        m[h // 4:h // 2, w // 5:w // 2] = True
+        lab = oracle.label(m)[0]
+        if k == 2:
+            lab[lab == 2] = 0                    # a gap in the numbering, as the label filters leave it
+        labs.append(lab)
+        imgs.append(rng.integers(0, 200, (h, w)).astype(np.uint8))
+    g = BatchGeometry.from_images(labs)
+    tables = [oracle.regionprops_table(l, im) for l, im in zip(labs, imgs)]
+    off = np.concatenate([[0], np.cumsum([len(t) for t in tables])]).astype(np.int32)
+    res = StageResult(g, g.pack_host([(l > 0).view(np.uint8) for l in labs]), g.pack_host(labs, dtype=np.int32), off,
+                      np.concatenate(tables))
+    for with_shape in (False, True):
+        res.shape_table = np.concatenate([oshape.label_shape(l) for l in labs]) if with_shape else None
+        for padding, min_int in ((75, None), (0, None), (3, 150)):
+            cols = zooprocess_table(res, padding=padding, min_intensity=min_int)
+            want = [(i, o) for i in range(len(labs)) for o in objects_of(res, i, padding=padding, min_intensity=min_int,
+                                                                         image=imgs[i])]
+            assert len(cols["image_index"]) == len(want) > 10
+            for j, (i, o) in enumerate(want):
+                assert cols["image_index"][j] == i
+                for key, v in o.items():
+                    got = cols[key][j]
+                    if isinstance(v, float) and v != v:
+                        assert got != got, key
+                    else:
+                        assert got == v, (key, got, v)
+                assert set(o) <= set(cols)
