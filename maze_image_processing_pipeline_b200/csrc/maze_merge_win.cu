@@ -15,6 +15,8 @@
 //      - `sum_distmap <= merge_dist + path_tolerance` outside the window needs sqrt(fillB) <= merge_dist +
 //        path_tolerance: rare (the window maximum is at least pad as soon as one margin is unclipped), and then a pass
 //        over the rest of the vignette evaluates it exactly;
+//  * the loop ends without a distance map when the popped label's minimum of distmap exceeds max_distance^2, and a
+//    vignette in which no foreign pixel comes within max_distance of l0 ends before the first map (proofs at the two tests in the kernel);
 //  * `distmap[labels == l].min(initial=max_dist)` is kept per label and lowered by the pixels whose distmap an
 //    iteration lowers; in the aliased call a label can LOSE pixels to a bridge: if the lost pixel sat on the label's
 //    bounding box or held its minimum, the label is recomputed over its old bounding box before the next pop.
@@ -78,7 +80,6 @@ struct MwShared {
     u64 uval;
     double dval;
     int ival;
-    int tmp[5];
     int n_dirty;
     int dirty[MW_DIRTY];
     int near, tested;
@@ -146,8 +147,9 @@ __device__ __forceinline__ double mw_min_double(MwShared &S, double v)
     return S.dval;
 }
 
-// Bounding boxes (r0, r1, c0, c1 inclusive) of every label 1 .. bound -- and, WITH_MIN, the minimum of A over its
-// pixels -- in one pass over the vignette: a warp per row, four 32-pixel groups in flight; the lanes of a group that
+// (Rebuild of the tables when one bridge took pixels from more labels than the kernel lists; the first boxes come
+// from k_mw_prepare.)  Bounding boxes (r0, r1, c0, c1 inclusive) of every label 1 .. bound -- and, WITH_MIN, the
+// minimum of A over its pixels -- in one pass over the vignette: a warp per row, four 32-pixel groups in flight; the lanes of a group that
 // hold the same label elect a leader, which knows the group's column extent from the match mask.
 template <bool WITH_MIN>
 __device__ void mw_scan_all(const int32_t *L, const int32_t *A, int H, int W, int bound, int *box, uint32_t *mintab)
