@@ -465,7 +465,7 @@ def run_b200(args):
         nv = npx = up = down = 0
         for r in st.map(host_batches):
             if r.compact:
-                down += r._runs.nbytes + r._band_out.nbytes + sum(5 * m.size for m, _ in r._dense.values())
+                down += r._runs.nbytes + r._band_out.nbytes + sum((0 if m is None else m.size) + (0 if l is None else 4 * l.size) for m, l in r._dense.values())
             else:
                 down += r.geometry.total_px * 5
             if materialize:

@@ -166,7 +166,14 @@ class StageResult:
 
     def _expand(self, i):
         if i in self._dense:
+            m, l = self._dense[i]
+            if m is None:  # merge_labels rewrote the label image (it came down dense); the mask is still in the runs
+                m = self._expand_runs(i)[0]
+                self._dense[i] = (m, l)
             return self._dense[i]
+        return self._expand_runs(i)
+
+    def _expand_runs(self, i):
         if i not in self._cache:
             g = self.geometry
             h, w = int(g.h[i]), int(g.w[i])
@@ -200,6 +207,8 @@ class StageResult:
         """Run list of vignette i (compact form): structured array with fields y, x0, x1 (inclusive), label."""
         if self._runs is None:
             raise ValueError("dense result: no run list")
+        if i in self._dense:
+            raise ValueError(f"vignette {i} has no run list of its label image (dense arrays: labels(i))")
         bo = self._band_out[int(self._band_off[i]):int(self._band_off[i + 1])]
         parts = [self._runs[int(b["base"]):int(b["base"]) + int(b["n_runs"])] for b in bo if b["base"] >= 0]
         return np.concatenate(parts) if parts else self._runs[:0]
@@ -254,7 +263,7 @@ class StageResult:
                 threads = min(16, max(1, len(os.sched_getaffinity(0)) // 2))
             except Exception:
                 threads = 4
-        todo = np.asarray([i for i in range(n) if i not in self._dense], np.int64)
+        todo = np.asarray([i for i in range(n) if i not in self._dense or self._dense[i][0] is None], np.int64)
         if len(todo):
             pm = (mask.ctypes.data + g.pix_off[todo]).astype(np.uint64)
             pl = (labels.ctypes.data + 4 * g.pix_off[todo]).astype(np.uint64)
@@ -266,7 +275,8 @@ class StageResult:
                                          hh.ctypes.data, ww.ctypes.data, len(todo), pm.ctypes.data, pl.ctypes.data,
                                          int(threads)), "maze_host_expand")
         for i, (m, l) in self._dense.items():
-            g.view(mask, i)[...] = m
+            if m is not None:
+                g.view(mask, i)[...] = m
             if l is not None:
                 g.view(labels, i)[...] = l
         self._mask, self._labels = mask, labels
@@ -517,6 +527,8 @@ class LokiSegmentationStage:
                                       tiles=batch.tiles_of(need))
                     batch.arena = saved_arena
                 r.merge_status = merge_status
+                r.n_merge = n_merge if len(need) else torch.zeros(n, dtype=torch.int32, device=batch.device)
+                r.compact = saved_compact  # (the step ran dense on the device; the TRANSPORT can still be compact)
                 r._sync_main = True
                 r.ready = torch.cuda.Event()
                 r.ready.record(lane)
@@ -1059,6 +1071,15 @@ class LokiSegmentationStage:
             else:
                 ss.wait_stream(main)
         compact = getattr(res, "compact", False) and res.runs is not None and len(res.dense_only) <= 64
+        merged = None
+        if compact and getattr(res, "n_merge", None) is not None:
+            # merge_labels rewrote the label images of the vignettes in which labels merged: the run list of the band
+            # step still gives their MASKS (merge_labels.py never touches foreground_pred) and everything of the other
+            # vignettes; the merged label images come down dense -- unless that is most of the batch anyway
+            with torch.cuda.stream(ss):
+                merged = np.nonzero(res.n_merge.cpu().numpy() > 0)[0]
+            if int(geom.npx[merged].sum()) * 2 > geom.total_px:
+                compact, merged = False, None
         if getattr(res, "compact", False) and not compact:
             with torch.cuda.stream(ss):  # (rare) most of the batch has no run list: dense download after all
                 h_mask = pool.get("mask", geom.total_px, torch.uint8)
@@ -1076,6 +1097,16 @@ class LokiSegmentationStage:
                 h_runs.copy_(res.runs[:n_runs], non_blocking=True)
                 h_bo = pool.get("band_out", 4 * max(n_bands, 1), torch.int32)[:4 * n_bands]
                 h_bo.copy_(res.band_out[:4 * n_bands], non_blocking=True)
+                if merged is not None and len(merged):
+                    sub_off = np.concatenate([[0], np.cumsum(geom.npx[merged])]).astype(np.int64)
+                    h_sub = pool.get("labels_merged", max(int(sub_off[-1]), 1), torch.int32)
+                    for k, i in enumerate(merged):
+                        o, npx = int(geom.pix_off[i]), int(geom.npx[i])
+                        h_sub[int(sub_off[k]):int(sub_off[k]) + npx].copy_(res.labels[o:o + npx], non_blocking=True)
+                    h_sub_np = h_sub.numpy()
+                    for k, i in enumerate(merged):
+                        dense[int(i)] = (None, h_sub_np[int(sub_off[k]):int(sub_off[k + 1])].reshape(int(geom.h[i]),
+                                                                                                    int(geom.w[i])))
                 for i in res.dense_only:  # vignettes of the per-operator kernels: their dense arrays
                     o, npx = int(geom.pix_off[i]), int(geom.npx[i])
                     shp = (int(geom.h[i]), int(geom.w[i]))

@@ -364,3 +364,41 @@ def test_stream_objects_emits_the_extract_roi_crops(mz, compact):
             assert meta["object_posx"] == sl[1].start and meta["object_posy"] == sl[0].start
             n += 1
     assert n > 6
+
+
+def test_merge_path_keeps_the_compact_transport(mz):
+    """merge_segments_distance > 0 with compact=True: vignettes in which labels merged bring their label images down
+    dense (their masks still come from the run list), all others stay run lists; masks, label images, object crops,
+    the whole-batch materialisation and the table against the reference chain."""
+    S = mz.stage
+    from maze_image_processing_pipeline_b200.regions import find_regions
+    batches = [mz.synth.synth_batch(300 + b, 24, lo=64, hi=220) for b in range(2)]
+    pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1, merge_segments_distance=10)
+    st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp, compact=True, merge_errors="ignore")
+    n_dense = n_runs = 0
+    for imgs, res in zip(batches, st.map(batches)):
+        assert res.compact
+        failed = set() if res.merge_failed is None else set(int(i) for i in res.merge_failed)
+        want = {}
+        for i, im in enumerate(imgs):
+            if i in failed:
+                continue
+            mask, labels, table = scipy_chain.loki_chain(im, 40, 1, 2, merge_segments_distance=10)
+            want[i] = (mask, labels)
+            assert np.array_equal(res.mask(i), mask) and np.array_equal(res.labels(i), labels), i
+            k = min(len(table), len(res.features(i)))
+            assert_tables_close(res.features(i)[:k], table[:k])
+            for r in find_regions(res, i, padding=5, image=im):
+                assert np.array_equal(r.image, labels[r.slice] == r.label)
+                assert np.array_equal(r.label_image, labels[r.slice])
+            if i in res._dense:
+                n_dense += 1
+                with pytest.raises(ValueError):
+                    res.runs(i)
+            else:
+                n_runs += 1
+                assert len(res.runs(i)) > 0 or not mask.any()
+        dense = res.materialize()
+        for i, (mask, labels) in want.items():
+            assert np.array_equal(dense.mask(i), mask) and np.array_equal(dense.labels(i), labels)
+    assert n_dense > 0 and n_runs > n_dense
