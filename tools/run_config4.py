@@ -26,6 +26,10 @@ pp = S.SegmentationPostprocessingConfig(closing_radius=2, opening_radius=1)
 st = S.LokiSegmentationStage(S.ThresholdSegmentationConfig(40), pp)
 n_batches = (args.vignettes + args.batch - 1) // args.batch
 mine = list(range(rank, n_batches, world))
+# size every lane's workspace for the largest batch of the job up front: a lane that has to grow its buffers inside a
+# step pays a cudaMalloc / cudaFree pair of gigabytes (the step then takes milliseconds instead of one)
+st.reserve([BatchGeometry(hs[b * args.batch:min((b + 1) * args.batch, args.vignettes)],
+                          ws[b * args.batch:min((b + 1) * args.batch, args.vignettes)]) for b in mine])
 ms = 0.0
 n_vig = n_px = n_obj = checked = fallbacks = 0
 for k, b in enumerate(mine):
