@@ -297,8 +297,8 @@ class StageResult:
 
 class Workspace:
     """Device buffers of the fused path, allocated once and grown on demand so that the steady state makes
-    no allocator calls.  The stage rotates n_lanes (default four) of them (each with its own lane / side stream and scratch
-    arena); results of run_device alias one and stay valid for the next two run_device calls."""
+    no allocator calls.  The stage rotates n_lanes (default six) of them (each with its own lane / side stream and scratch
+    arena); results of run_device alias one and stay valid for the next n_lanes - 1 run_device calls."""
 
     def __init__(self):
         self._t = {}
@@ -629,7 +629,7 @@ class LokiSegmentationStage:
         return DeviceResult(batch, bits, labels, lab_off, table, n_obj, merge_status=merge_status, mask=mask)
 
     def _run_fused_async(self, batch, d_src, d_image, t_int, passes) -> DeviceResult:
-        """n_lanes workspaces (default four), each with its own LANE stream, rotate: batch i+1 starts on the next lane while
+        """n_lanes workspaces (default six), each with its own LANE stream, rotate: batch i+1 starts on the next lane while
         the tail of batch i (label offsets, feature rows, stragglers of the big size class) still runs, so the
         GPU never drains between batches.  The caller's stream is joined at the start (inputs) only; the
         result carries a `ready` event and DeviceResult.finalize() waits for it."""
