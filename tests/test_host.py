@@ -254,6 +254,16 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     with pytest.raises(ValueError):
         _lib.check(_lib.MAZE_ERR_BADARG, "maze_label_shape")
     assert lib.maze_count_scan(None, -1, None, None) == _lib.MAZE_ERR_BADARG
+    # the graph variant of the step needs somewhere to put its handle
+    import ctypes
+    a = _lib.StepArgs()
+    assert lib.maze_stage_step_graph(ctypes.byref(a), None, None, None, None) == _lib.MAZE_ERR_BADARG
+    assert lib.maze_graph_destroy(None) == _lib.MAZE_OK
+    # merge_labels: an explicit index needs its offsets, the cluster size is 1 or 8
+    assert lib.maze_merge_labels_ex(None, None, None, 1, None, 1, ctypes.c_void_p(8), None, 1, 10.0, 5.0, None, None, None, None,
+                                    None, None, None, None, None, 0, 1, None) == _lib.MAZE_ERR_BADARG
+    assert lib.maze_merge_labels_ex(None, None, None, 1, None, 1, None, None, 1, 10.0, 5.0, None, None, None, None,
+                                    None, None, None, None, None, 0, 4, None) == _lib.MAZE_ERR_BADARG
 
 
 def test_crosses_footprints_and_minkowski_collapse():
