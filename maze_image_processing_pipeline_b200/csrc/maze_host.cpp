@@ -138,8 +138,9 @@ extern "C" int maze_host_pack_wait(void *handle)
 // into what the reference's stage returns (bool mask + int32 label image, loki/pipeline.py:459) or into the
 // padded crop of one object (what FindRegions / ExtractROI consume, loki/pipeline.py:589-602).
 // ---------------------------------------------------------------------------------------------------------
-static void expand_one(const maze_run_t *runs, const maze_band_out_t *band_out, int b_lo, int b_hi, int h, int w,
-                       uint8_t *mask, int32_t *labels)
+// memset + painting in place: any order of the runs
+static void expand_one_unordered(const maze_run_t *runs, const maze_band_out_t *band_out, int b_lo, int b_hi, int h, int w,
+                                 uint8_t *mask, int32_t *labels)
 {
     const size_t npx = (size_t)h * (size_t)w;
     if (mask) memset(mask, 0, npx);
@@ -149,6 +150,7 @@ static void expand_one(const maze_run_t *runs, const maze_band_out_t *band_out, 
         if (o.base < 0) continue;
         const maze_run_t *r = runs + o.base;
         for (int i = 0; i < o.n_runs; i++) {
+            if ((int)r[i].y >= h || r[i].x1 < r[i].x0 || (int)r[i].x1 >= w) continue; // (never written outside the vignette)
             const size_t off = (size_t)r[i].y * (size_t)w + r[i].x0;
             const int len = (int)r[i].x1 - (int)r[i].x0 + 1;
             if (mask) memset(mask + off, 1, (size_t)len);
@@ -159,6 +161,71 @@ static void expand_one(const maze_run_t *runs, const maze_band_out_t *band_out, 
             }
         }
     }
+}
+
+static void expand_one(const maze_run_t *runs, const maze_band_out_t *band_out, int b_lo, int b_hi, int h, int w,
+                       uint8_t *mask, int32_t *labels)
+{
+    {
+        // (the streaming composition below relies on raster order; the run list is ~1 % of the output bytes: check)
+        size_t last = 0;
+        for (int b = b_lo; b < b_hi; b++) {
+            const maze_band_out_t o = band_out[b];
+            if (o.base < 0) continue;
+            const maze_run_t *r = runs + o.base;
+            for (int i = 0; i < o.n_runs; i++) {
+                const size_t p = (size_t)r[i].y * (size_t)w + r[i].x0;
+                if (p < last || r[i].x1 < r[i].x0 || (int)r[i].x1 >= w || (int)r[i].y >= h) {
+                    expand_one_unordered(runs, band_out, b_lo, b_hi, h, w, mask, labels);
+                    return;
+                }
+                last = p;
+            }
+        }
+    }
+    // The runs of a vignette are in raster order (bands in order, raster order inside a band), and a vignette is one
+    // contiguous block of h * w pixels: the output is composed chunk by chunk in a buffer that stays in L1 / L2 (zeros,
+    // then the pieces of the runs that fall into the chunk) and leaves with non-temporal stores -- the arrays are
+    // written ONCE, no line is read for ownership (memset + painting in place costs the memory system twice the bytes).
+    const size_t npx = (size_t)h * (size_t)w;
+    constexpr size_t CH = 8192; // pixels per chunk: 8 KB of mask + 32 KB of labels
+    alignas(64) uint8_t mb[CH];
+    alignas(64) int32_t lb[CH];
+    int b = b_lo, i = 0;
+    size_t p0 = 0, p1 = 0; // current run as flat pixel range [p0, p1)
+    int32_t lab = 0;
+    bool have = false;
+    auto next_run = [&]() {
+        have = false;
+        while (b < b_hi) {
+            const maze_band_out_t o = band_out[b];
+            if (o.base < 0 || i >= o.n_runs) { b++; i = 0; continue; }
+            const maze_run_t r = runs[o.base + i++];
+            p0 = (size_t)r.y * (size_t)w + r.x0;
+            p1 = (size_t)r.y * (size_t)w + r.x1 + 1;
+            lab = r.label;
+            have = true;
+            return;
+        }
+    };
+    next_run();
+    for (size_t c0 = 0; c0 < npx; c0 += CH) {
+        const size_t c1 = c0 + CH < npx ? c0 + CH : npx, n = c1 - c0;
+        if (mask) memset(mb, 0, n);
+        if (labels) memset(lb, 0, n * sizeof(int32_t));
+        while (have && p0 < c1) {
+            const size_t a = (p0 > c0 ? p0 : c0) - c0, e = (p1 < c1 ? p1 : c1) - c0;
+            if (e > a) { // (a run that lies before the chunk -- runs out of raster order -- is dropped, not written wildly)
+                if (mask) memset(mb + a, 1, e - a);
+                if (labels)
+                    for (size_t x = a; x < e; x++) lb[x] = lab;
+            }
+            if (p1 <= c1) next_run(); else break;
+        }
+        if (mask) stream_copy((char *)(mask + c0), (const char *)mb, n);
+        if (labels) stream_copy((char *)(labels + c0), (const char *)lb, n * sizeof(int32_t));
+    }
+    fence_stores();
 }
 
 extern "C" int maze_host_expand(const maze_run_t *runs, const maze_band_out_t *band_out, const int32_t *band_lo,
