@@ -196,7 +196,11 @@ class BatchGeometry:
                 avail = len(os.sched_getaffinity(0))
             except Exception:
                 avail = os.cpu_count() or 2
-            threads = int(env) if env else min(16, max(1, avail // 2))
+            # ranks of one box share its cores (torchrun sets LOCAL_WORLD_SIZE): eight ranks with sixteen copy threads
+            # each oversubscribe a 32-core host (measured at N = 8: 478 k vignettes/s end to end with 16 threads per rank,
+            # 502 k with 4)
+            lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+            threads = int(env) if env else (min(16, max(1, avail // 2)) if lws == 1 else min(8, max(2, avail // lws)))
         return out, arrs, ptrs, nbytes, offs, threads
 
     def pack_host_start(self, images, out, dtype=np.uint8, threads=None):

@@ -260,7 +260,9 @@ class StageResult:
             threads = int(os.environ["MAZE_EXPAND_THREADS"])
         if threads is None:
             try:
-                threads = min(16, max(1, len(os.sched_getaffinity(0)) // 2))
+                avail = len(os.sched_getaffinity(0))
+                lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))  # ranks of one box share its cores
+                threads = min(16, max(1, avail // 2)) if lws == 1 else min(8, max(2, avail // lws))
             except Exception:
                 threads = 4
         todo = np.asarray([i for i in range(n) if i not in self._dense or self._dense[i][0] is None], np.int64)
