@@ -429,6 +429,51 @@ def test_host_expand_and_crops_from_run_lists():
         assert np.array_equal(dense.labels(i), lab) and np.array_equal(dense.mask(i), lab > 0)
 
 
+def test_host_expand_streams_large_vignettes_and_survives_unordered_runs():
+    """The expansion composes the output chunk by chunk (runs in raster order, chunks of 8192 pixels leave with
+    non-temporal stores): vignettes of several chunks with runs that cross chunk borders, the same run list in
+    shuffled order (falls back to painting in place) and a run outside the vignette (dropped, never written)."""
+    from maze_image_processing_pipeline_b200.device import BatchGeometry, RUN_DTYPE
+    from maze_image_processing_pipeline_b200.stage import StageResult
+    rng = np.random.default_rng(11)
+    labs = []
+    for (h, w) in [(300, 257), (64, 1000), (513, 64)]:
+        lab = np.zeros((h, w), np.int32)
+        for _ in range(40):  # long runs: many cross a chunk border
+            y0, x0 = int(rng.integers(0, h - 3)), int(rng.integers(0, w - 3))
+            lab[y0:y0 + int(rng.integers(1, 30)), x0:x0 + int(rng.integers(1, w))] = int(rng.integers(1, 9))
+        labs.append(lab)
+    g = BatchGeometry([l.shape[0] for l in labs], [l.shape[1] for l in labs])
+    for shuffle in (False, True):
+        all_runs, all_bo, band_off, rpbs = [], [], [0], [50, 64, 100]
+        for lab, rpb in zip(labs, rpbs):
+            r, bo = _runs_of(lab, rpb)
+            if shuffle:  # inside every band
+                for b in bo:
+                    seg = r[b["base"]:b["base"] + b["n_runs"]]
+                    seg[:] = seg[rng.permutation(len(seg))]
+            bo["base"] += sum(len(x) for x in all_runs)
+            all_runs.append(r)
+            all_bo.append(bo)
+            band_off.append(band_off[-1] + len(bo))
+        runs = np.concatenate(all_runs)
+        if shuffle:  # and one run that lies outside its vignette: it must not be written anywhere
+            bad = np.zeros(1, RUN_DTYPE)
+            bad["y"], bad["x0"], bad["x1"], bad["label"] = 60000, 0, 5, 3
+            k = int(all_bo[0][0]["base"])
+            runs[k] = bad[0]
+        res = StageResult.from_runs(g, runs, np.concatenate(all_bo), np.asarray(band_off, np.int32),
+                                    np.asarray(rpbs, np.int32), {}, np.zeros(4, np.int32), np.zeros((0, 64)))
+        dense = res.materialize(threads=2)
+        for i, lab in enumerate(labs):
+            got = dense.labels(i)
+            if shuffle and i == 0:  # (the overwritten run of vignette 0 is missing, nothing else differs)
+                assert ((got == lab) | (got == 0)).all() and (got != lab).sum() <= labs[0].shape[1]
+            else:
+                assert np.array_equal(got, lab), (shuffle, i)
+                assert np.array_equal(dense.mask(i), lab > 0)
+
+
 def test_band_plan_covers_every_row_once_and_fits_the_planes():
     """Band plan of maze_band_stage: the bands of a vignette are consecutive, cover its rows exactly once with a uniform
     height, and a band plus its halo never exceeds MAZE_BAND_PLANE_WORDS; vignettes that cannot be cut are listed."""
